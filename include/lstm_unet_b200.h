@@ -1,0 +1,123 @@
+/*
+ * lstm_unet_b200.h -- C-ABI of the B200-native ConvLSTM-UNet hot path (liblstm_unet_b200.so).
+ *
+ * The reference (arbellea/LSTM-UNet) has no FFI: its boundary for this path is the Python object protocol of
+ * Networks.ULSTMnet2D as used by train2D.py / Inference2D.py.  Each entry point below names the reference
+ * interface it replaces (file:line in the reference repository).  The Python mirror of that protocol
+ * (lstm_unet_b200/Networks.py) binds these with ctypes; INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error; lu_last_error() returns the message of the last
+ *     failing call on this thread (the reference raises Python ValueError; the shim re-raises it).
+ *   - all `dev` pointers are device pointers owned by the caller (torch.Tensor.data_ptr()); `stream` is a
+ *     cudaStream_t passed as void* (0 = default stream).  Work is enqueued on `stream`, nothing synchronises
+ *     unless stated.  One handle per GPU per model instance; not thread-safe (the reference calls the model
+ *     from the main thread only).
+ *   - there is NO CPU fallback: on a box without an sm_100 device every compute entry point fails.
+ */
+#ifndef LSTM_UNET_B200_H
+#define LSTM_UNET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LU_MAX_LEVELS 4
+#define LU_MAX_PER_LEVEL 4
+
+enum { LU_PREC_BF16 = 0, LU_PREC_BF16X3 = 1 };       /* tensor-core operand precision */
+enum { LU_ENGINE_TCGEN05 = 0, LU_ENGINE_SIMT = 1 };   /* SIMT = on-GPU scalar mirror used to debug the TC path */
+enum { LU_GATE_HARD_SIGMOID = 0, LU_GATE_SIGMOID = 1 };
+enum { LU_AMODE_HALO = 0, LU_AMODE_DIRECT = 1 };      /* how activation tiles are staged in shared memory */
+
+/* Architecture-as-data: mirrors the `net_kernel_params` dict (Params.py:49-69, Networks.py:12-32) plus the
+ * constructor arguments of ULSTMnet2D (Networks.py:179) and the first-call shapes that freeze the stateful
+ * ConvLSTM states (B,H,W). */
+typedef struct lu_config {
+  int32_t n_levels;
+  int32_t n_lstm[LU_MAX_LEVELS];
+  int32_t lstm_k[LU_MAX_LEVELS][LU_MAX_PER_LEVEL];
+  int32_t lstm_f[LU_MAX_LEVELS][LU_MAX_PER_LEVEL];
+  int32_t n_down[LU_MAX_LEVELS];
+  int32_t down_k[LU_MAX_LEVELS][LU_MAX_PER_LEVEL];
+  int32_t down_f[LU_MAX_LEVELS][LU_MAX_PER_LEVEL];
+  int32_t n_up[LU_MAX_LEVELS];
+  int32_t up_k[LU_MAX_LEVELS][LU_MAX_PER_LEVEL];
+  int32_t up_f[LU_MAX_LEVELS][LU_MAX_PER_LEVEL];
+  int32_t in_channels;     /* 1 for the CTC path */
+  int32_t channels_first;  /* data_format[1]=='C' (Networks.py:181-182) */
+  int32_t pad_image;       /* Networks.py:186,210 */
+  int32_t batch, max_t, height, width;
+  int32_t precision;       /* LU_PREC_* */
+  int32_t engine;          /* LU_ENGINE_* */
+  int32_t gate;            /* LU_GATE_* */
+  int32_t a_mode;          /* LU_AMODE_* */
+  int32_t train;           /* 1: allocate what forward(training=True)+backward need */
+} lu_config;
+
+typedef struct lu_handle_s* lu_handle;
+
+const char* lu_last_error(void);
+/* library/ABI version and whether this build is the CUDA product build (1) -- never 0 in a shipped .so */
+int lu_version(void);
+int lu_is_cuda_build(void);
+
+/* ULSTMnet2D.__init__ (Networks.py:179-206): validates the level counts (ValueError -> non-zero), derives the
+ * layer plan, parameter layout and workspace size.  No device memory is allocated. */
+int lu_create(const lu_config* cfg, lu_handle* out);
+int lu_destroy(lu_handle h);
+
+/* device workspace (activations, recurrent states, packed bf16 weights, tables); caller allocates, library
+ * zero-fills.  States live inside the workspace and persist across calls (stateful=True, Networks.py:48-50). */
+int lu_workspace_bytes(lu_handle h, size_t* bytes);
+int lu_bind_workspace(lu_handle h, void* dev_ws, size_t bytes, void* stream);
+
+/* Keras variable layout (model.trainable_variables / save_weights, train2D.py:92,236): tensors in Keras
+ * layouts (HWIO kernels, ConvLSTM (k,k,Cin,4F) gate order i,f,c,o) concatenated in one flat fp32 buffer,
+ * trainable tensors first, BN moving statistics after them. */
+int lu_param_count(lu_handle h, int32_t* n_tensors, int64_t* n_elements, int64_t* n_trainable_elements);
+int lu_param_info(lu_handle h, int32_t idx, char* name, int32_t name_cap, int64_t* shape4, int32_t* rank,
+                  int64_t* offset, int32_t* trainable);
+int lu_bind_params(lu_handle h, float* dev_params);
+/* call after the flat parameter buffer changed (load_weights / optimizer step): re-packs the tensor-core
+ * operand copies of the weights */
+int lu_params_changed(lu_handle h, void* stream);
+
+/* ULSTMnet2D.call (Networks.py:208-254): x is (B,T,C,H,W) [channels_first] or (B,T,H,W,C); writes logits and
+ * softmax of shape (B,T,3,H,W) / (B,T,H,W,3); mutates the recurrent states.  training selects BN batch
+ * statistics (and keeps what backward needs when cfg.train). */
+int lu_forward(lu_handle h, const float* dev_x, int32_t T, int32_t training, float* dev_logits,
+               float* dev_softmax, void* stream);
+
+/* reset_states_per_batch (Networks.py:77-84,279-281): h,c *= mask[b]; mask is (B,) fp32 on the device */
+int lu_reset_states(lu_handle h, const float* dev_mask, void* stream);
+/* get_states / set_states (Networks.py:86-98,283-291): one (B,F,H,W)/(B,H,W,F) fp32 tensor per call;
+ * which: 0 = h, 1 = c.  dev_in == NULL zeroes the state (Keras reset_states(None)). */
+int lu_state_shape(lu_handle h, int32_t level, int32_t layer, int64_t* shape4);
+int lu_get_state(lu_handle h, int32_t level, int32_t layer, int32_t which, float* dev_out, void* stream);
+int lu_set_state(lu_handle h, int32_t level, int32_t layer, int32_t which, const float* dev_in, void* stream);
+
+/* WeightedCELoss (losses.py:13-27) + tape.gradient (train2D.py:89-92) for the last lu_forward(training=1):
+ * labels (B,T,1,H,W)/(B,T,H,W,1) fp32 in {-1,0,1,2}; writes the scalar loss and the flat gradient of the
+ * trainable prefix of the parameter buffer. */
+int lu_loss_backward(lu_handle h, const float* dev_labels, const float* class_weights3, float* dev_loss,
+                     float* dev_grads, void* stream);
+/* optimizer.apply_gradients with Keras Adam (train2D.py:61,93): step is 1-based; m,v are flat fp32 buffers */
+int lu_adam_step(lu_handle h, const float* dev_grads, float* dev_m, float* dev_v, float lr, float beta1,
+                 float beta2, float eps, int64_t step, void* stream);
+
+/* counters for bench.py: kernels launched by this handle since the last reset */
+int lu_launch_count(lu_handle h, int64_t* launches, int32_t reset);
+/* algorithmic FLOPs (2*MAC, padding included) of one forward over T frames per sample at the bound shape */
+int lu_forward_flops(lu_handle h, int32_t T, double* flops);
+/* names the dominant kernel's last launches for profiling: sets a CUDA-event pair around every ConvLSTM
+ * tensor-core launch when enabled; returns accumulated milliseconds and launch count */
+int lu_lstm_kernel_time(lu_handle h, int32_t enable, float* ms_total, int32_t* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LSTM_UNET_B200_H */

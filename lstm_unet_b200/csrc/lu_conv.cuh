@@ -1,0 +1,452 @@
+// Table-driven implicit-GEMM convolution: shared epilogues, the scalar mirror kernel and the tcgen05 kernel.
+//
+// GEMM view: D[128 output pixels (16x8 tile), BN packed output columns] += A[pixels, 64-channel K block] * B.
+// A comes straight from NHWC bf16 activation buffers (no im2col/im2row buffer is ever materialised): a K block
+// is "source view, channel chunk, filter tap", and the tap only shifts which rows of a staged [rows x pitch]
+// pixel window the MMA reads.  B is the pre-packed K-major bf16 weight matrix [Npad][Ktot].
+#pragma once
+#include "lu_defs.h"
+
+struct LuConvParams {
+  LuSrcView src[LU_MAX_SRC];
+  const LuAStage* astages;
+  const uint16_t* taps;
+  const uint16_t* wpacked;        // [Npad][ktot]
+  int32_t n_astages, ktot;
+  int32_t tiles_x, tiles_y, frames, n_tiles_n, BN;
+  LuEpi epi;
+};
+
+// ---- 16-wide stores -----------------------------------------------------------------------------------------
+LU_HDI void lu_store16_f32(float* dst, const float* v) {
+#ifdef __CUDA_ARCH__
+  float4* d = reinterpret_cast<float4*>(dst);
+  d[0] = make_float4(v[0], v[1], v[2], v[3]);
+  d[1] = make_float4(v[4], v[5], v[6], v[7]);
+  d[2] = make_float4(v[8], v[9], v[10], v[11]);
+  d[3] = make_float4(v[12], v[13], v[14], v[15]);
+#else
+  for (int j = 0; j < 16; ++j) dst[j] = v[j];
+#endif
+}
+LU_HDI void lu_load16_f32(const float* src, float* v) {
+#ifdef __CUDA_ARCH__
+  const float4* s = reinterpret_cast<const float4*>(src);
+  float4 a = s[0], b = s[1], c = s[2], d = s[3];
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  v[8] = c.x; v[9] = c.y; v[10] = c.z; v[11] = c.w; v[12] = d.x; v[13] = d.y; v[14] = d.z; v[15] = d.w;
+#else
+  for (int j = 0; j < 16; ++j) v[j] = src[j];
+#endif
+}
+LU_HDI void lu_store16_bf16(uint16_t* dst, const uint16_t* h) {
+#ifdef __CUDA_ARCH__
+  uint4 a, b;
+  a.x = h[0] | ((uint32_t)h[1] << 16);  a.y = h[2] | ((uint32_t)h[3] << 16);
+  a.z = h[4] | ((uint32_t)h[5] << 16);  a.w = h[6] | ((uint32_t)h[7] << 16);
+  b.x = h[8] | ((uint32_t)h[9] << 16);  b.y = h[10] | ((uint32_t)h[11] << 16);
+  b.z = h[12] | ((uint32_t)h[13] << 16); b.w = h[14] | ((uint32_t)h[15] << 16);
+  reinterpret_cast<uint4*>(dst)[0] = a;
+  reinterpret_cast<uint4*>(dst)[1] = b;
+#else
+  for (int j = 0; j < 16; ++j) dst[j] = h[j];
+#endif
+}
+
+// ---- epilogues (one 16-column chunk of one output pixel) -------------------------------------------------
+// conv: v = acc + bias -> optional fp32 raw store; optional folded-BN + LeakyReLU -> bf16 (hi[,lo]) store.
+LU_HDI void lu_epi_conv_chunk(const LuEpi& e, int64_t pix, int n, float* v) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] += e.bias[n + j];
+  if (e.out_raw != nullptr && n < e.raw_cpad) lu_store16_f32(e.out_raw + pix * e.raw_cpad + n, v);
+  if (e.out_act != nullptr && n < e.out_cpad) {
+    uint16_t hi[16], lo[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      float a = v[j] * e.scale[n + j] + e.shift[n + j];
+      a = a > 0.f ? a : e.alpha * a;
+      lu_split(a, hi[j], lo[j]);
+    }
+    uint16_t* o = e.out_act + pix * (int64_t)(e.out_cpad * e.out_planes) + n;
+    lu_store16_bf16(o, hi);
+    if (e.out_planes == 2) lu_store16_bf16(o + e.out_cpad, lo);
+  }
+}
+
+// ConvLSTM cell (keras ConvLSTM2D defaults): z* are the pre-activations of gates i,f,c,o for 16
+// channels starting at ch0; sample = batch index (states), pix_out = pixel index in the h sequence buffer.
+LU_HDI void lu_epi_lstm_chunk(const LuEpi& e, int64_t pix_state, int64_t pix_out, int nbase, int jc, int ch0,
+                              const float* zi, const float* zf, const float* zg, const float* zo) {
+  const int CH = e.ch_tile;
+  const float* b = e.bias + nbase + jc;
+  float* cp = e.c_state + pix_state * e.f_pad + ch0;
+  float c[16], gi[16], gf[16], gg[16], go[16];
+  uint16_t hi[16], lo[16];
+  lu_load16_f32(cp, c);
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    float ai = zi[j] + b[j], af = zf[j] + b[CH + j], ag = zg[j] + b[2 * CH + j], ao = zo[j] + b[3 * CH + j];
+    if (e.gate_kind == 0) { gi[j] = lu_hard_sigmoid(ai); gf[j] = lu_hard_sigmoid(af); go[j] = lu_hard_sigmoid(ao); }
+    else { gi[j] = lu_sigmoid(ai); gf[j] = lu_sigmoid(af); go[j] = lu_sigmoid(ao); }
+    gg[j] = tanhf(ag);
+    c[j] = gf[j] * c[j] + gi[j] * gg[j];
+    float h = go[j] * tanhf(c[j]);
+    lu_split(h, hi[j], lo[j]);
+  }
+  lu_store16_f32(cp, c);
+  const int64_t ctot = (int64_t)e.f_pad * e.out_planes;
+  uint16_t* o = e.out_act + pix_out * ctot + ch0;
+  lu_store16_bf16(o, hi);
+  if (e.out_planes == 2) lu_store16_bf16(o + e.f_pad, lo);
+  if (e.h_state_out != nullptr) {
+    uint16_t* s = e.h_state_out + pix_state * ctot + ch0;
+    lu_store16_bf16(s, hi);
+    if (e.out_planes == 2) lu_store16_bf16(s + e.f_pad, lo);
+  }
+  if (e.save_c != nullptr) lu_store16_f32(e.save_c + pix_out * e.f_pad + ch0, c);
+  if (e.save_gates != nullptr) {
+    uint16_t t[16];
+    uint16_t* g = e.save_gates + pix_out * (int64_t)(4 * e.f_pad) + ch0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) t[j] = lu_f2bf(gi[j]);
+    lu_store16_bf16(g, t);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) t[j] = lu_f2bf(gf[j]);
+    lu_store16_bf16(g + e.f_pad, t);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) t[j] = lu_f2bf(gg[j]);
+    lu_store16_bf16(g + 2 * e.f_pad, t);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) t[j] = lu_f2bf(go[j]);
+    lu_store16_bf16(g + 3 * e.f_pad, t);
+  }
+}
+
+// ---- scalar mirror: executes exactly the same tables / packed weights with plain loads and FMAs -------------
+LU_HDI void lu_mirror_acc16(const LuConvParams& p, int frame, int y0, int x0, int m, int ncol, float* acc) {
+  const int ty = m / LU_TILE_W, tx = m % LU_TILE_W;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+  int kb = 0;
+  for (int s = 0; s < p.n_astages; ++s) {
+    const LuAStage st = p.astages[s];
+    const LuSrcView& v = p.src[st.src];
+    const int64_t n = (int64_t)frame * v.frame_mul + v.frame_add;
+    for (int t = 0; t < st.ntaps; ++t, ++kb) {
+      const int off = p.taps[st.tap_begin + t];
+      const int yy = y0 + st.dy + off / v.pitch + ty;
+      const int xx = x0 + st.dx + off % v.pitch + tx;
+      if (yy < 0 || yy >= v.dimH || xx < 0 || xx >= v.dimW) continue;      // TMA zero-fills out-of-bounds
+      const uint16_t* a = v.ptr + n * v.sn + (int64_t)yy * v.sh + (int64_t)st.plane * v.sp + (int64_t)xx * v.sw + st.c;
+      const uint16_t* w = p.wpacked + (int64_t)ncol * p.ktot + (int64_t)kb * LU_KBLK;
+      int cmax = v.dimC - st.c;
+      if (cmax > LU_KBLK) cmax = LU_KBLK;
+      for (int kk = 0; kk < cmax; ++kk) {
+        const float av = lu_bf2f(a[kk]);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] += av * lu_bf2f(w[(int64_t)j * p.ktot + kk]);
+      }
+    }
+  }
+}
+
+// item = ((m_tile * n_tiles_n + n_tile) * 128 + m) * chunks + chunk
+LU_HDI void lu_conv_mirror_item(const LuConvParams& p, int64_t item) {
+  const LuEpi& e = p.epi;
+  const int chunks = (e.kind == LU_EPI_LSTM) ? e.ch_tile / 16 : p.BN / 16;
+  const int chunk = (int)(item % chunks); item /= chunks;
+  const int m = (int)(item % 128); item /= 128;
+  const int nt = (int)(item % p.n_tiles_n); item /= p.n_tiles_n;
+  const int tx = (int)(item % p.tiles_x); item /= p.tiles_x;
+  const int ty = (int)(item % p.tiles_y); item /= p.tiles_y;
+  const int frame = (int)item;
+  const int y0 = ty * LU_TILE_H, x0 = tx * LU_TILE_W;
+  const int y = y0 + m / LU_TILE_W, x = x0 + m % LU_TILE_W;
+  if (y >= e.H || x >= e.W) return;
+  const int n0 = nt * p.BN;
+  const int64_t fout = (int64_t)frame * e.out_frame_mul + e.out_frame_add;
+  const int64_t pix_out = (fout * e.H + y) * e.W + x;
+  if (e.kind == LU_EPI_CONV) {
+    float v[16];
+    lu_mirror_acc16(p, frame, y0, x0, m, n0 + chunk * 16, v);
+    lu_epi_conv_chunk(e, pix_out, n0 + chunk * 16, v);
+  } else {
+    const int CH = e.ch_tile, jc = chunk * 16;
+    float zi[16], zf[16], zg[16], zo[16];
+    lu_mirror_acc16(p, frame, y0, x0, m, n0 + jc, zi);
+    lu_mirror_acc16(p, frame, y0, x0, m, n0 + CH + jc, zf);
+    lu_mirror_acc16(p, frame, y0, x0, m, n0 + 2 * CH + jc, zg);
+    lu_mirror_acc16(p, frame, y0, x0, m, n0 + 3 * CH + jc, zo);
+    const int64_t pix_state = ((int64_t)frame * e.H + y) * e.W + x;
+    lu_epi_lstm_chunk(e, pix_state, pix_out, n0, jc, nt * CH + jc, zi, zf, zg, zo);
+  }
+}
+
+#ifndef LU_HOST_EMU
+// =============================================================================================================
+// tcgen05 kernel (sm_100a): TMA-staged operands, single-thread UMMA issue, accumulators in TMEM.
+// =============================================================================================================
+#include <cuda.h>
+
+struct LuTcParams {
+  CUtensorMap tmA[LU_MAX_SRC];
+  CUtensorMap tmB;
+  LuConvParams cp;
+  int32_t n_a_stages, n_b_stages, a_stage_bytes, b_stage_bytes;
+  uint32_t idesc;
+  int32_t total_tiles;
+};
+
+namespace lutc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// K-major, 128-byte swizzle operand descriptor (cute::UMMA::SmemDescriptor layout, sm_100 version bit set)
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t sbo_bytes) {
+  uint64_t d = (uint64_t)((addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;                                  // LBO (ignored for swizzled K-major)
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;                   // stride between 8-row groups
+  d |= (uint64_t)1 << 46;                                  // descriptor version (Blackwell)
+  d |= (uint64_t)((addr >> 7) & 7u) << 49;                 // base offset: start not 1024-byte aligned (halo taps)
+  d |= (uint64_t)2 << 61;                                  // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+}
+// wait for outstanding tcgen05.ld; the "+f" operands pin the loaded registers behind the wait
+__device__ __forceinline__ void tmem_wait16(float* v) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]),
+                 "+f"(v[8]), "+f"(v[9]), "+f"(v[10]), "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15])
+               :
+               : "memory");
+}
+
+constexpr int kThreads = 256;      // warp 0: A producer, 1: MMA issuer, 2: TMEM allocator, 3: B producer, 4-7: epilogue
+constexpr int kTmemCols = 512;
+
+}  // namespace lutc
+
+template <int EPI>
+__global__ void __launch_bounds__(lutc::kThreads, 1) lu_conv_tc_kernel(const __grid_constant__ LuTcParams P) {
+  using namespace lutc;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t pad = ((raw_addr + 1023u) & ~1023u) - raw_addr;   // SWIZZLE_128B needs 1024-byte aligned stages
+  uint8_t* smem = smem_raw + pad;
+  const int nA = P.n_a_stages, nB = P.n_b_stages;
+  const uint32_t sA = smem_u32(smem);
+  const uint32_t sB = sA + (uint32_t)nA * P.a_stage_bytes;
+  const uint32_t bars = sB + (uint32_t)nB * P.b_stage_bytes;       // 8-byte mbarriers
+  const uint32_t full_a = bars, empty_a = full_a + 8u * nA, full_b = empty_a + 8u * nA, empty_b = full_b + 8u * nB;
+  const uint32_t tmem_full = empty_b + 8u * nB, tmem_empty = tmem_full + 16u, tmem_slot = tmem_empty + 16u;
+  uint32_t* tmem_slot_ptr =
+      reinterpret_cast<uint32_t*>(smem + (size_t)nA * P.a_stage_bytes + (size_t)nB * P.b_stage_bytes + 16u * (nA + nB) + 32u);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const LuConvParams& cp = P.cp;
+  const int BN = cp.BN;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < LU_MAX_SRC; ++i)
+      if (cp.src[i].rows > 0) prefetch_tmap(&P.tmA[i]);
+    prefetch_tmap(&P.tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < nA; ++i) { mbar_init(full_a + 8u * i, 1); mbar_init(empty_a + 8u * i, 1); }
+    for (int i = 0; i < nB; ++i) { mbar_init(full_b + 8u * i, 1); mbar_init(empty_b + 8u * i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tmem_full + 8u * i, 1); mbar_init(tmem_empty + 8u * i, 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int tiles_per_frame = cp.tiles_x * cp.tiles_y;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ A producer (activation windows)
+    if (lane == 0) {
+      int sa = 0; uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+        const int mt = tile / cp.n_tiles_n;
+        const int frame = mt / tiles_per_frame, rem = mt % tiles_per_frame;
+        const int y0 = (rem / cp.tiles_x) * LU_TILE_H, x0 = (rem % cp.tiles_x) * LU_TILE_W;
+        for (int s = 0; s < cp.n_astages; ++s) {
+          const LuAStage st = cp.astages[s];
+          const LuSrcView& v = cp.src[st.src];
+          mbar_wait(empty_a + 8u * sa, ph ^ 1u);
+          mbar_expect_tx(full_a + 8u * sa, (uint32_t)(v.rows * v.pitch) * 128u);
+          tma_load_5d(sA + (uint32_t)sa * P.a_stage_bytes, &P.tmA[st.src], full_a + 8u * sa, st.c, x0 + st.dx, st.plane,
+                      y0 + st.dy, frame * v.frame_mul + v.frame_add);
+          if (++sa == nA) { sa = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ------------------------------------------------------------------ B producer (packed weight K blocks)
+    if (lane == 0) {
+      int sb = 0; uint32_t ph = 0;
+      const int nkb = cp.ktot / LU_KBLK;
+      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+        const int nt = tile % cp.n_tiles_n;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(empty_b + 8u * sb, ph ^ 1u);
+          mbar_expect_tx(full_b + 8u * sb, (uint32_t)BN * 128u);
+          tma_load_2d(sB + (uint32_t)sb * P.b_stage_bytes, &P.tmB, full_b + 8u * sb, kb * LU_KBLK, nt * BN);
+          if (++sb == nB) { sb = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (one thread)
+    if (lane == 0) {
+      int sa = 0, sb = 0, acc = 0; uint32_t pha = 0, phb = 0, phacc = 0;
+      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+        mbar_wait(tmem_empty + 8u * acc, phacc ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        uint32_t accum = 0;
+        for (int s = 0; s < cp.n_astages; ++s) {
+          const LuAStage st = cp.astages[s];
+          const uint32_t sbo = (uint32_t)cp.src[st.src].pitch * 128u;
+          mbar_wait(full_a + 8u * sa, pha);
+          tc_fence_after();
+          const uint32_t a_base = sA + (uint32_t)sa * P.a_stage_bytes;
+          for (int t = 0; t < st.ntaps; ++t) {
+            const uint32_t off = cp.taps[st.tap_begin + t];
+            mbar_wait(full_b + 8u * sb, phb);
+            tc_fence_after();
+            const uint32_t b_base = sB + (uint32_t)sb * P.b_stage_bytes;
+#pragma unroll
+            for (int k = 0; k < LU_KBLK / 16; ++k) {
+              const uint64_t adesc = make_desc(a_base + off * 128u + (uint32_t)k * 32u, sbo);
+              const uint64_t bdesc = make_desc(b_base + (uint32_t)k * 32u, 1024u);
+              mma_bf16(d_tmem, adesc, bdesc, P.idesc, accum);
+              accum = 1;
+            }
+            tc_commit(empty_b + 8u * sb);           // frees the weight stage once these MMAs retire
+            if (++sb == nB) { sb = 0; phb ^= 1u; }
+          }
+          tc_commit(empty_a + 8u * sa);             // frees the activation window
+          if (++sa == nA) { sa = 0; pha ^= 1u; }
+        }
+        tc_commit(tmem_full + 8u * acc);            // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; phacc ^= 1u; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue: TMEM -> registers -> HBM
+    const int q = warp & 3;                         // TMEM lane quarter this warp may access
+    const int m = q * 32 + lane;
+    const LuEpi& e = cp.epi;
+    int acc = 0; uint32_t phacc = 0;
+    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+      const int nt = tile % cp.n_tiles_n, mt = tile / cp.n_tiles_n;
+      const int frame = mt / tiles_per_frame, rem = mt % tiles_per_frame;
+      const int y = (rem / cp.tiles_x) * LU_TILE_H + m / LU_TILE_W, x = (rem % cp.tiles_x) * LU_TILE_W + m % LU_TILE_W;
+      const bool valid = (y < e.H) && (x < e.W);
+      const int n0 = nt * BN;
+      const int64_t fout = (int64_t)frame * e.out_frame_mul + e.out_frame_add;
+      const int64_t pix_out = (fout * e.H + y) * e.W + x;
+      mbar_wait(tmem_full + 8u * acc, phacc);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(q * 32) << 16);
+      if (EPI == LU_EPI_CONV) {
+        for (int col = 0; col < BN; col += 16) {
+          float v[16];
+          tmem_ld16(taddr + (uint32_t)col, v);
+          tmem_wait16(v);
+          if (valid) lu_epi_conv_chunk(e, pix_out, n0 + col, v);
+        }
+      } else {
+        const int CH = e.ch_tile;
+        const int64_t pix_state = ((int64_t)frame * e.H + y) * e.W + x;
+        for (int jc = 0; jc < CH; jc += 16) {
+          float zi[16], zf[16], zg[16], zo[16];
+          tmem_ld16(taddr + (uint32_t)jc, zi);
+          tmem_ld16(taddr + (uint32_t)(CH + jc), zf);
+          tmem_ld16(taddr + (uint32_t)(2 * CH + jc), zg);
+          tmem_ld16(taddr + (uint32_t)(3 * CH + jc), zo);
+          tmem_wait16(zi); tmem_wait16(zf); tmem_wait16(zg); tmem_wait16(zo);
+          if (valid) lu_epi_lstm_chunk(e, pix_state, pix_out, n0, jc, nt * CH + jc, zi, zf, zg, zo);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tmem_empty + 8u * acc);
+      if (++acc == 2) { acc = 0; phacc ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+#endif  // !LU_HOST_EMU

@@ -1,0 +1,133 @@
+// Shared POD types and portable helpers for the ConvLSTM-UNet kernels.
+//
+// Everything in this header compiles two ways:
+//   * nvcc, sm_100a           -> the product library (liblstm_unet_b200.so)
+//   * g++ with -DLU_HOST_EMU  -> a TEST-ONLY host build (tests/_emu) in which the scalar "mirror" kernels and
+//     the elementwise kernels run as plain loops, so that plan/table generation, weight packing and epilogue
+//     maths can be checked against the oracle in a container without a GPU.  The product library never
+//     contains that path (lu_is_cuda_build() == 1) and has no CPU fallback.
+#pragma once
+#include <stdint.h>
+#include <string.h>
+#include <math.h>
+
+#ifdef LU_HOST_EMU
+#define LU_HD
+#define LU_HDI inline
+#else
+#include <cuda_runtime.h>
+#define LU_HD __host__ __device__
+#define LU_HDI __host__ __device__ __forceinline__
+#endif
+
+#define LU_MAX_SRC 4
+#define LU_TILE_H 16      // output pixels per tile: 16 rows x 8 columns = 128 = UMMA M
+#define LU_TILE_W 8
+#define LU_KBLK 64        // bf16 elements per K block (= one 128-byte swizzle row)
+
+// ---- bf16 <-> fp32 (round to nearest even), portable -----------------------------------------------------
+LU_HDI uint32_t lu_f2u(float f) {
+#ifdef __CUDA_ARCH__
+  return __float_as_uint(f);
+#else
+  uint32_t u; memcpy(&u, &f, 4); return u;
+#endif
+}
+LU_HDI float lu_u2f(uint32_t u) {
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(u);
+#else
+  float f; memcpy(&f, &u, 4); return f;
+#endif
+}
+LU_HDI uint16_t lu_f2bf(float f) {
+  uint32_t u = lu_f2u(f);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);   // NaN
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+LU_HDI float lu_bf2f(uint16_t h) { return lu_u2f(((uint32_t)h) << 16); }
+// split v into hi + lo bf16 parts (lo = bf16(v - hi)); used by the bf16x3 precision mode
+LU_HDI void lu_split(float v, uint16_t& hi, uint16_t& lo) {
+  hi = lu_f2bf(v);
+  lo = lu_f2bf(v - lu_bf2f(hi));
+}
+
+// ---- activation-tile staging tables ----------------------------------------------------------------------
+// One "A stage" = one TMA box of activations (a [rows x pitch] pixel window x 64 channels) that is reused by
+// `ntaps` consecutive K blocks; tap i of the stage reads the 128 output pixels' operand rows starting at row
+// offset taps[tap_begin + i] inside the box (halo staging) -- or at offset 0 when every tap has its own box
+// (direct staging).  K blocks (and with them the 64-wide column blocks of the packed weight matrix) are
+// numbered in table order.
+struct LuAStage {
+  int32_t c;          // channel coordinate (dim 0) of the box
+  int16_t dy, dx;     // box origin relative to the tile origin, in source pixel coordinates
+  uint8_t src;        // which source view / tensor map
+  uint8_t plane;      // coordinate in the extra dim (row parity of a stride-2 space-to-depth view)
+  uint16_t ntaps;
+  uint32_t tap_begin;
+};
+
+// 5-D view (c, w, p, h, n) of an NHWC bf16 buffer; element strides.  The same numbers feed
+// cuTensorMapEncodeTiled and the scalar mirror kernel.
+struct LuSrcView {
+  const uint16_t* ptr;
+  int64_t sn, sh, sp, sw;
+  int32_t dimC, dimW, dimP, dimH, dimN;
+  int32_t frame_mul, frame_add;    // n coordinate = tile_frame * frame_mul + frame_add
+  int32_t rows, pitch;             // box = {64, pitch, 1, rows, 1}
+};
+
+enum { LU_EPI_CONV = 0, LU_EPI_LSTM = 1 };
+
+struct LuEpi {
+  int32_t kind;
+  int32_t H, W;               // output spatial size (rows/cols beyond it are masked)
+  const float* bias;          // [Npad], packed column order
+  int32_t out_frame_mul, out_frame_add;
+  // conv
+  const float* scale;         // folded BN scale/shift in packed order (NULL: no activation output)
+  const float* shift;
+  uint16_t* out_act;          // NHWC bf16, channel layout [hi: cpad][lo: cpad] when planes == 2
+  int32_t out_cpad, out_planes;
+  float* out_raw;             // NHWC fp32 (acc + bias), NULL if unused
+  int32_t raw_cpad;
+  float alpha;                // LeakyReLU slope
+  // lstm
+  float* c_state;             // (B,H,W,f_pad) fp32, updated in place
+  uint16_t* h_state_out;      // (B,H,W,planes*f_pad) bf16 or NULL: written on the last step of a call
+  int32_t f_pad, ch_tile, gate_kind;
+  uint16_t* save_gates;       // training: (frames,H,W,4*f_pad) bf16 post-activation i,f,g,o (NULL otherwise)
+  float* save_c;              // training: (frames,H,W,f_pad) fp32 c_t
+};
+
+// Per-K-block weight packing descriptor (see lu_pack_weights).
+struct LuPackDesc {
+  int64_t w_off;              // offset of the Keras kernel tensor in the flat fp32 parameter buffer
+  int32_t tap_off;            // (ky*k+kx) * cin_total * cout_total
+  int32_t c_base;             // first input channel covered by this block
+  int32_t n_valid;            // valid channels (NORMAL) / unused (PATCH)
+  int32_t cin_total, cout_total;
+  int8_t wpart;               // 0: hi part of w, 1: lo part (w - hi)
+  int8_t kind;                // 0 NORMAL, 1 PATCH (block channel = tap index of a 1-channel image patch)
+  int8_t k, pw;               // PATCH: conv kernel size, patch window size
+  int8_t patch_x3;            // PATCH: channels [32,64) are the lo parts of the taps
+  int8_t patch_hi_only;       // PATCH: channels [32,64) get zero weights (the a_hi * w_lo block)
+  int8_t pad0, pad1;
+};
+
+enum { LU_COL_IDENTITY = 0, LU_COL_LSTM = 1 };
+struct LuColMap {
+  int32_t kind, n_real;       // conv: packed column n < n_real maps to itself
+  int32_t F, ch_tile;         // lstm: n = tile*4*ch + g*ch + j  ->  g*F + tile*ch + j  (if tile*ch + j < F)
+};
+LU_HDI int lu_col_of(const LuColMap& m, int n) {
+  if (m.kind == LU_COL_IDENTITY) return n < m.n_real ? n : -1;
+  int bn = 4 * m.ch_tile;
+  int tile = n / bn, r = n % bn, g = r / m.ch_tile, j = r % m.ch_tile;
+  int ch = tile * m.ch_tile + j;
+  return ch < m.F ? g * m.F + ch : -1;
+}
+
+LU_HDI float lu_hard_sigmoid(float x) { return fminf(fmaxf(0.2f * x + 0.5f, 0.0f), 1.0f); }
+LU_HDI float lu_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }

@@ -1,0 +1,288 @@
+// Bandwidth-bound kernels around the convolutions: input staging, up-sampling, batch-norm, soft-max, weight
+// packing, recurrent-state maintenance.  Written as index functors so the same code runs on the GPU
+// (grid-stride kernel) and, in the TEST-ONLY host build (LU_HOST_EMU), as plain loops.
+#pragma once
+#include "lu_defs.h"
+
+#ifdef LU_HOST_EMU
+template <class F>
+static void lu_parallel_for_impl(int64_t n, void* /*stream*/, F f) {
+  for (int64_t i = 0; i < n; ++i) f(i);
+}
+#else
+template <class F>
+__global__ void __launch_bounds__(256) lu_pf_kernel(int64_t n, F f) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) f(i);
+}
+template <class F>
+static void lu_parallel_for_impl(int64_t n, void* stream, F f) {
+  if (n <= 0) return;
+  int64_t blocks = (n + 255) / 256;
+  const int64_t cap = 148 * 32;
+  if (blocks > cap) blocks = cap;
+  lu_pf_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(n, f);
+}
+#endif
+LU_HDI void lu_atomic_add(double* p, double v) {
+#ifdef __CUDA_ARCH__
+  atomicAdd(p, v);
+#else
+  *p += v;
+#endif
+}
+LU_HDI void lu_atomic_add(float* p, float v) {
+#ifdef __CUDA_ARCH__
+  atomicAdd(p, v);
+#else
+  *p += v;
+#endif
+}
+
+LU_HDI int lu_reflect(int i, int n) {     // tf.pad REFLECT index (no edge repeat); pad < n guaranteed
+  if (i < 0) i = -i;
+  if (i >= n) i = 2 * (n - 1) - i;
+  return i;
+}
+
+// ---- input staging: reflect-pad (Networks.py:232) + pw x pw patch extraction of the 1-channel image ------------
+// out (N,Hp,Wp,64) bf16.  Channel t < pw*pw holds the padded image at (y + t/pw - (pw-1)/2, x + t%pw - (pw-1)/2),
+// zero outside the padded image (that is the SAME zero padding of the consuming convolutions).  In bf16x3 mode
+// channels [32, 32+pw*pw) hold the lo parts.
+struct LuPrepPatches {
+  const float* x; uint16_t* out;
+  int H, W, Hp, Wp, pad_y0, pad_x0, pw, x3;
+  LU_HD void operator()(int64_t i) const {
+    const int ch = (int)(i % 64); int64_t p = i / 64;
+    const int xx = (int)(p % Wp); p /= Wp;
+    const int yy = (int)(p % Hp); const int64_t n = p / Hp;
+    int t = ch, lo = 0;
+    if (x3 && ch >= 32) { t = ch - 32; lo = 1; }
+    uint16_t r = 0;
+    if (t < pw * pw && (x3 || ch < 64)) {
+      const int py = yy + t / pw - (pw - 1) / 2, px = xx + t % pw - (pw - 1) / 2;
+      if (py >= 0 && py < Hp && px >= 0 && px < Wp) {
+        const int sy = lu_reflect(py - pad_y0, H), sx = lu_reflect(px - pad_x0, W);
+        const float v = x[(n * H + sy) * W + sx];
+        uint16_t h, l; lu_split(v, h, l);
+        r = lo ? l : h;
+      }
+    }
+    out[i] = r;
+  }
+};
+
+// ---- bilinear x2 (tf.image.resize half-pixel centres == resize_images, Networks.py:143) -------------------------
+// in (N,h,w,planes*cpad) -> out (N,2h,2w,planes*cpad); value = hi + lo, re-split on store.
+struct LuUpsample2x {
+  const uint16_t* in; uint16_t* out;
+  int h, w, cpad, planes;
+  LU_HD void operator()(int64_t i) const {
+    const int c = (int)(i % cpad); int64_t p = i / cpad;
+    const int ox = (int)(p % (2 * w)); p /= (2 * w);
+    const int oy = (int)(p % (2 * h)); const int64_t n = p / (2 * h);
+    // out[2i] = .25 in[i-1] + .75 in[i]; out[2i+1] = .75 in[i] + .25 in[i+1] (edge clamped)
+    const int iy = oy >> 1, ix = ox >> 1;
+    const int y1 = (oy & 1) ? (iy + 1 < h ? iy + 1 : h - 1) : (iy > 0 ? iy - 1 : 0);
+    const int x1 = (ox & 1) ? (ix + 1 < w ? ix + 1 : w - 1) : (ix > 0 ? ix - 1 : 0);
+    const int ct = cpad * planes;
+    const uint16_t* b = in + n * (int64_t)h * w * ct;
+    float v00 = lu_bf2f(b[((int64_t)iy * w + ix) * ct + c]), v01 = lu_bf2f(b[((int64_t)iy * w + x1) * ct + c]);
+    float v10 = lu_bf2f(b[((int64_t)y1 * w + ix) * ct + c]), v11 = lu_bf2f(b[((int64_t)y1 * w + x1) * ct + c]);
+    if (planes == 2) {
+      v00 += lu_bf2f(b[((int64_t)iy * w + ix) * ct + cpad + c]); v01 += lu_bf2f(b[((int64_t)iy * w + x1) * ct + cpad + c]);
+      v10 += lu_bf2f(b[((int64_t)y1 * w + ix) * ct + cpad + c]); v11 += lu_bf2f(b[((int64_t)y1 * w + x1) * ct + cpad + c]);
+    }
+    const float top = 0.75f * v00 + 0.25f * v01, bot = 0.75f * v10 + 0.25f * v11;
+    const float v = 0.75f * top + 0.25f * bot;
+    uint16_t hi, lo; lu_split(v, hi, lo);
+    uint16_t* o = out + (((n * 2 * h + oy) * 2 * w) + ox) * (int64_t)ct + c;
+    o[0] = hi;
+    if (planes == 2) o[cpad] = lo;
+  }
+};
+
+// ---- batch norm (keras BatchNormalization, eps 1e-3, momentum .99) ----------------------------
+// pass 1: per-channel sum / sum of squares of the fp32 conv output; item = (pixel chunk, channel)
+struct LuBnStats {
+  const float* raw; double* sums;      // sums[0:cpad] = sum, sums[cpad:2cpad] = sum sq (about a per-channel shift)
+  const float* shift_src;              // per-channel shift (first pixel) to avoid cancellation
+  int64_t npix; int cpad, c_real, chunk;
+  LU_HD void operator()(int64_t i) const {
+    const int c = (int)(i % cpad); const int64_t pc = i / cpad;
+    if (c >= c_real) return;
+    const float sh = shift_src[c];
+    int64_t p0 = pc * chunk, p1 = p0 + chunk; if (p1 > npix) p1 = npix;
+    float s = 0.f, s2 = 0.f;
+    for (int64_t p = p0; p < p1; ++p) { const float v = raw[p * cpad + c] - sh; s += v; s2 += v * v; }
+    lu_atomic_add(&sums[c], (double)s);
+    lu_atomic_add(&sums[cpad + c], (double)s2);
+  }
+};
+// pass 2: scale/shift from batch statistics + moving-statistics update; item = channel
+struct LuBnFinalize {
+  double* sums; const float* shift_src; const float* gamma; const float* beta; float* mov_mean; float* mov_var;
+  float* scale; float* shift; float* save_mean; float* save_invstd;
+  int64_t npix; int cpad, c_real; float eps, momentum;
+  LU_HD void operator()(int64_t c) const {
+    if (c >= c_real) { scale[c] = 0.f; shift[c] = 0.f; return; }
+    const double n = (double)npix;
+    const double m0 = sums[c] / n;
+    double var = sums[cpad + c] / n - m0 * m0; if (var < 0) var = 0;
+    const double mean = m0 + (double)shift_src[c];
+    const double inv = 1.0 / sqrt(var + (double)eps);
+    scale[c] = (float)(gamma[c] * inv);
+    shift[c] = (float)(beta[c] - mean * gamma[c] * inv);
+    if (save_mean) { save_mean[c] = (float)mean; save_invstd[c] = (float)inv; }
+    const double unb = var * (n / (n > 1 ? n - 1 : 1));
+    mov_mean[c] = momentum * mov_mean[c] + (1.f - momentum) * (float)mean;
+    mov_var[c] = momentum * mov_var[c] + (1.f - momentum) * (float)unb;
+    sums[c] = 0; sums[cpad + c] = 0;
+  }
+};
+// pass 3: y = lrelu(raw*scale + shift) -> bf16 planes; item = (pixel, channel)
+struct LuBnApply {
+  const float* raw; const float* scale; const float* shift; uint16_t* out;
+  int raw_cpad, out_cpad, planes; float alpha;
+  LU_HD void operator()(int64_t i) const {
+    const int c = (int)(i % out_cpad); const int64_t p = i / out_cpad;
+    float a = 0.f;
+    if (c < raw_cpad) { a = raw[p * raw_cpad + c] * scale[c] + shift[c]; a = a > 0.f ? a : alpha * a; }
+    uint16_t hi, lo; lu_split(a, hi, lo);
+    uint16_t* o = out + p * (int64_t)(out_cpad * planes) + c;
+    o[0] = hi;
+    if (planes == 2) o[out_cpad] = lo;
+  }
+};
+// inference: fold moving statistics into per-channel scale/shift (applied in the conv epilogue)
+struct LuBnFold {
+  const float* gamma; const float* beta; const float* mov_mean; const float* mov_var; float* scale; float* shift;
+  int c_real; float eps;
+  LU_HD void operator()(int64_t c) const {
+    if (c >= c_real) { scale[c] = 0.f; shift[c] = 0.f; return; }
+    const float inv = 1.0f / sqrtf(mov_var[c] + eps);
+    scale[c] = gamma[c] * inv;
+    shift[c] = beta[c] - mov_mean[c] * gamma[c] * inv;
+  }
+};
+
+// ---- crop + soft-max (Networks.py:250-252) ------------------------------------------------------------------------
+// raw (B*T,Hp,Wp,raw_cpad) fp32 -> logits/softmax in the API layout.  channels_first: (B,T,D,H,W), softmax over D.
+// channels_last: (B,T,H,W,D) and -- reproducing the reference's Softmax(channel_axis+1) -- softmax over the BATCH axis.
+struct LuSoftmaxCrop {
+  const float* raw; float* logits; float* softmax;
+  int B, T, H, W, Hp, Wp, py0, px0, raw_cpad, D, channels_first;
+  LU_HD void operator()(int64_t i) const {
+    if (channels_first) {      // item = (b,t,y,x)
+      const int x = (int)(i % W); int64_t p = i / W;
+      const int y = (int)(p % H); const int64_t f = p / H;
+      const float* r = raw + ((f * Hp + y + py0) * Wp + x + px0) * (int64_t)raw_cpad;
+      float mx = r[0];
+      for (int d = 1; d < D; ++d) mx = fmaxf(mx, r[d]);
+      float s = 0.f;
+      for (int d = 0; d < D; ++d) s += expf(r[d] - mx);
+      for (int d = 0; d < D; ++d) {
+        const int64_t o = ((f * D + d) * H + y) * W + x;
+        logits[o] = r[d];
+        softmax[o] = expf(r[d] - mx) / s;
+      }
+    } else {                   // item = (t,y,x,d); loop over b
+      const int d = (int)(i % D); int64_t p = i / D;
+      const int x = (int)(p % W); p /= W;
+      const int y = (int)(p % H); const int t = (int)(p / H);
+      float mx = -3.4e38f;
+      for (int b = 0; b < B; ++b)
+        mx = fmaxf(mx, raw[((((int64_t)b * T + t) * Hp + y + py0) * Wp + x + px0) * raw_cpad + d]);
+      float s = 0.f;
+      for (int b = 0; b < B; ++b)
+        s += expf(raw[((((int64_t)b * T + t) * Hp + y + py0) * Wp + x + px0) * raw_cpad + d] - mx);
+      for (int b = 0; b < B; ++b) {
+        const float v = raw[((((int64_t)b * T + t) * Hp + y + py0) * Wp + x + px0) * raw_cpad + d];
+        const int64_t o = ((((int64_t)b * T + t) * H + y) * W + x) * D + d;
+        logits[o] = v;
+        softmax[o] = expf(v - mx) / s;
+      }
+    }
+  }
+};
+
+// ---- weight packing: Keras HWIO fp32 -> K-major bf16 [Npad][ktot] in table order ----------------------------------
+struct LuPackWeights {
+  const float* params; const LuPackDesc* descs; uint16_t* out; LuColMap cm; int ktot;
+  LU_HD void operator()(int64_t i) const {
+    const int k = (int)(i % ktot); const int n = (int)(i / ktot);
+    const int kb = k / LU_KBLK, kk = k % LU_KBLK;
+    const int col = lu_col_of(cm, n);
+    uint16_t r = 0;
+    if (col >= 0) {
+      const LuPackDesc d = descs[kb];
+      float w = 0.f; bool ok = false;
+      if (d.kind == 0) {
+        if (kk < d.n_valid) { w = params[d.w_off + d.tap_off + (int64_t)(d.c_base + kk) * d.cout_total + col]; ok = true; }
+      } else {
+        int t = kk; bool z = false;
+        if (d.patch_x3 && kk >= 32) { t = kk - 32; z = d.patch_hi_only != 0; }
+        if (!z && t < d.pw * d.pw) {
+          const int sh = (d.pw - 1) / 2 - (d.k - 1) / 2;
+          const int ky = t / d.pw - sh, kx = t % d.pw - sh;
+          if (ky >= 0 && ky < d.k && kx >= 0 && kx < d.k) {
+            w = params[d.w_off + ((int64_t)(ky * d.k + kx) * d.cin_total + d.c_base) * d.cout_total + col]; ok = true;
+          }
+        }
+      }
+      if (ok) { uint16_t hi, lo; lu_split(w, hi, lo); r = d.wpart ? lo : hi; }
+    }
+    out[i] = r;
+  }
+};
+struct LuPackVec {       // per-column vectors (bias, gamma...) into packed column order
+  const float* src; float* out; LuColMap cm;
+  LU_HD void operator()(int64_t n) const { const int col = lu_col_of(cm, (int)n); out[n] = col >= 0 ? src[col] : 0.f; }
+};
+
+// ---- recurrent state maintenance (Networks.py:77-98) ---------------------------------------------------------------
+struct LuStateMask {     // h *= mask[b] (bf16 planes; mask is 0/1 in the reference's use, so hi/lo scale exactly)
+  uint16_t* h; float* c; const float* mask; int64_t per_sample_h, per_sample_c;
+  LU_HD void operator()(int64_t i) const { h[i] = lu_f2bf(lu_bf2f(h[i]) * mask[i / per_sample_h]); }
+};
+struct LuStateMaskC {
+  float* c; const float* mask; int64_t per_sample;
+  LU_HD void operator()(int64_t i) const { c[i] *= mask[i / per_sample]; }
+};
+// internal (B,H,W,planes*fpad) bf16 / (B,H,W,fpad) fp32  <->  API (B,F,H,W) or (B,H,W,F) fp32
+struct LuStateGet {
+  const uint16_t* h; const float* c; float* out; int which, H, W, F, fpad, planes, channels_first;
+  LU_HD void operator()(int64_t i) const {
+    int f, y, x; int64_t b;
+    if (channels_first) { x = (int)(i % W); int64_t p = i / W; y = (int)(p % H); p /= H; f = (int)(p % F); b = p / F; }
+    else { f = (int)(i % F); int64_t p = i / F; x = (int)(p % W); p /= W; y = (int)(p % H); b = p / H; }
+    const int64_t pix = (b * H + y) * W + x;
+    if (which == 1) out[i] = c[pix * fpad + f];
+    else {
+      float v = lu_bf2f(h[pix * (int64_t)(fpad * planes) + f]);
+      if (planes == 2) v += lu_bf2f(h[pix * (int64_t)(fpad * planes) + fpad + f]);
+      out[i] = v;
+    }
+  }
+};
+struct LuStateSet {
+  uint16_t* h; float* c; const float* in; int which, H, W, F, fpad, planes, channels_first;
+  LU_HD void operator()(int64_t i) const {
+    int f, y, x; int64_t b;
+    if (channels_first) { x = (int)(i % W); int64_t p = i / W; y = (int)(p % H); p /= H; f = (int)(p % F); b = p / F; }
+    else { f = (int)(i % F); int64_t p = i / F; x = (int)(p % W); p /= W; y = (int)(p % H); b = p / H; }
+    const int64_t pix = (b * H + y) * W + x;
+    const float v = in ? in[i] : 0.f;
+    if (which == 1) c[pix * fpad + f] = v;
+    else {
+      uint16_t hi, lo; lu_split(v, hi, lo);
+      h[pix * (int64_t)(fpad * planes) + f] = hi;
+      if (planes == 2) h[pix * (int64_t)(fpad * planes) + fpad + f] = lo;
+    }
+  }
+};
+
+// generic conv-mirror launcher functor
+struct LuMirrorItem {
+  LuConvParams p;
+  LU_HD void operator()(int64_t i) const { lu_conv_mirror_item(p, i); }
+};

@@ -1,0 +1,146 @@
+"""Host-logic parity: the library's plan / tables / weight packing / epilogues, executed by the TEST-ONLY host build
+(scalar mirror engine), against the oracle.  The same tables drive the tcgen05 kernel on the GPU (tests -m gpu)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import lstm_unet_oracle as O
+from tests.emu_backend import emu_session, emu_forward
+
+NET_A = {   # exercises channel padding (non multiples of 64), 4 levels
+    'down_conv_kernels': [[(3, 8), (3, 8)], [(3, 12), (3, 12)], [(3, 12), (3, 12)], [(3, 16), (3, 16)]],
+    'lstm_kernels': [[(5, 8)], [(5, 12)], [(5, 12)], [(5, 16)]],
+    'up_conv_kernels': [[(3, 12), (3, 12)], [(3, 8), (3, 8)], [(3, 8), (3, 8)], [(3, 4), (3, 4), (1, 3)]],
+}
+NET_B = {   # 2 levels, 3x3 lstm, two lstm layers at level 0
+    'down_conv_kernels': [[(3, 6)], [(3, 10), (3, 10)]],
+    'lstm_kernels': [[(3, 5), (3, 7)], [(5, 9)]],
+    'up_conv_kernels': [[(3, 6)], [(3, 5), (1, 3)]],
+}
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+
+
+def oracle_params_np(net, seed):
+    p = O.init_params(net, seed=seed, randomize_bn=True)
+    return p, {k: v.numpy() for k, v in p.items()}
+
+
+@pytest.mark.parametrize("net,H,W,pad,a_mode", [
+    (NET_A, 16, 24, False, 'halo'),
+    (NET_A, 16, 24, False, 'direct'),
+    (NET_A, 19, 21, True, 'halo'),
+    (NET_B, 10, 12, False, 'halo'),
+    (NET_B, 9, 7, True, 'direct'),
+])
+def test_forward_inference_bf16x3_matches_oracle(net, H, W, pad, a_mode):
+    B, T = 2, 2
+    p_t, p_np = oracle_params_np(net, 3)
+    ora = O.OracleNet(net, 'NCHW', pad, params=p_t)
+    sess = emu_session(net, data_format='NCHW', pad_image=pad, batch=B, max_t=T, height=H, width=W,
+                       precision='bf16x3', a_mode=a_mode)
+    sess.set_params(p_np)
+    rng = np.random.default_rng(0)
+    for call in range(2):          # second call exercises the stateful carry
+        x = rng.standard_normal((B, T, 1, H, W)).astype(np.float32)
+        ref_l, ref_s = ora(torch.from_numpy(x), False)
+        got_l, got_s = emu_forward(sess, x, False)
+        assert rel_err(got_l, ref_l.numpy()) < 1e-3, (call, rel_err(got_l, ref_l.numpy()))
+        assert rel_err(got_s, ref_s.numpy()) < 1e-3
+    sess.close()
+
+
+def test_forward_training_bn_and_moving_stats():
+    net, B, T, H, W = NET_A, 2, 2, 16, 16
+    p_t, p_np = oracle_params_np(net, 5)
+    ora = O.OracleNet(net, 'NCHW', False, params=p_t)
+    sess = emu_session(net, data_format='NCHW', pad_image=False, batch=B, max_t=T, height=H, width=W,
+                       precision='bf16x3', train=True)
+    sess.set_params(p_np)
+    x = np.random.default_rng(1).standard_normal((B, T, 1, H, W)).astype(np.float32)
+    ref_l, _ = ora(torch.from_numpy(x), True)
+    got_l, _ = emu_forward(sess, x, True)
+    assert rel_err(got_l, ref_l.numpy()) < 1e-3, rel_err(got_l, ref_l.numpy())
+    got_p = sess.get_params()
+    for name in p_np:
+        if 'moving' in name:
+            np.testing.assert_allclose(got_p[name], ora.params[name].numpy(), rtol=2e-4, atol=2e-5, err_msg=name)
+    sess.close()
+
+
+def test_forward_bf16_mode_is_close():
+    net, B, T, H, W = NET_A, 1, 2, 16, 16
+    p_t, p_np = oracle_params_np(net, 7)
+    ora = O.OracleNet(net, 'NCHW', False, params=p_t)
+    sess = emu_session(net, data_format='NCHW', pad_image=False, batch=B, max_t=T, height=H, width=W, precision='bf16')
+    sess.set_params(p_np)
+    x = np.random.default_rng(2).standard_normal((B, T, 1, H, W)).astype(np.float32)
+    ref_l, _ = ora(torch.from_numpy(x), False)
+    got_l, _ = emu_forward(sess, x, False)
+    assert rel_err(got_l, ref_l.numpy()) < 5e-2, rel_err(got_l, ref_l.numpy())   # bf16 operands: ~3 decimal digits
+    sess.close()
+
+
+def test_channels_last_softmax_quirk():
+    net, B, T, H, W = NET_B, 2, 1, 8, 8
+    p_t, p_np = oracle_params_np(net, 9)
+    ora = O.OracleNet(net, 'NHWC', False, params=p_t)
+    sess = emu_session(net, data_format='NHWC', pad_image=False, batch=B, max_t=T, height=H, width=W,
+                       precision='bf16x3')
+    sess.set_params(p_np)
+    x = np.random.default_rng(3).standard_normal((B, T, H, W, 1)).astype(np.float32)
+    ref_l, ref_s = ora(torch.from_numpy(x), False)
+    got_l, got_s = emu_forward(sess, x, False)
+    assert got_l.shape == (B, T, H, W, 3)
+    assert rel_err(got_l, ref_l.numpy()) < 1e-3
+    assert rel_err(got_s, ref_s.numpy()) < 1e-3          # softmax over the batch axis, as the reference computes it
+    sess.close()
+
+
+def test_state_mask_get_set():
+    net, B, T, H, W = NET_B, 2, 2, 8, 8
+    p_t, p_np = oracle_params_np(net, 11)
+    ora = O.OracleNet(net, 'NCHW', False, params=p_t)
+    sess = emu_session(net, data_format='NCHW', pad_image=False, batch=B, max_t=T, height=H, width=W,
+                       precision='bf16x3')
+    sess.set_params(p_np)
+    x = np.random.default_rng(4).standard_normal((B, T, 1, H, W)).astype(np.float32)
+    ora(torch.from_numpy(x), False)
+    emu_forward(sess, x, False)
+    mask = np.array([1.0, 0.0], dtype=np.float32)
+    ora.reset_states_per_batch(mask)
+    sess.reset_states(mask.ctypes.data)
+    ref_states = ora.get_states()
+    for (lvl, lay) in [(0, 0), (0, 1), (1, 0)]:
+        shp = sess.state_shape(lvl, lay)
+        for which in (0, 1):
+            out = np.zeros(shp, dtype=np.float32)
+            sess.get_state(lvl, lay, which, out.ctypes.data)
+            ref = ref_states[lvl][lay][which]
+            assert out.shape == ref.shape
+            assert np.abs(out - ref).max() < 1e-4 * max(1.0, np.abs(ref).max())
+            assert np.all(out[1] == 0)
+    # set_state(NULL) zeroes; set_state(array) round-trips
+    shp = sess.state_shape(1, 0)
+    a = np.random.default_rng(5).standard_normal(shp).astype(np.float32)
+    sess.set_state(1, 0, 1, a.ctypes.data)
+    out = np.zeros(shp, dtype=np.float32)
+    sess.get_state(1, 0, 1, out.ctypes.data)
+    np.testing.assert_array_equal(out, a)
+    sess.set_state(1, 0, 0, None)
+    sess.get_state(1, 0, 0, out.ctypes.data)
+    assert np.all(out == 0)
+    sess.close()
+
+
+def test_config_errors():
+    from lstm_unet_b200 import _lib
+    bad = dict(NET_A, lstm_kernels=NET_A['lstm_kernels'][:3])
+    with pytest.raises(ValueError):
+        _lib.make_config(bad)
+    from lstm_unet_b200.session import LuError
+    with pytest.raises(LuError):     # REFLECT pad needs pad < dim
+        emu_session(NET_A, pad_image=True, batch=1, max_t=1, height=8, width=8)
