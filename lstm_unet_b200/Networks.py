@@ -1,0 +1,371 @@
+"""Drop-in mirror of the reference's ``Networks.py`` object protocol for the ConvLSTM-UNet hot path.
+
+Same names, constructor arguments, call signature and error behaviour as the reference
+(``/root/reference/Networks.py``); all arithmetic runs in hand-written sm_100a kernels behind the C-ABI of
+``liblstm_unet_b200.so`` (include/lstm_unet_b200.h).  PyTorch tensors are device containers only.
+
+    reference                                   here
+    ---------------------------------------------------------------------------------------------
+    DEFAULT_NET_DOWN_PARAMS (Networks.py:12-32)  DEFAULT_NET_DOWN_PARAMS (same values)
+    ULSTMnet2D(net_params, data_format,          ULSTMnet2D(net_params, data_format, pad_image, *, precision=...,
+               pad_image)     (:179)                        engine=..., gate=...)
+    model(inputs, training) -> (logits,          same; inputs: numpy / torch (host or cuda), 5-D; outputs are cuda
+          softmax)            (:208-254)          tensors with a ``.numpy()`` like tf.Tensor
+    reset_states_per_batch / get_states /        same semantics (mask 1 = keep, 0 = reset; nested
+          set_states          (:77-98,279-291)    [block][layer][h, c] numpy lists, None before the first call)
+    trainable_variables, save_weights,           named views into one flat fp32 device buffer; npz with Keras variable
+          load_weights (keras.Model)              names and layouts
+    DownBlock2D / UpBlock2D   (:35-175)           structural descriptors of the blocks (state fan-out goes through them)
+
+There is no CPU fallback: constructing a model without the CUDA library or calling it without a CUDA device raises.
+"""
+import math
+
+import numpy as np
+
+from . import _lib
+from .session import LuSession, LuError, TorchCudaBackend
+
+__all__ = ['DEFAULT_NET_DOWN_PARAMS', 'DownBlock2D', 'UpBlock2D', 'ULSTMnet2D']
+
+DEFAULT_NET_DOWN_PARAMS = {
+    'down_conv_kernels': [
+        [(5, 128), (5, 128)],
+        [(5, 256), (5, 256)],
+        [(5, 256), (5, 256)],
+        [(5, 512), (5, 512)],
+    ],
+    'lstm_kernels': [
+        [(5, 128)],
+        [(5, 256)],
+        [(5, 256)],
+        [(5, 512)],
+    ],
+    'up_conv_kernels': [
+        [(5, 256), (5, 256)],
+        [(5, 128), (5, 128)],
+        [(5, 64), (5, 64)],
+        [(5, 32), (5, 32), (1, 3)],
+    ],
+}
+
+
+def _device_array_type():
+    import torch
+
+    class DeviceArray(torch.Tensor):
+        """cuda tensor with tf.Tensor's ``.numpy()`` (device -> host copy), as Inference2D.py:60 uses it."""
+
+        def numpy(self):
+            return self.as_subclass(torch.Tensor).detach().cpu().numpy()
+
+    return DeviceArray
+
+
+_DeviceArray = None
+
+
+def _wrap(t):
+    global _DeviceArray
+    if _DeviceArray is None:
+        _DeviceArray = _device_array_type()
+    return t.as_subclass(_DeviceArray)
+
+
+class Variable:
+    """A named view into the flat parameter buffer (stands in for a tf.Variable of model.trainable_variables)."""
+
+    def __init__(self, name, view, trainable):
+        self.name, self.value, self.trainable = name, view, trainable
+        self.shape = tuple(view.shape)
+
+    def numpy(self):
+        return self.value.detach().cpu().numpy()
+
+    def assign(self, arr):
+        import torch
+        self.value.copy_(torch.as_tensor(np.asarray(arr, dtype=np.float32)).reshape(self.value.shape))
+
+
+class DownBlock2D:
+    """Structure of one encoder block (Networks.py:35-98): ConvLSTM2D x n then [Conv2D, BN, LeakyReLU] x m."""
+
+    def __init__(self, conv_kernels, lstm_kernels, stride=2, data_format='NCHW', _owner=None, _level=0):
+        self.conv_kernels, self.lstm_kernels, self.stride = list(conv_kernels), list(lstm_kernels), stride
+        self.data_format = data_format
+        self.total_stride = stride
+        self._owner, self._level = _owner, _level
+
+    def _need_owner(self):
+        if self._owner is None:
+            raise NotImplementedError('DownBlock2D runs as part of ULSTMnet2D on this backend')
+        return self._owner
+
+    def reset_states_per_batch(self, is_last_batch):
+        self._need_owner()._reset_level(self._level, is_last_batch)
+
+    def get_states(self):
+        return self._need_owner()._get_level_states(self._level)
+
+    def set_states(self, states):
+        self._need_owner()._set_level_states(self._level, states)
+
+
+class UpBlock2D:
+    """Structure of one decoder block (Networks.py:122-153): bilinear resize, concat([up, skip]), conv stack."""
+
+    def __init__(self, kernels, up_factor=2, data_format='NCHW', return_logits=False):
+        self.kernels, self.up_factor, self.data_format, self.return_logits = list(kernels), up_factor, data_format, return_logits
+
+
+def _glorot_uniform(shape, rng):
+    rf = int(np.prod(shape[:-2])) if len(shape) > 2 else 1
+    limit = math.sqrt(6.0 / (shape[-2] * rf + shape[-1] * rf))
+    return rng.uniform(-limit, limit, size=shape).astype(np.float32)
+
+
+def _orthogonal(shape, rng):
+    rows, cols = int(np.prod(shape[:-1])), shape[-1]
+    a = rng.standard_normal((max(rows, cols), min(rows, cols)))
+    q, r = np.linalg.qr(a)
+    q = q * np.sign(np.diag(r))[None, :]
+    if rows < cols:
+        q = q.T
+    return q[:rows, :cols].reshape(shape).astype(np.float32)
+
+
+def keras_default_init(layout, seed=0):
+    """Keras default initialisers for every variable of the layout."""
+    rng = np.random.default_rng(seed)
+    out = {}
+    for e in layout:
+        name, shape = e['name'], e['shape']
+        if name.endswith('recurrent_kernel'):
+            out[name] = _orthogonal(shape, rng)
+        elif name.endswith('kernel'):
+            out[name] = _glorot_uniform(shape, rng)
+        elif 'ConvLSTM' in name and name.endswith('bias'):
+            b = np.zeros(shape, np.float32)
+            f = shape[0] // 4
+            b[f:2 * f] = 1.0                      # unit_forget_bias
+            out[name] = b
+        elif name.endswith('gamma') or name.endswith('moving_variance'):
+            out[name] = np.ones(shape, np.float32)
+        else:
+            out[name] = np.zeros(shape, np.float32)
+    return out
+
+
+class ULSTMnet2D:
+    def __init__(self, net_params=DEFAULT_NET_DOWN_PARAMS, data_format='NCHW', pad_image=True, *, precision='bf16',
+                 engine='tcgen05', gate='hard_sigmoid', a_mode='halo', train=False, seed=0, device=None):
+        # Networks.py:188-193: same ValueErrors, raised before anything touches the device
+        _lib.make_config(net_params, data_format, pad_image)
+        self.net_params = net_params
+        self.data_format = data_format
+        self.data_format_keras = 'channels_first' if data_format[1] == 'C' else 'channels_last'
+        self.channel_axis = 1 if data_format[1] == 'C' else -1
+        self.pad_image = pad_image
+        self.precision, self.engine, self.gate, self.a_mode, self.train_capable = precision, engine, gate, a_mode, train
+        self.seed, self._device = seed, device
+        n = len(net_params['down_conv_kernels'])
+        self.DownLayers = [DownBlock2D(c, l, 2 if i < n - 1 else 1, data_format, self, i)
+                           for i, (c, l) in enumerate(zip(net_params['down_conv_kernels'], net_params['lstm_kernels']))]
+        self.UpLayers = [UpBlock2D(c, 2 if i > 0 else 1, data_format, i + 1 == n)
+                         for i, c in enumerate(net_params['up_conv_kernels'])]
+        self.total_stride = 2 ** (n - 1)
+        self.last_depth = net_params['up_conv_kernels'][-1][-1][1]
+        self._lib = _lib.load_library()           # fails loudly when the CUDA library is not built
+        self._sess = None
+        self._pending_weights = None
+        self._pending_states = None
+        self._shape = None                        # (B, H, W) frozen by the first call (stateful ConvLSTM)
+        self._x_pin = self._x_dev = None
+
+    # ---- session management --------------------------------------------------------------------------
+    def _build(self, B, T, H, W):
+        be = TorchCudaBackend(self._device)
+        old = self._sess
+        old_states = self.get_states() if old is not None else None
+        self._be = be
+        cfg = _lib.make_config(self.net_params, self.data_format, self.pad_image, batch=B, max_t=T, height=H, width=W,
+                               precision=self.precision, engine=self.engine, gate=self.gate, a_mode=self.a_mode,
+                               train=self.train_capable)
+        sess = LuSession(self._lib, be, cfg)
+        if old is not None:                       # longer unroll than before: carry weights and states over
+            sess.params.copy_(old.params)
+            sess.params_changed()
+            self._sess = sess
+            self.set_states(old_states)
+            old.close()
+        else:
+            w = self._pending_weights or keras_default_init(sess.layout, self.seed)
+            sess.set_params(w)
+            self._pending_weights = None
+            self._sess = sess
+            if self._pending_states is not None:
+                self.set_states(self._pending_states)
+                self._pending_states = None
+        self._shape = (B, H, W)
+        self._max_t = T
+        return sess
+
+    def _ensure(self, B, T, H, W):
+        if self._sess is None:
+            return self._build(B, T, H, W)
+        if (B, H, W) != self._shape:
+            raise ValueError('stateful ConvLSTM states were built for (B,H,W)=%s, got %s' % (self._shape, (B, H, W)))
+        if T > self._max_t:
+            return self._build(B, T, H, W)
+        return self._sess
+
+    # ---- call (Networks.py:208-254) ------------------------------------------------------------------
+    def __call__(self, inputs, training=None, mask=None):
+        import torch
+        x = inputs
+        if not isinstance(x, torch.Tensor):
+            x = torch.from_numpy(np.ascontiguousarray(np.asarray(x, dtype=np.float32)))
+        if x.dim() != 5:
+            raise ValueError('expected a 5-D input, got shape %s' % (tuple(x.shape),))
+        if self.channel_axis == 1:
+            B, T, C, H, W = x.shape
+        else:
+            B, T, H, W, C = x.shape
+        if C != 1:
+            raise ValueError('only single-channel images are supported on this backend (got %d channels)' % C)
+        sess = self._ensure(B, T, H, W)
+        dev = self._be.device
+        if x.device.type != 'cuda':
+            # host input: pinned staging buffer + async H2D on the compute stream
+            n = x.numel()
+            if self._x_pin is None or self._x_pin.numel() < n:
+                self._x_pin = torch.empty(n, dtype=torch.float32, pin_memory=True)
+                self._x_dev = torch.empty(n, dtype=torch.float32, device=dev)
+            self._x_pin[:n].copy_(x.reshape(-1).to(torch.float32))
+            xd = self._x_dev[:n]
+            xd.copy_(self._x_pin[:n], non_blocking=True)
+        else:
+            xd = x.to(device=dev, dtype=torch.float32).contiguous().reshape(-1)
+        shape = (B, T, self.last_depth, H, W) if self.channel_axis == 1 else (B, T, H, W, self.last_depth)
+        logits = torch.empty(shape, dtype=torch.float32, device=dev)
+        softmax = torch.empty(shape, dtype=torch.float32, device=dev)
+        sess.forward(xd.data_ptr(), T, bool(training), logits.data_ptr(), softmax.data_ptr())
+        return _wrap(logits), _wrap(softmax)
+
+    call = __call__
+
+    # ---- recurrent state API (Networks.py:77-98, 279-291) ---------------------------------------------
+    def _n_lstm(self, level):
+        return len(self.net_params['lstm_kernels'][level])
+
+    def _reset_level(self, level, is_last_batch):
+        # the library masks all levels at once; per-level fan-out keeps the reference's call structure
+        if level == 0:
+            self.reset_states_per_batch(is_last_batch)
+
+    def reset_states_per_batch(self, is_last_batch):
+        import torch
+        if self._sess is None:
+            return
+        m = torch.as_tensor(np.asarray(is_last_batch, dtype=np.float32)).reshape(-1)
+        if m.numel() != self._shape[0]:
+            raise ValueError('mask has %d entries for batch size %d' % (m.numel(), self._shape[0]))
+        md = m.to(self._be.device)
+        self._sess.reset_states(md.data_ptr())
+        torch.cuda.current_stream(self._be.device).synchronize()      # md must outlive the kernel
+
+    def _get_level_states(self, level):
+        import torch
+        out = []
+        for j in range(self._n_lstm(level)):
+            if self._sess is None:
+                out.append([None, None])
+                continue
+            shp = self._sess.state_shape(level, j)
+            pair = []
+            for which in (0, 1):
+                t = torch.empty(shp, dtype=torch.float32, device=self._be.device)
+                self._sess.get_state(level, j, which, t.data_ptr())
+                pair.append(t.cpu().numpy())
+            out.append(pair)
+        return out
+
+    def get_states(self):
+        return [self._get_level_states(i) for i in range(len(self.DownLayers))]
+
+    def _set_level_states(self, level, states):
+        import torch
+        if self._sess is None:
+            if self._pending_states is None:
+                self._pending_states = [[[None, None] for _ in range(self._n_lstm(i))] for i in range(len(self.DownLayers))]
+            self._pending_states[level] = states
+            return
+        for j, st in enumerate(states):
+            shp = self._sess.state_shape(level, j)
+            for which in (0, 1):
+                if st is None or st[0] is None:
+                    self._sess.set_state(level, j, which, None)     # keras reset_states(None): zeros
+                else:
+                    a = np.asarray(st[which], dtype=np.float32)
+                    if tuple(a.shape) != shp:
+                        raise ValueError('state shape %s does not match %s' % (a.shape, shp))
+                    t = torch.from_numpy(np.ascontiguousarray(a)).to(self._be.device)
+                    self._sess.set_state(level, j, which, t.data_ptr())
+                    torch.cuda.current_stream(self._be.device).synchronize()
+
+    def set_states(self, states):
+        for i, st in enumerate(states):
+            self._set_level_states(i, st)
+
+    # ---- variables / weights (keras.Model surface used by train2D.py:92-93,236 and Inference2D.py:34) --
+    def _need_session(self):
+        if self._sess is None:
+            raise RuntimeError('the model is built by its first call (Keras builds variables lazily too)')
+        return self._sess
+
+    @property
+    def variables(self):
+        s = self._need_session()
+        return [Variable(e['name'], s.params[e['offset']:e['offset'] + e['count']].view(e['shape']), e['trainable'])
+                for e in s.layout]
+
+    @property
+    def trainable_variables(self):
+        return [v for v in self.variables if v.trainable]
+
+    def get_weights_dict(self):
+        return self._need_session().get_params()
+
+    def set_weights_dict(self, named):
+        if self._sess is None:
+            self._pending_weights = {k: np.asarray(v, dtype=np.float32) for k, v in named.items()}
+        else:
+            self._sess.set_params(named)
+
+    def save_weights(self, path, save_format=None):
+        """Keras variable names/layouts in an .npz (the TF tensor-bundle format is SURVEY 8f row 1)."""
+        w = self.get_weights_dict() if self._sess is not None else self._pending_weights
+        if w is None:
+            raise RuntimeError('nothing to save: the model has no weights yet')
+        with open(path if str(path).endswith('.npz') else str(path) + '.npz', 'wb') as f:
+            np.savez(f, **{k.replace('/', '|'): v for k, v in w.items()})
+
+    def load_weights(self, path):
+        p = path if str(path).endswith('.npz') else str(path) + '.npz'
+        with np.load(p) as z:
+            self.set_weights_dict({k.replace('|', '/'): z[k] for k in z.files})
+
+    def forward_flops(self, T):
+        return self._need_session().forward_flops(T)
+
+    def launch_count(self, reset=False):
+        return self._need_session().launch_count(reset)
+
+    @classmethod
+    def unit_test(cls):
+        """Networks.py:256-277 (shape contract), channels-first single-channel variant for this backend."""
+        model = cls(DEFAULT_NET_DOWN_PARAMS, 'NCHW', True)
+        for i in range(4):
+            x = np.random.randn(2, 2, 1, 35, 35).astype(np.float32)
+            out = model(x, True)
+            print(i, tuple(out[0].shape))
