@@ -631,6 +631,7 @@ static int launch_conv(lu_handle_s* h, ConvPlan& cv, int frames, const int* mul,
   tp.n_a_stages = cv.nA; tp.n_b_stages = cv.nB; tp.a_stage_bytes = cv.a_bytes; tp.b_stage_bytes = cv.b_bytes;
   tp.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(cv.BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   tp.total_tiles = (int)(m_tiles * cv.n_tiles_n);
+
   int grid = tp.total_tiles < h->num_sms ? tp.total_tiles : h->num_sms;
   const int ei = epi.kind == LU_EPI_LSTM ? 1 : 0;
   if (!attr_set[ei]) {

@@ -244,12 +244,14 @@ __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 // K-major, 128-byte swizzle operand descriptor (cute::UMMA::SmemDescriptor layout, sm_100 version bit set)
+// The 128-byte swizzle is a function of the shared-memory ADDRESS bits (measured on B200: a start address that is a
+// multiple of 128 but not of 1024 bytes reads the rows TMA wrote there when the base-offset field is left 0), which is
+// what lets a filter tap be a mere row offset into the staged halo window.
 __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t sbo_bytes) {
   uint64_t d = (uint64_t)((addr & 0x3FFFFu) >> 4);
   d |= (uint64_t)1 << 16;                                  // LBO (ignored for swizzled K-major)
   d |= (uint64_t)(sbo_bytes >> 4) << 32;                   // stride between 8-row groups
   d |= (uint64_t)1 << 46;                                  // descriptor version (Blackwell)
-  d |= (uint64_t)((addr >> 7) & 7u) << 49;                 // base offset: start not 1024-byte aligned (halo taps)
   d |= (uint64_t)2 << 61;                                  // SWIZZLE_128B
   return d;
 }
