@@ -1,0 +1,262 @@
+#!/usr/bin/env python
+"""Benchmark of the ConvLSTM-UNet hot path: frames/sec at 512x512, T=8, batch 4 per GPU (BASELINE.json configs[1]:
+inference-only forward through the Inference2D model call: pad_image=True, training=False, stateful h/c carried
+between iterations).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mode infer]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" = one model call over a (4, 8, 1, 512, 512) batch of synthetic z-scored frames (N(0,1), DataHandeling.py:103).
+Prints ONE JSON line (rank 0).  `value` = frames/s with the batch resident in HBM; `e2e` = the same through the public
+API with HOST buffers (pinned H2D of the frames + D2H of the soft-max, inside the timed region).  `roofline` is for
+the dominant kernel (the tcgen05 ConvLSTM step kernel, 93 % of the FLOPs), timed live with CUDA events around every
+launch.  `cpu_baseline` times the CPU restatement of the reference (oracle/, torch-CPU: TensorFlow, which the reference
+needs, is not installable in this image) on a bounded sample.  `--impl reference` runs only that CPU arm.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'frames/sec (512x512, T=8, bf16)'
+CTC_NET = {   # Params.py:49-69
+    'down_conv_kernels': [[(3, 128), (3, 128)], [(3, 256), (3, 256)], [(3, 256), (3, 256)], [(3, 512), (3, 512)]],
+    'lstm_kernels': [[(5, 128)], [(5, 256)], [(5, 256)], [(5, 512)]],
+    'up_conv_kernels': [[(3, 256), (3, 256)], [(3, 128), (3, 128)], [(3, 64), (3, 64)], [(3, 32), (3, 32), (1, 3)]],
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d.get('bf16_tflops_sustained', d.get('bf16_tflops', 1590.0)), d.get('bf16_tflops', 1590.0), 'measured'
+    return 1400.0, 1590.0, 'fallback'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+             'clocks_event_reasons.sw_power_cap')
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for j, nme in enumerate(names):
+                    if r[5 + j].lower().startswith('active'):
+                        reasons.add(nme)
+            except Exception:
+                continue
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def cpu_reference_run(steps, warmup, B=1, T=4, H=128, W=128):
+    """CPU restatement of the reference forward (Inference2D call: pad_image=True, training=False) on a bounded
+    sample of the workload (smaller frames / batch, same network, same T-unrolled stateful call)."""
+    import torch
+    from oracle import lstm_unet_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    net = O.OracleNet(O.CTC_NET_PARAMS, 'NCHW', True, seed=0)
+    x = torch.randn(B, T, 1, H, W)
+    with torch.no_grad():
+        for _ in range(warmup):
+            net(x, False)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            net(x, False)
+        dt = time.perf_counter() - t0
+    fps = B * T * steps / dt
+    # frames differ in size from the workload's: scale by pixels so the number is frames/s of 512x512 frames
+    scale = (H * W) / (512.0 * 512.0)
+    return {'value': fps * scale, 'unit': 'frames/s', 'cores': cores, 'kind': 'port',
+            'sample': 'oracle (torch-CPU restatement; TF not installable) forward, CTC net, B=%d T=%d %dx%d pad_image, '
+                      '%d steps; %.3f frames/s at %dx%d scaled by pixel count to 512x512' % (B, T, H, W, steps, fps, H, W),
+            'ms_per_step': dt / steps * 1e3}
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 5))
+    cb = cpu_reference_run(steps, max(1, min(args.warmup, 1)))
+    line = {'impl': 'reference', 'metric': METRIC, 'value': cb['value'], 'unit': 'frames/s', 'n_gpus': args.gpus,
+            'steps': steps, 'warmup': 1, 'ms_per_step': cb['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': 'C2 inference forward 512x512 T=8 B=4 (bounded sample, see cpu_baseline.sample)'},
+            'cpu_baseline': {k: cb[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')},
+            'e2e': {'value': cb['value'], 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    import __graft_entry__ as ge
+    ge.build()
+    from lstm_unet_b200.Networks import ULSTMnet2D
+
+    B, T, H, W = args.batch, args.unroll, args.size, args.size
+    training = args.mode == 'train'
+    model = ULSTMnet2D(CTC_NET, 'NCHW', pad_image=not training, precision=args.precision, a_mode=args.a_mode,
+                       seed=rank)
+    rng = np.random.default_rng(1234 + rank)
+    x_host = rng.standard_normal((B, T, 1, H, W)).astype(np.float32)
+    x_dev = torch.from_numpy(x_host).cuda()
+    # shard by batch: every rank owns its B samples and their recurrent states (weak scaling, no data-path collective)
+    model(x_dev, training)
+    torch.cuda.synchronize()
+    sess = model._sess
+    flops_step = sess.forward_flops(T) * B
+    lstm_flops_step = sess.lstm_flops(T) * B
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        model(x_dev, training)
+    barrier()
+    sess.launch_count(reset=True)
+    sess.lstm_kernel_time(True)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        model(x_dev, training)        # states carry over between iterations, like the train / inference loops
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = sess.launch_count()
+    lstm_ms, lstm_n = sess.lstm_kernel_time(False)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # end to end through the public API with host buffers: pinned H2D of the frames + D2H of the soft-max
+    for _ in range(2):
+        model(x_host, training)[1].numpy()
+    barrier()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    e2e_steps = max(2, min(args.steps, 5))
+    for _ in range(e2e_steps):
+        sm = model(x_host, training)[1].numpy()
+    e1.record()
+    barrier()
+    e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3 * 0.0)
+    e2e_wall_ms = (time.perf_counter() - t0) * 1e3
+
+    if world > 1:
+        t = torch.tensor([ms, e2e_ms, e2e_wall_ms], device='cuda', dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_ms, e2e_wall_ms = [float(v) for v in t.tolist()]
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    frames = B * T * args.steps * world
+    value = frames / (ms * 1e-3)
+    e2e_value = B * T * e2e_steps * world / (e2e_wall_ms * 1e-3)
+    sustained, burst, which = peaks()
+    lstm_tflops = (lstm_flops_step * args.steps / (lstm_ms * 1e-3)) / 1e12 if lstm_ms > 0 else None
+    cb = cpu_reference_run(2, 1) if (world == 1 and not args.no_cpu) else None
+    line = {
+        'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'bf16' if args.precision == 'bf16' else 'bf16x3(split-bf16, fp32-equivalent)', 'data': 'synthetic',
+        'config': {'workload': 'C2: ConvLSTM-UNet (CTCParams net, 74.6M params) %s forward, %dx%d, T=%d, batch %d per GPU, '
+                               'pad_image=%s, stateful' % ('training-mode' if training else 'inference', H, W, T, B, not training),
+                   'global_batch': B * world, 'parallelism': 'batch-sharded replicas x%d (no data-path collective)' % world,
+                   'l2_policy': 'inputs+activations per step (>6 GB) exceed the 126 MB L2; no flush needed',
+                   'a_mode': args.a_mode, 'step_tflop': flops_step / 1e12},
+        'e2e': {'value': e2e_value, 'unit': 'frames/s', 'h2d_bytes_per_step': int(x_host.nbytes),
+                'd2h_bytes_per_step': int(sm.nbytes), 'steps': e2e_steps, 'ms_per_step': e2e_wall_ms / e2e_steps},
+        'gpu_launches': int(launches),
+        'clocks': clocks,
+        'roofline': {'bound': 'tensor', 'achieved': lstm_tflops, 'peak': sustained, 'unit': 'TFLOP/s',
+                     'frac': (lstm_tflops / sustained) if lstm_tflops else None, 'traffic': None,
+                     'kernel': 'lu_conv_tc_kernel<LSTM> (all 4 ConvLSTM levels, %d launches)' % lstm_n,
+                     'kernel_ms_per_step': lstm_ms / args.steps, 'kernel_share_of_step': lstm_ms / ms if ms else None,
+                     'peak_source': which + ' bf16_tflops_sustained (kernel timed inside a long step); burst %.1f' % burst,
+                     'whole_step_tflops': flops_step * args.steps / (ms * 1e-3) / 1e12},
+    }
+    if cb is not None:
+        line['cpu_baseline'] = {k: cb[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--mode', default='infer', choices=['infer', 'train'])
+    ap.add_argument('--precision', default='bf16', choices=['bf16', 'bf16x3'])
+    ap.add_argument('--a-mode', dest='a_mode', default='halo', choices=['halo', 'direct'])
+    ap.add_argument('--batch', type=int, default=4)
+    ap.add_argument('--unroll', type=int, default=8)
+    ap.add_argument('--size', type=int, default=512)
+    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

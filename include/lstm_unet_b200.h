@@ -113,8 +113,11 @@ int lu_adam_step(lu_handle h, const float* dev_grads, float* dev_m, float* dev_v
 int lu_launch_count(lu_handle h, int64_t* launches, int32_t reset);
 /* algorithmic FLOPs (2*MAC, padding included) of one forward over T frames per sample at the bound shape */
 int lu_forward_flops(lu_handle h, int32_t T, double* flops);
-/* names the dominant kernel's last launches for profiling: sets a CUDA-event pair around every ConvLSTM
- * tensor-core launch when enabled; returns accumulated milliseconds and launch count */
+/* the ConvLSTM layers' share of lu_forward_flops (the dominant kernel's algorithmic work) */
+int lu_lstm_flops(lu_handle h, int32_t T, double* flops);
+/* timing of the dominant kernel for bench.py's roofline: returns the milliseconds and launch count accumulated by
+ * CUDA-event pairs recorded around every ConvLSTM launch since the last call (synchronises on the last event),
+ * then enables / disables the recording for the following forwards */
 int lu_lstm_kernel_time(lu_handle h, int32_t enable, float* ms_total, int32_t* launches);
 
 #ifdef __cplusplus

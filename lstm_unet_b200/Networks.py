@@ -50,6 +50,23 @@ DEFAULT_NET_DOWN_PARAMS = {
 }
 
 
+_PINNED_RING = {}
+
+
+def _pinned_like(t):
+    """Ring of three pinned host buffers per (shape, dtype): device->host copies run at DMA speed.  The array returned
+    by ``.numpy()`` therefore stays valid until three later ``.numpy()`` calls on same-shaped outputs (the reference's
+    inference loop consumes it within the iteration, Inference2D.py:60-131)."""
+    import torch
+    key = (tuple(t.shape), t.dtype)
+    ring = _PINNED_RING.setdefault(key, {'bufs': [], 'next': 0})
+    if len(ring['bufs']) < 3:
+        ring['bufs'].append(torch.empty(t.shape, dtype=t.dtype, pin_memory=True))
+        return ring['bufs'][-1]
+    ring['next'] = (ring['next'] + 1) % 3
+    return ring['bufs'][ring['next']]
+
+
 def _device_array_type():
     import torch
 
@@ -57,7 +74,11 @@ def _device_array_type():
         """cuda tensor with tf.Tensor's ``.numpy()`` (device -> host copy), as Inference2D.py:60 uses it."""
 
         def numpy(self):
-            return self.as_subclass(torch.Tensor).detach().cpu().numpy()
+            t = self.as_subclass(torch.Tensor).detach()
+            host = _pinned_like(t)
+            host.copy_(t, non_blocking=True)
+            torch.cuda.current_stream(t.device).synchronize()
+            return host.numpy()
 
     return DeviceArray
 
@@ -338,7 +359,7 @@ class ULSTMnet2D:
 
     def set_weights_dict(self, named):
         if self._sess is None:
-            self._pending_weights = {k: np.asarray(v, dtype=np.float32) for k, v in named.items()}
+            self._pending_weights = {k: np.array(v, dtype=np.float32, copy=True) for k, v in named.items()}
         else:
             self._sess.set_params(named)
 

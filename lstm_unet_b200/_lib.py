@@ -61,6 +61,7 @@ def bind(lib):
         'lu_adam_step': [vp, vp, vp, vp, f32, f32, f32, f32, i64, vp],
         'lu_launch_count': [vp, P(i64), i32],
         'lu_forward_flops': [vp, i32, P(ctypes.c_double)],
+        'lu_lstm_flops': [vp, i32, P(ctypes.c_double)],
         'lu_lstm_kernel_time': [vp, i32, P(f32), P(i32)],
     }
     for name, args in sigs.items():
@@ -73,7 +74,8 @@ def bind(lib):
 EXPORTED_SYMBOLS = ['lu_last_error', 'lu_version', 'lu_is_cuda_build', 'lu_create', 'lu_destroy', 'lu_workspace_bytes',
                     'lu_bind_workspace', 'lu_param_count', 'lu_param_info', 'lu_bind_params', 'lu_params_changed',
                     'lu_forward', 'lu_reset_states', 'lu_state_shape', 'lu_get_state', 'lu_set_state',
-                    'lu_loss_backward', 'lu_adam_step', 'lu_launch_count', 'lu_forward_flops', 'lu_lstm_kernel_time']
+                    'lu_loss_backward', 'lu_adam_step', 'lu_launch_count', 'lu_forward_flops', 'lu_lstm_flops',
+                    'lu_lstm_kernel_time']
 
 _LIB = None
 

@@ -122,10 +122,17 @@ struct lu_handle_s {
   bool bound = false, packed = false;
   int num_sms = 148;
   TrainState tr;
+  // optional CUDA-event timing of every ConvLSTM launch (bench.py roofline)
+  bool time_lstm = false;
+  size_t ev_used = 0;
+#ifndef LU_HOST_EMU
+  std::vector<cudaEvent_t> events;
+#endif
 };
 
 static void train_layout(lu_handle_s* h, size_t& off);
 static void train_destroy(lu_handle_s* h);
+extern "C" int lu_lstm_flops(lu_handle h, int32_t T, double* flops);
 
 static int find_param(lu_handle_s* h, const std::string& name) {
   for (size_t i = 0; i < h->params.size(); ++i)
@@ -275,9 +282,11 @@ static int build_tables(lu_handle_s* h, ConvPlan& cv) {
       v.sw = 2 * ctot; v.sp = (int64_t)ab.W * ctot; v.sh = 2 * (int64_t)ab.W * ctot; v.sn = (int64_t)ab.H * ab.W * ctot;
     }
     if (halo) {
+      // exact halo window: (16 + kh - 1) rows of (8 + kw - 1) pixels.  The UMMA descriptor's 8-row group stride is
+      // pitch*128 bytes; it need not be a multiple of the 1024-byte swizzle atom because the swizzle is a function
+      // of the shared-memory address bits (see make_desc in lu_conv.cuh).
       v.rows = LU_TILE_H + (a_max - a_min);
-      v.pitch = (b_max > b_min) ? 2 * LU_TILE_W : LU_TILE_W;
-      LU_REQUIRE(LU_TILE_W + (b_max - b_min) <= v.pitch, "kernel too wide for the halo window");
+      v.pitch = LU_TILE_W + (b_max - b_min);
     } else {
       v.rows = LU_TILE_H; v.pitch = LU_TILE_W;
     }
@@ -329,12 +338,17 @@ static int build_tables(lu_handle_s* h, ConvPlan& cv) {
   // shared-memory pipeline shape
   cv.a_bytes = 0;
   for (int i = 0; i < cv.n_views; ++i) {
-    const int b = cv.views[i].rows * cv.views[i].pitch * 128;
+    const int b = (int)align_up((size_t)cv.views[i].rows * cv.views[i].pitch * 128, 1024);
     cv.a_bytes = b > cv.a_bytes ? b : cv.a_bytes;
   }
   cv.b_bytes = cv.BN * 128;
   const int budget = 232448 - 1024 - 512;
-  cv.nA = halo ? 2 : 4;
+  // weight stages first (one is consumed per tap: >= 4 in flight), then as many activation windows as fit
+  const int nkb = (int)cv.packs.size();
+  int nb_min = nkb < 4 ? (nkb < 2 ? 2 : nkb) : 4;
+  cv.nA = (budget - nb_min * cv.b_bytes) / cv.a_bytes;
+  if (cv.nA > 6) cv.nA = 6;
+  LU_REQUIRE(cv.nA >= 2, "shared memory budget exceeded for %s", cv.name.c_str());
   cv.nB = (budget - cv.nA * cv.a_bytes) / cv.b_bytes;
   if (cv.nB > 8) cv.nB = 8;
   LU_REQUIRE(cv.nB >= 2, "shared memory budget exceeded for %s", cv.name.c_str());
@@ -839,7 +853,7 @@ static int run_conv_layer(lu_handle_s* h, ConvPlan& cv, int T, int training, voi
     ap.raw = raw; ap.scale = fin.scale; ap.shift = fin.shift;
     ap.out = reinterpret_cast<uint16_t*>(h->ws + ob.off); ap.raw_cpad = cv.raw_cpad; ap.out_cpad = ob.cpad; ap.planes = ob.planes;
     ap.alpha = 0.3f;
-    pf(h, npix * ob.cpad, stream, ap);
+    pf(h, npix * (ob.cpad / 8), stream, ap);
   }
   return 0;
 }
@@ -863,7 +877,16 @@ static int run_lstm_layer(lu_handle_s* h, ConvPlan& cv, int T, int training, voi
       e.save_gates = reinterpret_cast<uint16_t*>(h->ws + cv.off_save_gates);
       e.save_c = reinterpret_cast<float*>(h->ws + cv.off_save_c);
     }
+#ifndef LU_HOST_EMU
+    if (h->time_lstm) {
+      while (h->events.size() < h->ev_used + 2) { cudaEvent_t ev; cudaEventCreate(&ev); h->events.push_back(ev); }
+      cudaEventRecord(h->events[h->ev_used], (cudaStream_t)stream);
+    }
+#endif
     if (launch_conv(h, cv, h->cfg.batch, mul, add, sel, e, stream)) return 1;
+#ifndef LU_HOST_EMU
+    if (h->time_lstm) { cudaEventRecord(h->events[h->ev_used + 1], (cudaStream_t)stream); h->ev_used += 2; }
+#endif
   }
   return 0;
 }
@@ -881,7 +904,7 @@ int lu_forward(lu_handle h, const float* dev_x, int32_t T, int32_t training, flo
     pp.x = dev_x; pp.out = reinterpret_cast<uint16_t*>(h->ws + h->off_patches);
     pp.H = c.height; pp.W = c.width; pp.Hp = h->Hp; pp.Wp = h->Wp; pp.pad_y0 = h->pad_y0; pp.pad_x0 = h->pad_x0;
     pp.pw = h->pw; pp.x3 = h->planes == 2;
-    pf(h, (int64_t)N * h->Hp * h->Wp * 64, stream, pp);
+    pf(h, (int64_t)N * h->Hp * h->Wp * 8, stream, pp);
   }
   for (int l = 0; l < h->L; ++l) {
     for (int ci : h->lstm_of_level[l])
@@ -896,7 +919,7 @@ int lu_forward(lu_handle h, const float* dev_x, int32_t T, int32_t training, flo
       LuUpsample2x up;
       up.in = reinterpret_cast<const uint16_t*>(h->ws + s.off); up.out = reinterpret_cast<uint16_t*>(h->ws + d.off);
       up.h = s.H; up.w = s.W; up.cpad = s.cpad; up.planes = s.planes;
-      pf(h, (int64_t)N * d.H * d.W * d.cpad, stream, up);
+      pf(h, (int64_t)N * d.H * d.W * (d.cpad / 8), stream, up);
     }
     for (int ci : h->conv_of_up[u])
       if (run_conv_layer(h, h->convs[ci], T, training, stream)) return 1;
@@ -991,11 +1014,32 @@ int lu_forward_flops(lu_handle h, int32_t T, double* flops) {
   return 0;
 }
 
+int lu_lstm_flops(lu_handle h, int32_t T, double* flops) {
+  LU_REQUIRE(h && flops, "null argument");
+  double macs = 0;
+  for (auto& cv : h->convs) if (cv.kind == LU_EPI_LSTM) macs += cv.macs_per_frame;
+  *flops = 2.0 * macs * T;
+  return 0;
+}
+
 int lu_lstm_kernel_time(lu_handle h, int32_t enable, float* ms_total, int32_t* launches) {
   LU_REQUIRE(h, "null handle");
-  (void)enable;
-  if (ms_total) *ms_total = 0.f;
-  if (launches) *launches = 0;
+  float total = 0.f; int n = 0;
+#ifndef LU_HOST_EMU
+  if (h->ev_used) {
+    cudaError_t e = cudaEventSynchronize(h->events[h->ev_used - 1]);
+    LU_REQUIRE(e == cudaSuccess, "event sync: %s", cudaGetErrorString(e));
+    for (size_t i = 0; i + 1 < h->ev_used; i += 2) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, h->events[i], h->events[i + 1]);
+      total += ms; ++n;
+    }
+  }
+#endif
+  h->ev_used = 0;
+  h->time_lstm = enable != 0;
+  if (ms_total) *ms_total = total;
+  if (launches) *launches = n;
   return 0;
 }
 

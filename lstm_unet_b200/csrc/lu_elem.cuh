@@ -38,6 +38,27 @@ LU_HDI void lu_atomic_add(float* p, float v) {
 #endif
 }
 
+// 8 x bf16 (16 bytes) loads / stores
+LU_HDI void lu_load8_bf16(const uint16_t* src, float* v) {
+#ifdef __CUDA_ARCH__
+  const uint4 q = *reinterpret_cast<const uint4*>(src);
+  v[0] = lu_u2f(q.x << 16); v[1] = lu_u2f(q.x & 0xffff0000u); v[2] = lu_u2f(q.y << 16); v[3] = lu_u2f(q.y & 0xffff0000u);
+  v[4] = lu_u2f(q.z << 16); v[5] = lu_u2f(q.z & 0xffff0000u); v[6] = lu_u2f(q.w << 16); v[7] = lu_u2f(q.w & 0xffff0000u);
+#else
+  for (int j = 0; j < 8; ++j) v[j] = lu_bf2f(src[j]);
+#endif
+}
+LU_HDI void lu_store8_bf16(uint16_t* dst, const uint16_t* h) {
+#ifdef __CUDA_ARCH__
+  uint4 a;
+  a.x = h[0] | ((uint32_t)h[1] << 16); a.y = h[2] | ((uint32_t)h[3] << 16);
+  a.z = h[4] | ((uint32_t)h[5] << 16); a.w = h[6] | ((uint32_t)h[7] << 16);
+  *reinterpret_cast<uint4*>(dst) = a;
+#else
+  for (int j = 0; j < 8; ++j) dst[j] = h[j];
+#endif
+}
+
 LU_HDI int lu_reflect(int i, int n) {     // tf.pad REFLECT index (no edge repeat); pad < n guaranteed
   if (i < 0) i = -i;
   if (i >= n) i = 2 * (n - 1) - i;
@@ -51,23 +72,28 @@ LU_HDI int lu_reflect(int i, int n) {     // tf.pad REFLECT index (no edge repea
 struct LuPrepPatches {
   const float* x; uint16_t* out;
   int H, W, Hp, Wp, pad_y0, pad_x0, pw, x3;
-  LU_HD void operator()(int64_t i) const {
-    const int ch = (int)(i % 64); int64_t p = i / 64;
+  LU_HD void operator()(int64_t i) const {        // item = (pixel, group of 8 channels)
+    const int g = (int)(i % 8); int64_t p = i / 8;
     const int xx = (int)(p % Wp); p /= Wp;
     const int yy = (int)(p % Hp); const int64_t n = p / Hp;
-    int t = ch, lo = 0;
-    if (x3 && ch >= 32) { t = ch - 32; lo = 1; }
-    uint16_t r = 0;
-    if (t < pw * pw && (x3 || ch < 64)) {
-      const int py = yy + t / pw - (pw - 1) / 2, px = xx + t % pw - (pw - 1) / 2;
-      if (py >= 0 && py < Hp && px >= 0 && px < Wp) {
-        const int sy = lu_reflect(py - pad_y0, H), sx = lu_reflect(px - pad_x0, W);
-        const float v = x[(n * H + sy) * W + sx];
-        uint16_t h, l; lu_split(v, h, l);
-        r = lo ? l : h;
+    uint16_t r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int ch = g * 8 + j;
+      int t = ch, lo = 0;
+      if (x3 && ch >= 32) { t = ch - 32; lo = 1; }
+      r[j] = 0;
+      if (t < pw * pw) {
+        const int py = yy + t / pw - (pw - 1) / 2, px = xx + t % pw - (pw - 1) / 2;
+        if (py >= 0 && py < Hp && px >= 0 && px < Wp) {
+          const int sy = lu_reflect(py - pad_y0, H), sx = lu_reflect(px - pad_x0, W);
+          const float v = x[(n * H + sy) * W + sx];
+          uint16_t h, l; lu_split(v, h, l);
+          r[j] = lo ? l : h;
+        }
       }
     }
-    out[i] = r;
+    lu_store8_bf16(out + i * 8, r);
   }
 };
 
@@ -76,8 +102,9 @@ struct LuPrepPatches {
 struct LuUpsample2x {
   const uint16_t* in; uint16_t* out;
   int h, w, cpad, planes;
-  LU_HD void operator()(int64_t i) const {
-    const int c = (int)(i % cpad); int64_t p = i / cpad;
+  LU_HD void operator()(int64_t i) const {        // item = (n, oy, ox, group of 8 channels)
+    const int cg = cpad / 8;
+    const int c = (int)(i % cg) * 8; int64_t p = i / cg;
     const int ox = (int)(p % (2 * w)); p /= (2 * w);
     const int oy = (int)(p % (2 * h)); const int64_t n = p / (2 * h);
     // out[2i] = .25 in[i-1] + .75 in[i]; out[2i+1] = .75 in[i] + .25 in[i+1] (edge clamped)
@@ -85,19 +112,34 @@ struct LuUpsample2x {
     const int y1 = (oy & 1) ? (iy + 1 < h ? iy + 1 : h - 1) : (iy > 0 ? iy - 1 : 0);
     const int x1 = (ox & 1) ? (ix + 1 < w ? ix + 1 : w - 1) : (ix > 0 ? ix - 1 : 0);
     const int ct = cpad * planes;
-    const uint16_t* b = in + n * (int64_t)h * w * ct;
-    float v00 = lu_bf2f(b[((int64_t)iy * w + ix) * ct + c]), v01 = lu_bf2f(b[((int64_t)iy * w + x1) * ct + c]);
-    float v10 = lu_bf2f(b[((int64_t)y1 * w + ix) * ct + c]), v11 = lu_bf2f(b[((int64_t)y1 * w + x1) * ct + c]);
+    const uint16_t* b = in + n * (int64_t)h * w * ct + c;
+    float v00[8], v01[8], v10[8], v11[8];
+    lu_load8_bf16(b + ((int64_t)iy * w + ix) * ct, v00); lu_load8_bf16(b + ((int64_t)iy * w + x1) * ct, v01);
+    lu_load8_bf16(b + ((int64_t)y1 * w + ix) * ct, v10); lu_load8_bf16(b + ((int64_t)y1 * w + x1) * ct, v11);
     if (planes == 2) {
-      v00 += lu_bf2f(b[((int64_t)iy * w + ix) * ct + cpad + c]); v01 += lu_bf2f(b[((int64_t)iy * w + x1) * ct + cpad + c]);
-      v10 += lu_bf2f(b[((int64_t)y1 * w + ix) * ct + cpad + c]); v11 += lu_bf2f(b[((int64_t)y1 * w + x1) * ct + cpad + c]);
+      float t[8];
+      lu_load8_bf16(b + ((int64_t)iy * w + ix) * ct + cpad, t);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v00[j] += t[j];
+      lu_load8_bf16(b + ((int64_t)iy * w + x1) * ct + cpad, t);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v01[j] += t[j];
+      lu_load8_bf16(b + ((int64_t)y1 * w + ix) * ct + cpad, t);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v10[j] += t[j];
+      lu_load8_bf16(b + ((int64_t)y1 * w + x1) * ct + cpad, t);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v11[j] += t[j];
     }
-    const float top = 0.75f * v00 + 0.25f * v01, bot = 0.75f * v10 + 0.25f * v11;
-    const float v = 0.75f * top + 0.25f * bot;
-    uint16_t hi, lo; lu_split(v, hi, lo);
+    uint16_t hi[8], lo[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float top = 0.75f * v00[j] + 0.25f * v01[j], bot = 0.75f * v10[j] + 0.25f * v11[j];
+      lu_split(0.75f * top + 0.25f * bot, hi[j], lo[j]);
+    }
     uint16_t* o = out + (((n * 2 * h + oy) * 2 * w) + ox) * (int64_t)ct + c;
-    o[0] = hi;
-    if (planes == 2) o[cpad] = lo;
+    lu_store8_bf16(o, hi);
+    if (planes == 2) lu_store8_bf16(o + cpad, lo);
   }
 };
 
@@ -143,14 +185,19 @@ struct LuBnFinalize {
 struct LuBnApply {
   const float* raw; const float* scale; const float* shift; uint16_t* out;
   int raw_cpad, out_cpad, planes; float alpha;
-  LU_HD void operator()(int64_t i) const {
-    const int c = (int)(i % out_cpad); const int64_t p = i / out_cpad;
-    float a = 0.f;
-    if (c < raw_cpad) { a = raw[p * raw_cpad + c] * scale[c] + shift[c]; a = a > 0.f ? a : alpha * a; }
-    uint16_t hi, lo; lu_split(a, hi, lo);
+  LU_HD void operator()(int64_t i) const {        // item = (pixel, group of 8 channels)
+    const int cg = out_cpad / 8;
+    const int c = (int)(i % cg) * 8; const int64_t p = i / cg;
+    uint16_t hi[8], lo[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float a = 0.f;
+      if (c + j < raw_cpad) { a = raw[p * raw_cpad + c + j] * scale[c + j] + shift[c + j]; a = a > 0.f ? a : alpha * a; }
+      lu_split(a, hi[j], lo[j]);
+    }
     uint16_t* o = out + p * (int64_t)(out_cpad * planes) + c;
-    o[0] = hi;
-    if (planes == 2) o[out_cpad] = lo;
+    lu_store8_bf16(o, hi);
+    if (planes == 2) lu_store8_bf16(o + out_cpad, lo);
   }
 };
 // inference: fold moving statistics into per-channel scale/shift (applied in the conv epilogue)

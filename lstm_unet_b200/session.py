@@ -145,3 +145,14 @@ class LuSession:
         f = ctypes.c_double()
         self._check(self.lib.lu_forward_flops(self.h, int(T), ctypes.byref(f)))
         return f.value
+
+    def lstm_flops(self, T):
+        f = ctypes.c_double()
+        self._check(self.lib.lu_lstm_flops(self.h, int(T), ctypes.byref(f)))
+        return f.value
+
+    def lstm_kernel_time(self, enable):
+        """-> (milliseconds, launches) accumulated since the last call; then switches the event recording."""
+        ms, n = ctypes.c_float(), ctypes.c_int32()
+        self._check(self.lib.lu_lstm_kernel_time(self.h, 1 if enable else 0, ctypes.byref(ms), ctypes.byref(n)))
+        return ms.value, n.value

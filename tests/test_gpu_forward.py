@@ -37,7 +37,7 @@ def make_pair(net, data_format, pad, seed, **kw):
     params = O.init_params(net, seed=seed, randomize_bn=True)
     ora = O.OracleNet(net, data_format, pad, params=params)
     model = ULSTMnet2D(net, data_format, pad, **kw)
-    model.set_weights_dict({k: v.numpy() for k, v in params.items()})
+    model.set_weights_dict({k: v.numpy().copy() for k, v in params.items()})
     return ora, model
 
 
