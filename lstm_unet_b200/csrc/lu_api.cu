@@ -83,6 +83,9 @@ struct ConvPlan {
   size_t off_bscale = 0, off_bshift = 0, off_sums = 0, off_save_mean = 0, off_save_invstd = 0;
   int ktot = 0;
   int nA = 2, nB = 4, a_bytes = 0, b_bytes = 0, smem = 0;
+  bool ptab_ok = false;                 // staging tables fit the kernel-parameter copies
+  std::vector<LuAStage> pstages;        // stages with tap_begin remapped into the de-duplicated tap list
+  std::vector<uint16_t> ptaps;
   double macs_per_frame = 0;
   // lstm only
   int F = 0, fpad = 0, level = 0, layer = 0;
@@ -335,6 +338,20 @@ static int build_tables(lu_handle_s* h, ConvPlan& cv) {
       }
   }
   cv.ktot = (int)cv.packs.size() * LU_KBLK;
+  // kernel-parameter copies of the tables: identical tap lists are stored once
+  cv.pstages = cv.astages; cv.ptaps.clear();
+  for (auto& st : cv.pstages) {
+    const uint16_t* lst = cv.taps.data() + st.tap_begin;
+    int found = -1;
+    for (int b = 0; b + (int)st.ntaps <= (int)cv.ptaps.size() && found < 0; ++b) {
+      bool same = true;
+      for (int t = 0; t < st.ntaps && same; ++t) same = cv.ptaps[b + t] == lst[t];
+      if (same) found = b;
+    }
+    if (found < 0) { found = (int)cv.ptaps.size(); cv.ptaps.insert(cv.ptaps.end(), lst, lst + st.ntaps); }
+    st.tap_begin = (uint32_t)found;
+  }
+  cv.ptab_ok = (int)cv.pstages.size() <= LU_PT_STAGES && (int)cv.ptaps.size() <= LU_PT_TAPS;
   // shared-memory pipeline shape
   cv.a_bytes = 0;
   for (int i = 0; i < cv.n_views; ++i) {
@@ -342,7 +359,7 @@ static int build_tables(lu_handle_s* h, ConvPlan& cv) {
     cv.a_bytes = b > cv.a_bytes ? b : cv.a_bytes;
   }
   cv.b_bytes = cv.BN * 128;
-  const int budget = 232448 - 1024 - 512;
+  const int budget = 232448 - 1024 - 512 - 6144;   // alignment slack, barriers, epilogue constants
   // weight stages first (one is consumed per tap: >= 4 in flight), then as many activation windows as fit
   const int nkb = (int)cv.packs.size();
   int nb_min = nkb < 4 ? (nkb < 2 ? 2 : nkb) : 4;
@@ -352,7 +369,7 @@ static int build_tables(lu_handle_s* h, ConvPlan& cv) {
   cv.nB = (budget - cv.nA * cv.a_bytes) / cv.b_bytes;
   if (cv.nB > 8) cv.nB = 8;
   LU_REQUIRE(cv.nB >= 2, "shared memory budget exceeded for %s", cv.name.c_str());
-  cv.smem = cv.nA * cv.a_bytes + cv.nB * cv.b_bytes + 1024 + 512;
+  cv.smem = cv.nA * cv.a_bytes + cv.nB * cv.b_bytes + 1024 + 512 + 6144;
   return 0;
 }
 
@@ -645,6 +662,11 @@ static int launch_conv(lu_handle_s* h, ConvPlan& cv, int frames, const int* mul,
   tp.n_a_stages = cv.nA; tp.n_b_stages = cv.nB; tp.a_stage_bytes = cv.a_bytes; tp.b_stage_bytes = cv.b_bytes;
   tp.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(cv.BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   tp.total_tiles = (int)(m_tiles * cv.n_tiles_n);
+  tp.tables_in_params = cv.ptab_ok ? 1 : 0;
+  if (cv.ptab_ok) {
+    memcpy(tp.st_tab, cv.pstages.data(), cv.pstages.size() * sizeof(LuAStage));
+    memcpy(tp.tap_tab, cv.ptaps.data(), cv.ptaps.size() * sizeof(uint16_t));
+  }
 
   int grid = tp.total_tiles < h->num_sms ? tp.total_tiles : h->num_sms;
   const int ei = epi.kind == LU_EPI_LSTM ? 1 : 0;
@@ -904,7 +926,7 @@ int lu_forward(lu_handle h, const float* dev_x, int32_t T, int32_t training, flo
     pp.x = dev_x; pp.out = reinterpret_cast<uint16_t*>(h->ws + h->off_patches);
     pp.H = c.height; pp.W = c.width; pp.Hp = h->Hp; pp.Wp = h->Wp; pp.pad_y0 = h->pad_y0; pp.pad_x0 = h->pad_x0;
     pp.pw = h->pw; pp.x3 = h->planes == 2;
-    pf(h, (int64_t)N * h->Hp * h->Wp * 8, stream, pp);
+    pf(h, (int64_t)N * h->Hp * h->Wp, stream, pp);
   }
   for (int l = 0; l < h->L; ++l) {
     for (int ci : h->lstm_of_level[l])

@@ -6,6 +6,12 @@
 // pixel window the MMA reads.  B is the pre-packed K-major bf16 weight matrix [Npad][Ktot].
 #pragma once
 #include "lu_defs.h"
+#ifndef LU_HOST_EMU
+#include <cuda_bf16.h>
+#endif
+
+#define LU_PT_STAGES 40
+#define LU_PT_TAPS 160
 
 struct LuConvParams {
   LuSrcView src[LU_MAX_SRC];
@@ -53,72 +59,83 @@ LU_HDI void lu_store16_bf16(uint16_t* dst, const uint16_t* h) {
 #endif
 }
 
-// ---- epilogues (one 16-column chunk of one output pixel) -------------------------------------------------
-// conv: v = acc + bias -> optional fp32 raw store; optional folded-BN + LeakyReLU -> bf16 (hi[,lo]) store.
-LU_HDI void lu_epi_conv_chunk(const LuEpi& e, int64_t pix, int n, float* v) {
+// ---- bf16 packing of 16 values (hi plane, optional lo plane) ---------------------------------------------------
+LU_HDI void lu_store16_split(uint16_t* dst, int lo_off, bool want_lo, const float* a) {
+#ifdef __CUDA_ARCH__
+  uint32_t h[8], l[8];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) v[j] += e.bias[n + j];
+  for (int j = 0; j < 8; ++j) {
+    const __nv_bfloat162 hv = __floats2bfloat162_rn(a[2 * j], a[2 * j + 1]);
+    h[j] = *reinterpret_cast<const uint32_t*>(&hv);
+    if (want_lo) {
+      const float2 hf = __bfloat1622float2(hv);
+      const __nv_bfloat162 lv = __floats2bfloat162_rn(a[2 * j] - hf.x, a[2 * j + 1] - hf.y);
+      l[j] = *reinterpret_cast<const uint32_t*>(&lv);
+    }
+  }
+  reinterpret_cast<uint4*>(dst)[0] = make_uint4(h[0], h[1], h[2], h[3]);
+  reinterpret_cast<uint4*>(dst)[1] = make_uint4(h[4], h[5], h[6], h[7]);
+  if (want_lo) {
+    reinterpret_cast<uint4*>(dst + lo_off)[0] = make_uint4(l[0], l[1], l[2], l[3]);
+    reinterpret_cast<uint4*>(dst + lo_off)[1] = make_uint4(l[4], l[5], l[6], l[7]);
+  }
+#else
+  for (int j = 0; j < 16; ++j) {
+    uint16_t hi, lo; lu_split(a[j], hi, lo);
+    dst[j] = hi;
+    if (want_lo) dst[lo_off + j] = lo;
+  }
+#endif
+}
+
+// ---- epilogues (one 16-column chunk of one output pixel) -------------------------------------------------
+// bias/scale/shift point at the 16 per-column constants of this chunk (shared memory in the tcgen05 kernel).
+// conv: v = acc + bias -> optional fp32 raw store; optional folded-BN + LeakyReLU -> bf16 (hi[,lo]) store.
+LU_HDI void lu_epi_conv_chunk(const LuEpi& e, int64_t pix, int n, float* v, const float* bias, const float* scale,
+                              const float* shift) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] += bias[j];
   if (e.out_raw != nullptr && n < e.raw_cpad) lu_store16_f32(e.out_raw + pix * e.raw_cpad + n, v);
   if (e.out_act != nullptr && n < e.out_cpad) {
-    uint16_t hi[16], lo[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      float a = v[j] * e.scale[n + j] + e.shift[n + j];
-      a = a > 0.f ? a : e.alpha * a;
-      lu_split(a, hi[j], lo[j]);
+      const float a = v[j] * scale[j] + shift[j];
+      v[j] = a > 0.f ? a : e.alpha * a;
     }
-    uint16_t* o = e.out_act + pix * (int64_t)(e.out_cpad * e.out_planes) + n;
-    lu_store16_bf16(o, hi);
-    if (e.out_planes == 2) lu_store16_bf16(o + e.out_cpad, lo);
+    lu_store16_split(e.out_act + pix * (int64_t)(e.out_cpad * e.out_planes) + n, e.out_cpad, e.out_planes == 2, v);
   }
 }
 
 // ConvLSTM cell (keras ConvLSTM2D defaults): z* are the pre-activations of gates i,f,c,o for 16
-// channels starting at ch0; sample = batch index (states), pix_out = pixel index in the h sequence buffer.
-LU_HDI void lu_epi_lstm_chunk(const LuEpi& e, int64_t pix_state, int64_t pix_out, int nbase, int jc, int ch0,
-                              const float* zi, const float* zf, const float* zg, const float* zo) {
-  const int CH = e.ch_tile;
-  const float* b = e.bias + nbase + jc;
+// channels starting at ch0; b* the matching bias slices; pix_state indexes the per-sample states, pix_out the h
+// sequence buffer.
+LU_HDI void lu_epi_lstm_chunk(const LuEpi& e, int64_t pix_state, int64_t pix_out, int ch0, const float* zi,
+                              const float* zf, const float* zg, const float* zo, const float* bi, const float* bf,
+                              const float* bg, const float* bo) {
   float* cp = e.c_state + pix_state * e.f_pad + ch0;
-  float c[16], gi[16], gf[16], gg[16], go[16];
-  uint16_t hi[16], lo[16];
+  float c[16], gi[16], gf[16], gg[16], go[16], hh[16];
   lu_load16_f32(cp, c);
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
-    float ai = zi[j] + b[j], af = zf[j] + b[CH + j], ag = zg[j] + b[2 * CH + j], ao = zo[j] + b[3 * CH + j];
+    const float ai = zi[j] + bi[j], af = zf[j] + bf[j], ag = zg[j] + bg[j], ao = zo[j] + bo[j];
     if (e.gate_kind == 0) { gi[j] = lu_hard_sigmoid(ai); gf[j] = lu_hard_sigmoid(af); go[j] = lu_hard_sigmoid(ao); }
     else { gi[j] = lu_sigmoid(ai); gf[j] = lu_sigmoid(af); go[j] = lu_sigmoid(ao); }
     gg[j] = tanhf(ag);
     c[j] = gf[j] * c[j] + gi[j] * gg[j];
-    float h = go[j] * tanhf(c[j]);
-    lu_split(h, hi[j], lo[j]);
+    hh[j] = go[j] * tanhf(c[j]);
   }
   lu_store16_f32(cp, c);
   const int64_t ctot = (int64_t)e.f_pad * e.out_planes;
-  uint16_t* o = e.out_act + pix_out * ctot + ch0;
-  lu_store16_bf16(o, hi);
-  if (e.out_planes == 2) lu_store16_bf16(o + e.f_pad, lo);
-  if (e.h_state_out != nullptr) {
-    uint16_t* s = e.h_state_out + pix_state * ctot + ch0;
-    lu_store16_bf16(s, hi);
-    if (e.out_planes == 2) lu_store16_bf16(s + e.f_pad, lo);
-  }
+  const bool lo = e.out_planes == 2;
+  lu_store16_split(e.out_act + pix_out * ctot + ch0, e.f_pad, lo, hh);
+  if (e.h_state_out != nullptr) lu_store16_split(e.h_state_out + pix_state * ctot + ch0, e.f_pad, lo, hh);
   if (e.save_c != nullptr) lu_store16_f32(e.save_c + pix_out * e.f_pad + ch0, c);
   if (e.save_gates != nullptr) {
-    uint16_t t[16];
     uint16_t* g = e.save_gates + pix_out * (int64_t)(4 * e.f_pad) + ch0;
-#pragma unroll
-    for (int j = 0; j < 16; ++j) t[j] = lu_f2bf(gi[j]);
-    lu_store16_bf16(g, t);
-#pragma unroll
-    for (int j = 0; j < 16; ++j) t[j] = lu_f2bf(gf[j]);
-    lu_store16_bf16(g + e.f_pad, t);
-#pragma unroll
-    for (int j = 0; j < 16; ++j) t[j] = lu_f2bf(gg[j]);
-    lu_store16_bf16(g + 2 * e.f_pad, t);
-#pragma unroll
-    for (int j = 0; j < 16; ++j) t[j] = lu_f2bf(go[j]);
-    lu_store16_bf16(g + 3 * e.f_pad, t);
+    lu_store16_split(g, 0, false, gi);
+    lu_store16_split(g + e.f_pad, 0, false, gf);
+    lu_store16_split(g + 2 * e.f_pad, 0, false, gg);
+    lu_store16_split(g + 3 * e.f_pad, 0, false, go);
   }
 }
 
@@ -169,7 +186,8 @@ LU_HDI void lu_conv_mirror_item(const LuConvParams& p, int64_t item) {
   if (e.kind == LU_EPI_CONV) {
     float v[16];
     lu_mirror_acc16(p, frame, y0, x0, m, n0 + chunk * 16, v);
-    lu_epi_conv_chunk(e, pix_out, n0 + chunk * 16, v);
+    const int n = n0 + chunk * 16;
+    lu_epi_conv_chunk(e, pix_out, n, v, e.bias + n, e.scale ? e.scale + n : nullptr, e.shift ? e.shift + n : nullptr);
   } else {
     const int CH = e.ch_tile, jc = chunk * 16;
     float zi[16], zf[16], zg[16], zo[16];
@@ -178,7 +196,8 @@ LU_HDI void lu_conv_mirror_item(const LuConvParams& p, int64_t item) {
     lu_mirror_acc16(p, frame, y0, x0, m, n0 + 2 * CH + jc, zg);
     lu_mirror_acc16(p, frame, y0, x0, m, n0 + 3 * CH + jc, zo);
     const int64_t pix_state = ((int64_t)frame * e.H + y) * e.W + x;
-    lu_epi_lstm_chunk(e, pix_state, pix_out, n0, jc, nt * CH + jc, zi, zf, zg, zo);
+    const float* b = e.bias + n0 + jc;
+    lu_epi_lstm_chunk(e, pix_state, pix_out, nt * CH + jc, zi, zf, zg, zo, b, b + CH, b + 2 * CH, b + 3 * CH);
   }
 }
 
@@ -195,6 +214,13 @@ struct LuTcParams {
   int32_t n_a_stages, n_b_stages, a_stage_bytes, b_stage_bytes;
   uint32_t idesc;
   int32_t total_tiles;
+  // Copies of the staging tables in kernel-parameter (constant) space: the issuing warps index them with
+  // warp-uniform loop counters, so descriptors and TMA coordinates stay in uniform registers (no per-instruction
+  // divergence "waterfall" around tcgen05.mma / TMA).  tap lists are de-duplicated; tables_in_params == 0 falls
+  // back to the global-memory tables (direct staging, exotic shapes).
+  int32_t tables_in_params;
+  LuAStage st_tab[LU_PT_STAGES];
+  uint16_t tap_tab[LU_PT_TAPS];
 };
 
 namespace lutc {
@@ -234,6 +260,11 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm,
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
@@ -282,7 +313,9 @@ __device__ __forceinline__ void tmem_wait16(float* v) {
                : "memory");
 }
 
-constexpr int kThreads = 256;      // warp 0: A producer, 1: MMA issuer, 2: TMEM allocator, 3: B producer, 4-7: epilogue
+constexpr int kThreads = 384;      // warp 0: A producer, 1: MMA issuer, 2: TMEM allocator, 3: B producer, 4-11: epilogue
+constexpr int kEpiThreads = 256;   // two warps per TMEM lane quarter: one SMSP-resident warp cannot hide the epilogue latency
+constexpr int kConstFloats = 3 * 256;   // per accumulator stage: bias | scale | shift of the tile's BN columns
 constexpr int kTmemCols = 512;
 
 }  // namespace lutc
@@ -300,8 +333,9 @@ __global__ void __launch_bounds__(lutc::kThreads, 1) lu_conv_tc_kernel(const __g
   const uint32_t bars = sB + (uint32_t)nB * P.b_stage_bytes;       // 8-byte mbarriers
   const uint32_t full_a = bars, empty_a = full_a + 8u * nA, full_b = empty_a + 8u * nA, empty_b = full_b + 8u * nB;
   const uint32_t tmem_full = empty_b + 8u * nB, tmem_empty = tmem_full + 16u, tmem_slot = tmem_empty + 16u;
-  uint32_t* tmem_slot_ptr =
-      reinterpret_cast<uint32_t*>(smem + (size_t)nA * P.a_stage_bytes + (size_t)nB * P.b_stage_bytes + 16u * (nA + nB) + 32u);
+  uint8_t* after_bars = smem + (size_t)nA * P.a_stage_bytes + (size_t)nB * P.b_stage_bytes + 16u * (nA + nB) + 32u;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(after_bars);
+  float* s_const = reinterpret_cast<float*>(after_bars + 16);        // [2][kConstFloats]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const LuConvParams& cp = P.cp;
@@ -315,7 +349,7 @@ __global__ void __launch_bounds__(lutc::kThreads, 1) lu_conv_tc_kernel(const __g
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < nA; ++i) { mbar_init(full_a + 8u * i, 1); mbar_init(empty_a + 8u * i, 1); }
     for (int i = 0; i < nB; ++i) { mbar_init(full_b + 8u * i, 1); mbar_init(empty_b + 8u * i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(tmem_full + 8u * i, 1); mbar_init(tmem_empty + 8u * i, 128); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tmem_full + 8u * i, 1); mbar_init(tmem_empty + 8u * i, kEpiThreads); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -330,81 +364,91 @@ __global__ void __launch_bounds__(lutc::kThreads, 1) lu_conv_tc_kernel(const __g
 
   const int tiles_per_frame = cp.tiles_x * cp.tiles_y;
 
+  // The three issuing roles run with warp-uniform control flow (all 32 lanes walk the loops and wait on the
+  // barriers); one elected lane issues the asynchronous instruction.
+  const bool ptab = P.tables_in_params != 0;
   if (warp == 0) {
     // ------------------------------------------------------------------ A producer (activation windows)
-    if (lane == 0) {
-      int sa = 0; uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-        const int mt = tile / cp.n_tiles_n;
-        const int frame = mt / tiles_per_frame, rem = mt % tiles_per_frame;
-        const int y0 = (rem / cp.tiles_x) * LU_TILE_H, x0 = (rem % cp.tiles_x) * LU_TILE_W;
-        for (int s = 0; s < cp.n_astages; ++s) {
-          const LuAStage st = cp.astages[s];
-          const LuSrcView& v = cp.src[st.src];
-          mbar_wait(empty_a + 8u * sa, ph ^ 1u);
+    int sa = 0; uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+      const int mt = tile / cp.n_tiles_n;
+      const int frame = mt / tiles_per_frame, rem = mt % tiles_per_frame;
+      const int y0 = (rem / cp.tiles_x) * LU_TILE_H, x0 = (rem % cp.tiles_x) * LU_TILE_W;
+      for (int s = 0; s < cp.n_astages; ++s) {
+        const LuAStage st = ptab ? P.st_tab[s] : cp.astages[s];
+        const LuSrcView& v = cp.src[st.src];
+        mbar_wait(empty_a + 8u * sa, ph ^ 1u);
+        if (elect_one()) {
           mbar_expect_tx(full_a + 8u * sa, (uint32_t)(v.rows * v.pitch) * 128u);
           tma_load_5d(sA + (uint32_t)sa * P.a_stage_bytes, &P.tmA[st.src], full_a + 8u * sa, st.c, x0 + st.dx, st.plane,
                       y0 + st.dy, frame * v.frame_mul + v.frame_add);
-          if (++sa == nA) { sa = 0; ph ^= 1u; }
         }
+        __syncwarp();
+        if (++sa == nA) { sa = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 3) {
     // ------------------------------------------------------------------ B producer (packed weight K blocks)
-    if (lane == 0) {
-      int sb = 0; uint32_t ph = 0;
-      const int nkb = cp.ktot / LU_KBLK;
-      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-        const int nt = tile % cp.n_tiles_n;
-        for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(empty_b + 8u * sb, ph ^ 1u);
+    int sb = 0; uint32_t ph = 0;
+    const int nkb = cp.ktot / LU_KBLK;
+    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+      const int nt = tile % cp.n_tiles_n;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(empty_b + 8u * sb, ph ^ 1u);
+        if (elect_one()) {
           mbar_expect_tx(full_b + 8u * sb, (uint32_t)BN * 128u);
           tma_load_2d(sB + (uint32_t)sb * P.b_stage_bytes, &P.tmB, full_b + 8u * sb, kb * LU_KBLK, nt * BN);
-          if (++sb == nB) { sb = 0; ph ^= 1u; }
         }
+        __syncwarp();
+        if (++sb == nB) { sb = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (one thread)
-    if (lane == 0) {
-      int sa = 0, sb = 0, acc = 0; uint32_t pha = 0, phb = 0, phacc = 0;
-      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-        mbar_wait(tmem_empty + 8u * acc, phacc ^ 1u);
+    // ------------------------------------------------------------------ MMA issuer
+    int sa = 0, sb = 0, acc = 0; uint32_t pha = 0, phb = 0, phacc = 0;
+    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+      mbar_wait(tmem_empty + 8u * acc, phacc ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+      uint32_t accum = 0;
+      for (int s = 0; s < cp.n_astages; ++s) {
+        const LuAStage st = ptab ? P.st_tab[s] : cp.astages[s];
+        const uint32_t sbo = (uint32_t)cp.src[st.src].pitch * 128u;
+        mbar_wait(full_a + 8u * sa, pha);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-        uint32_t accum = 0;
-        for (int s = 0; s < cp.n_astages; ++s) {
-          const LuAStage st = cp.astages[s];
-          const uint32_t sbo = (uint32_t)cp.src[st.src].pitch * 128u;
-          mbar_wait(full_a + 8u * sa, pha);
+        const uint32_t a_base = sA + (uint32_t)sa * P.a_stage_bytes;
+        for (int t = 0; t < st.ntaps; ++t) {
+          const uint32_t off = ptab ? (uint32_t)P.tap_tab[st.tap_begin + t] : (uint32_t)cp.taps[st.tap_begin + t];
+          mbar_wait(full_b + 8u * sb, phb);
           tc_fence_after();
-          const uint32_t a_base = sA + (uint32_t)sa * P.a_stage_bytes;
-          for (int t = 0; t < st.ntaps; ++t) {
-            const uint32_t off = cp.taps[st.tap_begin + t];
-            mbar_wait(full_b + 8u * sb, phb);
-            tc_fence_after();
-            const uint32_t b_base = sB + (uint32_t)sb * P.b_stage_bytes;
+          const uint32_t b_base = sB + (uint32_t)sb * P.b_stage_bytes;
+          if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < LU_KBLK / 16; ++k) {
               const uint64_t adesc = make_desc(a_base + off * 128u + (uint32_t)k * 32u, sbo);
               const uint64_t bdesc = make_desc(b_base + (uint32_t)k * 32u, 1024u);
-              mma_bf16(d_tmem, adesc, bdesc, P.idesc, accum);
-              accum = 1;
+              mma_bf16(d_tmem, adesc, bdesc, P.idesc, accum | (uint32_t)k);
             }
             tc_commit(empty_b + 8u * sb);           // frees the weight stage once these MMAs retire
-            if (++sb == nB) { sb = 0; phb ^= 1u; }
           }
-          tc_commit(empty_a + 8u * sa);             // frees the activation window
-          if (++sa == nA) { sa = 0; pha ^= 1u; }
+          __syncwarp();
+          accum = 1;
+          if (++sb == nB) { sb = 0; phb ^= 1u; }
         }
-        tc_commit(tmem_full + 8u * acc);            // accumulator complete -> epilogue
-        if (++acc == 2) { acc = 0; phacc ^= 1u; }
+        if (elect_one()) tc_commit(empty_a + 8u * sa);   // frees the activation window
+        __syncwarp();
+        if (++sa == nA) { sa = 0; pha ^= 1u; }
       }
+      if (elect_one()) tc_commit(tmem_full + 8u * acc);  // accumulator complete -> epilogue
+      __syncwarp();
+      if (++acc == 2) { acc = 0; phacc ^= 1u; }
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue: TMEM -> registers -> HBM
     const int q = warp & 3;                         // TMEM lane quarter this warp may access
+    const int half = (warp - 4) >> 2;               // the two warps of a quarter take alternate 16-column chunks
     const int m = q * 32 + lane;
+    const int ep_tid = threadIdx.x - 128;
     const LuEpi& e = cp.epi;
     int acc = 0; uint32_t phacc = 0;
     for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
@@ -415,27 +459,37 @@ __global__ void __launch_bounds__(lutc::kThreads, 1) lu_conv_tc_kernel(const __g
       const int n0 = nt * BN;
       const int64_t fout = (int64_t)frame * e.out_frame_mul + e.out_frame_add;
       const int64_t pix_out = (fout * e.H + y) * e.W + x;
+      // per-column constants of this tile -> shared memory (double-buffered with the accumulator stage)
+      float* cst = s_const + acc * kConstFloats;
+      for (int i = ep_tid; i < 3 * BN; i += kEpiThreads) {
+        const int which = i / BN, j = i - which * BN;
+        const float* src = which == 0 ? e.bias : (which == 1 ? e.scale : e.shift);
+        cst[which * 256 + j] = (src != nullptr) ? src[n0 + j] : 0.f;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
       mbar_wait(tmem_full + 8u * acc, phacc);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(q * 32) << 16);
       if (EPI == LU_EPI_CONV) {
-        for (int col = 0; col < BN; col += 16) {
+        for (int col = half * 16; col < BN; col += 32) {
           float v[16];
           tmem_ld16(taddr + (uint32_t)col, v);
           tmem_wait16(v);
-          if (valid) lu_epi_conv_chunk(e, pix_out, n0 + col, v);
+          if (valid) lu_epi_conv_chunk(e, pix_out, n0 + col, v, cst + col, cst + 256 + col, cst + 512 + col);
         }
       } else {
         const int CH = e.ch_tile;
         const int64_t pix_state = ((int64_t)frame * e.H + y) * e.W + x;
-        for (int jc = 0; jc < CH; jc += 16) {
+        for (int jc = half * 16; jc < CH; jc += 32) {
           float zi[16], zf[16], zg[16], zo[16];
           tmem_ld16(taddr + (uint32_t)jc, zi);
           tmem_ld16(taddr + (uint32_t)(CH + jc), zf);
           tmem_ld16(taddr + (uint32_t)(2 * CH + jc), zg);
           tmem_ld16(taddr + (uint32_t)(3 * CH + jc), zo);
           tmem_wait16(zi); tmem_wait16(zf); tmem_wait16(zg); tmem_wait16(zo);
-          if (valid) lu_epi_lstm_chunk(e, pix_state, pix_out, n0, jc, nt * CH + jc, zi, zf, zg, zo);
+          if (valid)
+            lu_epi_lstm_chunk(e, pix_state, pix_out, nt * CH + jc, zi, zf, zg, zo, cst + jc, cst + CH + jc,
+                              cst + 2 * CH + jc, cst + 3 * CH + jc);
         }
       }
       tc_fence_before();

@@ -72,28 +72,30 @@ LU_HDI int lu_reflect(int i, int n) {     // tf.pad REFLECT index (no edge repea
 struct LuPrepPatches {
   const float* x; uint16_t* out;
   int H, W, Hp, Wp, pad_y0, pad_x0, pw, x3;
-  LU_HD void operator()(int64_t i) const {        // item = (pixel, group of 8 channels)
-    const int g = (int)(i % 8); int64_t p = i / 8;
-    const int xx = (int)(p % Wp); p /= Wp;
-    const int yy = (int)(p % Hp); const int64_t n = p / Hp;
-    uint16_t r[8];
+  LU_HD void operator()(int64_t p) const {        // item = one pixel of the padded frame: 64 channels = 128 bytes
+    const int xx = (int)(p % Wp); int64_t q = p / Wp;
+    const int yy = (int)(q % Hp); const int64_t n = q / Hp;
+    uint16_t r[64];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int ch = g * 8 + j;
-      int t = ch, lo = 0;
-      if (x3 && ch >= 32) { t = ch - 32; lo = 1; }
-      r[j] = 0;
-      if (t < pw * pw) {
-        const int py = yy + t / pw - (pw - 1) / 2, px = xx + t % pw - (pw - 1) / 2;
-        if (py >= 0 && py < Hp && px >= 0 && px < Wp) {
-          const int sy = lu_reflect(py - pad_y0, H), sx = lu_reflect(px - pad_x0, W);
-          const float v = x[(n * H + sy) * W + sx];
-          uint16_t h, l; lu_split(v, h, l);
-          r[j] = lo ? l : h;
-        }
+    for (int j = 0; j < 64; ++j) r[j] = 0;
+    const int c = (pw - 1) / 2;
+    const float* img = x + n * (int64_t)H * W;
+    for (int dy = 0; dy < pw; ++dy) {
+      const int py = yy + dy - c;
+      if (py < 0 || py >= Hp) continue;
+      const float* row = img + (int64_t)lu_reflect(py - pad_y0, H) * W;
+      for (int dx = 0; dx < pw; ++dx) {
+        const int px = xx + dx - c;
+        if (px < 0 || px >= Wp) continue;
+        uint16_t h, l; lu_split(row[lu_reflect(px - pad_x0, W)], h, l);
+        const int t = dy * pw + dx;
+        r[t] = h;
+        if (x3) r[32 + t] = l;
       }
     }
-    lu_store8_bf16(out + i * 8, r);
+    uint16_t* o = out + p * 64;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) lu_store8_bf16(o + g * 8, r + g * 8);
   }
 };
 

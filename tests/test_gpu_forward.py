@@ -111,7 +111,8 @@ def test_states_mask_get_set_and_streaming():
     model.set_states(saved)
     a, _ = model(x2[:, :1], False)
     b, _ = model(x2[:, 1:], False)
-    np.testing.assert_allclose(np.concatenate([a.numpy(), b.numpy()], 1), full.numpy(), rtol=1e-5, atol=1e-6)
+    # (get/set_states round-trips h through fp32 and re-splits it into bf16 hi+lo: last-bit differences)
+    np.testing.assert_allclose(np.concatenate([a.numpy(), b.numpy()], 1), full.numpy(), rtol=1e-4, atol=1e-5)
     with pytest.raises(ValueError):
         model(np.zeros((2, 1, 1, 24, 16), np.float32), False)      # B,H,W are frozen by the first call
 
