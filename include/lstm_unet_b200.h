@@ -109,6 +109,10 @@ int lu_loss_backward(lu_handle h, const float* dev_labels, const float* class_we
 int lu_adam_step(lu_handle h, const float* dev_grads, float* dev_m, float* dev_v, float lr, float beta1,
                  float beta2, float eps, int64_t step, void* stream);
 
+/* test hook: copy an internal NHWC buffer of the layer called `name` (e.g. "UpLayers/1/Conv/0") to fp32.
+ * kind 0 = activation output, 1 = gradient of it (after lu_loss_backward), 2 = ConvLSTM gate pre-activation gradient */
+int lu_debug_buffer(lu_handle h, const char* name, int32_t kind, float* dev_out, int64_t* shape4, void* stream);
+
 /* counters for bench.py: kernels launched by this handle since the last reset */
 int lu_launch_count(lu_handle h, int64_t* launches, int32_t reset);
 /* algorithmic FLOPs (2*MAC, padding included) of one forward over T frames per sample at the bound shape */

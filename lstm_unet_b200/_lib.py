@@ -59,6 +59,7 @@ def bind(lib):
         'lu_set_state': [vp, i32, i32, i32, vp, vp],
         'lu_loss_backward': [vp, vp, P(f32), vp, vp, vp],
         'lu_adam_step': [vp, vp, vp, vp, f32, f32, f32, f32, i64, vp],
+        'lu_debug_buffer': [vp, ctypes.c_char_p, i32, vp, P(i64), vp],
         'lu_launch_count': [vp, P(i64), i32],
         'lu_forward_flops': [vp, i32, P(ctypes.c_double)],
         'lu_lstm_flops': [vp, i32, P(ctypes.c_double)],
@@ -74,7 +75,7 @@ def bind(lib):
 EXPORTED_SYMBOLS = ['lu_last_error', 'lu_version', 'lu_is_cuda_build', 'lu_create', 'lu_destroy', 'lu_workspace_bytes',
                     'lu_bind_workspace', 'lu_param_count', 'lu_param_info', 'lu_bind_params', 'lu_params_changed',
                     'lu_forward', 'lu_reset_states', 'lu_state_shape', 'lu_get_state', 'lu_set_state',
-                    'lu_loss_backward', 'lu_adam_step', 'lu_launch_count', 'lu_forward_flops', 'lu_lstm_flops',
+                    'lu_loss_backward', 'lu_adam_step', 'lu_debug_buffer', 'lu_launch_count', 'lu_forward_flops', 'lu_lstm_flops',
                     'lu_lstm_kernel_time']
 
 _LIB = None

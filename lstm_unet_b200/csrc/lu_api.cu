@@ -15,7 +15,9 @@
 #ifdef LU_HOST_EMU
 #define LU_MEMSET(p, v, n, s) memset((p), (v), (n))
 #define LU_H2D(d, s_, n, st) memcpy((d), (s_), (n))
+#define LU_D2D(d, s_, n, st) memcpy((d), (s_), (n))
 #else
+#define LU_D2D(d, s_, n, st) cudaMemcpyAsync((d), (s_), (n), cudaMemcpyDeviceToDevice, (cudaStream_t)(st))
 #define LU_MEMSET(p, v, n, s) cudaMemsetAsync((p), (v), (n), (cudaStream_t)(s))
 #define LU_H2D(d, s_, n, st) cudaMemcpyAsync((d), (s_), (n), cudaMemcpyHostToDevice, (cudaStream_t)(st))
 #endif
@@ -82,7 +84,7 @@ struct ConvPlan {
   size_t off_astages = 0, off_taps = 0, off_packs = 0, off_w = 0, off_bias = 0, off_scale = 0, off_shift = 0;
   size_t off_bscale = 0, off_bshift = 0, off_sums = 0, off_save_mean = 0, off_save_invstd = 0;
   int ktot = 0;
-  int nA = 2, nB = 4, a_bytes = 0, b_bytes = 0, smem = 0;
+  int nA = 2, nB = 4, a_bytes = 0, b_bytes = 0, smem = 0, b_group = 1;
   bool ptab_ok = false;                 // staging tables fit the kernel-parameter copies
   std::vector<LuAStage> pstages;        // stages with tap_begin remapped into the de-duplicated tap list
   std::vector<uint16_t> ptaps;
@@ -91,6 +93,13 @@ struct ConvPlan {
   int F = 0, fpad = 0, level = 0, layer = 0;
   size_t off_hstate[2] = {0, 0}, off_cstate = 0, off_save_gates = 0, off_save_c = 0;
   int hseq_buf = -1;
+  // training (cfg.train): data-gradient plans per input, packed-space weight-gradient maps, BPTT buffers
+  int fwd = -1, fwd_in = 0;             // LU_EPI_GRAD plans: the forward conv / input they differentiate
+  int oy_mul = 1, oy_add = 0, ox_mul = 1, ox_add = 0, OH = 0, OW = 0;
+  int dz_buf = -1;                      // lstm: gradient wrt the gate pre-activations (frames,H,W,4*fpad)
+  std::vector<int> dgrads[2];
+  std::vector<uint16_t> kb_stage, kb_tap;
+  size_t off_kb_stage = 0, off_kb_tap = 0, off_bwd_sums = 0, off_c_init = 0, off_dc = 0;
 #ifndef LU_HOST_EMU
   CUtensorMap tmA[LU_MAX_SRC];
   CUtensorMap tmB;
@@ -125,6 +134,9 @@ struct lu_handle_s {
   bool bound = false, packed = false;
   int num_sms = 148;
   TrainState tr;
+  std::vector<int> gidx;          // activation buffer -> its gradient twin (cfg.train)
+  int g_logits_buf = -1;
+  size_t tr_off_dwp = 0, tr_dwp_bytes = 0;
   // optional CUDA-event timing of every ConvLSTM launch (bench.py roofline)
   bool time_lstm = false;
   size_t ev_used = 0;
@@ -134,6 +146,8 @@ struct lu_handle_s {
 };
 
 static void train_layout(lu_handle_s* h, size_t& off);
+static int build_train_plan(lu_handle_s* h);
+static void train_upload(lu_handle_s* h, void* stream);
 static void train_destroy(lu_handle_s* h);
 extern "C" int lu_lstm_flops(lu_handle h, int32_t T, double* flops);
 
@@ -228,6 +242,8 @@ static void tf_same(int in, int k, int s, int* out, int* before) {
   if (total < 0) total = 0;
   *before = total / 2;
 }
+
+static int finish_tables(lu_handle_s* h, ConvPlan& cv);
 
 static int build_tables(lu_handle_s* h, ConvPlan& cv) {
   const bool x3 = h->cfg.precision == LU_PREC_BF16X3;
@@ -337,6 +353,13 @@ static int build_tables(lu_handle_s* h, ConvPlan& cv) {
         }
       }
   }
+  return finish_tables(h, cv);
+}
+
+// K extent, kernel-parameter table copies and shared-memory pipeline shape of a conv whose tables are complete
+static int finish_tables(lu_handle_s* h, ConvPlan& cv) {
+  const bool halo = true;
+  (void)h;
   cv.ktot = (int)cv.packs.size() * LU_KBLK;
   // kernel-parameter copies of the tables: identical tap lists are stored once
   cv.pstages = cv.astages; cv.ptaps.clear();
@@ -358,11 +381,15 @@ static int build_tables(lu_handle_s* h, ConvPlan& cv) {
     const int b = (int)align_up((size_t)cv.views[i].rows * cv.views[i].pitch * 128, 1024);
     cv.a_bytes = b > cv.a_bytes ? b : cv.a_bytes;
   }
-  cv.b_bytes = cv.BN * 128;
+  // weight stage = b_group K blocks (about 16-32 KB): one barrier round trip per group instead of per tap
+  cv.b_group = 256 / cv.BN;
+  if (cv.b_group > 8) cv.b_group = 8;
+  if (cv.b_group > (int)cv.packs.size()) cv.b_group = (int)cv.packs.size();
+  cv.b_bytes = cv.b_group * cv.BN * 128;
   const int budget = 232448 - 1024 - 512 - 6144;   // alignment slack, barriers, epilogue constants
   // weight stages first (one is consumed per tap: >= 4 in flight), then as many activation windows as fit
-  const int nkb = (int)cv.packs.size();
-  int nb_min = nkb < 4 ? (nkb < 2 ? 2 : nkb) : 4;
+  const int ngrp = ((int)cv.packs.size() + cv.b_group - 1) / cv.b_group;
+  int nb_min = ngrp < 4 ? (ngrp < 2 ? 2 : ngrp) : 4;
   cv.nA = (budget - nb_min * cv.b_bytes) / cv.a_bytes;
   if (cv.nA > 6) cv.nA = 6;
   LU_REQUIRE(cv.nA >= 2, "shared memory budget exceeded for %s", cv.name.c_str());
@@ -510,6 +537,7 @@ static int build_plan(lu_handle_s* h) {
   }
   LU_REQUIRE(h->logits_conv >= 0, "network has no output convolution");
   (void)B;
+  if (c.train && build_train_plan(h)) return 1;
   return 0;
 }
 
@@ -532,6 +560,7 @@ static void layout_workspace(lu_handle_s* h) {
     cv.off_bias = take((size_t)cv.npad * 4);
     cv.off_scale = take((size_t)cv.npad * 4);
     cv.off_shift = take((size_t)cv.npad * 4);
+    if (cv.kind == LU_EPI_GRAD) continue;
     if (cv.kind == LU_EPI_LSTM) {
       const size_t px = (size_t)B * cv.Hout * cv.Wout;
       cv.off_hstate[0] = take(px * cv.fpad * h->planes * 2);
@@ -539,7 +568,7 @@ static void layout_workspace(lu_handle_s* h) {
       cv.off_cstate = take(px * cv.fpad * 4);
       if (c.train) {
         const size_t pn = (size_t)N * cv.Hout * cv.Wout;
-        cv.off_save_gates = take(pn * 4 * cv.fpad * 2);
+        cv.off_save_gates = take(pn * 4 * cv.fpad * h->planes * 2);
         cv.off_save_c = take(pn * cv.fpad * 4);
       }
     } else {
@@ -652,7 +681,7 @@ static int launch_conv(lu_handle_s* h, ConvPlan& cv, int frames, const int* mul,
 #ifdef LU_HOST_EMU
   LU_FAIL("the tcgen05 engine does not exist in the host test build");
 #else
-  static bool attr_set[2] = {false, false};
+  static bool attr_set[3] = {false, false, false};
   LuTcParams tp;
   memset(&tp, 0, sizeof tp);
   for (int i = 0; i < cv.n_views; ++i) tp.tmA[i] = cv.tmA[i];
@@ -660,6 +689,7 @@ static int launch_conv(lu_handle_s* h, ConvPlan& cv, int frames, const int* mul,
   tp.tmB = cv.tmB;
   tp.cp = p;
   tp.n_a_stages = cv.nA; tp.n_b_stages = cv.nB; tp.a_stage_bytes = cv.a_bytes; tp.b_stage_bytes = cv.b_bytes;
+  tp.b_group = cv.b_group;
   tp.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(cv.BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   tp.total_tiles = (int)(m_tiles * cv.n_tiles_n);
   tp.tables_in_params = cv.ptab_ok ? 1 : 0;
@@ -669,15 +699,17 @@ static int launch_conv(lu_handle_s* h, ConvPlan& cv, int frames, const int* mul,
   }
 
   int grid = tp.total_tiles < h->num_sms ? tp.total_tiles : h->num_sms;
-  const int ei = epi.kind == LU_EPI_LSTM ? 1 : 0;
+  const int ei = epi.kind;
   if (!attr_set[ei]) {
-    cudaError_t e = ei ? cudaFuncSetAttribute(lu_conv_tc_kernel<LU_EPI_LSTM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448)
-                       : cudaFuncSetAttribute(lu_conv_tc_kernel<LU_EPI_CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    cudaError_t e = ei == LU_EPI_LSTM ? cudaFuncSetAttribute(lu_conv_tc_kernel<LU_EPI_LSTM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448)
+                  : ei == LU_EPI_GRAD ? cudaFuncSetAttribute(lu_conv_tc_kernel<LU_EPI_GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448)
+                                      : cudaFuncSetAttribute(lu_conv_tc_kernel<LU_EPI_CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     LU_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set[ei] = true;
   }
   h->launches++;
-  if (ei) lu_conv_tc_kernel<LU_EPI_LSTM><<<grid, lutc::kThreads, cv.smem, (cudaStream_t)stream>>>(tp);
+  if (ei == LU_EPI_LSTM) lu_conv_tc_kernel<LU_EPI_LSTM><<<grid, lutc::kThreads, cv.smem, (cudaStream_t)stream>>>(tp);
+  else if (ei == LU_EPI_GRAD) lu_conv_tc_kernel<LU_EPI_GRAD><<<grid, lutc::kThreads, cv.smem, (cudaStream_t)stream>>>(tp);
   else lu_conv_tc_kernel<LU_EPI_CONV><<<grid, lutc::kThreads, cv.smem, (cudaStream_t)stream>>>(tp);
   cudaError_t e = cudaGetLastError();
   LU_REQUIRE(e == cudaSuccess, "conv launch (%s) failed: %s", cv.name.c_str(), cudaGetErrorString(e));
@@ -759,6 +791,7 @@ int lu_bind_workspace(lu_handle h, void* dev_ws, size_t bytes, void* stream) {
     LU_H2D(h->ws + cv.off_taps, cv.taps.data(), cv.taps.size() * sizeof(uint16_t), stream);
     LU_H2D(h->ws + cv.off_packs, cv.packs.data(), cv.packs.size() * sizeof(LuPackDesc), stream);
   }
+  train_upload(h, stream);
 #ifndef LU_HOST_EMU
   if (h->cfg.engine == LU_ENGINE_TCGEN05) {
     if (get_encode()) return 1;
@@ -816,6 +849,7 @@ int lu_params_changed(lu_handle h, void* stream) {
     pw.params = h->dparams; pw.descs = reinterpret_cast<const LuPackDesc*>(h->ws + cv.off_packs);
     pw.out = reinterpret_cast<uint16_t*>(h->ws + cv.off_w); pw.cm = cv.cm; pw.ktot = cv.ktot;
     pf(h, (int64_t)cv.npad * cv.ktot, stream, pw);
+    if (cv.kind == LU_EPI_GRAD) continue;
     LuPackVec pb;
     pb.src = h->dparams + h->params[cv.bias_param].offset; pb.out = reinterpret_cast<float*>(h->ws + cv.off_bias); pb.cm = cv.cm;
     pf(h, cv.npad, stream, pb);
@@ -839,6 +873,7 @@ static int run_conv_layer(lu_handle_s* h, ConvPlan& cv, int T, int training, voi
   LuEpi e;
   memset(&e, 0, sizeof e);
   e.kind = LU_EPI_CONV; e.H = cv.Hout; e.W = cv.Wout;
+  e.oy_mul = 1; e.ox_mul = 1; e.OH = cv.Hout; e.OW = cv.Wout;
   e.bias = reinterpret_cast<const float*>(h->ws + cv.off_bias);
   e.out_frame_mul = 1; e.out_frame_add = 0; e.alpha = 0.3f;
   e.raw_cpad = cv.raw_cpad;
@@ -882,6 +917,8 @@ static int run_conv_layer(lu_handle_s* h, ConvPlan& cv, int T, int training, voi
 
 static int run_lstm_layer(lu_handle_s* h, ConvPlan& cv, int T, int training, void* stream) {
   const ActBuf& hs = h->acts[cv.hseq_buf];
+  if (training && h->cfg.train)      // BPTT needs c before the first step of this call (c is updated in place)
+    LU_D2D(h->ws + cv.off_c_init, h->ws + cv.off_cstate, (size_t)h->cfg.batch * cv.Hout * cv.Wout * cv.fpad * 4, stream);
   for (int t = 0; t < T; ++t) {
     int mul[LU_MAX_SRC] = {T, T, 1, 1}, add[LU_MAX_SRC] = {t, t - 1, 0, 0};
     int sel = -1;
@@ -889,6 +926,7 @@ static int run_lstm_layer(lu_handle_s* h, ConvPlan& cv, int T, int training, voi
     LuEpi e;
     memset(&e, 0, sizeof e);
     e.kind = LU_EPI_LSTM; e.H = cv.Hout; e.W = cv.Wout;
+    e.oy_mul = 1; e.ox_mul = 1; e.OH = cv.Hout; e.OW = cv.Wout;
     e.bias = reinterpret_cast<const float*>(h->ws + cv.off_bias);
     e.out_frame_mul = T; e.out_frame_add = t;
     e.out_act = reinterpret_cast<uint16_t*>(h->ws + hs.off); e.out_cpad = hs.cpad; e.out_planes = hs.planes;
@@ -1031,7 +1069,7 @@ int lu_launch_count(lu_handle h, int64_t* launches, int32_t reset) {
 int lu_forward_flops(lu_handle h, int32_t T, double* flops) {
   LU_REQUIRE(h && flops, "null argument");
   double macs = 0;
-  for (auto& cv : h->convs) macs += cv.macs_per_frame;
+  for (auto& cv : h->convs) if (cv.kind != LU_EPI_GRAD) macs += cv.macs_per_frame;
   *flops = 2.0 * macs * T;
   return 0;
 }
@@ -1063,6 +1101,28 @@ int lu_lstm_kernel_time(lu_handle h, int32_t enable, float* ms_total, int32_t* l
   if (ms_total) *ms_total = total;
   if (launches) *launches = n;
   return 0;
+}
+
+// debug / test hook: copy one internal buffer of the conv named `name` to `out` as fp32 NHWC with the real channel
+// count.  kind 0: activation output, 1: its gradient twin (after backward), 2: gate pre-activation gradient (lstm)
+int lu_debug_buffer(lu_handle h, const char* name, int32_t kind, float* out, int64_t* shape4, void* stream) {
+  LU_REQUIRE(h && h->bound && name && shape4, "null argument / unbound handle");
+  for (auto& cv : h->convs) {
+    if (cv.name != name) continue;
+    int buf = cv.out_buf;
+    if (kind == 1) { LU_REQUIRE(h->cfg.train, "no gradient buffers"); buf = buf >= 0 ? h->gidx[buf] : h->g_logits_buf; }
+    if (kind == 2) buf = cv.dz_buf;
+    LU_REQUIRE(buf >= 0, "no such buffer for %s", name);
+    const ActBuf& a = h->acts[buf];
+    shape4[0] = a.frames; shape4[1] = a.H; shape4[2] = a.W; shape4[3] = a.creal;
+    if (out) {
+      LuDebugRead r;
+      r.src = reinterpret_cast<const uint16_t*>(h->ws + a.off); r.out = out; r.creal = a.creal; r.cpad = a.cpad; r.planes = a.planes;
+      pf(h, (int64_t)a.frames * a.H * a.W * a.creal, stream, r);
+    }
+    return 0;
+  }
+  LU_FAIL("no conv named %s", name);
 }
 
 int lu_loss_backward(lu_handle h, const float* dev_labels, const float* class_weights3, float* dev_loss, float* dev_grads,

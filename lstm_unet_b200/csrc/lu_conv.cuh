@@ -106,6 +106,20 @@ LU_HDI void lu_epi_conv_chunk(const LuEpi& e, int64_t pix, int n, float* v, cons
   }
 }
 
+// gradient convolution: store (or accumulate into) a bf16 hi[/lo] gradient buffer
+LU_HDI void lu_epi_grad_chunk(const LuEpi& e, int64_t pix, int n, float* v) {
+  if (n >= e.out_cpad) return;
+  uint16_t* o = e.out_act + pix * (int64_t)(e.out_cpad * e.out_planes) + n;
+  if (e.accumulate) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      v[j] += lu_bf2f(o[j]);
+      if (e.out_planes == 2) v[j] += lu_bf2f(o[e.out_cpad + j]);
+    }
+  }
+  lu_store16_split(o, e.out_cpad, e.out_planes == 2, v);
+}
+
 // ConvLSTM cell (keras ConvLSTM2D defaults): z* are the pre-activations of gates i,f,c,o for 16
 // channels starting at ch0; b* the matching bias slices; pix_state indexes the per-sample states, pix_out the h
 // sequence buffer.
@@ -131,11 +145,11 @@ LU_HDI void lu_epi_lstm_chunk(const LuEpi& e, int64_t pix_state, int64_t pix_out
   if (e.h_state_out != nullptr) lu_store16_split(e.h_state_out + pix_state * ctot + ch0, e.f_pad, lo, hh);
   if (e.save_c != nullptr) lu_store16_f32(e.save_c + pix_out * e.f_pad + ch0, c);
   if (e.save_gates != nullptr) {
-    uint16_t* g = e.save_gates + pix_out * (int64_t)(4 * e.f_pad) + ch0;
-    lu_store16_split(g, 0, false, gi);
-    lu_store16_split(g + e.f_pad, 0, false, gf);
-    lu_store16_split(g + 2 * e.f_pad, 0, false, gg);
-    lu_store16_split(g + 3 * e.f_pad, 0, false, go);
+    uint16_t* g = e.save_gates + pix_out * (int64_t)(4 * e.f_pad * e.out_planes) + ch0;
+    lu_store16_split(g, 4 * e.f_pad, lo, gi);
+    lu_store16_split(g + e.f_pad, 4 * e.f_pad, lo, gf);
+    lu_store16_split(g + 2 * e.f_pad, 4 * e.f_pad, lo, gg);
+    lu_store16_split(g + 3 * e.f_pad, 4 * e.f_pad, lo, go);
   }
 }
 
@@ -182,12 +196,18 @@ LU_HDI void lu_conv_mirror_item(const LuConvParams& p, int64_t item) {
   if (y >= e.H || x >= e.W) return;
   const int n0 = nt * p.BN;
   const int64_t fout = (int64_t)frame * e.out_frame_mul + e.out_frame_add;
-  const int64_t pix_out = (fout * e.H + y) * e.W + x;
+  const int yo = y * e.oy_mul + e.oy_add, xo = x * e.ox_mul + e.ox_add;
+  if (yo >= e.OH || xo >= e.OW) return;
+  const int64_t pix_out = (fout * e.OH + yo) * e.OW + xo;
   if (e.kind == LU_EPI_CONV) {
     float v[16];
     lu_mirror_acc16(p, frame, y0, x0, m, n0 + chunk * 16, v);
     const int n = n0 + chunk * 16;
     lu_epi_conv_chunk(e, pix_out, n, v, e.bias + n, e.scale ? e.scale + n : nullptr, e.shift ? e.shift + n : nullptr);
+  } else if (e.kind == LU_EPI_GRAD) {
+    float v[16];
+    lu_mirror_acc16(p, frame, y0, x0, m, n0 + chunk * 16, v);
+    lu_epi_grad_chunk(e, pix_out, n0 + chunk * 16, v);
   } else {
     const int CH = e.ch_tile, jc = chunk * 16;
     float zi[16], zf[16], zg[16], zo[16];
@@ -212,6 +232,7 @@ struct LuTcParams {
   CUtensorMap tmB;
   LuConvParams cp;
   int32_t n_a_stages, n_b_stages, a_stage_bytes, b_stage_bytes;
+  int32_t b_group;               // K blocks per weight stage (one mbarrier wait / commit per group)
   uint32_t idesc;
   int32_t total_tiles;
   // Copies of the staging tables in kernel-parameter (constant) space: the issuing warps index them with
@@ -286,12 +307,19 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t sbo_bytes)
   d |= (uint64_t)2 << 61;                                  // SWIZZLE_128B
   return d;
 }
-__device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+// high / low words of the K-major SWIZZLE_128B descriptor (see make_desc): hi = SBO | version | layout,
+// lo = (address >> 4) | LBO.  Taps and K sub-steps only add to the low word.
+__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes) { return (sbo_bytes >> 4) | (1u << 14) | (2u << 29); }
+__device__ __forceinline__ uint32_t desc_lo(uint32_t addr) { return ((addr & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                         uint32_t idesc, uint32_t acc) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc)
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
@@ -390,14 +418,17 @@ __global__ void __launch_bounds__(lutc::kThreads, 1) lu_conv_tc_kernel(const __g
   } else if (warp == 3) {
     // ------------------------------------------------------------------ B producer (packed weight K blocks)
     int sb = 0; uint32_t ph = 0;
-    const int nkb = cp.ktot / LU_KBLK;
+    const int nkb = cp.ktot / LU_KBLK, G = P.b_group;
     for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
       const int nt = tile % cp.n_tiles_n;
-      for (int kb = 0; kb < nkb; ++kb) {
+      for (int kb = 0; kb < nkb; kb += G) {
+        const int g = (nkb - kb) < G ? (nkb - kb) : G;
         mbar_wait(empty_b + 8u * sb, ph ^ 1u);
         if (elect_one()) {
-          mbar_expect_tx(full_b + 8u * sb, (uint32_t)BN * 128u);
-          tma_load_2d(sB + (uint32_t)sb * P.b_stage_bytes, &P.tmB, full_b + 8u * sb, kb * LU_KBLK, nt * BN);
+          mbar_expect_tx(full_b + 8u * sb, (uint32_t)(g * BN) * 128u);
+          for (int j = 0; j < g; ++j)
+            tma_load_2d(sB + (uint32_t)sb * P.b_stage_bytes + (uint32_t)(j * BN) * 128u, &P.tmB, full_b + 8u * sb,
+                        (kb + j) * LU_KBLK, nt * BN);
         }
         __syncwarp();
         if (++sb == nB) { sb = 0; ph ^= 1u; }
@@ -406,40 +437,55 @@ __global__ void __launch_bounds__(lutc::kThreads, 1) lu_conv_tc_kernel(const __g
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     int sa = 0, sb = 0, acc = 0; uint32_t pha = 0, phb = 0, phacc = 0;
+    const int G = P.b_group;
+    const uint32_t b_hi = desc_hi(1024u);
+    const uint32_t bn_bytes16 = (uint32_t)BN * 8u;            // one K block of weights, in 16-byte units
     for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
       mbar_wait(tmem_empty + 8u * acc, phacc ^ 1u);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
       uint32_t accum = 0;
+      int gi = 0;                                             // position inside the current weight group
+      uint32_t b_lo = 0;
       for (int s = 0; s < cp.n_astages; ++s) {
         const LuAStage st = ptab ? P.st_tab[s] : cp.astages[s];
-        const uint32_t sbo = (uint32_t)cp.src[st.src].pitch * 128u;
+        const uint32_t a_hi = desc_hi((uint32_t)cp.src[st.src].pitch * 128u);
         mbar_wait(full_a + 8u * sa, pha);
         tc_fence_after();
-        const uint32_t a_base = sA + (uint32_t)sa * P.a_stage_bytes;
+        const uint32_t a_lo = desc_lo(sA + (uint32_t)sa * P.a_stage_bytes);
         for (int t = 0; t < st.ntaps; ++t) {
-          const uint32_t off = ptab ? (uint32_t)P.tap_tab[st.tap_begin + t] : (uint32_t)cp.taps[st.tap_begin + t];
-          mbar_wait(full_b + 8u * sb, phb);
-          tc_fence_after();
-          const uint32_t b_base = sB + (uint32_t)sb * P.b_stage_bytes;
+          // tap offset in rows of 128 bytes -> 16-byte units
+          const uint32_t off8 = (ptab ? (uint32_t)P.tap_tab[st.tap_begin + t] : (uint32_t)cp.taps[st.tap_begin + t]) * 8u;
+          if (gi == 0) {
+            mbar_wait(full_b + 8u * sb, phb);
+            tc_fence_after();
+            b_lo = desc_lo(sB + (uint32_t)sb * P.b_stage_bytes);
+          }
           if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < LU_KBLK / 16; ++k) {
-              const uint64_t adesc = make_desc(a_base + off * 128u + (uint32_t)k * 32u, sbo);
-              const uint64_t bdesc = make_desc(b_base + (uint32_t)k * 32u, 1024u);
-              mma_bf16(d_tmem, adesc, bdesc, P.idesc, accum | (uint32_t)k);
-            }
-            tc_commit(empty_b + 8u * sb);           // frees the weight stage once these MMAs retire
+            for (int k = 0; k < LU_KBLK / 16; ++k)
+              mma_bf16(d_tmem, a_lo + off8 + 2u * k, a_hi, b_lo + 2u * k, b_hi, P.idesc, accum | (uint32_t)k);
           }
           __syncwarp();
           accum = 1;
-          if (++sb == nB) { sb = 0; phb ^= 1u; }
+          b_lo += bn_bytes16;
+          if (++gi == G) {
+            if (elect_one()) tc_commit(empty_b + 8u * sb);     // frees the weight stage once its MMAs retire
+            __syncwarp();
+            gi = 0;
+            if (++sb == nB) { sb = 0; phb ^= 1u; }
+          }
         }
-        if (elect_one()) tc_commit(empty_a + 8u * sa);   // frees the activation window
+        if (elect_one()) tc_commit(empty_a + 8u * sa);         // frees the activation window
         __syncwarp();
         if (++sa == nA) { sa = 0; pha ^= 1u; }
       }
-      if (elect_one()) tc_commit(tmem_full + 8u * acc);  // accumulator complete -> epilogue
+      if (gi != 0) {                                           // partial last weight group of the tile
+        if (elect_one()) tc_commit(empty_b + 8u * sb);
+        __syncwarp();
+        if (++sb == nB) { sb = 0; phb ^= 1u; }
+      }
+      if (elect_one()) tc_commit(tmem_full + 8u * acc);        // accumulator complete -> epilogue
       __syncwarp();
       if (++acc == 2) { acc = 0; phacc ^= 1u; }
     }
@@ -455,16 +501,19 @@ __global__ void __launch_bounds__(lutc::kThreads, 1) lu_conv_tc_kernel(const __g
       const int nt = tile % cp.n_tiles_n, mt = tile / cp.n_tiles_n;
       const int frame = mt / tiles_per_frame, rem = mt % tiles_per_frame;
       const int y = (rem / cp.tiles_x) * LU_TILE_H + m / LU_TILE_W, x = (rem % cp.tiles_x) * LU_TILE_W + m % LU_TILE_W;
-      const bool valid = (y < e.H) && (x < e.W);
+      const int yo = y * e.oy_mul + e.oy_add, xo = x * e.ox_mul + e.ox_add;
+      const bool valid = (y < e.H) && (x < e.W) && (yo < e.OH) && (xo < e.OW);
       const int n0 = nt * BN;
       const int64_t fout = (int64_t)frame * e.out_frame_mul + e.out_frame_add;
-      const int64_t pix_out = (fout * e.H + y) * e.W + x;
+      const int64_t pix_out = (fout * e.OH + yo) * e.OW + xo;
       // per-column constants of this tile -> shared memory (double-buffered with the accumulator stage)
       float* cst = s_const + acc * kConstFloats;
-      for (int i = ep_tid; i < 3 * BN; i += kEpiThreads) {
-        const int which = i / BN, j = i - which * BN;
-        const float* src = which == 0 ? e.bias : (which == 1 ? e.scale : e.shift);
-        cst[which * 256 + j] = (src != nullptr) ? src[n0 + j] : 0.f;
+      if (EPI != LU_EPI_GRAD) {
+        for (int i = ep_tid; i < 3 * BN; i += kEpiThreads) {
+          const int which = i / BN, j = i - which * BN;
+          const float* src = which == 0 ? e.bias : (which == 1 ? e.scale : e.shift);
+          cst[which * 256 + j] = (src != nullptr) ? src[n0 + j] : 0.f;
+        }
       }
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
       mbar_wait(tmem_full + 8u * acc, phacc);
@@ -476,6 +525,13 @@ __global__ void __launch_bounds__(lutc::kThreads, 1) lu_conv_tc_kernel(const __g
           tmem_ld16(taddr + (uint32_t)col, v);
           tmem_wait16(v);
           if (valid) lu_epi_conv_chunk(e, pix_out, n0 + col, v, cst + col, cst + 256 + col, cst + 512 + col);
+        }
+      } else if (EPI == LU_EPI_GRAD) {
+        for (int col = half * 16; col < BN; col += 32) {
+          float v[16];
+          tmem_ld16(taddr + (uint32_t)col, v);
+          tmem_wait16(v);
+          if (valid) lu_epi_grad_chunk(e, pix_out, n0 + col, v);
         }
       } else {
         const int CH = e.ch_tile;

@@ -78,11 +78,15 @@ struct LuSrcView {
   int32_t rows, pitch;             // box = {64, pitch, 1, rows, 1}
 };
 
-enum { LU_EPI_CONV = 0, LU_EPI_LSTM = 1 };
+enum { LU_EPI_CONV = 0, LU_EPI_LSTM = 1, LU_EPI_GRAD = 2 };
 
 struct LuEpi {
   int32_t kind;
-  int32_t H, W;               // output spatial size (rows/cols beyond it are masked)
+  int32_t H, W;               // tile-grid spatial size (rows/cols beyond it are masked)
+  // output pixel = (y*oy_mul + oy_add, x*ox_mul + ox_add) in an OH x OW frame (identity except for the parity
+  // classes of a stride-2 convolution's data gradient)
+  int32_t oy_mul, oy_add, ox_mul, ox_add, OH, OW;
+  int32_t accumulate;         // LU_EPI_GRAD: add to the existing contents of out_act
   const float* bias;          // [Npad], packed column order
   int32_t out_frame_mul, out_frame_add;
   // conv
@@ -113,7 +117,9 @@ struct LuPackDesc {
   int8_t k, pw;               // PATCH: conv kernel size, patch window size
   int8_t patch_x3;            // PATCH: channels [32,64) are the lo parts of the taps
   int8_t patch_hi_only;       // PATCH: channels [32,64) get zero weights (the a_hi * w_lo block)
-  int8_t pad0, pad1;
+  int8_t transposed;          // data-gradient operand: block channel indexes cout, packed column indexes cin
+  int8_t pad1;
+  int32_t col_base;           // transposed: first input channel (concat offset) of the packed columns
 };
 
 enum { LU_COL_IDENTITY = 0, LU_COL_LSTM = 1 };

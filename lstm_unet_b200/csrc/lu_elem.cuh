@@ -265,7 +265,9 @@ struct LuPackWeights {
     if (col >= 0) {
       const LuPackDesc d = descs[kb];
       float w = 0.f; bool ok = false;
-      if (d.kind == 0) {
+      if (d.kind == 0 && d.transposed) {
+        if (kk < d.n_valid) { w = params[d.w_off + d.tap_off + (int64_t)(d.col_base + col) * d.cout_total + d.c_base + kk]; ok = true; }
+      } else if (d.kind == 0) {
         if (kk < d.n_valid) { w = params[d.w_off + d.tap_off + (int64_t)(d.c_base + kk) * d.cout_total + col]; ok = true; }
       } else {
         int t = kk; bool z = false;
@@ -327,6 +329,16 @@ struct LuStateSet {
       h[pix * (int64_t)(fpad * planes) + f] = hi;
       if (planes == 2) h[pix * (int64_t)(fpad * planes) + fpad + f] = lo;
     }
+  }
+};
+
+struct LuDebugRead {     // bf16 planes NHWC (padded channels) -> fp32 NHWC (real channels)
+  const uint16_t* src; float* out; int creal, cpad, planes;
+  LU_HD void operator()(int64_t i) const {
+    const int c = (int)(i % creal); const int64_t p = i / creal;
+    float v = lu_bf2f(src[p * (int64_t)(cpad * planes) + c]);
+    if (planes == 2) v += lu_bf2f(src[p * (int64_t)(cpad * planes) + cpad + c]);
+    out[i] = v;
   }
 };
 

@@ -1,6 +1,11 @@
-// Training-side kernels: weighted cross-entropy, backward passes, Keras Adam.
+// Training-side kernels: weighted cross-entropy (losses.py:13-27), backward passes of BN / LeakyReLU / bilinear
+// resize / ConvLSTM cell, bias and weight gradients, Keras Adam (train2D.py:61,87-93).
+// Data gradients of the convolutions run through the same table-driven implicit-GEMM kernel as the forward
+// (transposed weight packing, LU_EPI_GRAD epilogue); see lu_train_host.inl.
 #pragma once
 #include "lu_defs.h"
+#include "lu_conv.cuh"
+#include "lu_elem.cuh"
 
 struct TrainState {
   size_t off_loss_acc = 0;     // double[2]: sum(weighted ce), sum(valid)
@@ -15,5 +20,285 @@ struct LuAdam {
     const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
     m[i] = mi; v[i] = vi;
     p[i] -= lr_t * mi / (sqrtf(vi) + eps);
+  }
+};
+
+// ---- weighted cross entropy over the raw logits (N,Hp,Wp,raw_cpad) ------------------------------------------------
+// labels: (B,T,1,H,W) == (B,T,H,W,1) floats in {-1,0,1,2}; -1 = ignore (one_hot(-1) = 0 and valid = 0).
+struct LuCeReduce {      // item = chunk of pixels of the un-padded frames
+  const float* raw; const float* labels; double* acc;
+  int64_t npix; int H, W, Hp, Wp, py0, px0, raw_cpad, chunk; float w0, w1, w2;
+  LU_HD void operator()(int64_t it) const {
+    int64_t p0 = it * chunk, p1 = p0 + chunk; if (p1 > npix) p1 = npix;
+    float s = 0.f, nv = 0.f;
+    for (int64_t p = p0; p < p1; ++p) {
+      const int x = (int)(p % W); int64_t q = p / W; const int y = (int)(q % H); const int64_t f = q / H;
+      const float lab = labels[p];
+      if (!(lab > -1.f)) continue;
+      nv += 1.f;
+      const int li = (int)lab;
+      const float* r = raw + ((f * Hp + y + py0) * Wp + x + px0) * (int64_t)raw_cpad;
+      const float mx = fmaxf(r[0], fmaxf(r[1], r[2]));
+      const float lse = mx + logf(expf(r[0] - mx) + expf(r[1] - mx) + expf(r[2] - mx));
+      const float w = li == 0 ? w0 : (li == 1 ? w1 : w2);
+      s += (lse - r[li < 0 ? 0 : (li > 2 ? 2 : li)]) * w;
+    }
+    lu_atomic_add(&acc[0], (double)s);
+    lu_atomic_add(&acc[1], (double)nv);
+  }
+};
+// loss = acc0 / (acc1 + 1e-5); dlogits -> bf16 planes buffer (N,Hp,Wp,planes*cpad), zero in the padding border
+struct LuCeGrad {        // item = pixel of the PADDED frame
+  const float* raw; const float* labels; const double* acc; float* loss_out; uint16_t* g;
+  int H, W, Hp, Wp, py0, px0, raw_cpad, cpad, planes; float w0, w1, w2;
+  LU_HD void operator()(int64_t p) const {
+    const int xx = (int)(p % Wp); int64_t q = p / Wp; const int yy = (int)(q % Hp); const int64_t f = q / Hp;
+    if (p == 0) loss_out[0] = (float)(acc[0] / (acc[1] + 0.00001));
+    float d[3] = {0.f, 0.f, 0.f};
+    const int y = yy - py0, x = xx - px0;
+    if (y >= 0 && y < H && x >= 0 && x < W) {
+      const float lab = labels[(f * H + y) * W + x];
+      if (lab > -1.f) {
+        const int li = (int)lab;
+        const float* r = raw + p * (int64_t)raw_cpad;
+        const float mx = fmaxf(r[0], fmaxf(r[1], r[2]));
+        const float e0 = expf(r[0] - mx), e1 = expf(r[1] - mx), e2 = expf(r[2] - mx);
+        const float inv = 1.f / (e0 + e1 + e2);
+        const float w = (li == 0 ? w0 : (li == 1 ? w1 : w2)) / (float)(acc[1] + 0.00001);
+        d[0] = w * (e0 * inv - (li == 0 ? 1.f : 0.f));
+        d[1] = w * (e1 * inv - (li == 1 ? 1.f : 0.f));
+        d[2] = w * (e2 * inv - (li == 2 ? 1.f : 0.f));
+      }
+    }
+    uint16_t* o = g + p * (int64_t)(cpad * planes);
+    for (int c = 0; c < 3; ++c) {
+      uint16_t hi, lo; lu_split(d[c], hi, lo);
+      o[c] = hi;
+      if (planes == 2) o[cpad + c] = lo;
+    }
+  }
+};
+
+struct LuCeLossOnly {
+  const double* acc; float* loss_out;
+  LU_HD void operator()(int64_t) const { loss_out[0] = (float)(acc[0] / (acc[1] + 0.00001)); }
+};
+
+LU_HDI float lu_ldplanes(const uint16_t* p, int cpad, int planes) {
+  float v = lu_bf2f(p[0]);
+  if (planes == 2) v += lu_bf2f(p[cpad]);
+  return v;
+}
+LU_HDI void lu_stplanes(uint16_t* p, int cpad, int planes, float v) {
+  uint16_t hi, lo; lu_split(v, hi, lo);
+  p[0] = hi;
+  if (planes == 2) p[cpad] = lo;
+}
+
+// ---- BatchNorm (training) + LeakyReLU backward ------------------------------------------------------------------
+// g = dA * lrelu'(bn_out); sums: [0:cpad) = sum g, [cpad:2cpad) = sum g * xhat        item = (pixel chunk, channel)
+struct LuBnBwdReduce {
+  const uint16_t* dA; const float* raw; const float* scale; const float* shift; const float* mean; const float* invstd;
+  double* sums; int64_t npix; int cpad, planes, raw_cpad, c_real, chunk; float alpha;
+  LU_HD void operator()(int64_t i) const {
+    const int c = (int)(i % raw_cpad); const int64_t pc = i / raw_cpad;
+    if (c >= c_real) return;
+    int64_t p0 = pc * chunk, p1 = p0 + chunk; if (p1 > npix) p1 = npix;
+    float s = 0.f, sx = 0.f;
+    for (int64_t p = p0; p < p1; ++p) {
+      const float r = raw[p * raw_cpad + c];
+      const float bn = r * scale[c] + shift[c];
+      const float g = lu_ldplanes(dA + p * (int64_t)(cpad * planes) + c, cpad, planes) * (bn > 0.f ? 1.f : alpha);
+      s += g; sx += g * (r - mean[c]) * invstd[c];
+    }
+    lu_atomic_add(&sums[c], (double)s);
+    lu_atomic_add(&sums[raw_cpad + c], (double)sx);
+  }
+};
+// dRaw = scale * (g - sum_g/n - xhat * sum_gx/n), written IN PLACE over dA; item = (pixel, channel)
+struct LuBnBwdApply {
+  uint16_t* dA; const float* raw; const float* scale; const float* shift; const float* mean; const float* invstd;
+  const double* sums; int64_t npix; int cpad, planes, raw_cpad, c_real; float alpha;
+  LU_HD void operator()(int64_t i) const {
+    const int c = (int)(i % cpad); const int64_t p = i / cpad;
+    uint16_t* o = dA + p * (int64_t)(cpad * planes) + c;
+    float d = 0.f;
+    if (c < c_real) {
+      const float r = raw[p * raw_cpad + c];
+      const float bn = r * scale[c] + shift[c];
+      const float g = lu_ldplanes(o, cpad, planes) * (bn > 0.f ? 1.f : alpha);
+      const float xh = (r - mean[c]) * invstd[c];
+      d = scale[c] * (g - (float)(sums[c] / (double)npix) - xh * (float)(sums[raw_cpad + c] / (double)npix));
+    }
+    lu_stplanes(o, cpad, planes, d);
+  }
+};
+struct LuBnBwdParams {   // dgamma = sum g*xhat, dbeta = sum g; item = channel
+  const double* sums; float* dgamma; float* dbeta; int raw_cpad, c_real;
+  LU_HD void operator()(int64_t c) const {
+    if (c >= c_real) return;
+    dbeta[c] = (float)sums[c];
+    dgamma[c] = (float)sums[raw_cpad + c];
+  }
+};
+
+// ---- bilinear x2 backward (transpose of LuUpsample2x): dsrc (=|+=) sum of the up-sampled gradient ---------------
+struct LuUpsample2xBwd {   // item = (n, iy, ix, c)
+  const uint16_t* gup; uint16_t* gsrc; int h, w, cpad, planes, accumulate;
+  LU_HD static int taps1d(int j, int n, int* idx, float* wt) {
+    int k = 0;
+    if (j >= 1) { idx[k] = 2 * j - 1; wt[k++] = 0.25f; }
+    idx[k] = 2 * j; wt[k++] = 0.75f;
+    idx[k] = 2 * j + 1; wt[k++] = 0.75f;
+    if (j <= n - 2) { idx[k] = 2 * j + 2; wt[k++] = 0.25f; }
+    if (j == 0) { idx[k] = 0; wt[k++] = 0.25f; }                 // clamped i-1 at the first output
+    if (j == n - 1) { idx[k] = 2 * n - 1; wt[k++] = 0.25f; }     // clamped i+1 at the last output
+    return k;
+  }
+  LU_HD void operator()(int64_t i) const {
+    const int c = (int)(i % cpad); int64_t p = i / cpad;
+    const int ix = (int)(p % w); p /= w; const int iy = (int)(p % h); const int64_t n = p / h;
+    int yi[6], xi[6]; float yw[6], xw[6];
+    const int ny = taps1d(iy, h, yi, yw), nx = taps1d(ix, w, xi, xw);
+    const int ct = cpad * planes;
+    float s = 0.f;
+    for (int a = 0; a < ny; ++a)
+      for (int b = 0; b < nx; ++b)
+        s += yw[a] * xw[b] * lu_ldplanes(gup + (((n * 2 * h + yi[a]) * 2 * w) + xi[b]) * (int64_t)ct + c, cpad, planes);
+    uint16_t* o = gsrc + ((n * h + iy) * w + ix) * (int64_t)ct + c;
+    if (accumulate) s += lu_ldplanes(o, cpad, planes);
+    lu_stplanes(o, cpad, planes, s);
+  }
+};
+
+// ---- ConvLSTM cell backward for one time step ----------------------------------------------------------------------
+// item = (sample pixel, channel < fpad).  gates: (frames,H,W,planes*4*fpad) [i|f|g|o]; dZ same layout (bf16 planes).
+struct LuLstmCellBwd {
+  const uint16_t* dH; const uint16_t* gates; const float* c_t; const float* c_prev; float* dC; uint16_t* dZ;
+  int64_t pix_per_sample; int T, t, fpad, planes, gate_kind, c_prev_is_init, first;
+  LU_HD void operator()(int64_t i) const {
+    const int ch = (int)(i % fpad); const int64_t sp = i / fpad;            // sp = b*HW + pixel
+    const int64_t b = sp / pix_per_sample, px = sp % pix_per_sample;
+    const int64_t fp = (b * T + t) * pix_per_sample + px;                   // pixel index in frame-major buffers
+    const int g4 = 4 * fpad;
+    const uint16_t* gp = gates + fp * (int64_t)(g4 * planes) + ch;
+    const float gi = lu_ldplanes(gp, g4, planes), gf = lu_ldplanes(gp + fpad, g4, planes);
+    const float gg = lu_ldplanes(gp + 2 * fpad, g4, planes), go = lu_ldplanes(gp + 3 * fpad, g4, planes);
+    const float ct = c_t[fp * fpad + ch];
+    const float cp = c_prev_is_init ? c_prev[sp * fpad + ch] : c_prev[(fp - pix_per_sample) * fpad + ch];
+    const float dh = lu_ldplanes(dH + fp * (int64_t)(fpad * planes) + ch, fpad, planes);
+    const float th = tanhf(ct);
+    float dc = (first ? 0.f : dC[sp * fpad + ch]) + dh * go * (1.f - th * th);
+    const float d_o = dh * th, d_i = dc * gg, d_g = dc * gi, d_f = dc * cp;
+    dC[sp * fpad + ch] = dc * gf;
+    float zi, zf, zo;
+    if (gate_kind == 0) {
+      zi = (gi > 0.f && gi < 1.f) ? 0.2f * d_i : 0.f;
+      zf = (gf > 0.f && gf < 1.f) ? 0.2f * d_f : 0.f;
+      zo = (go > 0.f && go < 1.f) ? 0.2f * d_o : 0.f;
+    } else {
+      zi = d_i * gi * (1.f - gi); zf = d_f * gf * (1.f - gf); zo = d_o * go * (1.f - go);
+    }
+    const float zg = d_g * (1.f - gg * gg);
+    uint16_t* zp = dZ + fp * (int64_t)(g4 * planes) + ch;
+    lu_stplanes(zp, g4, planes, zi); lu_stplanes(zp + fpad, g4, planes, zf);
+    lu_stplanes(zp + 2 * fpad, g4, planes, zg); lu_stplanes(zp + 3 * fpad, g4, planes, zo);
+  }
+};
+
+// ---- bias gradient: column sums of a gradient buffer; item = (pixel chunk, channel) -----------------------------
+struct LuColSumGrad {
+  const uint16_t* g; float* dst; int64_t npix; int cpad, planes, chunk;
+  int c_real;        // identity layout: channel c < c_real -> dst[c]
+  int gate_F, gate_fpad;   // gate layout (gate_F > 0): channel gate*fpad + ch -> dst[gate*F + ch]
+  LU_HD void operator()(int64_t i) const {
+    const int c = (int)(i % cpad); const int64_t pc = i / cpad;
+    int d;
+    if (gate_F > 0) { const int gt = c / gate_fpad, ch = c % gate_fpad; if (ch >= gate_F) return; d = gt * gate_F + ch; }
+    else { if (c >= c_real) return; d = c; }
+    int64_t p0 = pc * chunk, p1 = p0 + chunk; if (p1 > npix) p1 = npix;
+    float s = 0.f;
+    for (int64_t p = p0; p < p1; ++p) s += lu_ldplanes(g + p * (int64_t)(cpad * planes) + c, cpad, planes);
+    lu_atomic_add(&dst[d], s);
+  }
+};
+
+// ---- weight gradient in PACKED space (scalar engine): dWp[n][k] = sum_pixels A_k[pixel] * dY[pixel][n] --------------
+// A_k is exactly the forward operand of K block k/64, channel k%64 (same staging tables), so the mapping back to the
+// Keras tensor is the weight-packing descriptor read backwards (LuUnpackWgrad).
+struct LuWgradMirror {
+  LuConvParams p;                 // forward tables / views (frame mapping set by the launcher)
+  const uint16_t* kb_stage;       // K block -> stage index
+  const uint16_t* kb_tap;         // K block -> tap offset inside the stage's window
+  const uint16_t* dY; int dy_cpad, dy_planes; int64_t dy_frame_mul, dy_frame_add;
+  LuColMap cm; int gate_fpad;     // packed column -> dY channel (identity, or lstm gate layout)
+  float* dWp; int npad, H, W, frames, chunk;
+  int only_src;                   // >= 0: only K blocks of this source view
+  int skip_t0_src, T;             // source whose contribution is skipped for frames with t == 0 (h_{t-1} of step 0)
+  LU_HD void operator()(int64_t it) const {
+    const int64_t npix = (int64_t)frames * H * W;
+    const int64_t nchunk = (npix + chunk - 1) / chunk;
+    const int64_t pc = it % nchunk; int64_t r = it / nchunk;
+    const int n16 = (int)(r % (npad / 16)); r /= (npad / 16);
+    const int k = (int)r, kb = k / LU_KBLK, kk = k % LU_KBLK;
+    const LuAStage st = p.astages[kb_stage[kb]];
+    if (only_src >= 0 && st.src != only_src) return;
+    const LuSrcView& v = p.src[st.src];
+    if (st.c + kk >= v.dimC) return;
+    const int off = kb_tap[kb];
+    int dch[16]; bool any = false;
+    for (int j = 0; j < 16; ++j) {
+      const int n = n16 * 16 + j;
+      int d = -1;
+      if (cm.kind == LU_COL_IDENTITY) d = n < cm.n_real ? n : -1;
+      else { const int bn = 4 * cm.ch_tile, tile = n / bn, rr = n % bn, g = rr / cm.ch_tile, jj = rr % cm.ch_tile;
+             const int ch = tile * cm.ch_tile + jj; d = ch < cm.F ? g * gate_fpad + ch : -1; }
+      dch[j] = d; any = any || d >= 0;
+    }
+    if (!any) return;
+    float acc[16];
+    for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+    int64_t p0 = pc * chunk, p1 = p0 + chunk; if (p1 > npix) p1 = npix;
+    for (int64_t px = p0; px < p1; ++px) {
+      const int x = (int)(px % W); int64_t q = px / W; const int y = (int)(q % H); const int64_t f = q / H;
+      if (st.src == skip_t0_src && (f % T) == 0) continue;
+      const int yy = y + st.dy + off / v.pitch, xx = x + st.dx + off % v.pitch;
+      if (yy < 0 || yy >= v.dimH || xx < 0 || xx >= v.dimW) continue;
+      const int64_t n = f * v.frame_mul + v.frame_add;
+      const float a = lu_bf2f(v.ptr[n * v.sn + (int64_t)yy * v.sh + (int64_t)st.plane * v.sp + (int64_t)xx * v.sw + st.c + kk]);
+      if (a == 0.f) continue;
+      const uint16_t* dy = dY + (((f * dy_frame_mul + dy_frame_add) * H + y) * W + x) * (int64_t)(dy_cpad * dy_planes);
+      for (int j = 0; j < 16; ++j)
+        if (dch[j] >= 0) acc[j] += a * lu_ldplanes(dy + dch[j], dy_cpad, dy_planes);
+    }
+    for (int j = 0; j < 16; ++j)
+      if (dch[j] >= 0 && acc[j] != 0.f) lu_atomic_add(&dWp[(int64_t)(n16 * 16 + j) * p.ktot + k], acc[j]);
+  }
+};
+// scatter-add the packed gradient into the Keras-layout gradient tensor; item = (n, k).  Blocks that pair the
+// activation with the LO part of the weight (bf16x3) are duplicates of the hi block and are skipped.
+struct LuUnpackWgrad {
+  const float* dWp; const LuPackDesc* descs; float* grads; LuColMap cm; int ktot;
+  LU_HD void operator()(int64_t i) const {
+    const int k = (int)(i % ktot); const int n = (int)(i / ktot);
+    const float g = dWp[i];
+    if (g == 0.f) return;
+    const int kb = k / LU_KBLK, kk = k % LU_KBLK;
+    const int col = lu_col_of(cm, n);
+    if (col < 0) return;
+    const LuPackDesc d = descs[kb];
+    if (d.wpart != 0) return;
+    if (d.kind == 0) {
+      if (kk < d.n_valid) lu_atomic_add(&grads[d.w_off + d.tap_off + (int64_t)(d.c_base + kk) * d.cout_total + col], g);
+    } else {
+      int t = kk;
+      if (d.patch_x3 && kk >= 32) t = kk - 32;
+      if (t < d.pw * d.pw) {
+        const int sh = (d.pw - 1) / 2 - (d.k - 1) / 2;
+        const int ky = t / d.pw - sh, kx = t % d.pw - sh;
+        if (ky >= 0 && ky < d.k && kx >= 0 && kx < d.k)
+          lu_atomic_add(&grads[d.w_off + ((int64_t)(ky * d.k + kx) * d.cin_total + d.c_base) * d.cout_total + col], g);
+      }
+    }
   }
 };

@@ -1,13 +1,359 @@
-// Host side of the training step (included by lu_api.cu).
+// Host side of the training step (included by lu_api.cu): backward plan (data-gradient convolutions, buffers) and the
+// reverse traversal of the layer graph.  Mirrors what tf.GradientTape + tape.gradient do for train2D.py:89-92.
+//
+// Gradient buffers are bf16 hi[/lo] planes with the same NHWC layout as the activations ("twin" ActBufs), so the data
+// gradient of every convolution is just another table-driven implicit-GEMM convolution over the upstream gradient with
+// transposed weight packing (LU_EPI_GRAD epilogue; first writer stores, later writers accumulate).
+
+static int add_dgrad(lu_handle_s* h, int fi, int in_idx, int ry, int rx) {
+  const bool x3 = h->planes == 2;
+  ConvPlan d;
+  {
+    const ConvPlan& f = h->convs[fi];
+    const ConvIn& fin = f.in[in_idx];
+    const ParamT& wp = h->params[fin.w_param];
+    const int k = f.k, s = f.stride;
+    const int cin_total = (int)wp.shape[2], cout_total = (int)wp.shape[3];
+    char nm[160];
+    snprintf(nm, sizeof nm, "dgrad[%s in%d p%d%d]", f.name.c_str(), in_idx, ry, rx);
+    d.name = nm; d.kind = LU_EPI_GRAD; d.k = k; d.stride = 1; d.fwd = fi; d.fwd_in = in_idx;
+    const int gsrc = f.kind == LU_EPI_LSTM ? f.dz_buf : (f.out_buf >= 0 ? h->gidx[f.out_buf] : h->g_logits_buf);
+    const ActBuf& gb = h->acts[gsrc];
+    d.n_in = 1; d.in[0].buf = gsrc; d.in[0].creal = gb.creal; d.in[0].w_param = fin.w_param; d.in[0].c_base = 0;
+    d.out_buf = h->gidx[fin.buf];
+    d.cout = fin.creal; d.BN = pick_bn(d.cout); d.npad = ceil_to(d.cout, d.BN); d.n_tiles_n = d.npad / d.BN;
+    d.cm.kind = LU_COL_IDENTITY; d.cm.n_real = d.cout;
+    d.Hin = d.Hout = gb.H; d.Win = d.Wout = gb.W;
+    d.oy_mul = s; d.oy_add = ry; d.ox_mul = s; d.ox_add = rx; d.OH = f.Hin; d.OW = f.Win;
+    int ho, wo, pt, pl;
+    tf_same(f.Hin, k, s, &ho, &pt);
+    tf_same(f.Win, k, s, &wo, &pl);
+    std::vector<int> kys, kxs, as, bs;
+    for (int ky = 0; ky < k; ++ky) if (((ry + pt - ky) % s + s) % s == 0) { kys.push_back(ky); as.push_back(floordiv(ry + pt - ky, s)); }
+    for (int kx = 0; kx < k; ++kx) if (((rx + pl - kx) % s + s) % s == 0) { kxs.push_back(kx); bs.push_back(floordiv(rx + pl - kx, s)); }
+    if (kys.empty() || kxs.empty()) return -1;
+    int a_min = as[0], a_max = as[0], b_min = bs[0], b_max = bs[0];
+    for (int a : as) { a_min = a < a_min ? a : a_min; a_max = a > a_max ? a : a_max; }
+    for (int b : bs) { b_min = b < b_min ? b : b_min; b_max = b > b_max ? b : b_max; }
+    LuSrcView v; memset(&v, 0, sizeof v);
+    const int ctot = gb.cpad * gb.planes;
+    v.dimC = ctot; v.dimW = gb.W; v.dimP = 1; v.dimH = gb.H; v.dimN = gb.frames;
+    v.sw = ctot; v.sh = (int64_t)gb.W * ctot; v.sp = v.sh; v.sn = (int64_t)gb.H * gb.W * ctot;
+    v.frame_mul = 1; v.frame_add = 0;
+    v.rows = LU_TILE_H + (a_max - a_min); v.pitch = LU_TILE_W + (b_max - b_min);
+    d.n_views = 1; d.views[0] = v; d.view_buf[0] = gsrc;
+    const int nchunks = gb.cpad / LU_KBLK;
+    for (int ch = 0; ch < nchunks; ++ch) {
+      int c_base, nvalid;
+      if (f.kind == LU_EPI_LSTM) {
+        const int per = f.fpad / LU_KBLK, gate = ch / per, cc = ch % per;
+        c_base = gate * f.F + cc * LU_KBLK; nvalid = f.F - cc * LU_KBLK;
+      } else { c_base = ch * LU_KBLK; nvalid = f.cout - ch * LU_KBLK; }
+      nvalid = nvalid < 0 ? 0 : (nvalid > LU_KBLK ? LU_KBLK : nvalid);
+      if (nvalid == 0) continue;
+      for (int aplane = 0; aplane < (x3 ? 2 : 1); ++aplane) {
+        const int nw = (x3 && aplane == 0) ? 2 : 1;
+        LuAStage st; memset(&st, 0, sizeof st);
+        st.src = 0; st.plane = 0; st.c = aplane * gb.cpad + ch * LU_KBLK;
+        st.dy = (int16_t)a_min; st.dx = (int16_t)b_min; st.tap_begin = (uint32_t)d.taps.size(); st.ntaps = 0;
+        for (int wpart = 0; wpart < nw; ++wpart)
+          for (size_t iy = 0; iy < kys.size(); ++iy)
+            for (size_t ix = 0; ix < kxs.size(); ++ix) {
+              LuPackDesc pd; memset(&pd, 0, sizeof pd);
+              pd.w_off = wp.offset; pd.tap_off = (kys[iy] * k + kxs[ix]) * cin_total * cout_total;
+              pd.c_base = c_base; pd.n_valid = nvalid; pd.cin_total = cin_total; pd.cout_total = cout_total;
+              pd.wpart = (int8_t)wpart; pd.kind = 0; pd.transposed = 1; pd.col_base = fin.c_base;
+              d.packs.push_back(pd);
+              d.taps.push_back((uint16_t)((as[iy] - a_min) * v.pitch + (bs[ix] - b_min)));
+              st.ntaps++;
+            }
+        d.astages.push_back(st);
+      }
+    }
+  }
+  if (finish_tables(h, d)) return -2;
+  d.macs_per_frame = 0;
+  h->convs.push_back(d);
+  return (int)h->convs.size() - 1;
+}
+
+static int new_act_raw(lu_handle_s* h, int frames, int H, int W, int creal) { return new_act(h, frames, H, W, creal); }
+
+// called at the end of build_plan when cfg.train
+static int build_train_plan(lu_handle_s* h) {
+  const int N = h->cfg.batch * h->cfg.max_t;
+  const int n_fwd_acts = (int)h->acts.size();
+  h->gidx.assign(n_fwd_acts, -1);
+  for (int i = 0; i < n_fwd_acts; ++i) {
+    const ActBuf a = h->acts[i];
+    h->gidx[i] = new_act_raw(h, a.frames, a.H, a.W, a.creal);
+  }
+  {
+    const ConvPlan& lc = h->convs[h->logits_conv];
+    h->g_logits_buf = new_act_raw(h, N, lc.Hout, lc.Wout, lc.cout);
+  }
+  const int n_fwd = (int)h->convs.size();
+  for (int fi = 0; fi < n_fwd; ++fi)
+    if (h->convs[fi].kind == LU_EPI_LSTM) {
+      const int H = h->convs[fi].Hout, W = h->convs[fi].Wout, fp = h->convs[fi].fpad;
+      const int b = new_act_raw(h, N, H, W, 4 * fp);
+      h->convs[fi].dz_buf = b;
+    }
+  for (int fi = 0; fi < n_fwd; ++fi) {
+    const int n_in = h->convs[fi].n_in, s = h->convs[fi].stride;
+    for (int i = 0; i < n_in; ++i) {
+      if (h->convs[fi].in[i].buf < 0) continue;                 // the image needs no gradient
+      for (int ry = 0; ry < s; ++ry)
+        for (int rx = 0; rx < s; ++rx) {
+          const int di = add_dgrad(h, fi, i, ry, rx);
+          if (di == -2) return 1;
+          if (di >= 0) h->convs[fi].dgrads[i].push_back(di);
+        }
+    }
+  }
+  // K block -> (stage, tap) maps for the packed-space weight gradient
+  for (int fi = 0; fi < n_fwd; ++fi) {
+    ConvPlan& f = h->convs[fi];
+    for (size_t s = 0; s < f.astages.size(); ++s)
+      for (int t = 0; t < f.astages[s].ntaps; ++t) {
+        f.kb_stage.push_back((uint16_t)s);
+        f.kb_tap.push_back(f.taps[f.astages[s].tap_begin + t]);
+      }
+  }
+  return 0;
+}
+
 static void train_layout(lu_handle_s* h, size_t& off) {
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return o; };
   h->tr.off_loss_acc = take(64);
+  if (!h->cfg.train) return;
+  size_t dwp = 0;
+  for (auto& cv : h->convs) {
+    if (cv.kind == LU_EPI_GRAD) continue;
+    cv.off_kb_stage = take(cv.kb_stage.size() * 2);
+    cv.off_kb_tap = take(cv.kb_tap.size() * 2);
+    cv.off_bwd_sums = take((size_t)cv.npad * 2 * 8);
+    const size_t b = (size_t)cv.npad * cv.ktot * 4;
+    if (b > dwp) dwp = b;
+    if (cv.kind == LU_EPI_LSTM) {
+      const size_t px = (size_t)h->cfg.batch * cv.Hout * cv.Wout;
+      cv.off_c_init = take(px * cv.fpad * 4);
+      cv.off_dc = take(px * cv.fpad * 4);
+    }
+  }
+  h->tr_off_dwp = take(dwp);
+  h->tr_dwp_bytes = dwp;
 }
 static void train_destroy(lu_handle_s*) {}
 
-static int train_loss_backward(lu_handle_s* h, const float*, const float*, float*, float*, void*) {
-  LU_REQUIRE(h, "null handle");
-  LU_FAIL("lu_loss_backward: backward pass not built yet");
+static void train_upload(lu_handle_s* h, void* stream) {
+  if (!h->cfg.train) return;
+  for (auto& cv : h->convs) {
+    if (cv.kind == LU_EPI_GRAD) continue;
+    LU_H2D(h->ws + cv.off_kb_stage, cv.kb_stage.data(), cv.kb_stage.size() * 2, stream);
+    LU_H2D(h->ws + cv.off_kb_tap, cv.kb_tap.data(), cv.kb_tap.size() * 2, stream);
+  }
+}
+
+static uint16_t* act_ptr(lu_handle_s* h, int buf) { return reinterpret_cast<uint16_t*>(h->ws + h->acts[buf].off); }
+
+// ---- pieces of the reverse traversal -------------------------------------------------------------------------------
+static int run_dgrads(lu_handle_s* h, ConvPlan& f, int in_idx, int frames, int src_mul, int src_add, int out_mul,
+                      int out_add, int force_acc, std::vector<char>& gwritten, void* stream) {
+  if (f.in[in_idx].buf < 0) return 0;
+  const int gdst = h->gidx[f.in[in_idx].buf];
+  const int acc = force_acc >= 0 ? force_acc : (gwritten[gdst] ? 1 : 0);
+  for (int di : f.dgrads[in_idx]) {
+    ConvPlan& d = h->convs[di];
+    const ActBuf& ob = h->acts[gdst];
+    int mul[LU_MAX_SRC] = {src_mul, 1, 1, 1}, add[LU_MAX_SRC] = {src_add, 0, 0, 0};
+    LuEpi e; memset(&e, 0, sizeof e);
+    e.kind = LU_EPI_GRAD; e.H = d.Hout; e.W = d.Wout;
+    e.oy_mul = d.oy_mul; e.oy_add = d.oy_add; e.ox_mul = d.ox_mul; e.ox_add = d.ox_add; e.OH = d.OH; e.OW = d.OW;
+    e.accumulate = acc; e.out_frame_mul = out_mul; e.out_frame_add = out_add;
+    e.out_act = act_ptr(h, gdst); e.out_cpad = ob.cpad; e.out_planes = ob.planes;
+    e.bias = reinterpret_cast<const float*>(h->ws + d.off_bias);
+    if (launch_conv(h, d, frames, mul, add, -1, e, stream)) return 1;
+  }
+  gwritten[gdst] = 1;
+  return 0;
+}
+
+static void run_colsum(lu_handle_s* h, int gbuf, int frames_used, float* dst, int c_real, int gate_F, int gate_fpad,
+                       void* stream) {
+  const ActBuf& g = h->acts[gbuf];
+  LuColSumGrad cs;
+  cs.g = act_ptr(h, gbuf); cs.dst = dst; cs.npix = (int64_t)frames_used * g.H * g.W; cs.cpad = g.cpad; cs.planes = g.planes;
+  cs.chunk = 256; cs.c_real = c_real; cs.gate_F = gate_F; cs.gate_fpad = gate_fpad;
+  pf(h, ((cs.npix + cs.chunk - 1) / cs.chunk) * g.cpad, stream, cs);
+}
+
+// weight gradient of forward conv f from the upstream gradient buffer gbuf (packed space, scalar engine)
+static int run_wgrad(lu_handle_s* h, ConvPlan& f, int gbuf, int T, float* grads, void* stream) {
+  const ActBuf& g = h->acts[gbuf];
+  float* dwp = reinterpret_cast<float*>(h->ws + h->tr_off_dwp);
+  LU_MEMSET(dwp, 0, (size_t)f.npad * f.ktot * 4, stream);
+  const int n_launch = f.kind == LU_EPI_LSTM ? 2 : 1;
+  for (int pass = 0; pass < n_launch; ++pass) {
+    LuWgradMirror w; memset(&w, 0, sizeof w);
+    for (int i = 0; i < f.n_views; ++i) {
+      w.p.src[i] = f.views[i];
+      w.p.src[i].ptr = view_ptr(h, f.view_buf[i]);
+      w.p.src[i].frame_mul = 1; w.p.src[i].frame_add = 0;
+    }
+    w.p.astages = reinterpret_cast<const LuAStage*>(h->ws + f.off_astages);
+    w.p.ktot = f.ktot; w.p.n_astages = (int)f.astages.size();
+    w.kb_stage = reinterpret_cast<const uint16_t*>(h->ws + f.off_kb_stage);
+    w.kb_tap = reinterpret_cast<const uint16_t*>(h->ws + f.off_kb_tap);
+    w.dY = act_ptr(h, gbuf); w.dy_cpad = g.cpad; w.dy_planes = g.planes; w.dy_frame_mul = 1; w.dy_frame_add = 0;
+    w.cm = f.cm; w.gate_fpad = f.fpad; w.dWp = dwp; w.npad = f.npad; w.H = f.Hout; w.W = f.Wout;
+    w.frames = h->cfg.batch * T; w.chunk = 2048; w.only_src = -1; w.skip_t0_src = -1; w.T = T;
+    if (f.kind == LU_EPI_LSTM) {
+      if (pass == 0) {                 // all frames; h_{t-1} = h sequence shifted by one frame, nothing for t == 0
+        w.p.src[1].frame_add = -1; w.skip_t0_src = 1;
+      } else {                         // t == 0 frames against the initial state h_init (state buffer before the call)
+        w.frames = h->cfg.batch; w.only_src = 1;
+        w.p.src[1].ptr = reinterpret_cast<const uint16_t*>(h->ws + f.off_hstate[h->hcur ^ 1]);
+        w.p.src[1].dimN = h->cfg.batch;
+        w.dy_frame_mul = T; w.dy_frame_add = 0;
+      }
+    }
+    const int64_t npix = (int64_t)w.frames * w.H * w.W;
+    const int64_t nchunk = (npix + w.chunk - 1) / w.chunk;
+    pf(h, (int64_t)f.ktot * (f.npad / 16) * nchunk, stream, w);
+  }
+  LuUnpackWgrad u;
+  u.dWp = dwp; u.descs = reinterpret_cast<const LuPackDesc*>(h->ws + f.off_packs); u.grads = grads; u.cm = f.cm; u.ktot = f.ktot;
+  pf(h, (int64_t)f.npad * f.ktot, stream, u);
+  return 0;
+}
+
+static int bwd_conv_layer(lu_handle_s* h, ConvPlan& f, int T, float* grads, std::vector<char>& gwritten, void* stream) {
+  const int N = h->cfg.batch * T;
+  const int gbuf = f.out_buf >= 0 ? h->gidx[f.out_buf] : h->g_logits_buf;
+  const int64_t npix = (int64_t)N * f.Hout * f.Wout;
+  if (f.has_bn) {
+    const ActBuf& gb = h->acts[gbuf];
+    double* sums = reinterpret_cast<double*>(h->ws + f.off_bwd_sums);
+    LU_MEMSET(sums, 0, (size_t)f.raw_cpad * 2 * 8, stream);
+    LuBnBwdReduce r;
+    r.dA = act_ptr(h, gbuf); r.raw = reinterpret_cast<const float*>(h->ws + f.off_raw);
+    r.scale = reinterpret_cast<const float*>(h->ws + f.off_bscale); r.shift = reinterpret_cast<const float*>(h->ws + f.off_bshift);
+    r.mean = reinterpret_cast<const float*>(h->ws + f.off_save_mean); r.invstd = reinterpret_cast<const float*>(h->ws + f.off_save_invstd);
+    r.sums = sums; r.npix = npix; r.cpad = gb.cpad; r.planes = gb.planes; r.raw_cpad = f.raw_cpad; r.c_real = f.cout;
+    r.chunk = 256; r.alpha = 0.3f;
+    pf(h, ((npix + r.chunk - 1) / r.chunk) * f.raw_cpad, stream, r);
+    LuBnBwdParams bp;
+    bp.sums = sums; bp.dgamma = grads + h->params[f.gamma].offset; bp.dbeta = grads + h->params[f.beta].offset;
+    bp.raw_cpad = f.raw_cpad; bp.c_real = f.cout;
+    pf(h, f.cout, stream, bp);
+    LuBnBwdApply a;
+    a.dA = act_ptr(h, gbuf); a.raw = r.raw; a.scale = r.scale; a.shift = r.shift; a.mean = r.mean; a.invstd = r.invstd;
+    a.sums = sums; a.npix = npix; a.cpad = gb.cpad; a.planes = gb.planes; a.raw_cpad = f.raw_cpad; a.c_real = f.cout; a.alpha = 0.3f;
+    pf(h, npix * gb.cpad, stream, a);
+  }
+  run_colsum(h, gbuf, N, grads + h->params[f.bias_param].offset, f.cout, 0, 0, stream);
+  if (run_wgrad(h, f, gbuf, T, grads, stream)) return 1;
+  for (int i = 0; i < f.n_in; ++i)
+    if (run_dgrads(h, f, i, N, 1, 0, 1, 0, -1, gwritten, stream)) return 1;
+  return 0;
+}
+
+static int bwd_lstm_layer(lu_handle_s* h, ConvPlan& f, int T, float* grads, std::vector<char>& gwritten, void* stream) {
+  const int B = h->cfg.batch;
+  const int gH = h->gidx[f.hseq_buf];
+  const ActBuf& gh = h->acts[gH];
+  const int64_t pps = (int64_t)f.Hout * f.Wout;
+  if (!gwritten[gH]) {                      // no consumer wrote a gradient (cannot happen in ULSTMnet2D): zero it
+    LU_MEMSET(act_ptr(h, gH), 0, gh.bytes(), stream);
+    gwritten[gH] = 1;
+  }
+  for (int t = T - 1; t >= 0; --t) {
+    LuLstmCellBwd c;
+    c.dH = act_ptr(h, gH); c.gates = reinterpret_cast<const uint16_t*>(h->ws + f.off_save_gates);
+    c.c_t = reinterpret_cast<const float*>(h->ws + f.off_save_c);
+    c.c_prev_is_init = t == 0;
+    c.c_prev = t == 0 ? reinterpret_cast<const float*>(h->ws + f.off_c_init) : c.c_t;
+    c.dC = reinterpret_cast<float*>(h->ws + f.off_dc); c.dZ = act_ptr(h, f.dz_buf);
+    c.pix_per_sample = pps; c.T = T; c.t = t; c.fpad = f.fpad; c.planes = h->planes; c.gate_kind = h->cfg.gate;
+    c.first = t == T - 1;
+    pf(h, (int64_t)B * pps * f.fpad, stream, c);
+    if (t > 0)                              // dh_{t-1} += conv^T(dz_t, recurrent_kernel)
+      if (run_dgrads(h, f, 1, B, T, t, T, t - 1, 1, gwritten, stream)) return 1;
+  }
+  run_colsum(h, f.dz_buf, B * T, grads + h->params[f.bias_param].offset, 0, f.F, f.fpad, stream);
+  if (run_wgrad(h, f, f.dz_buf, T, grads, stream)) return 1;
+  if (run_dgrads(h, f, 0, B * T, 1, 0, 1, 0, -1, gwritten, stream)) return 1;   // dx_t for all frames at once
+  return 0;
+}
+
+static int train_loss_only(lu_handle_s* h, const float* labels, const float* cw, float* loss_out, uint16_t* gout,
+                           void* stream) {
+  const lu_config& c = h->cfg;
+  ConvPlan& lc = h->convs[h->logits_conv];
+  LU_REQUIRE(lc.cout == 3, "WeightedCELoss is defined for 3 classes (losses.py:20), network has %d", lc.cout);
+  const int T = h->last_T, N = c.batch * T;
+  double* acc = reinterpret_cast<double*>(h->ws + h->tr.off_loss_acc);
+  LU_MEMSET(acc, 0, 16, stream);
+  LuCeReduce r;
+  r.raw = reinterpret_cast<const float*>(h->ws + lc.off_raw); r.labels = labels; r.acc = acc;
+  r.npix = (int64_t)N * c.height * c.width; r.H = c.height; r.W = c.width; r.Hp = h->Hp; r.Wp = h->Wp;
+  r.py0 = h->pad_y0; r.px0 = h->pad_x0; r.raw_cpad = lc.raw_cpad; r.chunk = 256; r.w0 = cw[0]; r.w1 = cw[1]; r.w2 = cw[2];
+  pf(h, (r.npix + r.chunk - 1) / r.chunk, stream, r);
+  LuCeGrad g;
+  g.raw = r.raw; g.labels = labels; g.acc = acc; g.loss_out = loss_out; g.g = gout;
+  g.H = c.height; g.W = c.width; g.Hp = h->Hp; g.Wp = h->Wp; g.py0 = h->pad_y0; g.px0 = h->pad_x0; g.raw_cpad = lc.raw_cpad;
+  g.w0 = cw[0]; g.w1 = cw[1]; g.w2 = cw[2]; g.cpad = 0; g.planes = 1;
+  if (gout != nullptr) {
+    const ActBuf& gb = h->acts[h->g_logits_buf];
+    g.cpad = gb.cpad; g.planes = gb.planes;
+    pf(h, (int64_t)N * h->Hp * h->Wp, stream, g);
+  } else {
+    LuCeLossOnly lo; lo.acc = acc; lo.loss_out = loss_out;
+    pf(h, 1, stream, lo);
+  }
+  return 0;
+}
+
+static int train_loss_backward(lu_handle_s* h, const float* labels, const float* cw, float* loss_out, float* grads,
+                               void* stream) {
+  LU_REQUIRE(h && h->bound && h->dparams, "bind workspace and parameters first");
+  LU_REQUIRE(labels && cw && loss_out, "null argument");
+  LU_REQUIRE(h->last_T > 0, "call lu_forward first");
+  if (grads == nullptr) return train_loss_only(h, labels, cw, loss_out, nullptr, stream);
+  LU_REQUIRE(h->cfg.train, "handle was created without train=1");
+  LU_REQUIRE(h->last_training, "lu_loss_backward needs a preceding lu_forward(training=1)");
+  const int T = h->last_T;
+  LU_MEMSET(grads, 0, (size_t)h->n_train * 4, stream);
+  if (train_loss_only(h, labels, cw, loss_out, act_ptr(h, h->g_logits_buf), stream)) return 1;
+  std::vector<char> gwritten(h->acts.size(), 0);
+  for (int u = h->L - 1; u >= 0; --u) {
+    const std::vector<int>& cl = h->conv_of_up[u];
+    for (int j = (int)cl.size() - 1; j >= 0; --j)
+      if (bwd_conv_layer(h, h->convs[cl[j]], T, grads, gwritten, stream)) return 1;
+    if (h->ups[u].src_buf >= 0) {
+      const ActBuf& s = h->acts[h->ups[u].src_buf];
+      const int gs = h->gidx[h->ups[u].src_buf], gd = h->gidx[h->ups[u].dst_buf];
+      LuUpsample2xBwd ub;
+      ub.gup = act_ptr(h, gd); ub.gsrc = act_ptr(h, gs); ub.h = s.H; ub.w = s.W; ub.cpad = s.cpad; ub.planes = s.planes;
+      ub.accumulate = gwritten[gs] ? 1 : 0;
+      pf(h, (int64_t)h->cfg.batch * T * s.H * s.W * s.cpad, stream, ub);
+      gwritten[gs] = 1;
+    }
+  }
+  for (int l = h->L - 1; l >= 0; --l) {
+    const std::vector<int>& cl = h->conv_of_level[l];
+    for (int j = (int)cl.size() - 1; j >= 0; --j)
+      if (bwd_conv_layer(h, h->convs[cl[j]], T, grads, gwritten, stream)) return 1;
+    const std::vector<int>& ll = h->lstm_of_level[l];
+    for (int j = (int)ll.size() - 1; j >= 0; --j)
+      if (bwd_lstm_layer(h, h->convs[ll[j]], T, grads, gwritten, stream)) return 1;
+  }
+#ifndef LU_HOST_EMU
+  cudaError_t e = cudaGetLastError();
+  LU_REQUIRE(e == cudaSuccess, "backward: %s", cudaGetErrorString(e));
+#endif
+  return 0;
 }
 
 static int train_adam(lu_handle_s* h, const float* g, float* m, float* v, float lr, float b1, float b2, float eps,

@@ -156,3 +156,12 @@ class LuSession:
         ms, n = ctypes.c_float(), ctypes.c_int32()
         self._check(self.lib.lu_lstm_kernel_time(self.h, 1 if enable else 0, ctypes.byref(ms), ctypes.byref(n)))
         return ms.value, n.value
+
+    def debug_buffer(self, name, kind=0):
+        """Test hook: an internal NHWC buffer of layer `name` as a host fp32 array (frames, H, W, C)."""
+        shape = (ctypes.c_int64 * 4)()
+        self._check(self.lib.lu_debug_buffer(self.h, name.encode(), kind, None, shape, self.be.stream()))
+        shp = tuple(int(v) for v in shape)
+        buf = self.be.zeros(int(np.prod(shp)), np.float32)
+        self._check(self.lib.lu_debug_buffer(self.h, name.encode(), kind, self.be.ptr(buf), shape, self.be.stream()))
+        return self.be.to_host(buf).reshape(shp)
