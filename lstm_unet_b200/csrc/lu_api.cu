@@ -35,6 +35,7 @@ static thread_local std::string g_err;
     if (!(cond)) LU_FAIL(__VA_ARGS__); \
   } while (0)
 
+#define LU_WG_MAX_TASKS 4096
 static inline int ceil_to(int v, int m) { return (v + m - 1) / m * m; }
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -99,7 +100,7 @@ struct ConvPlan {
   int dz_buf = -1;                      // lstm: gradient wrt the gate pre-activations (frames,H,W,4*fpad)
   std::vector<int> dgrads[2];
   std::vector<uint16_t> kb_stage, kb_tap;
-  size_t off_kb_stage = 0, off_kb_tap = 0, off_bwd_sums = 0, off_c_init = 0, off_dc = 0;
+  size_t off_kb_stage = 0, off_kb_tap = 0, off_bwd_sums = 0, off_c_init = 0, off_dc = 0, off_wg_tasks = 0;
 #ifndef LU_HOST_EMU
   CUtensorMap tmA[LU_MAX_SRC];
   CUtensorMap tmB;
@@ -134,6 +135,9 @@ struct lu_handle_s {
   bool bound = false, packed = false;
   int num_sms = 148;
   TrainState tr;
+#ifndef LU_HOST_EMU
+  std::vector<CUtensorMap> acts_tm;   // cfg.train: dense 16x8-tile map of every activation buffer (dY operand of wgrad)
+#endif
   std::vector<int> gidx;          // activation buffer -> its gradient twin (cfg.train)
   int g_logits_buf = -1;
   size_t tr_off_dwp = 0, tr_dwp_bytes = 0;
@@ -805,6 +809,18 @@ int lu_bind_workspace(lu_handle h, void* dev_ws, size_t bytes, void* stream) {
           if (encode_view(&cv.tmHstate[s], v, h->ws + cv.off_hstate[s])) return 1;
         }
       if (encode_weights(&cv.tmB, h->ws + cv.off_w, cv.npad, cv.ktot, cv.BN)) return 1;
+    }
+    if (h->cfg.train) {
+      h->acts_tm.resize(h->acts.size());
+      for (size_t i = 0; i < h->acts.size(); ++i) {
+        const ActBuf& a = h->acts[i];
+        LuSrcView v; memset(&v, 0, sizeof v);
+        const int ctot = a.cpad * a.planes;
+        v.dimC = ctot; v.dimW = a.W; v.dimP = 1; v.dimH = a.H; v.dimN = a.frames;
+        v.sw = ctot; v.sh = (int64_t)a.W * ctot; v.sp = v.sh; v.sn = (int64_t)a.H * a.W * ctot;
+        v.rows = LU_TILE_H; v.pitch = LU_TILE_W;
+        if (encode_view(&h->acts_tm[i], v, h->ws + a.off)) return 1;
+      }
     }
   }
   cudaError_t e = cudaGetLastError();

@@ -562,3 +562,173 @@ __global__ void __launch_bounds__(lutc::kThreads, 1) lu_conv_tc_kernel(const __g
   }
 }
 #endif  // !LU_HOST_EMU
+
+#ifndef LU_HOST_EMU
+// =============================================================================================================
+// Weight gradient on tcgen05: dWp[n][k] += sum over pixels  A_k[pixel] * dY[pixel][n]      (packed space)
+//
+// Both operands are NHWC, i.e. MN-major for a reduction over pixels: the MMA "K" rows are pixels (128-byte rows of
+// 64 channels), exactly what the forward's halo windows already are.  One task = (up to 2 activation stages = 128
+// rows of channels, up to 4 taps, one 64/128-column slab of output channels, a range of pixel tiles); the 4 taps'
+// accumulators (128 x N fp32 each) stay in TMEM for the whole pixel range and are flushed with fp32 atomics.
+// =============================================================================================================
+struct LuWgTask {
+  int16_t stage0, stage1;        // forward A stages giving rows [0,64) / [64,128); stage1 < 0: rows 64.. unused
+  int16_t ntaps, a_is_lo;        // a_is_lo: bf16x3 lo plane of the activation (pairs with the hi plane of dY only)
+  int32_t n0, nch;               // first packed column, number of 64-column chunks (1 or 2)
+  int32_t tile0, tile1;          // pixel-tile range [tile0, tile1)
+  int32_t off[4];                // tap offsets (rows) inside the window
+  int32_t kb0[4], kb1[4];        // K block (64 rows of dWp) written by each tap for stage0 / stage1
+  int32_t ychan[2];              // channel coordinate in dY of each 64-column chunk
+};
+
+struct LuWgParams {
+  CUtensorMap tmA[LU_MAX_SRC];
+  CUtensorMap tmY;
+  LuConvParams cp;               // forward views / stage table
+  const LuWgTask* tasks;
+  float* dWp;
+  int32_t tiles_x, tiles_y, T, skip_t0_src;
+  int32_t dy_frame_mul, dy_frame_add, dy_planes, dy_cpad;
+  int32_t a_win_bytes, stage_bytes, n_stages;
+};
+
+namespace lutc {
+__device__ __forceinline__ uint32_t desc_hi_mn(uint32_t sbo_bytes) { return (sbo_bytes >> 4) | (1u << 14) | (2u << 29); }
+__device__ __forceinline__ uint32_t desc_lo_mn(uint32_t addr, uint32_t lbo_bytes) {
+  return ((addr & 0x3FFFFu) >> 4) | ((lbo_bytes >> 4) << 16);
+}
+}  // namespace lutc
+
+__global__ void __launch_bounds__(256, 1) lu_wgrad_tc_kernel(const __grid_constant__ LuWgParams P) {
+  using namespace lutc;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t pad = ((raw_addr + 1023u) & ~1023u) - raw_addr;
+  uint8_t* smem = smem_raw + pad;
+  const int nS = P.n_stages;
+  const uint32_t s0 = smem_u32(smem);
+  const uint32_t bars = s0 + (uint32_t)nS * P.stage_bytes;
+  const uint32_t full = bars, empty = full + 8u * nS, done = empty + 8u * nS, tmem_slot = done + 8u;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem + (size_t)nS * P.stage_bytes + 16u * nS + 8u);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const LuWgTask tk = P.tasks[blockIdx.x];
+  const LuConvParams& cp = P.cp;
+  const LuAStage st0 = cp.astages[tk.stage0];
+  const LuAStage st1 = cp.astages[tk.stage1 >= 0 ? tk.stage1 : tk.stage0];
+  const LuSrcView& v = cp.src[st0.src];
+  const int N = tk.nch * 64;
+  const int nyp = (P.dy_planes == 2 && !tk.a_is_lo) ? 2 : 1;
+  const uint32_t b_off = 2u * (uint32_t)P.a_win_bytes;            // B region inside a stage
+  const int tiles_per_frame = P.tiles_x * P.tiles_y;
+
+  if (warp == 0 && lane == 0) { prefetch_tmap(&P.tmA[st0.src]); prefetch_tmap(&P.tmY); }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < nS; ++i) { mbar_init(full + 8u * i, 1); mbar_init(empty + 8u * i, 1); }
+    mbar_init(done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- producer: activation windows + dY tiles
+    int s = 0; uint32_t ph = 0;
+    const uint32_t bytes = (uint32_t)(v.rows * v.pitch) * 128u * (tk.stage1 >= 0 ? 2u : 1u) + (uint32_t)(nyp * tk.nch) * 16384u;
+    for (int tile = tk.tile0; tile < tk.tile1; ++tile) {
+      const int frame = tile / tiles_per_frame, rem = tile % tiles_per_frame;
+      if (st0.src == P.skip_t0_src && (frame % P.T) == 0) continue;
+      const int y0 = (rem / P.tiles_x) * LU_TILE_H, x0 = (rem % P.tiles_x) * LU_TILE_W;
+      mbar_wait(empty + 8u * s, ph ^ 1u);
+      if (elect_one()) {
+        const uint32_t base = s0 + (uint32_t)s * P.stage_bytes;
+        mbar_expect_tx(full + 8u * s, bytes);
+        const int fa = frame * v.frame_mul + v.frame_add;
+        tma_load_5d(base, &P.tmA[st0.src], full + 8u * s, st0.c, x0 + st0.dx, st0.plane, y0 + st0.dy, fa);
+        if (tk.stage1 >= 0)
+          tma_load_5d(base + (uint32_t)P.a_win_bytes, &P.tmA[st1.src], full + 8u * s, st1.c, x0 + st1.dx, st1.plane, y0 + st1.dy, fa);
+        const int fy = frame * P.dy_frame_mul + P.dy_frame_add;
+        for (int dp = 0; dp < nyp; ++dp)
+          for (int c = 0; c < tk.nch; ++c)
+            tma_load_5d(base + b_off + (uint32_t)(dp * 2 + c) * 16384u, &P.tmY, full + 8u * s,
+                        tk.ychan[c] + dp * P.dy_cpad, x0, 0, y0, fy);
+      }
+      __syncwarp();
+      if (++s == nS) { s = 0; ph ^= 1u; }
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer (MN-major A and B)
+    int s = 0; uint32_t ph = 0;
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t a_hi = desc_hi_mn((uint32_t)v.pitch * 128u), b_hi = desc_hi_mn(1024u);
+    const uint32_t a_lbo = tk.stage1 >= 0 ? (uint32_t)P.a_win_bytes : 0u;
+    const uint32_t row2 = (uint32_t)v.pitch * 128u * 2u;           // two image rows = 16 pixels = one MMA K step
+    uint32_t first = 1;
+    for (int tile = tk.tile0; tile < tk.tile1; ++tile) {
+      const int frame = tile / tiles_per_frame;
+      if (st0.src == P.skip_t0_src && (frame % P.T) == 0) continue;
+      mbar_wait(full + 8u * s, ph);
+      tc_fence_after();
+      const uint32_t base = s0 + (uint32_t)s * P.stage_bytes;
+      if (elect_one()) {
+        for (int ti = 0; ti < tk.ntaps; ++ti) {
+          const uint32_t d_tmem = tmem_base + (uint32_t)(ti * N);
+          const uint32_t a0 = base + (uint32_t)tk.off[ti] * 128u;
+          for (int dp = 0; dp < nyp; ++dp) {
+            const uint32_t b0 = base + b_off + (uint32_t)(dp * 2) * 16384u;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              mma_bf16(d_tmem, desc_lo_mn(a0 + (uint32_t)j * row2, a_lbo), a_hi, desc_lo_mn(b0 + (uint32_t)j * 2048u, 16384u), b_hi,
+                       idesc, (first && dp == 0 && j == 0) ? 0u : 1u);
+          }
+        }
+        tc_commit(empty + 8u * s);
+      }
+      __syncwarp();
+      first = 0;
+      if (++s == nS) { s = 0; ph ^= 1u; }
+    }
+    if (elect_one()) tc_commit(done);
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ---------------------------------------------------------------- epilogue: TMEM -> fp32 atomics into dWp
+    const int q = warp & 3;
+    const int row = q * 32 + lane;                   // D row = channel row of the task
+    // was anything accumulated?  (a task whose frames are all skipped leaves TMEM untouched)
+    bool any = false;
+    for (int tile = tk.tile0; tile < tk.tile1 && !any; ++tile)
+      any = !(st0.src == P.skip_t0_src && ((tile / tiles_per_frame) % P.T) == 0);
+    mbar_wait(done, 0);
+    tc_fence_after();
+    if (any) {
+      const int half = row >> 6, kk = row & 63;
+      for (int ti = 0; ti < tk.ntaps; ++ti) {
+        const int kb = half ? (tk.stage1 >= 0 ? tk.kb1[ti] : -1) : tk.kb0[ti];
+        const uint32_t taddr = tmem_base + (uint32_t)(ti * N) + ((uint32_t)(q * 32) << 16);
+        for (int col = 0; col < N; col += 16) {
+          float vv[16];
+          tmem_ld16(taddr + (uint32_t)col, vv);
+          tmem_wait16(vv);
+          if (kb >= 0) {
+            float* dst = P.dWp + (int64_t)(tk.n0 + col) * cp.ktot + (int64_t)kb * LU_KBLK + kk;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) atomicAdd(dst + (int64_t)j * cp.ktot, vv[j]);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+#endif  // !LU_HOST_EMU

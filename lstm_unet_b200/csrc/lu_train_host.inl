@@ -133,6 +133,7 @@ static void train_layout(lu_handle_s* h, size_t& off) {
     cv.off_kb_stage = take(cv.kb_stage.size() * 2);
     cv.off_kb_tap = take(cv.kb_tap.size() * 2);
     cv.off_bwd_sums = take((size_t)cv.npad * 2 * 8);
+    cv.off_wg_tasks = take((size_t)2 * LU_WG_MAX_TASKS * 96);
     const size_t b = (size_t)cv.npad * cv.ktot * 4;
     if (b > dwp) dwp = b;
     if (cv.kind == LU_EPI_LSTM) {
@@ -188,12 +189,96 @@ static void run_colsum(lu_handle_s* h, int gbuf, int frames_used, float* dst, in
   pf(h, ((cs.npix + cs.chunk - 1) / cs.chunk) * g.cpad, stream, cs);
 }
 
-// weight gradient of forward conv f from the upstream gradient buffer gbuf (packed space, scalar engine)
+#ifndef LU_HOST_EMU
+// ---- tcgen05 weight gradient: task list for one forward conv (see lu_wgrad_tc_kernel) --------------------------------
+static void build_wg_tasks(lu_handle_s* h, const ConvPlan& f, int frames, int only_src, std::vector<LuWgTask>& out) {
+  const bool x3 = h->planes == 2;
+  const int tiles = frames * ((f.Hout + LU_TILE_H - 1) / LU_TILE_H) * ((f.Wout + LU_TILE_W - 1) / LU_TILE_W);
+  // K block index of the first tap of every stage
+  std::vector<int> kb_begin(f.astages.size());
+  { int kb = 0; for (size_t s = 0; s < f.astages.size(); ++s) { kb_begin[s] = kb; kb += f.astages[s].ntaps; } }
+  struct Base { int s0, s1; std::vector<int> taps; int a_is_lo; };
+  std::vector<Base> bases;
+  std::vector<char> used(f.astages.size(), 0);
+  auto valid_taps = [&](int s) {
+    std::vector<int> t;
+    for (int i = 0; i < f.astages[s].ntaps; ++i) if (f.packs[kb_begin[s] + i].wpart == 0) t.push_back(i);
+    return t;
+  };
+  auto a_is_lo = [&](int s) {
+    const LuAStage& st = f.astages[s];
+    const int buf = f.view_buf[st.src];
+    if (!x3 || buf < 0) return 0;
+    const ActBuf& ab = h->acts[buf];
+    const int ctot = ab.cpad * ab.planes;
+    return ((st.c % ctot) >= ab.cpad) ? 1 : 0;
+  };
+  for (size_t s = 0; s < f.astages.size(); ++s) {
+    if (used[s]) continue;
+    const LuAStage& a = f.astages[s];
+    if (only_src >= 0 && a.src != only_src) continue;
+    Base b; b.s0 = (int)s; b.s1 = -1; b.taps = valid_taps((int)s); b.a_is_lo = a_is_lo((int)s);
+    used[s] = 1;
+    for (size_t s2 = s + 1; s2 < f.astages.size() && b.s1 < 0; ++s2) {
+      if (used[s2]) continue;
+      const LuAStage& c = f.astages[s2];
+      if (c.src != a.src || c.plane != a.plane || c.dy != a.dy || c.dx != a.dx || a_is_lo((int)s2) != b.a_is_lo) continue;
+      std::vector<int> t2 = valid_taps((int)s2);
+      if (t2.size() != b.taps.size()) continue;
+      bool same = true;
+      for (size_t i = 0; i < t2.size() && same; ++i)
+        same = f.taps[c.tap_begin + t2[i]] == f.taps[a.tap_begin + b.taps[i]];
+      if (!same) continue;
+      b.s1 = (int)s2; used[s2] = 1;
+    }
+    if (!b.taps.empty()) bases.push_back(b);
+  }
+  // output-column slabs: 64-column chunks that exist in dY
+  const int nch_max = x3 ? 1 : 2;
+  std::vector<std::pair<int, int>> slabs;      // (first chunk, number of chunks)
+  const int n_chunks = f.kind == LU_EPI_LSTM ? f.npad / 64 : ceil_to(f.cout, 64) / 64;
+  for (int c = 0; c < n_chunks; c += nch_max) slabs.push_back({c, (n_chunks - c) < nch_max ? (n_chunks - c) : nch_max});
+  int base_tasks = 0;
+  for (auto& b : bases) base_tasks += (int)((b.taps.size() + 3) / 4) * (int)slabs.size();
+  int split = (4 * h->num_sms + base_tasks - 1) / (base_tasks > 0 ? base_tasks : 1);
+  if (split < 1) split = 1;
+  if (split > tiles) split = tiles;
+  for (auto& b : bases)
+    for (size_t t0 = 0; t0 < b.taps.size(); t0 += 4)
+      for (auto& sl : slabs)
+        for (int sp = 0; sp < split; ++sp) {
+          LuWgTask tk; memset(&tk, 0, sizeof tk);
+          tk.stage0 = (int16_t)b.s0; tk.stage1 = (int16_t)b.s1; tk.a_is_lo = (int16_t)b.a_is_lo;
+          tk.ntaps = (int16_t)((b.taps.size() - t0) < 4 ? (b.taps.size() - t0) : 4);
+          for (int i = 0; i < tk.ntaps; ++i) {
+            const int ti = b.taps[t0 + i];
+            tk.off[i] = f.taps[f.astages[b.s0].tap_begin + ti];
+            tk.kb0[i] = kb_begin[b.s0] + ti;
+            tk.kb1[i] = b.s1 >= 0 ? kb_begin[b.s1] + ti : -1;
+          }
+          tk.n0 = sl.first * 64; tk.nch = sl.second;
+          for (int c = 0; c < sl.second; ++c) {
+            const int ci = sl.first + c;
+            tk.ychan[c] = f.kind == LU_EPI_LSTM ? (ci % 4) * f.fpad + (ci / 4) * 64 : ci * 64;
+          }
+          tk.tile0 = (int)((int64_t)tiles * sp / split); tk.tile1 = (int)((int64_t)tiles * (sp + 1) / split);
+          if (tk.tile1 > tk.tile0) out.push_back(tk);
+        }
+}
+#endif
+
+// weight gradient of forward conv f from the upstream gradient buffer gbuf, in packed space:
+// tcgen05 kernel (product) or the scalar mirror (engine=simt / host test build)
 static int run_wgrad(lu_handle_s* h, ConvPlan& f, int gbuf, int T, float* grads, void* stream) {
   const ActBuf& g = h->acts[gbuf];
   float* dwp = reinterpret_cast<float*>(h->ws + h->tr_off_dwp);
   LU_MEMSET(dwp, 0, (size_t)f.npad * f.ktot * 4, stream);
   const int n_launch = f.kind == LU_EPI_LSTM ? 2 : 1;
+  // LU_WGRAD_ENGINE=simt forces the scalar engine for the weight gradient only (test hook: same forward, same
+  // upstream gradients, so the two weight-gradient engines can be compared without activation-kink noise)
+  const char* wg_env = getenv("LU_WGRAD_ENGINE");
+  const bool use_tc = h->cfg.engine == LU_ENGINE_TCGEN05 && h->cfg.a_mode == LU_AMODE_HALO &&
+                      !(wg_env && strcmp(wg_env, "simt") == 0);
   for (int pass = 0; pass < n_launch; ++pass) {
     LuWgradMirror w; memset(&w, 0, sizeof w);
     for (int i = 0; i < f.n_views; ++i) {
@@ -218,6 +303,44 @@ static int run_wgrad(lu_handle_s* h, ConvPlan& f, int gbuf, int T, float* grads,
         w.dy_frame_mul = T; w.dy_frame_add = 0;
       }
     }
+#ifndef LU_HOST_EMU
+    if (use_tc) {
+      std::vector<LuWgTask> tasks;
+      build_wg_tasks(h, f, w.frames, w.only_src, tasks);
+      if (tasks.empty()) continue;
+      LU_REQUIRE(tasks.size() <= (size_t)LU_WG_MAX_TASKS, "too many weight-gradient tasks (%zu)", tasks.size());
+      LuWgTask* dtasks = reinterpret_cast<LuWgTask*>(h->ws + f.off_wg_tasks) + (size_t)pass * LU_WG_MAX_TASKS;
+      cudaError_t e = cudaMemcpyAsync(dtasks, tasks.data(), tasks.size() * sizeof(LuWgTask), cudaMemcpyHostToDevice, (cudaStream_t)stream);
+      LU_REQUIRE(e == cudaSuccess, "task upload: %s", cudaGetErrorString(e));
+      e = cudaStreamSynchronize((cudaStream_t)stream);          // the host vector dies at scope exit
+      LU_REQUIRE(e == cudaSuccess, "task upload sync: %s", cudaGetErrorString(e));
+      LuWgParams wp; memset(&wp, 0, sizeof wp);
+      for (int i = 0; i < f.n_views; ++i) wp.tmA[i] = f.tmA[i];
+      if (pass == 1) wp.tmA[1] = f.tmHstate[h->hcur ^ 1];
+      wp.tmY = h->acts_tm[gbuf];
+      wp.cp = w.p;
+      wp.tasks = dtasks; wp.dWp = dwp;
+      wp.tiles_x = (f.Wout + LU_TILE_W - 1) / LU_TILE_W; wp.tiles_y = (f.Hout + LU_TILE_H - 1) / LU_TILE_H;
+      wp.T = T; wp.skip_t0_src = w.skip_t0_src;
+      wp.dy_frame_mul = (int)w.dy_frame_mul; wp.dy_frame_add = (int)w.dy_frame_add; wp.dy_planes = g.planes; wp.dy_cpad = g.cpad;
+      wp.a_win_bytes = f.a_bytes; wp.stage_bytes = 2 * f.a_bytes + 4 * 16384;
+      const int budget = 232448 - 1024 - 256;
+      wp.n_stages = budget / wp.stage_bytes;
+      if (wp.n_stages > 3) wp.n_stages = 3;
+      LU_REQUIRE(wp.n_stages >= 1, "weight-gradient stage does not fit shared memory");
+      static bool attr = false;
+      if (!attr) {
+        e = cudaFuncSetAttribute(lu_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+        LU_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        attr = true;
+      }
+      h->launches++;
+      lu_wgrad_tc_kernel<<<(unsigned)tasks.size(), 256, wp.n_stages * wp.stage_bytes + 1024 + 256, (cudaStream_t)stream>>>(wp);
+      e = cudaGetLastError();
+      LU_REQUIRE(e == cudaSuccess, "wgrad launch (%s) failed: %s", f.name.c_str(), cudaGetErrorString(e));
+      continue;
+    }
+#endif
     const int64_t npix = (int64_t)w.frames * w.H * w.W;
     const int64_t nchunk = (npix + w.chunk - 1) / w.chunk;
     pf(h, (int64_t)f.ktot * (f.npad / 16) * nchunk, stream, w);

@@ -84,3 +84,44 @@ def test_inference2d_mirror_streaming_matches_oracle(tmp_path):
     ref = [ora(torch.from_numpy(f).reshape(1, 1, 1, 20, 28), False)[1][0, 0].numpy() for f in seq][2:]
     for a, b in zip(outs, ref):
         assert np.abs(a - b).max() < 1e-3
+
+
+@pytest.mark.parametrize("precision,tol", [('bf16x3', 5e-5), ('bf16', 5e-5)])
+def test_wgrad_tcgen05_matches_scalar_wgrad_wide(precision, tol):
+    """Weight gradients of a network with full 64-channel chunks (pairs of activation stages, 128-column slabs,
+    stride-2 parity planes, two-source convs, patches): the tcgen05 weight-gradient kernel vs the scalar engine on the
+    SAME forward activations and upstream gradients (LU_WGRAD_ENGINE switches only the weight-gradient engine; the
+    backward is idempotent), so the comparison is free of activation-kink noise.  Both accumulate the same bf16
+    products in fp32; only the summation order differs."""
+    import os
+    from lstm_unet_b200.Networks import ULSTMnet2D
+    net = {'down_conv_kernels': [[(3, 64), (3, 64)], [(3, 128), (3, 128)], [(3, 192), (3, 192)]],
+           'lstm_kernels': [[(5, 64)], [(5, 128)], [(3, 192)]],
+           'up_conv_kernels': [[(3, 128), (3, 128)], [(3, 64), (3, 64)], [(3, 32), (3, 32), (1, 3)]]}
+    params = O.init_params(net, seed=2, randomize_bn=True)
+    rng = np.random.default_rng(0)
+    B, T, H, W = 2, 3, 48, 40
+    m = ULSTMnet2D(net, 'NCHW', False, precision=precision, train=True)
+    m.set_weights_dict({k: v.numpy().copy() for k, v in params.items()})
+    for call in range(2):                       # second call: non-zero initial states (h_init pass of the recurrent wgrad)
+        x = rng.standard_normal((B, T, 1, H, W)).astype(np.float32)
+        lab = rng.integers(-1, 3, size=(B, T, 1, H, W)).astype(np.float32)
+        m(x, True)
+        os.environ.pop('LU_WGRAD_ENGINE', None)
+        l1, g = m.backward(lab, CW)
+        g1 = g.cpu().numpy().copy()
+        os.environ['LU_WGRAD_ENGINE'] = 'simt'
+        try:
+            l0, g = m.backward(lab, CW)
+            g0 = g.cpu().numpy().copy()
+        finally:
+            os.environ.pop('LU_WGRAD_ENGINE', None)
+        assert float(l0) == float(l1)
+        for e in m._sess.layout:
+            if not e['trainable']:
+                continue
+            a, b = g0[e['offset']:e['offset'] + e['count']], g1[e['offset']:e['offset'] + e['count']]
+            scale = np.abs(a).max()
+            if scale < 1e-6 or (e['name'].endswith('bias') and scale < 1e-4):
+                continue          # conv biases in front of a BatchNorm: analytically zero, atomics-order noise
+            assert np.abs(a - b).max() / scale < tol, (call, e['name'], np.abs(a - b).max() / scale)
