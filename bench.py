@@ -147,15 +147,35 @@ def run_ours(args):
     B, T, H, W = args.batch, args.unroll, args.size, args.size
     training = args.mode == 'train'
     model = ULSTMnet2D(CTC_NET, 'NCHW', pad_image=not training, precision=args.precision, a_mode=args.a_mode,
-                       seed=rank)
+                       seed=0 if training else rank, train=training)
     rng = np.random.default_rng(1234 + rank)
     x_host = rng.standard_normal((B, T, 1, H, W)).astype(np.float32)
     x_dev = torch.from_numpy(x_host).cuda()
+    if training:
+        # config 3/4: full train step = forward(training=True) + weighted CE + backward + (N>1: one NCCL all-reduce of
+        # the flat gradients) + Keras Adam; same initial weights on every rank (seed 0), batch-sharded data
+        from lstm_unet_b200.Networks import Adam
+        from lstm_unet_b200.parallel import all_reduce_mean_
+        lab_host = rng.integers(-1, 3, size=(B, T, 1, H, W)).astype(np.float32)
+        lab_dev = torch.from_numpy(lab_host).cuda()
+        opt = Adam(lr=1e-5)
+        cw = [0.15, 0.25, 0.6]
+        fwd = model
+
+        class _Step:
+            def __call__(self, x, tr):
+                lab = lab_dev if x.__class__ is not np.ndarray else lab_host
+                sm, lg, loss = fwd.train_step(x, lab, cw, opt, all_reduce_mean_ if world > 1 else None)
+                return loss, sm
+        step_fn = _Step()
+    else:
+        step_fn = None
+    run = (lambda x, tr: step_fn(x, tr)) if training else (lambda x, tr: model(x, tr))
     # shard by batch: every rank owns its B samples and their recurrent states (weak scaling, no data-path collective)
-    model(x_dev, training)
+    run(x_dev, training)
     torch.cuda.synchronize()
     sess = model._sess
-    flops_step = sess.forward_flops(T) * B
+    flops_step = sess.forward_flops(T) * B * (3 if training else 1)     # train step = 3 x forward
     lstm_flops_step = sess.lstm_flops(T) * B
 
     def barrier():
@@ -164,7 +184,7 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     for _ in range(args.warmup):
-        model(x_dev, training)
+        run(x_dev, training)
     barrier()
     sess.launch_count(reset=True)
     sess.lstm_kernel_time(True)
@@ -174,7 +194,7 @@ def run_ours(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):
-        model(x_dev, training)        # states carry over between iterations, like the train / inference loops
+        run(x_dev, training)          # states carry over between iterations, like the train / inference loops
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
@@ -183,15 +203,19 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
 
     # end to end through the public API with host buffers: pinned H2D of the frames + D2H of the soft-max
+    def e2e_once():
+        out = run(x_host, training)
+        # inference: D2H of the soft-max (Inference2D.py:60); training: D2H of the loss (train2D.py:103 -> metrics)
+        return out[1].numpy() if not training else np.asarray(float(out[0]), dtype=np.float32)
     for _ in range(2):
-        model(x_host, training)[1].numpy()
+        e2e_once()
     barrier()
     t0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     e2e_steps = max(2, min(args.steps, 5))
     for _ in range(e2e_steps):
-        sm = model(x_host, training)[1].numpy()
+        sm = e2e_once()
     e1.record()
     barrier()
     e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3 * 0.0)
@@ -215,18 +239,20 @@ def run_ours(args):
         'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'bf16' if args.precision == 'bf16' else 'bf16x3(split-bf16, fp32-equivalent)', 'data': 'synthetic',
-        'config': {'workload': 'C2: ConvLSTM-UNet (CTCParams net, 74.6M params) %s forward, %dx%d, T=%d, batch %d per GPU, '
-                               'pad_image=%s, stateful' % ('training-mode' if training else 'inference', H, W, T, B, not training),
+        'config': {'workload': '%s: ConvLSTM-UNet (CTCParams net, 74.6M params) %s, %dx%d, T=%d, batch %d per GPU, '
+                               'pad_image=%s, stateful' % ('C3' if training else 'C2', 'full train step (fwd+loss+bwd+Adam)' if training
+                                                           else 'inference forward', H, W, T, B, not training),
                    'global_batch': B * world, 'parallelism': 'batch-sharded replicas x%d (no data-path collective)' % world,
                    'l2_policy': 'inputs+activations per step (>6 GB) exceed the 126 MB L2; no flush needed',
                    'a_mode': args.a_mode, 'step_tflop': flops_step / 1e12},
-        'e2e': {'value': e2e_value, 'unit': 'frames/s', 'h2d_bytes_per_step': int(x_host.nbytes),
+        'e2e': {'value': e2e_value, 'unit': 'frames/s',
+                'h2d_bytes_per_step': int(x_host.nbytes) * (2 if training else 1),
                 'd2h_bytes_per_step': int(sm.nbytes), 'steps': e2e_steps, 'ms_per_step': e2e_wall_ms / e2e_steps},
         'gpu_launches': int(launches),
         'clocks': clocks,
         'roofline': {'bound': 'tensor', 'achieved': lstm_tflops, 'peak': sustained, 'unit': 'TFLOP/s',
                      'frac': (lstm_tflops / sustained) if lstm_tflops else None, 'traffic': None,
-                     'kernel': 'lu_conv_tc_kernel<LSTM> (all 4 ConvLSTM levels, %d launches)' % lstm_n,
+                     'kernel': 'lu_conv_tc_kernel<LSTM> forward launches (all 4 ConvLSTM levels, %d launches)' % lstm_n,
                      'kernel_ms_per_step': lstm_ms / args.steps, 'kernel_share_of_step': lstm_ms / ms if ms else None,
                      'peak_source': which + ' bf16_tflops_sustained (kernel timed inside a long step); burst %.1f' % burst,
                      'whole_step_tflops': flops_step * args.steps / (ms * 1e-3) / 1e12},

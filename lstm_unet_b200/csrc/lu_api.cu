@@ -100,7 +100,7 @@ struct ConvPlan {
   int dz_buf = -1;                      // lstm: gradient wrt the gate pre-activations (frames,H,W,4*fpad)
   std::vector<int> dgrads[2];
   std::vector<uint16_t> kb_stage, kb_tap;
-  size_t off_kb_stage = 0, off_kb_tap = 0, off_bwd_sums = 0, off_c_init = 0, off_dc = 0, off_wg_tasks = 0;
+  size_t off_kb_stage = 0, off_kb_tap = 0, off_bwd_sums = 0, off_c_init = 0, off_dc = 0, off_wg_tasks = 0, off_bwd_means = 0;
 #ifndef LU_HOST_EMU
   CUtensorMap tmA[LU_MAX_SRC];
   CUtensorMap tmB;

@@ -95,6 +95,40 @@ LU_HDI void lu_stplanes(uint16_t* p, int cpad, int planes, float v) {
   if (planes == 2) p[cpad] = lo;
 }
 
+// 8 consecutive channels of a hi[/lo] planes buffer
+LU_HDI void lu_ld8planes(const uint16_t* p, int cpad, int planes, float* v) {
+  lu_load8_bf16(p, v);
+  if (planes == 2) {
+    float t[8];
+    lu_load8_bf16(p + cpad, t);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] += t[j];
+  }
+}
+LU_HDI void lu_st8planes(uint16_t* p, int cpad, int planes, const float* v) {
+  uint16_t hi[8], lo[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) lu_split(v[j], hi[j], lo[j]);
+  lu_store8_bf16(p, hi);
+  if (planes == 2) lu_store8_bf16(p + cpad, lo);
+}
+LU_HDI void lu_ld8f(const float* p, float* v) {
+#ifdef __CUDA_ARCH__
+  const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+#else
+  for (int j = 0; j < 8; ++j) v[j] = p[j];
+#endif
+}
+LU_HDI void lu_st8f(float* p, const float* v) {
+#ifdef __CUDA_ARCH__
+  reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+#else
+  for (int j = 0; j < 8; ++j) p[j] = v[j];
+#endif
+}
+
 // ---- BatchNorm (training) + LeakyReLU backward ------------------------------------------------------------------
 // g = dA * lrelu'(bn_out); sums: [0:cpad) = sum g, [cpad:2cpad) = sum g * xhat        item = (pixel chunk, channel)
 struct LuBnBwdReduce {
@@ -116,29 +150,48 @@ struct LuBnBwdReduce {
   }
 };
 // dRaw = scale * (g - sum_g/n - xhat * sum_gx/n), written IN PLACE over dA; item = (pixel, channel)
-struct LuBnBwdApply {
+struct LuBnBwdApply {    // item = (pixel, group of 8 channels); means = [mean g | mean g*xhat] per channel (fp32)
   uint16_t* dA; const float* raw; const float* scale; const float* shift; const float* mean; const float* invstd;
-  const double* sums; int64_t npix; int cpad, planes, raw_cpad, c_real; float alpha;
+  const float* means; int64_t npix; int cpad, planes, raw_cpad, c_real; float alpha;
   LU_HD void operator()(int64_t i) const {
-    const int c = (int)(i % cpad); const int64_t p = i / cpad;
+    const int cg = cpad / 8;
+    const int c = (int)(i % cg) * 8; const int64_t p = i / cg;
     uint16_t* o = dA + p * (int64_t)(cpad * planes) + c;
-    float d = 0.f;
-    if (c < c_real) {
-      const float r = raw[p * raw_cpad + c];
-      const float bn = r * scale[c] + shift[c];
-      const float g = lu_ldplanes(o, cpad, planes) * (bn > 0.f ? 1.f : alpha);
-      const float xh = (r - mean[c]) * invstd[c];
-      d = scale[c] * (g - (float)(sums[c] / (double)npix) - xh * (float)(sums[raw_cpad + c] / (double)npix));
+    float g[8], d[8];
+    lu_ld8planes(o, cpad, planes, g);
+    if (c + 8 <= c_real) {
+      float r[8], sc[8], sh[8], mu[8], is[8], mg[8], mx[8];
+      lu_ld8f(raw + p * raw_cpad + c, r); lu_ld8f(scale + c, sc); lu_ld8f(shift + c, sh); lu_ld8f(mean + c, mu);
+      lu_ld8f(invstd + c, is); lu_ld8f(means + c, mg); lu_ld8f(means + raw_cpad + c, mx);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float bn = r[j] * sc[j] + sh[j];
+        const float gg = g[j] * (bn > 0.f ? 1.f : alpha);
+        d[j] = sc[j] * (gg - mg[j] - (r[j] - mu[j]) * is[j] * mx[j]);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        d[j] = 0.f;
+        if (c + j < c_real) {
+          const float r = raw[p * raw_cpad + c + j];
+          const float bn = r * scale[c + j] + shift[c + j];
+          const float gg = g[j] * (bn > 0.f ? 1.f : alpha);
+          d[j] = scale[c + j] * (gg - means[c + j] - (r - mean[c + j]) * invstd[c + j] * means[raw_cpad + c + j]);
+        }
+      }
     }
-    lu_stplanes(o, cpad, planes, d);
+    lu_st8planes(o, cpad, planes, d);
   }
 };
-struct LuBnBwdParams {   // dgamma = sum g*xhat, dbeta = sum g; item = channel
-  const double* sums; float* dgamma; float* dbeta; int raw_cpad, c_real;
+struct LuBnBwdParams {   // dgamma = sum g*xhat, dbeta = sum g, per-channel means for the apply pass; item = channel
+  const double* sums; float* dgamma; float* dbeta; float* means; int64_t npix; int raw_cpad, c_real;
   LU_HD void operator()(int64_t c) const {
-    if (c >= c_real) return;
+    if (c >= c_real) { means[c] = 0.f; means[raw_cpad + c] = 0.f; return; }
     dbeta[c] = (float)sums[c];
     dgamma[c] = (float)sums[raw_cpad + c];
+    means[c] = (float)(sums[c] / (double)npix);
+    means[raw_cpad + c] = (float)(sums[raw_cpad + c] / (double)npix);
   }
 };
 
@@ -155,54 +208,76 @@ struct LuUpsample2xBwd {   // item = (n, iy, ix, c)
     if (j == n - 1) { idx[k] = 2 * n - 1; wt[k++] = 0.25f; }     // clamped i+1 at the last output
     return k;
   }
-  LU_HD void operator()(int64_t i) const {
-    const int c = (int)(i % cpad); int64_t p = i / cpad;
+  LU_HD void operator()(int64_t i) const {          // item = (n, iy, ix, group of 8 channels)
+    const int cg = cpad / 8;
+    const int c = (int)(i % cg) * 8; int64_t p = i / cg;
     const int ix = (int)(p % w); p /= w; const int iy = (int)(p % h); const int64_t n = p / h;
     int yi[6], xi[6]; float yw[6], xw[6];
     const int ny = taps1d(iy, h, yi, yw), nx = taps1d(ix, w, xi, xw);
     const int ct = cpad * planes;
-    float s = 0.f;
+    float s[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = 0.f;
     for (int a = 0; a < ny; ++a)
-      for (int b = 0; b < nx; ++b)
-        s += yw[a] * xw[b] * lu_ldplanes(gup + (((n * 2 * h + yi[a]) * 2 * w) + xi[b]) * (int64_t)ct + c, cpad, planes);
+      for (int b = 0; b < nx; ++b) {
+        float t[8];
+        lu_ld8planes(gup + (((n * 2 * h + yi[a]) * 2 * w) + xi[b]) * (int64_t)ct + c, cpad, planes, t);
+        const float wgt = yw[a] * xw[b];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s[j] += wgt * t[j];
+      }
     uint16_t* o = gsrc + ((n * h + iy) * w + ix) * (int64_t)ct + c;
-    if (accumulate) s += lu_ldplanes(o, cpad, planes);
-    lu_stplanes(o, cpad, planes, s);
+    if (accumulate) {
+      float t[8];
+      lu_ld8planes(o, cpad, planes, t);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s[j] += t[j];
+    }
+    lu_st8planes(o, cpad, planes, s);
   }
 };
 
 // ---- ConvLSTM cell backward for one time step ----------------------------------------------------------------------
 // item = (sample pixel, channel < fpad).  gates: (frames,H,W,planes*4*fpad) [i|f|g|o]; dZ same layout (bf16 planes).
-struct LuLstmCellBwd {
+struct LuLstmCellBwd {    // item = (sample pixel, group of 8 channels)
   const uint16_t* dH; const uint16_t* gates; const float* c_t; const float* c_prev; float* dC; uint16_t* dZ;
   int64_t pix_per_sample; int T, t, fpad, planes, gate_kind, c_prev_is_init, first;
   LU_HD void operator()(int64_t i) const {
-    const int ch = (int)(i % fpad); const int64_t sp = i / fpad;            // sp = b*HW + pixel
+    const int cg = fpad / 8;
+    const int ch = (int)(i % cg) * 8; const int64_t sp = i / cg;            // sp = b*HW + pixel
     const int64_t b = sp / pix_per_sample, px = sp % pix_per_sample;
     const int64_t fp = (b * T + t) * pix_per_sample + px;                   // pixel index in frame-major buffers
     const int g4 = 4 * fpad;
     const uint16_t* gp = gates + fp * (int64_t)(g4 * planes) + ch;
-    const float gi = lu_ldplanes(gp, g4, planes), gf = lu_ldplanes(gp + fpad, g4, planes);
-    const float gg = lu_ldplanes(gp + 2 * fpad, g4, planes), go = lu_ldplanes(gp + 3 * fpad, g4, planes);
-    const float ct = c_t[fp * fpad + ch];
-    const float cp = c_prev_is_init ? c_prev[sp * fpad + ch] : c_prev[(fp - pix_per_sample) * fpad + ch];
-    const float dh = lu_ldplanes(dH + fp * (int64_t)(fpad * planes) + ch, fpad, planes);
-    const float th = tanhf(ct);
-    float dc = (first ? 0.f : dC[sp * fpad + ch]) + dh * go * (1.f - th * th);
-    const float d_o = dh * th, d_i = dc * gg, d_g = dc * gi, d_f = dc * cp;
-    dC[sp * fpad + ch] = dc * gf;
-    float zi, zf, zo;
-    if (gate_kind == 0) {
-      zi = (gi > 0.f && gi < 1.f) ? 0.2f * d_i : 0.f;
-      zf = (gf > 0.f && gf < 1.f) ? 0.2f * d_f : 0.f;
-      zo = (go > 0.f && go < 1.f) ? 0.2f * d_o : 0.f;
-    } else {
-      zi = d_i * gi * (1.f - gi); zf = d_f * gf * (1.f - gf); zo = d_o * go * (1.f - go);
+    float gi[8], gf[8], gg[8], go[8], ct[8], cp[8], dh[8], dc[8], zi[8], zf[8], zg[8], zo[8];
+    lu_ld8planes(gp, g4, planes, gi); lu_ld8planes(gp + fpad, g4, planes, gf);
+    lu_ld8planes(gp + 2 * fpad, g4, planes, gg); lu_ld8planes(gp + 3 * fpad, g4, planes, go);
+    lu_ld8f(c_t + fp * fpad + ch, ct);
+    lu_ld8f(c_prev_is_init ? c_prev + sp * fpad + ch : c_prev + (fp - pix_per_sample) * fpad + ch, cp);
+    lu_ld8planes(dH + fp * (int64_t)(fpad * planes) + ch, fpad, planes, dh);
+    if (first) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dc[j] = 0.f;
+    } else lu_ld8f(dC + sp * fpad + ch, dc);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float th = tanhf(ct[j]);
+      const float d = dc[j] + dh[j] * go[j] * (1.f - th * th);
+      const float d_o = dh[j] * th, d_i = d * gg[j], d_g = d * gi[j], d_f = d * cp[j];
+      dc[j] = d * gf[j];
+      if (gate_kind == 0) {
+        zi[j] = (gi[j] > 0.f && gi[j] < 1.f) ? 0.2f * d_i : 0.f;
+        zf[j] = (gf[j] > 0.f && gf[j] < 1.f) ? 0.2f * d_f : 0.f;
+        zo[j] = (go[j] > 0.f && go[j] < 1.f) ? 0.2f * d_o : 0.f;
+      } else {
+        zi[j] = d_i * gi[j] * (1.f - gi[j]); zf[j] = d_f * gf[j] * (1.f - gf[j]); zo[j] = d_o * go[j] * (1.f - go[j]);
+      }
+      zg[j] = d_g * (1.f - gg[j] * gg[j]);
     }
-    const float zg = d_g * (1.f - gg * gg);
+    lu_st8f(dC + sp * fpad + ch, dc);
     uint16_t* zp = dZ + fp * (int64_t)(g4 * planes) + ch;
-    lu_stplanes(zp, g4, planes, zi); lu_stplanes(zp + fpad, g4, planes, zf);
-    lu_stplanes(zp + 2 * fpad, g4, planes, zg); lu_stplanes(zp + 3 * fpad, g4, planes, zo);
+    lu_st8planes(zp, g4, planes, zi); lu_st8planes(zp + fpad, g4, planes, zf);
+    lu_st8planes(zp + 2 * fpad, g4, planes, zg); lu_st8planes(zp + 3 * fpad, g4, planes, zo);
   }
 };
 

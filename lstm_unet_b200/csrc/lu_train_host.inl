@@ -133,6 +133,7 @@ static void train_layout(lu_handle_s* h, size_t& off) {
     cv.off_kb_stage = take(cv.kb_stage.size() * 2);
     cv.off_kb_tap = take(cv.kb_tap.size() * 2);
     cv.off_bwd_sums = take((size_t)cv.npad * 2 * 8);
+    cv.off_bwd_means = take((size_t)cv.npad * 2 * 4);
     cv.off_wg_tasks = take((size_t)2 * LU_WG_MAX_TASKS * 96);
     const size_t b = (size_t)cv.npad * cv.ktot * 4;
     if (b > dwp) dwp = b;
@@ -368,12 +369,13 @@ static int bwd_conv_layer(lu_handle_s* h, ConvPlan& f, int T, float* grads, std:
     pf(h, ((npix + r.chunk - 1) / r.chunk) * f.raw_cpad, stream, r);
     LuBnBwdParams bp;
     bp.sums = sums; bp.dgamma = grads + h->params[f.gamma].offset; bp.dbeta = grads + h->params[f.beta].offset;
-    bp.raw_cpad = f.raw_cpad; bp.c_real = f.cout;
-    pf(h, f.cout, stream, bp);
+    bp.raw_cpad = f.raw_cpad; bp.c_real = f.cout; bp.npix = npix;
+    bp.means = reinterpret_cast<float*>(h->ws + f.off_bwd_means);
+    pf(h, f.raw_cpad, stream, bp);
     LuBnBwdApply a;
     a.dA = act_ptr(h, gbuf); a.raw = r.raw; a.scale = r.scale; a.shift = r.shift; a.mean = r.mean; a.invstd = r.invstd;
-    a.sums = sums; a.npix = npix; a.cpad = gb.cpad; a.planes = gb.planes; a.raw_cpad = f.raw_cpad; a.c_real = f.cout; a.alpha = 0.3f;
-    pf(h, npix * gb.cpad, stream, a);
+    a.means = bp.means; a.npix = npix; a.cpad = gb.cpad; a.planes = gb.planes; a.raw_cpad = f.raw_cpad; a.c_real = f.cout; a.alpha = 0.3f;
+    pf(h, npix * (gb.cpad / 8), stream, a);
   }
   run_colsum(h, gbuf, N, grads + h->params[f.bias_param].offset, f.cout, 0, 0, stream);
   if (run_wgrad(h, f, gbuf, T, grads, stream)) return 1;
@@ -400,7 +402,7 @@ static int bwd_lstm_layer(lu_handle_s* h, ConvPlan& f, int T, float* grads, std:
     c.dC = reinterpret_cast<float*>(h->ws + f.off_dc); c.dZ = act_ptr(h, f.dz_buf);
     c.pix_per_sample = pps; c.T = T; c.t = t; c.fpad = f.fpad; c.planes = h->planes; c.gate_kind = h->cfg.gate;
     c.first = t == T - 1;
-    pf(h, (int64_t)B * pps * f.fpad, stream, c);
+    pf(h, (int64_t)B * pps * (f.fpad / 8), stream, c);
     if (t > 0)                              // dh_{t-1} += conv^T(dz_t, recurrent_kernel)
       if (run_dgrads(h, f, 1, B, T, t, T, t - 1, 1, gwritten, stream)) return 1;
   }
@@ -460,7 +462,7 @@ static int train_loss_backward(lu_handle_s* h, const float* labels, const float*
       LuUpsample2xBwd ub;
       ub.gup = act_ptr(h, gd); ub.gsrc = act_ptr(h, gs); ub.h = s.H; ub.w = s.W; ub.cpad = s.cpad; ub.planes = s.planes;
       ub.accumulate = gwritten[gs] ? 1 : 0;
-      pf(h, (int64_t)h->cfg.batch * T * s.H * s.W * s.cpad, stream, ub);
+      pf(h, (int64_t)h->cfg.batch * T * s.H * s.W * (s.cpad / 8), stream, ub);
       gwritten[gs] = 1;
     }
   }
