@@ -34,6 +34,20 @@ CTC_NET = {   # Params.py:49-69
 }
 
 
+def lstm_traffic_bytes():
+    """DRAM bytes of one level-1 ConvLSTM launch from the committed `ncu --set full` summary (profiles/), or None."""
+    p = os.path.join(ROOT, 'profiles', 'r1_ncu_prof_lstm_l1.txt')
+    try:
+        tot = 0.0
+        for line in open(p):
+            f = line.split()
+            if f and f[0] in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
+                tot += float(f[2]) * {'Mbyte': 1e6, 'Gbyte': 1e9, 'Kbyte': 1e3, 'byte': 1.0}[f[1]]
+        return tot or None
+    except Exception:
+        return None
+
+
 def peaks():
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
@@ -251,7 +265,8 @@ def run_ours(args):
         'gpu_launches': int(launches),
         'clocks': clocks,
         'roofline': {'bound': 'tensor', 'achieved': lstm_tflops, 'peak': sustained, 'unit': 'TFLOP/s',
-                     'frac': (lstm_tflops / sustained) if lstm_tflops else None, 'traffic': None,
+                     'frac': (lstm_tflops / sustained) if lstm_tflops else None, 'traffic': lstm_traffic_bytes(),
+                     'traffic_note': 'DRAM bytes of one level-1 ConvLSTM launch (ncu --set full, profiles/r1_ncu_prof_lstm_l1.txt)',
                      'kernel': 'lu_conv_tc_kernel<LSTM> forward launches (all 4 ConvLSTM levels, %d launches)' % lstm_n,
                      'kernel_ms_per_step': lstm_ms / args.steps, 'kernel_share_of_step': lstm_ms / ms if ms else None,
                      'peak_source': which + ' bf16_tflops_sustained (kernel timed inside a long step); burst %.1f' % burst,

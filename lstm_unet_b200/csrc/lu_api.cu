@@ -685,7 +685,7 @@ static int launch_conv(lu_handle_s* h, ConvPlan& cv, int frames, const int* mul,
 #ifdef LU_HOST_EMU
   LU_FAIL("the tcgen05 engine does not exist in the host test build");
 #else
-  static bool attr_set[3] = {false, false, false};
+  static bool attr_set[6] = {false, false, false, false, false, false};
   LuTcParams tp;
   memset(&tp, 0, sizeof tp);
   for (int i = 0; i < cv.n_views; ++i) tp.tmA[i] = cv.tmA[i];
@@ -703,18 +703,18 @@ static int launch_conv(lu_handle_s* h, ConvPlan& cv, int frames, const int* mul,
   }
 
   int grid = tp.total_tiles < h->num_sms ? tp.total_tiles : h->num_sms;
-  const int ei = epi.kind;
+  const int ei = epi.kind * 2 + (cv.ptab_ok ? 1 : 0);
+  typedef void (*KernelFn)(const LuTcParams);
+  static const KernelFn kfn[6] = {lu_conv_tc_kernel<LU_EPI_CONV, false>, lu_conv_tc_kernel<LU_EPI_CONV, true>,
+                                  lu_conv_tc_kernel<LU_EPI_LSTM, false>, lu_conv_tc_kernel<LU_EPI_LSTM, true>,
+                                  lu_conv_tc_kernel<LU_EPI_GRAD, false>, lu_conv_tc_kernel<LU_EPI_GRAD, true>};
   if (!attr_set[ei]) {
-    cudaError_t e = ei == LU_EPI_LSTM ? cudaFuncSetAttribute(lu_conv_tc_kernel<LU_EPI_LSTM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448)
-                  : ei == LU_EPI_GRAD ? cudaFuncSetAttribute(lu_conv_tc_kernel<LU_EPI_GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448)
-                                      : cudaFuncSetAttribute(lu_conv_tc_kernel<LU_EPI_CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    cudaError_t e = cudaFuncSetAttribute(kfn[ei], cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     LU_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set[ei] = true;
   }
   h->launches++;
-  if (ei == LU_EPI_LSTM) lu_conv_tc_kernel<LU_EPI_LSTM><<<grid, lutc::kThreads, cv.smem, (cudaStream_t)stream>>>(tp);
-  else if (ei == LU_EPI_GRAD) lu_conv_tc_kernel<LU_EPI_GRAD><<<grid, lutc::kThreads, cv.smem, (cudaStream_t)stream>>>(tp);
-  else lu_conv_tc_kernel<LU_EPI_CONV><<<grid, lutc::kThreads, cv.smem, (cudaStream_t)stream>>>(tp);
+  kfn[ei]<<<grid, lutc::kThreads, cv.smem, (cudaStream_t)stream>>>(tp);
   cudaError_t e = cudaGetLastError();
   LU_REQUIRE(e == cudaSuccess, "conv launch (%s) failed: %s", cv.name.c_str(), cudaGetErrorString(e));
   return 0;

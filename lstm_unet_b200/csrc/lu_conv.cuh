@@ -348,7 +348,7 @@ constexpr int kTmemCols = 512;
 
 }  // namespace lutc
 
-template <int EPI>
+template <int EPI, bool PTAB>
 __global__ void __launch_bounds__(lutc::kThreads, 1) lu_conv_tc_kernel(const __grid_constant__ LuTcParams P) {
   using namespace lutc;
   extern __shared__ uint8_t smem_raw[];
@@ -394,7 +394,7 @@ __global__ void __launch_bounds__(lutc::kThreads, 1) lu_conv_tc_kernel(const __g
 
   // The three issuing roles run with warp-uniform control flow (all 32 lanes walk the loops and wait on the
   // barriers); one elected lane issues the asynchronous instruction.
-  const bool ptab = P.tables_in_params != 0;
+  constexpr bool ptab = PTAB;
   if (warp == 0) {
     // ------------------------------------------------------------------ A producer (activation windows)
     int sa = 0; uint32_t ph = 0;
@@ -436,59 +436,61 @@ __global__ void __launch_bounds__(lutc::kThreads, 1) lu_conv_tc_kernel(const __g
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    int sa = 0, sb = 0, acc = 0; uint32_t pha = 0, phb = 0, phacc = 0;
-    const int G = P.b_group;
-    const uint32_t b_hi = desc_hi(1024u);
-    const uint32_t bn_bytes16 = (uint32_t)BN * 8u;            // one K block of weights, in 16-byte units
-    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-      mbar_wait(tmem_empty + 8u * acc, phacc ^ 1u);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-      uint32_t accum = 0;
-      int gi = 0;                                             // position inside the current weight group
-      uint32_t b_lo = 0;
-      for (int s = 0; s < cp.n_astages; ++s) {
-        const LuAStage st = ptab ? P.st_tab[s] : cp.astages[s];
-        const uint32_t a_hi = desc_hi((uint32_t)cp.src[st.src].pitch * 128u);
-        mbar_wait(full_a + 8u * sa, pha);
+    // One lane is elected ONCE and runs the whole loop nest (waits included); inside, everything it touches is
+    // warp-uniform by construction, so ptxas keeps descriptors in uniform registers and the per-tap cost is a
+    // handful of instructions.
+    if (elect_one()) {
+      int sa = 0, sb = 0, acc = 0; uint32_t pha = 0, phb = 0, phacc = 0;
+      const int G = P.b_group;
+      const uint32_t b_hi = desc_hi(1024u);
+      const uint32_t bn_bytes16 = (uint32_t)BN * 8u;            // one K block of weights, in 16-byte units
+      const uint32_t idesc = P.idesc;
+      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+        mbar_wait(tmem_empty + 8u * acc, phacc ^ 1u);
         tc_fence_after();
-        const uint32_t a_lo = desc_lo(sA + (uint32_t)sa * P.a_stage_bytes);
-        for (int t = 0; t < st.ntaps; ++t) {
-          // tap offset in rows of 128 bytes -> 16-byte units
-          const uint32_t off8 = (ptab ? (uint32_t)P.tap_tab[st.tap_begin + t] : (uint32_t)cp.taps[st.tap_begin + t]) * 8u;
-          if (gi == 0) {
-            mbar_wait(full_b + 8u * sb, phb);
-            tc_fence_after();
-            b_lo = desc_lo(sB + (uint32_t)sb * P.b_stage_bytes);
-          }
-          if (elect_one()) {
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        uint32_t accum = 0;
+        int gi = 0;                                             // position inside the current weight group
+        uint32_t b_lo = 0;
+        for (int s = 0; s < cp.n_astages; ++s) {
+          const LuAStage st = PTAB ? P.st_tab[s] : cp.astages[s];
+          const uint32_t a_hi = desc_hi((uint32_t)cp.src[st.src].pitch * 128u);
+          mbar_wait(full_a + 8u * sa, pha);
+          tc_fence_after();
+          const uint32_t a_lo = desc_lo(sA + (uint32_t)sa * P.a_stage_bytes);
+          const int ntaps = st.ntaps;
+          const uint32_t tb = st.tap_begin;
+          for (int t = 0; t < ntaps; ++t) {
+            // tap offset in rows of 128 bytes -> 16-byte units
+            const uint32_t off8 = (PTAB ? (uint32_t)P.tap_tab[tb + t] : (uint32_t)cp.taps[tb + t]) * 8u;
+            if (gi == 0) {
+              mbar_wait(full_b + 8u * sb, phb);
+              tc_fence_after();
+              b_lo = desc_lo(sB + (uint32_t)sb * P.b_stage_bytes);
+            }
 #pragma unroll
             for (int k = 0; k < LU_KBLK / 16; ++k)
-              mma_bf16(d_tmem, a_lo + off8 + 2u * k, a_hi, b_lo + 2u * k, b_hi, P.idesc, accum | (uint32_t)k);
+              mma_bf16(d_tmem, a_lo + off8 + 2u * k, a_hi, b_lo + 2u * k, b_hi, idesc, accum | (uint32_t)k);
+            accum = 1;
+            b_lo += bn_bytes16;
+            if (++gi == G) {
+              tc_commit(empty_b + 8u * sb);                     // frees the weight stage once its MMAs retire
+              gi = 0;
+              if (++sb == nB) { sb = 0; phb ^= 1u; }
+            }
           }
-          __syncwarp();
-          accum = 1;
-          b_lo += bn_bytes16;
-          if (++gi == G) {
-            if (elect_one()) tc_commit(empty_b + 8u * sb);     // frees the weight stage once its MMAs retire
-            __syncwarp();
-            gi = 0;
-            if (++sb == nB) { sb = 0; phb ^= 1u; }
-          }
+          tc_commit(empty_a + 8u * sa);                         // frees the activation window
+          if (++sa == nA) { sa = 0; pha ^= 1u; }
         }
-        if (elect_one()) tc_commit(empty_a + 8u * sa);         // frees the activation window
-        __syncwarp();
-        if (++sa == nA) { sa = 0; pha ^= 1u; }
+        if (gi != 0) {                                          // partial last weight group of the tile
+          tc_commit(empty_b + 8u * sb);
+          if (++sb == nB) { sb = 0; phb ^= 1u; }
+        }
+        tc_commit(tmem_full + 8u * acc);                        // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; phacc ^= 1u; }
       }
-      if (gi != 0) {                                           // partial last weight group of the tile
-        if (elect_one()) tc_commit(empty_b + 8u * sb);
-        __syncwarp();
-        if (++sb == nB) { sb = 0; phb ^= 1u; }
-      }
-      if (elect_one()) tc_commit(tmem_full + 8u * acc);        // accumulator complete -> epilogue
-      __syncwarp();
-      if (++acc == 2) { acc = 0; phacc ^= 1u; }
     }
+    __syncwarp();
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue: TMEM -> registers -> HBM
     const int q = warp & 3;                         // TMEM lane quarter this warp may access
