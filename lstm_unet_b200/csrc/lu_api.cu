@@ -103,7 +103,7 @@ struct ConvPlan {
   size_t off_kb_stage = 0, off_kb_tap = 0, off_bwd_sums = 0, off_c_init = 0, off_dc = 0, off_wg_tasks = 0, off_bwd_means = 0;
 #ifndef LU_HOST_EMU
   CUtensorMap tmA[LU_MAX_SRC];
-  CUtensorMap tmB;
+  CUtensorMap tmB, tmBh;
   CUtensorMap tmHstate[2];
 #endif
 };
@@ -685,7 +685,7 @@ static int launch_conv(lu_handle_s* h, ConvPlan& cv, int frames, const int* mul,
 #ifdef LU_HOST_EMU
   LU_FAIL("the tcgen05 engine does not exist in the host test build");
 #else
-  static bool attr_set[6] = {false, false, false, false, false, false};
+  static bool attr_set[7] = {false, false, false, false, false, false, false};
   LuTcParams tp;
   memset(&tp, 0, sizeof tp);
   for (int i = 0; i < cv.n_views; ++i) tp.tmA[i] = cv.tmA[i];
@@ -695,26 +695,45 @@ static int launch_conv(lu_handle_s* h, ConvPlan& cv, int frames, const int* mul,
   tp.n_a_stages = cv.nA; tp.n_b_stages = cv.nB; tp.a_stage_bytes = cv.a_bytes; tp.b_stage_bytes = cv.b_bytes;
   tp.b_group = cv.b_group;
   tp.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(cv.BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-  tp.total_tiles = (int)(m_tiles * cv.n_tiles_n);
+  // thread-block clusters of 2 (weight multicast) for the ConvLSTM launches; LU_CLUSTER=1 disables
+  static int cluster_env = -1;
+  if (cluster_env < 0) { const char* ce = getenv("LU_CLUSTER"); cluster_env = ce ? atoi(ce) : 2; }
+  const bool cl2 = cluster_env == 2 && epi.kind == LU_EPI_LSTM && cv.ptab_ok && (h->num_sms % 2 == 0);
+  tp.num_mt = (int)m_tiles;
+  tp.total_tiles = cl2 ? (int)(((m_tiles + 1) / 2) * cv.n_tiles_n) : (int)(m_tiles * cv.n_tiles_n);
+  tp.tmBh = cv.tmBh;
   tp.tables_in_params = cv.ptab_ok ? 1 : 0;
   if (cv.ptab_ok) {
     memcpy(tp.st_tab, cv.pstages.data(), cv.pstages.size() * sizeof(LuAStage));
     memcpy(tp.tap_tab, cv.ptaps.data(), cv.ptaps.size() * sizeof(uint16_t));
   }
-
-  int grid = tp.total_tiles < h->num_sms ? tp.total_tiles : h->num_sms;
-  const int ei = epi.kind * 2 + (cv.ptab_ok ? 1 : 0);
+  int grid = tp.total_tiles * (cl2 ? 2 : 1) < h->num_sms ? tp.total_tiles * (cl2 ? 2 : 1) : h->num_sms;
+  const int ei = cl2 ? 6 : epi.kind * 2 + (cv.ptab_ok ? 1 : 0);
   typedef void (*KernelFn)(const LuTcParams);
-  static const KernelFn kfn[6] = {lu_conv_tc_kernel<LU_EPI_CONV, false>, lu_conv_tc_kernel<LU_EPI_CONV, true>,
-                                  lu_conv_tc_kernel<LU_EPI_LSTM, false>, lu_conv_tc_kernel<LU_EPI_LSTM, true>,
-                                  lu_conv_tc_kernel<LU_EPI_GRAD, false>, lu_conv_tc_kernel<LU_EPI_GRAD, true>};
+  static const KernelFn kfn[7] = {lu_conv_tc_kernel<LU_EPI_CONV, false, 1>, lu_conv_tc_kernel<LU_EPI_CONV, true, 1>,
+                                  lu_conv_tc_kernel<LU_EPI_LSTM, false, 1>, lu_conv_tc_kernel<LU_EPI_LSTM, true, 1>,
+                                  lu_conv_tc_kernel<LU_EPI_GRAD, false, 1>, lu_conv_tc_kernel<LU_EPI_GRAD, true, 1>,
+                                  lu_conv_tc_kernel<LU_EPI_LSTM, true, 2>};
   if (!attr_set[ei]) {
     cudaError_t e = cudaFuncSetAttribute(kfn[ei], cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     LU_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set[ei] = true;
   }
   h->launches++;
-  kfn[ei]<<<grid, lutc::kThreads, cv.smem, (cudaStream_t)stream>>>(tp);
+  if (cl2) {
+    cudaLaunchConfig_t lc;
+    memset(&lc, 0, sizeof lc);
+    lc.gridDim = dim3((unsigned)grid); lc.blockDim = dim3(lutc::kThreads); lc.dynamicSmemBytes = cv.smem;
+    lc.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    lc.attrs = at; lc.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&lc, kfn[ei], tp);
+    LU_REQUIRE(e == cudaSuccess, "cluster launch (%s) failed: %s", cv.name.c_str(), cudaGetErrorString(e));
+  } else {
+    kfn[ei]<<<grid, lutc::kThreads, cv.smem, (cudaStream_t)stream>>>(tp);
+  }
   cudaError_t e = cudaGetLastError();
   LU_REQUIRE(e == cudaSuccess, "conv launch (%s) failed: %s", cv.name.c_str(), cudaGetErrorString(e));
   return 0;
@@ -809,6 +828,7 @@ int lu_bind_workspace(lu_handle h, void* dev_ws, size_t bytes, void* stream) {
           if (encode_view(&cv.tmHstate[s], v, h->ws + cv.off_hstate[s])) return 1;
         }
       if (encode_weights(&cv.tmB, h->ws + cv.off_w, cv.npad, cv.ktot, cv.BN)) return 1;
+      if (encode_weights(&cv.tmBh, h->ws + cv.off_w, cv.npad, cv.ktot, cv.BN / 2)) return 1;
     }
     if (h->cfg.train) {
       h->acts_tm.resize(h->acts.size());

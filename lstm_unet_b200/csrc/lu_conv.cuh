@@ -230,11 +230,13 @@ LU_HDI void lu_conv_mirror_item(const LuConvParams& p, int64_t item) {
 struct LuTcParams {
   CUtensorMap tmA[LU_MAX_SRC];
   CUtensorMap tmB;
+  CUtensorMap tmBh;              // half-height weight box (BN/2 rows): each CTA of a 2-CTA cluster multicasts one half
   LuConvParams cp;
   int32_t n_a_stages, n_b_stages, a_stage_bytes, b_stage_bytes;
   int32_t b_group;               // K blocks per weight stage (one mbarrier wait / commit per group)
   uint32_t idesc;
-  int32_t total_tiles;
+  int32_t total_tiles;           // work items: tiles (cluster 1) or pairs of M tiles sharing an N tile (cluster 2)
+  int32_t num_mt;                // number of M tiles (frames * tiles per frame)
   // Copies of the staging tables in kernel-parameter (constant) space: the issuing warps index them with
   // warp-uniform loop counters, so descriptors and TMA coordinates stay in uniform registers (no per-instruction
   // divergence "waterfall" around tcgen05.mma / TMA).  tap lists are de-duplicated; tables_in_params == 0 falls
@@ -286,6 +288,25 @@ __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
   return pred != 0;
+}
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
@@ -348,7 +369,10 @@ constexpr int kTmemCols = 512;
 
 }  // namespace lutc
 
-template <int EPI, bool PTAB>
+// CL = thread-block cluster size.  CL == 2: the two CTAs of a cluster work on two M tiles of the SAME N tile and each
+// multicasts one half of every weight K block into both CTAs' shared memory (half the L2->SM weight traffic); the MMA
+// and the accumulators stay per-CTA (cta_group::1).
+template <int EPI, bool PTAB, int CL>
 __global__ void __launch_bounds__(lutc::kThreads, 1) lu_conv_tc_kernel(const __grid_constant__ LuTcParams P) {
   using namespace lutc;
   extern __shared__ uint8_t smem_raw[];
@@ -376,7 +400,7 @@ __global__ void __launch_bounds__(lutc::kThreads, 1) lu_conv_tc_kernel(const __g
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < nA; ++i) { mbar_init(full_a + 8u * i, 1); mbar_init(empty_a + 8u * i, 1); }
-    for (int i = 0; i < nB; ++i) { mbar_init(full_b + 8u * i, 1); mbar_init(empty_b + 8u * i, 1); }
+    for (int i = 0; i < nB; ++i) { mbar_init(full_b + 8u * i, 1); mbar_init(empty_b + 8u * i, CL); }
     for (int i = 0; i < 2; ++i) { mbar_init(tmem_full + 8u * i, 1); mbar_init(tmem_empty + 8u * i, kEpiThreads); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -386,11 +410,24 @@ __global__ void __launch_bounds__(lutc::kThreads, 1) lu_conv_tc_kernel(const __g
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
-  __syncthreads();
+  if (CL == 1) __syncthreads(); else cluster_sync_all();       // barrier inits visible cluster-wide before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   const int tiles_per_frame = cp.tiles_x * cp.tiles_y;
+  // work decomposition: item -> (N tile, M tile).  cluster 1: item = tile, N fastest.  cluster 2: item = pair of
+  // consecutive M tiles of one N tile; an odd tail pair re-does the last M tile in the second CTA with stores masked.
+  const int crank = (CL == 2) ? (int)cluster_ctarank() : 0;
+  const int item0 = (CL == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int item_step = (CL == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int mpairs = (P.num_mt + 1) >> 1;
+  auto decode = [&](int item, int& nt, int& mt, bool& dummy) {
+    if (CL == 2) {
+      nt = item / mpairs; mt = 2 * (item - nt * mpairs) + crank;
+      dummy = mt >= P.num_mt;
+      if (dummy) mt = P.num_mt - 1;
+    } else { nt = item % cp.n_tiles_n; mt = item / cp.n_tiles_n; dummy = false; }
+  };
 
   // The three issuing roles run with warp-uniform control flow (all 32 lanes walk the loops and wait on the
   // barriers); one elected lane issues the asynchronous instruction.
@@ -398,8 +435,9 @@ __global__ void __launch_bounds__(lutc::kThreads, 1) lu_conv_tc_kernel(const __g
   if (warp == 0) {
     // ------------------------------------------------------------------ A producer (activation windows)
     int sa = 0; uint32_t ph = 0;
-    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-      const int mt = tile / cp.n_tiles_n;
+    for (int tile = item0; tile < P.total_tiles; tile += item_step) {
+      int nt, mt; bool dummy;
+      decode(tile, nt, mt, dummy);
       const int frame = mt / tiles_per_frame, rem = mt % tiles_per_frame;
       const int y0 = (rem / cp.tiles_x) * LU_TILE_H, x0 = (rem % cp.tiles_x) * LU_TILE_W;
       for (int s = 0; s < cp.n_astages; ++s) {
@@ -419,16 +457,22 @@ __global__ void __launch_bounds__(lutc::kThreads, 1) lu_conv_tc_kernel(const __g
     // ------------------------------------------------------------------ B producer (packed weight K blocks)
     int sb = 0; uint32_t ph = 0;
     const int nkb = cp.ktot / LU_KBLK, G = P.b_group;
-    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-      const int nt = tile % cp.n_tiles_n;
+    for (int tile = item0; tile < P.total_tiles; tile += item_step) {
+      int nt, mt; bool dummy;
+      decode(tile, nt, mt, dummy);
       for (int kb = 0; kb < nkb; kb += G) {
         const int g = (nkb - kb) < G ? (nkb - kb) : G;
-        mbar_wait(empty_b + 8u * sb, ph ^ 1u);
+        mbar_wait(empty_b + 8u * sb, ph ^ 1u);               // cluster 2: released by BOTH CTAs' MMA issuers
         if (elect_one()) {
           mbar_expect_tx(full_b + 8u * sb, (uint32_t)(g * BN) * 128u);
-          for (int j = 0; j < g; ++j)
-            tma_load_2d(sB + (uint32_t)sb * P.b_stage_bytes + (uint32_t)(j * BN) * 128u, &P.tmB, full_b + 8u * sb,
-                        (kb + j) * LU_KBLK, nt * BN);
+          for (int j = 0; j < g; ++j) {
+            const uint32_t dst = sB + (uint32_t)sb * P.b_stage_bytes + (uint32_t)(j * BN) * 128u;
+            if (CL == 2)
+              tma_load_2d_mc(dst + (uint32_t)(crank * (BN >> 1)) * 128u, &P.tmBh, full_b + 8u * sb, (kb + j) * LU_KBLK,
+                             nt * BN + crank * (BN >> 1), (uint16_t)3);
+            else
+              tma_load_2d(dst, &P.tmB, full_b + 8u * sb, (kb + j) * LU_KBLK, nt * BN);
+          }
         }
         __syncwarp();
         if (++sb == nB) { sb = 0; ph ^= 1u; }
@@ -445,7 +489,7 @@ __global__ void __launch_bounds__(lutc::kThreads, 1) lu_conv_tc_kernel(const __g
       const uint32_t b_hi = desc_hi(1024u);
       const uint32_t bn_bytes16 = (uint32_t)BN * 8u;            // one K block of weights, in 16-byte units
       const uint32_t idesc = P.idesc;
-      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+      for (int tile = item0; tile < P.total_tiles; tile += item_step) {
         mbar_wait(tmem_empty + 8u * acc, phacc ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -474,7 +518,8 @@ __global__ void __launch_bounds__(lutc::kThreads, 1) lu_conv_tc_kernel(const __g
             accum = 1;
             b_lo += bn_bytes16;
             if (++gi == G) {
-              tc_commit(empty_b + 8u * sb);                     // frees the weight stage once its MMAs retire
+              if (CL == 2) tc_commit_mc(empty_b + 8u * sb, (uint16_t)3);   // weight stage is shared by the cluster
+              else tc_commit(empty_b + 8u * sb);                // frees the weight stage once its MMAs retire
               gi = 0;
               if (++sb == nB) { sb = 0; phb ^= 1u; }
             }
@@ -483,7 +528,8 @@ __global__ void __launch_bounds__(lutc::kThreads, 1) lu_conv_tc_kernel(const __g
           if (++sa == nA) { sa = 0; pha ^= 1u; }
         }
         if (gi != 0) {                                          // partial last weight group of the tile
-          tc_commit(empty_b + 8u * sb);
+          if (CL == 2) tc_commit_mc(empty_b + 8u * sb, (uint16_t)3);
+          else tc_commit(empty_b + 8u * sb);
           if (++sb == nB) { sb = 0; phb ^= 1u; }
         }
         tc_commit(tmem_full + 8u * acc);                        // accumulator complete -> epilogue
@@ -499,12 +545,13 @@ __global__ void __launch_bounds__(lutc::kThreads, 1) lu_conv_tc_kernel(const __g
     const int ep_tid = threadIdx.x - 128;
     const LuEpi& e = cp.epi;
     int acc = 0; uint32_t phacc = 0;
-    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-      const int nt = tile % cp.n_tiles_n, mt = tile / cp.n_tiles_n;
+    for (int tile = item0; tile < P.total_tiles; tile += item_step) {
+      int nt, mt; bool dummy;
+      decode(tile, nt, mt, dummy);
       const int frame = mt / tiles_per_frame, rem = mt % tiles_per_frame;
       const int y = (rem / cp.tiles_x) * LU_TILE_H + m / LU_TILE_W, x = (rem % cp.tiles_x) * LU_TILE_W + m % LU_TILE_W;
       const int yo = y * e.oy_mul + e.oy_add, xo = x * e.ox_mul + e.ox_add;
-      const bool valid = (y < e.H) && (x < e.W) && (yo < e.OH) && (xo < e.OW);
+      const bool valid = !dummy && (y < e.H) && (x < e.W) && (yo < e.OH) && (xo < e.OW);
       const int n0 = nt * BN;
       const int64_t fout = (int64_t)frame * e.out_frame_mul + e.out_frame_add;
       const int64_t pix_out = (fout * e.OH + yo) * e.OW + xo;
@@ -557,7 +604,7 @@ __global__ void __launch_bounds__(lutc::kThreads, 1) lu_conv_tc_kernel(const __g
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CL == 1) __syncthreads(); else cluster_sync_all();       // no CTA may exit while its peer can still multicast into it
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
