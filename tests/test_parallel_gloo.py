@@ -42,7 +42,8 @@ def _worker(rank, world, port, out_dir):
     grads = np.zeros(sess.n_trainable, dtype=np.float32)
     loss = np.zeros(1, dtype=np.float32)
     emu_forward(sess, x[lo:hi], True)
-    sess.loss_backward(np.ascontiguousarray(lab[lo:hi]).ctypes.data, CW, loss.ctypes.data, grads.ctypes.data)
+    lab_r = np.ascontiguousarray(lab[lo:hi])     # keep alive while the library reads it
+    sess.loss_backward(lab_r.ctypes.data, CW, loss.ctypes.data, grads.ctypes.data)
     g = torch.from_numpy(grads)
     all_reduce_mean_(g)
     t = max_over_ranks(1.0 + rank)
