@@ -35,7 +35,7 @@ static thread_local std::string g_err;
     if (!(cond)) LU_FAIL(__VA_ARGS__); \
   } while (0)
 
-#define LU_WG_MAX_TASKS 4096
+#define LU_WG_MAX_TASKS 16384
 static inline int ceil_to(int v, int m) { return (v + m - 1) / m * m; }
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -100,6 +100,7 @@ struct ConvPlan {
   int dz_buf = -1;                      // lstm: gradient wrt the gate pre-activations (frames,H,W,4*fpad)
   std::vector<int> dgrads[2];
   std::vector<uint16_t> kb_stage, kb_tap;
+  int wg_cached_T[2] = {-1, -1}, wg_n_tasks[2] = {0, 0};   // weight-gradient task lists resident on the device
   size_t off_kb_stage = 0, off_kb_tap = 0, off_bwd_sums = 0, off_c_init = 0, off_dc = 0, off_wg_tasks = 0, off_bwd_means = 0;
 #ifndef LU_HOST_EMU
   CUtensorMap tmA[LU_MAX_SRC];
@@ -810,6 +811,7 @@ int lu_bind_workspace(lu_handle h, void* dev_ws, size_t bytes, void* stream) {
 #endif
   LU_MEMSET(h->ws, 0, h->ws_bytes, stream);
   for (auto& cv : h->convs) {
+    cv.wg_cached_T[0] = cv.wg_cached_T[1] = -1;       // device-resident task lists were just wiped
     LU_H2D(h->ws + cv.off_astages, cv.astages.data(), cv.astages.size() * sizeof(LuAStage), stream);
     LU_H2D(h->ws + cv.off_taps, cv.taps.data(), cv.taps.size() * sizeof(uint16_t), stream);
     LU_H2D(h->ws + cv.off_packs, cv.packs.data(), cv.packs.size() * sizeof(LuPackDesc), stream);
