@@ -705,7 +705,7 @@ __global__ void __launch_bounds__(256, 1) lu_wgrad_tc_kernel(const __grid_consta
         const int fy = frame * P.dy_frame_mul + P.dy_frame_add;
         for (int dp = 0; dp < nyp; ++dp)
           for (int c = 0; c < tk.nch; ++c)
-            tma_load_5d(base + b_off + (uint32_t)(dp * 2 + c) * 16384u, &P.tmY, full + 8u * s,
+            tma_load_5d(base + b_off + (uint32_t)(dp * tk.nch + c) * 16384u, &P.tmY, full + 8u * s,
                         tk.ychan[c] + dp * P.dy_cpad, x0, 0, y0, fy);
       }
       __syncwarp();
@@ -730,7 +730,7 @@ __global__ void __launch_bounds__(256, 1) lu_wgrad_tc_kernel(const __grid_consta
           const uint32_t d_tmem = tmem_base + (uint32_t)(ti * N);
           const uint32_t a0 = base + (uint32_t)tk.off[ti] * 128u;
           for (int dp = 0; dp < nyp; ++dp) {
-            const uint32_t b0 = base + b_off + (uint32_t)(dp * 2) * 16384u;
+            const uint32_t b0 = base + b_off + (uint32_t)(dp * tk.nch) * 16384u;
 #pragma unroll
             for (int j = 0; j < 8; ++j)
               mma_bf16(d_tmem, desc_lo_mn(a0 + (uint32_t)j * row2, a_lbo), a_hi, desc_lo_mn(b0 + (uint32_t)j * 2048u, 16384u), b_hi,

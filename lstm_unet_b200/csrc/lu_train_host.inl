@@ -339,10 +339,11 @@ static int run_wgrad(lu_handle_s* h, ConvPlan& f, int gbuf, int T, float* grads,
       wp.tiles_x = (f.Wout + LU_TILE_W - 1) / LU_TILE_W; wp.tiles_y = (f.Hout + LU_TILE_H - 1) / LU_TILE_H;
       wp.T = T; wp.skip_t0_src = w.skip_t0_src;
       wp.dy_frame_mul = (int)w.dy_frame_mul; wp.dy_frame_add = (int)w.dy_frame_add; wp.dy_planes = g.planes; wp.dy_cpad = g.cpad;
-      wp.a_win_bytes = f.a_bytes; wp.stage_bytes = 2 * f.a_bytes + 4 * 16384;
+      // stage = two activation windows + two 16 KB dY boxes (bf16: 2 column chunks; bf16x3: hi and lo plane of one chunk)
+      wp.a_win_bytes = f.a_bytes; wp.stage_bytes = 2 * f.a_bytes + 2 * 16384;
       const int budget = 232448 - 1024 - 256;
       wp.n_stages = budget / wp.stage_bytes;
-      if (wp.n_stages > 3) wp.n_stages = 3;
+      if (wp.n_stages > 4) wp.n_stages = 4;
       LU_REQUIRE(wp.n_stages >= 1, "weight-gradient stage does not fit shared memory");
       static bool attr = false;
       if (!attr) {
