@@ -223,6 +223,18 @@ class ULSTMnet2D:
         self._shape = None                        # (B, H, W) frozen by the first call (stateful ConvLSTM)
         self._x_pin = self._x_dev = None
 
+    def close(self):
+        """Release the library handle and the device workspace."""
+        if getattr(self, '_sess', None) is not None:
+            self._sess.close()
+            self._sess = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
     # ---- session management --------------------------------------------------------------------------
     def _build(self, B, T, H, W):
         be = TorchCudaBackend(self._device)

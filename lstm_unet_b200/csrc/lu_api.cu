@@ -363,7 +363,6 @@ static int build_tables(lu_handle_s* h, ConvPlan& cv) {
 
 // K extent, kernel-parameter table copies and shared-memory pipeline shape of a conv whose tables are complete
 static int finish_tables(lu_handle_s* h, ConvPlan& cv) {
-  const bool halo = true;
   (void)h;
   cv.ktot = (int)cv.packs.size() * LU_KBLK;
   // kernel-parameter copies of the tables: identical tap lists are stored once

@@ -316,19 +316,15 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-// K-major, 128-byte swizzle operand descriptor (cute::UMMA::SmemDescriptor layout, sm_100 version bit set)
+// K-major, 128-byte swizzle operand descriptor (cute::UMMA::SmemDescriptor layout, sm_100 version bit set):
+//   bits [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (ignored for swizzled K-major) |
+//   [32,46) stride byte offset >> 4 = distance between 8-row groups | [46,48) version = 1 | [49,52) base offset = 0 |
+//   [61,64) layout = 2 (SWIZZLE_128B).
 // The 128-byte swizzle is a function of the shared-memory ADDRESS bits (measured on B200: a start address that is a
-// multiple of 128 but not of 1024 bytes reads the rows TMA wrote there when the base-offset field is left 0), which is
-// what lets a filter tap be a mere row offset into the staged halo window.
-__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t sbo_bytes) {
-  uint64_t d = (uint64_t)((addr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)1 << 16;                                  // LBO (ignored for swizzled K-major)
-  d |= (uint64_t)(sbo_bytes >> 4) << 32;                   // stride between 8-row groups
-  d |= (uint64_t)1 << 46;                                  // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;                                  // SWIZZLE_128B
-  return d;
-}
-// high / low words of the K-major SWIZZLE_128B descriptor (see make_desc): hi = SBO | version | layout,
+// multiple of 128 but not of 1024 bytes reads the rows TMA wrote there when the base-offset field is left 0; setting it
+// to (addr >> 7) & 7 gives wrong results), which is what lets a filter tap be a mere row offset into the staged halo
+// window, and lets the 8-row group stride be pitch*128 bytes for any pitch.
+// high / low words of the K-major SWIZZLE_128B descriptor (layout above): hi = SBO | version | layout,
 // lo = (address >> 4) | LBO.  Taps and K sub-steps only add to the low word.
 __device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes) { return (sbo_bytes >> 4) | (1u << 14) | (2u << 29); }
 __device__ __forceinline__ uint32_t desc_lo(uint32_t addr) { return ((addr & 0x3FFFFu) >> 4) | (1u << 16); }
