@@ -166,6 +166,10 @@ def run_ours(args):
         os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')      # keep stdout to the one JSON line
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     import __graft_entry__ as ge
+    if world > 1:                      # one rank (re)builds the in-tree library if it is stale, the others wait
+        if rank == 0:
+            ge.build()
+        dist.barrier()
     ge.build()
     from lstm_unet_b200.Networks import ULSTMnet2D
 

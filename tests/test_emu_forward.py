@@ -144,3 +144,51 @@ def test_config_errors():
     from lstm_unet_b200.session import LuError
     with pytest.raises(LuError):     # REFLECT pad needs pad < dim
         emu_session(NET_A, pad_image=True, batch=1, max_t=1, height=8, width=8)
+
+
+def test_variable_unroll_length_and_minimal_sizes():
+    """T may change between calls (T <= max_t): frames are addressed b*T+t per call; states carry over.  Also the
+    smallest legal frame (8x8 for total_stride 8) and a 1x1-sample batch."""
+    net = NET_A
+    p_t, p_np = oracle_params_np(net, 13)
+    ora = O.OracleNet(net, 'NCHW', False, params=p_t)
+    sess = emu_session(net, data_format='NCHW', pad_image=False, batch=1, max_t=3, height=8, width=8, precision='bf16x3')
+    sess.set_params(p_np)
+    rng = np.random.default_rng(6)
+    for T in (3, 1, 2):
+        x = rng.standard_normal((1, T, 1, 8, 8)).astype(np.float32)
+        ref_l, _ = ora(torch.from_numpy(x), False)
+        got_l, _ = emu_forward(sess, x, False)
+        assert got_l.shape == (1, T, 3, 8, 8)
+        assert rel_err(got_l, ref_l.numpy()) < 1e-3, T
+    from lstm_unet_b200.session import LuError
+    with pytest.raises(LuError):
+        emu_forward(sess, rng.standard_normal((1, 4, 1, 8, 8)).astype(np.float32), False)     # T > max_t
+    sess.close()
+
+
+def test_channels_last_training_step():
+    """NHWC ('NWHC' in the reference's CLI, train2D.py:319): labels (B,T,H,W,1); logits gradients are layout-free."""
+    net, B, T, H, W = NET_B, 2, 1, 8, 8
+    p_t, p_np = oracle_params_np(net, 15)
+    ora = O.OracleNet(net, 'NWHC', False, params=p_t)
+    sess = emu_session(net, data_format='NWHC', pad_image=False, batch=B, max_t=T, height=H, width=W,
+                       precision='bf16x3', train=True)
+    sess.set_params(p_np)
+    rng = np.random.default_rng(8)
+    x = rng.standard_normal((B, T, H, W, 1)).astype(np.float32)
+    lab = rng.integers(-1, 3, size=(B, T, H, W, 1)).astype(np.float32)
+    names = ora.trainable_names()
+    m = {n: torch.zeros_like(ora.params[n]) for n in names}
+    v = {n: torch.zeros_like(ora.params[n]) for n in names}
+    ref_loss, ref_logits, _, ref_grads = O.train_step(ora, torch.from_numpy(x), torch.from_numpy(lab), [0.15, 0.25, 0.6], m, v, 1, 0.0)
+    logits, _ = emu_forward(sess, x, True)
+    assert rel_err(logits, ref_logits.numpy()) < 1e-3
+    grads = np.zeros(sess.n_trainable, np.float32)
+    loss = np.zeros(1, np.float32)
+    sess.loss_backward(lab.ctypes.data, [0.15, 0.25, 0.6], loss.ctypes.data, grads.ctypes.data)
+    assert abs(float(loss[0]) - float(ref_loss)) < 1e-4
+    e = [e for e in sess.layout if e['name'] == 'UpLayers/1/Conv/1/kernel'][0]
+    g = grads[e['offset']:e['offset'] + e['count']].reshape(e['shape'])
+    assert rel_err(g, ref_grads[e['name']].numpy()) < 5e-3
+    sess.close()

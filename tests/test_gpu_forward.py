@@ -143,3 +143,17 @@ def test_linearity_of_logits_conv_at_scale():
         outs.append(m(x, False)[0].numpy())
     np.testing.assert_array_equal(outs[0], outs[1])
     assert rel_err(outs[2], outs[0]) < 1e-4
+
+
+def test_unroll_length_may_change_and_grow():
+    """T <= max_t reuses the handle; a longer unroll rebuilds it and carries weights and recurrent states over
+    (Keras only freezes B, H, W of a stateful layer)."""
+    ora, model = make_pair(NET_TWO, 'NCHW', False, 17, precision='bf16x3')
+    rng = np.random.default_rng(9)
+    for T in (2, 1, 4, 3):
+        x = rng.standard_normal((2, T, 1, 16, 24)).astype(np.float32)
+        ref_l, _ = ora(torch.from_numpy(x), False)
+        logits, _ = model(x, False)
+        assert tuple(logits.shape) == (2, T, 3, 16, 24)
+        assert rel_err(logits.numpy(), ref_l.numpy()) < 1e-3, T
+    model.close()
