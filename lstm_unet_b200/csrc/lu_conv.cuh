@@ -416,10 +416,9 @@ __global__ void __launch_bounds__(lutc::kThreads, 1) lu_conv_tc_kernel(const __g
   const int crank = (CL == 2) ? (int)cluster_ctarank() : 0;
   const int item0 = (CL == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int item_step = (CL == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  const int mpairs = (P.num_mt + 1) >> 1;
   auto decode = [&](int item, int& nt, int& mt, bool& dummy) {
     if (CL == 2) {
-      nt = item / mpairs; mt = 2 * (item - nt * mpairs) + crank;
+      nt = item % cp.n_tiles_n; mt = 2 * (item / cp.n_tiles_n) + crank;      // N fastest: concurrent clusters share the activation tiles (L2)
       dummy = mt >= P.num_mt;
       if (dummy) mt = P.num_mt - 1;
     } else { nt = item % cp.n_tiles_n; mt = item / cp.n_tiles_n; dummy = false; }
