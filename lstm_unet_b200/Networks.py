@@ -398,14 +398,43 @@ class ULSTMnet2D:
             self._sess.set_params(named)
 
     def save_weights(self, path, save_format=None):
-        """Keras variable names/layouts in an .npz (the TF tensor-bundle format is SURVEY 8f row 1)."""
+        """``save_format='tf'`` (train2D.py:236): a TF2 tensor bundle ``<path>.index`` + ``<path>.data-00000-of-00001`` with
+        the Keras object-graph variable keys (written without TensorFlow, see tf_checkpoint.py).  Otherwise an ``.npz``
+        with the Keras variable names / layouts."""
         w = self.get_weights_dict() if self._sess is not None else self._pending_weights
         if w is None:
             raise RuntimeError('nothing to save: the model has no weights yet')
+        if save_format == 'tf':
+            from . import tf_checkpoint
+            tf_checkpoint.save_model_weights(str(path), w)
+            return
         with open(path if str(path).endswith('.npz') else str(path) + '.npz', 'wb') as f:
             np.savez(f, **{k.replace('/', '|'): v for k, v in w.items()})
 
+    def _variable_names(self):
+        if self._sess is not None:
+            return [e['name'] for e in self._sess.layout]
+        cfg = _lib.make_config(self.net_params, self.data_format, self.pad_image, batch=1, max_t=1, height=64, width=64)
+        import ctypes
+        h = ctypes.c_void_p()
+        if self._lib.lu_create(ctypes.byref(cfg), ctypes.byref(h)) != 0:
+            raise LuError(self._lib.lu_last_error().decode())
+        nt = ctypes.c_int32()
+        self._lib.lu_param_count(h, ctypes.byref(nt), None, None)
+        buf, names = ctypes.create_string_buffer(256), []
+        for i in range(nt.value):
+            self._lib.lu_param_info(h, i, buf, 256, None, None, None, None)
+            names.append(buf.value.decode())
+        self._lib.lu_destroy(h)
+        return names
+
     def load_weights(self, path):
+        """Accepts a TF2 checkpoint prefix (``model.ckpt`` -> ``model.ckpt.index``; Inference2D.py:34) or an ``.npz``."""
+        import os
+        if os.path.exists(str(path) + '.index'):
+            from . import tf_checkpoint
+            self.set_weights_dict(tf_checkpoint.load_model_weights(str(path), self._variable_names()))
+            return
         p = path if str(path).endswith('.npz') else str(path) + '.npz'
         with np.load(p) as z:
             self.set_weights_dict({k.replace('|', '/'): z[k] for k in z.files})

@@ -1,0 +1,111 @@
+"""TF2 checkpoint (tensor bundle) reader / writer without TensorFlow: known-answer vectors for CRC-32C and Snappy,
+SSTable round trips (multi-block, prefix compression, a Snappy-compressed block), bundle round trip with the Keras
+object-graph keys of ULSTMnet2D."""
+import os
+import struct
+
+import numpy as np
+import pytest
+
+from lstm_unet_b200 import tf_checkpoint as T
+
+
+def test_crc32c_known_answers():
+    assert T.crc32c(b'123456789') == 0xE3069283            # the standard CRC-32C check value
+    assert T.crc32c(b'') == 0
+    assert T.crc32c(bytes(32)) == 0x8A9136AA               # RFC 3720 B.4: 32 bytes of zeros
+    assert T.crc32c(bytes([0xFF] * 32)) == 0x62A8AB43      # RFC 3720 B.4: 32 bytes of ones
+    assert T.mask_crc(0) == 0xa282ead8
+
+
+def test_snappy_decoder_vectors():
+    # literal only
+    assert T.snappy_uncompress(bytes([5, (5 - 1) << 2]) + b'hello') == b'hello'
+    # literal "ab" + copy (1-byte offset form): len 6, offset 2  -> "abababab"
+    comp = bytes([8, (2 - 1) << 2]) + b'ab' + bytes([((6 - 4) << 2) | 1, 2])
+    assert T.snappy_uncompress(comp) == b'abababab'
+    # 2-byte offset copy: literal "0123456789" then copy len 10 offset 10
+    comp = bytes([20, (10 - 1) << 2]) + b'0123456789' + bytes([((10 - 1) << 2) | 2, 10, 0])
+    assert T.snappy_uncompress(comp) == b'01234567890123456789'
+    # long literal (length in one extra byte)
+    lit = bytes(range(200))
+    comp = bytes([200, 1, 60 << 2, 199]) + lit
+    assert T.snappy_uncompress(comp) == lit
+    with pytest.raises(ValueError):
+        T.snappy_uncompress(bytes([4, ((4 - 4) << 2) | 1, 9]))      # copy before any output
+
+
+def test_sstable_round_trip_multi_block(tmp_path):
+    items = [(('key/%05d/suffix' % i).encode(), os.urandom(1 + i % 97)) for i in range(700)]
+    items.sort()
+    path = str(tmp_path / 't.index')
+    T.write_table(path, items, block_size=512)
+    got = T.read_table(path)
+    assert got == dict(items)
+    raw = bytearray(open(path, 'rb').read())
+    raw[10] ^= 0xFF                                          # corrupt a data block -> checksum error
+    open(path, 'wb').write(bytes(raw))
+    with pytest.raises(ValueError):
+        T.read_table(path)
+
+
+def test_reads_snappy_compressed_block(tmp_path):
+    """A table whose data block is stored Snappy-compressed (type byte 1), as TensorFlow's table builder does when it pays."""
+    items = [(b'a/%d' % i, b'v' * 20) for i in range(5)]
+    block = T._build_block(items)
+    # all-literal snappy encoding of the block
+    n = len(block)
+    comp = T._put_varint(n) + bytes([60 << 2, n - 1]) + block if n > 60 else T._put_varint(n) + bytes([(n - 1) << 2]) + block
+    f = bytearray()
+    f += comp + b'\x01' + struct.pack('<I', T.mask_crc(T.crc32c(comp + b'\x01')))
+    data_handle = T._put_varint(0) + T._put_varint(len(comp))
+
+    def emit(blk):
+        off = len(f)
+        f.extend(blk + b'\x00' + struct.pack('<I', T.mask_crc(T.crc32c(blk + b'\x00'))))
+        return off, len(blk)
+    moff, msize = emit(T._build_block([]))
+    ioff, isize = emit(T._build_block([(items[-1][0], data_handle)], restart_interval=1))
+    footer = T._put_varint(moff) + T._put_varint(msize) + T._put_varint(ioff) + T._put_varint(isize)
+    f += footer + b'\x00' * (40 - len(footer)) + struct.pack('<Q', T.TABLE_MAGIC)
+    path = str(tmp_path / 's.index')
+    open(path, 'wb').write(bytes(f))
+    assert T.read_table(path) == dict(items)
+
+
+def test_bundle_round_trip_with_keras_keys(tmp_path):
+    from oracle import lstm_unet_oracle as O
+    net = {'down_conv_kernels': [[(3, 6)], [(3, 10), (3, 10)]], 'lstm_kernels': [[(3, 5), (3, 7)], [(5, 9)]],
+           'up_conv_kernels': [[(3, 6)], [(3, 5), (1, 3)]]}
+    params = {k: v.numpy() for k, v in O.init_params(net, seed=3, randomize_bn=True).items()}
+    prefix = str(tmp_path / 'model.ckpt')
+    T.save_model_weights(prefix, params)
+    assert os.path.exists(prefix + '.index') and os.path.exists(prefix + '.data-00000-of-00001')
+    raw = T.read_bundle(prefix)
+    assert 'DownLayers/0/ConvLSTM/1/cell/recurrent_kernel/.ATTRIBUTES/VARIABLE_VALUE' in raw
+    assert 'UpLayers/1/Conv/1/bias/.ATTRIBUTES/VARIABLE_VALUE' in raw
+    assert 'DownLayers/1/BN/0/moving_variance/.ATTRIBUTES/VARIABLE_VALUE' in raw
+    got = T.load_model_weights(prefix, list(params))
+    for k in params:
+        np.testing.assert_array_equal(got[k], params[k])
+    # the same variables under tf.train.Checkpoint(net=model) (train2D.py:62)
+    T.save_model_weights(prefix + '2', params, root='net/')
+    got = T.load_model_weights(prefix + '2', list(params))
+    np.testing.assert_array_equal(got['DownLayers/0/Conv/0/kernel'], params['DownLayers/0/Conv/0/kernel'])
+    with pytest.raises(KeyError):
+        T.load_model_weights(prefix, list(params) + ['DownLayers/9/Conv/0/kernel'])
+
+
+def test_model_save_load_tf_format(tmp_path):
+    """ULSTMnet2D.save_weights(save_format='tf') / load_weights(prefix) -- no GPU needed before the first call."""
+    from lstm_unet_b200.Networks import ULSTMnet2D
+    from oracle import lstm_unet_oracle as O
+    net = {'down_conv_kernels': [[(3, 6)]], 'lstm_kernels': [[(3, 5)]], 'up_conv_kernels': [[(3, 5), (1, 3)]]}
+    params = {k: v.numpy() for k, v in O.init_params(net, seed=4, randomize_bn=True).items()}
+    m = ULSTMnet2D(net, 'NCHW', True)
+    m.set_weights_dict(params)
+    m.save_weights(str(tmp_path / 'model.ckpt'), save_format='tf')
+    m2 = ULSTMnet2D(net, 'NCHW', True)
+    m2.load_weights(str(tmp_path / 'model.ckpt'))
+    for k in params:
+        np.testing.assert_array_equal(m2._pending_weights[k], params[k])
