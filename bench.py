@@ -295,6 +295,127 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_postprocess(args):
+    """--mode postprocess: instance labelling of the soft-max of one C2 batch (B*T = 32 frames of
+    512x512) on the device.  value: soft-max resident in HBM; e2e: host soft-max in, host uint16 labels out;
+    cpu_baseline: the reference's numpy / SciPy / OpenCV algorithm (oracle pinned to the reference's own vectors) on a
+    few of the same frames.  HBM-bound integer work: algorithmic bytes = 12 B/px soft-max read + 2 B/px labels."""
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    import __graft_entry__ as ge
+    if world > 1:
+        if rank == 0:
+            ge.build()
+        dist.barrier()
+    ge.build()
+    from lstm_unet_b200.postprocess import PostProcessor
+    from lstm_unet_b200 import _lib
+    from oracle import postprocess_oracle as P
+    n, H, W = args.batch * args.unroll, args.size, args.size
+    kw = dict(edge_dist=2, min_cell_size=10, max_cell_size=100, FOV=0)          # CTCInferenceParams defaults
+    distinct = [P.synthetic_softmax(H, W, 1000 + 17 * rank + i, 'cells') for i in range(min(n, 8))]
+    sm_host = torch.from_numpy(np.stack([distinct[i % len(distinct)] for i in range(n)])).pin_memory()
+    sm_dev = sm_host.cuda()
+    pp = PostProcessor(**kw)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    labels = pp(sm_dev)
+    if rank == 0:       # the checker: first frames against the oracle
+        got = labels.numpy()
+        for i in range(2):
+            assert np.array_equal(got[i], P.postprocess_frame(distinct[i], **kw)), 'post-processing differs from the oracle'
+    for _ in range(args.warmup):
+        pp(sm_dev)
+    barrier()
+    lib = _lib.load_library()
+    lib.lu_post_launch_count(None, 1)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        pp(sm_dev)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    import ctypes
+    nl = ctypes.c_int64()
+    lib.lu_post_launch_count(ctypes.byref(nl), 0)
+    clocks = sampler.stop() if rank == 0 else None
+    dev_buf = torch.empty_like(sm_dev)
+
+    def e2e_once():
+        dev_buf.copy_(sm_host, non_blocking=True)
+        return pp(dev_buf).numpy()
+    for _ in range(2):
+        e2e_once()
+    barrier()
+    e2e_steps = max(2, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        out = e2e_once()
+    barrier()
+    e2e_wall_ms = (time.perf_counter() - t0) * 1e3
+    if world > 1:
+        t = torch.tensor([ms, e2e_wall_ms], device='cuda', dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_wall_ms = [float(v) for v in t.tolist()]
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    value = n * args.steps * world / (ms * 1e-3)
+    alg_bytes = n * H * W * 14.0
+    hbm = 6550.0
+    pk = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    src = 'fallback'
+    if os.path.exists(pk):
+        with open(pk) as f:
+            hbm = json.load(f).get('hbm_gbs', hbm)
+        src = 'measured hbm_gbs'
+    achieved = alg_bytes * args.steps / (ms * 1e-3) / 1e9
+    line = {
+        'metric': 'frames/sec (512x512 soft-max -> uint16 instance labels)', 'value': value, 'unit': 'frames/s',
+        'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8/i32', 'data': 'synthetic',
+        'config': {'workload': 'SURVEY 8f row 3: Inference2D.py:64-123 instance labelling of %d soft-max frames %dx%d per GPU '
+                               '(synthetic cell-like maps, ~700 components per frame), CTCInferenceParams defaults' % (n, H, W),
+                   'l2_policy': 'soft-max batch + workspace (%.0f MB) exceed the 126 MB L2' % (n * H * W * (12 + 31) / 1e6)},
+        'e2e': {'value': n * e2e_steps * world / (e2e_wall_ms * 1e-3), 'unit': 'frames/s',
+                'h2d_bytes_per_step': int(sm_host.numel() * 4), 'd2h_bytes_per_step': int(out.nbytes),
+                'steps': e2e_steps, 'ms_per_step': e2e_wall_ms / e2e_steps},
+        'gpu_launches': int(nl.value), 'clocks': clocks,
+        'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': hbm, 'unit': 'GB/s', 'frac': achieved / hbm,
+                     'traffic': None, 'peak_source': src,
+                     'kernel': 'whole lu_postprocess pipeline (%d launches per batch); algorithmic bytes = 14 B/pixel'
+                               % (nl.value // max(1, args.steps))},
+    }
+    if world == 1 and not args.no_cpu:
+        k = 4
+        t0 = time.perf_counter()
+        for i in range(k):
+            P.postprocess_frame(distinct[i % len(distinct)], **kw)
+        dt = time.perf_counter() - t0
+        line['cpu_baseline'] = {'value': k / dt, 'unit': 'frames/s', 'cores': 1, 'kind': 'port',
+                                'sample': 'oracle/postprocess_oracle.postprocess_frame (the reference\'s numpy + SciPy + '
+                                          'OpenCV steps, pinned to vectors made by the reference\'s own statements) on %d '
+                                          'of the same frames' % k}
+    emit(line)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     # stdout carries exactly ONE JSON line: libraries that print to fd 1 (NCCL's version banner) are sent to stderr
     global _REAL_STDOUT
@@ -306,7 +427,7 @@ def main():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--mode', default='infer', choices=['infer', 'train', 'stream'],
+    ap.add_argument('--mode', default='infer', choices=['infer', 'train', 'stream', 'postprocess'],
                     help="infer = C2 (default, headline); train = C3/C4 full train step; stream = Inference2D's real per-frame call (B=1, T=1)")
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'bf16x3'])
     ap.add_argument('--a-mode', dest='a_mode', default='halo', choices=['halo', 'direct'])
@@ -320,6 +441,8 @@ def main():
         args.batch, args.unroll = 1, 1
     if args.impl == 'reference':
         run_reference(args)
+    elif args.mode == 'postprocess':
+        run_postprocess(args)
     else:
         run_ours(args)
 

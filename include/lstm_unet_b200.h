@@ -124,6 +124,26 @@ int lu_lstm_flops(lu_handle h, int32_t T, double* flops);
  * then enables / disables the recording for the following forwards */
 int lu_lstm_kernel_time(lu_handle h, int32_t enable, float* ms_total, int32_t* launches);
 
+/* ---- instance labelling of the soft-max maps (Inference2D.py:64-123): replaces the reference's numpy / SciPy / OpenCV
+ * post-processing that follows the model call; results are bit-identical to it.  Stateless: everything
+ * lives in the caller's workspace. */
+typedef struct lu_post_params {
+  float edge_thresh;        /* 0.2 in the reference (Inference2D.py:66) */
+  int32_t edge_d2_limit;    /* an edge pixel joins the nearest cell if its SQUARED distance is < this; the host derives
+                               it from params.edge_dist with the reference's float64 `sqrt(d2) < edge_dist` (:78) */
+  int32_t min_cell_size;    /* params.min_cell_size / max_cell_size on the core area (:117-118) */
+  int32_t max_cell_size;
+  int32_t fov;              /* params.FOV (:94-104), 0 = off */
+  int32_t channels_first;   /* 1: soft-max is (frames,3,H,W) [the reference's NCHW path]; 0: (frames,H,W,3) */
+} lu_post_params;
+int lu_post_workspace_bytes(int32_t frames, int32_t H, int32_t W, size_t* bytes);
+/* dev_softmax: fp32 soft-max of `frames` frames; dev_labels: uint16 (frames,H,W) instance labels 1..kept, 0 = none;
+ * dev_info (optional): int32 (frames,4) = {components found incl. background (cv2's count), labels kept,
+ * 1 if the frame needed the sequential per-label pass, 0} */
+int lu_postprocess(const float* dev_softmax, int32_t frames, int32_t H, int32_t W, const lu_post_params* params,
+                   uint16_t* dev_labels, int32_t* dev_info, void* dev_ws, size_t ws_bytes, void* stream);
+int lu_post_launch_count(int64_t* launches, int32_t reset);
+
 #ifdef __cplusplus
 }
 #endif

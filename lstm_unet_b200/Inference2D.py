@@ -1,8 +1,11 @@
 """Mirror of the model-call part of the reference's ``Inference2D.inference`` (Inference2D.py:25-62): the model is
 built with pad_image=True and called once per frame with B=1, T=1, the recurrence living in the stateful h/c; the
-first ``pre_sequence_frames`` frames, played in reverse, warm the state up (DataHandeling.py:1583-1585).  The CPU
-instance-labelling post-processing and TIFF output (Inference2D.py:64-131) are out of scope: each
-frame's soft-max is handed to ``on_frame(t, softmax_numpy)`` instead.  Usage: set ``params`` and call ``inference()``."""
+first ``pre_sequence_frames`` frames, played in reverse, warm the state up (DataHandeling.py:1583-1585).  Unless
+``params.dry_run``, the instance labelling that follows in the reference (Inference2D.py:64-123: numpy / SciPy / OpenCV
+on the host) runs on the device from the soft-max that is still in HBM (postprocess.PostProcessor -> lu_postprocess,
+bit-identical results); the uint16 label image goes to ``on_labels(t, labels)``, to ``last_labels`` and -- if
+``params.output_path`` is set and OpenCV is importable -- to ``mask{t:03d}.tif`` like Inference2D.py:124-126.  Each
+frame's soft-max is handed to ``on_frame(t, softmax_numpy)``.  Usage: set ``params`` and call ``inference()``."""
 import os
 import pickle
 
@@ -11,13 +14,15 @@ import numpy as np
 from . import Networks as Nets
 
 params = None
+last_labels = []
 
 
 def get_model(name):
     return getattr(Nets, name)            # utils.py:38-40
 
 
-def inference(frames=None, on_frame=None, model=None):
+def inference(frames=None, on_frame=None, model=None, on_labels=None):
+    global last_labels
     if model is None:
         with open(os.path.join(params.model_path, 'model_params.pickle'), 'rb') as fobj:
             model_dict = pickle.load(fobj)
@@ -29,6 +34,11 @@ def inference(frames=None, on_frame=None, model=None):
     pre = params.pre_sequence_frames
     sequence = frames[:pre][::-1] + frames
     outputs = []
+    last_labels = []
+    post = None
+    if not getattr(params, 'dry_run', False):
+        from .postprocess import PostProcessor
+        post = PostProcessor(params)
     for T, image in enumerate(sequence):
         t = T - pre
         image = np.asarray(image, dtype=np.float32)
@@ -45,4 +55,18 @@ def inference(frames=None, on_frame=None, model=None):
         outputs.append(image_softmax_np.copy())
         if on_frame is not None:
             on_frame(t, image_softmax_np)
+        if post is not None:
+            labels_out = post(image_softmax[0, 0]).numpy().copy()
+            last_labels.append(labels_out)
+            if on_labels is not None:
+                on_labels(t, labels_out)
+            out_dir = getattr(params, 'output_path', None)
+            if out_dir:
+                try:
+                    import cv2
+                except ImportError:
+                    cv2 = None
+                if cv2 is not None:
+                    os.makedirs(out_dir, exist_ok=True)
+                    cv2.imwrite(os.path.join(out_dir, 'mask{time:03d}.tif'.format(time=t)), labels_out)
     return outputs

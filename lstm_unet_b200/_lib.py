@@ -29,6 +29,11 @@ class lu_config(ctypes.Structure):
     ]
 
 
+class lu_post_params(ctypes.Structure):
+    _fields_ = [('edge_thresh', ctypes.c_float), ('edge_d2_limit', _I32), ('min_cell_size', _I32),
+                ('max_cell_size', _I32), ('fov', _I32), ('channels_first', _I32)]
+
+
 LIB_NAME = 'liblstm_unet_b200.so'
 
 
@@ -64,6 +69,9 @@ def bind(lib):
         'lu_forward_flops': [vp, i32, P(ctypes.c_double)],
         'lu_lstm_flops': [vp, i32, P(ctypes.c_double)],
         'lu_lstm_kernel_time': [vp, i32, P(f32), P(i32)],
+        'lu_post_workspace_bytes': [i32, i32, i32, P(ctypes.c_size_t)],
+        'lu_postprocess': [vp, i32, i32, i32, P(lu_post_params), vp, vp, vp, ctypes.c_size_t, vp],
+        'lu_post_launch_count': [P(i64), i32],
     }
     for name, args in sigs.items():
         fn = getattr(lib, name)
@@ -76,7 +84,7 @@ EXPORTED_SYMBOLS = ['lu_last_error', 'lu_version', 'lu_is_cuda_build', 'lu_creat
                     'lu_bind_workspace', 'lu_param_count', 'lu_param_info', 'lu_bind_params', 'lu_params_changed',
                     'lu_forward', 'lu_reset_states', 'lu_state_shape', 'lu_get_state', 'lu_set_state',
                     'lu_loss_backward', 'lu_adam_step', 'lu_debug_buffer', 'lu_launch_count', 'lu_forward_flops', 'lu_lstm_flops',
-                    'lu_lstm_kernel_time']
+                    'lu_lstm_kernel_time', 'lu_post_workspace_bytes', 'lu_postprocess', 'lu_post_launch_count']
 
 _LIB = None
 

@@ -11,6 +11,7 @@
 #include "lu_conv.cuh"
 #include "lu_elem.cuh"
 #include "lu_train.cuh"
+#include "lu_post.cuh"
 
 #ifdef LU_HOST_EMU
 #define LU_MEMSET(p, v, n, s) memset((p), (v), (n))
@@ -1173,3 +1174,6 @@ int lu_adam_step(lu_handle h, const float* dev_grads, float* dev_m, float* dev_v
 }
 
 }  // extern "C"
+
+#include "lu_post_host.inl"
+

@@ -236,7 +236,6 @@ def synthetic_softmax(H, W, seed, kind='cells', n_cells=None):
         z = rng.standard_normal((3, H, W)).astype(np.float32) * 1.5
         z[2] -= 1.0
     else:
-        yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
         z = np.zeros((3, H, W), np.float32)
         z[0] = 2.0
         if n_cells is None:
@@ -247,22 +246,31 @@ def synthetic_softmax(H, W, seed, kind='cells', n_cells=None):
             if rng.random() < 0.05:
                 a, b = a * 3, b * 3                      # oversize blob
             th = rng.uniform(0, np.pi)
+            ring_w = rng.uniform(0.15, 0.6)
+            draws = rng.random(3)
+            hole_r, hole_cls = rng.uniform(0.2, 0.5), int(rng.integers(0, 3))
+            R = int(np.ceil(2.0 * max(a, b))) + 2        # everything painted below lies within r < 1.9
+            y0, y1 = max(0, int(cy) - R), min(H, int(cy) + R + 1)
+            x0, x1 = max(0, int(cx) - R), min(W, int(cx) + R + 1)
+            if y0 >= y1 or x0 >= x1:
+                continue
+            yy, xx = np.mgrid[y0:y1, x0:x1].astype(np.float32)
+            zz = z[:, y0:y1, x0:x1]
             u = (yy - cy) * np.cos(th) + (xx - cx) * np.sin(th)
             v = -(yy - cy) * np.sin(th) + (xx - cx) * np.cos(th)
             r = np.sqrt((u / a) ** 2 + (v / b) ** 2)
-            ring_w = rng.uniform(0.15, 0.6)
             inside = r < 1
             ring = (r >= 1) & (r < 1 + ring_w)
-            z[1][inside] = 4.0
-            z[2][inside] = np.minimum(z[2][inside], 0)
-            z[2][ring & (z[1] < 3)] = 3.5
-            if rng.random() < 0.25:                      # a hole (background or edge class) inside the cell
-                hole = r < rng.uniform(0.2, 0.5)
-                z[1][hole] = 0
-                z[rng.integers(0, 3, 1)[0] if rng.random() < 0.5 else 0][hole] = 4.5
-            if rng.random() < 0.1:                       # ring of edge pixels far outside (nesting)
+            zz[1][inside] = 4.0
+            zz[2][inside] = np.minimum(zz[2][inside], 0)
+            zz[2][ring & (zz[1] < 3)] = 3.5
+            if draws[0] < 0.25:                          # a hole (background or edge class) inside the cell
+                hole = r < hole_r
+                zz[1][hole] = 0
+                zz[hole_cls if draws[1] < 0.5 else 0][hole] = 4.5
+            if draws[2] < 0.1:                           # ring of edge pixels far outside (nesting)
                 far = (r >= 1.6) & (r < 1.9)
-                z[2][far] = 3.5
+                zz[2][far] = 3.5
         z += rng.standard_normal((3, H, W)).astype(np.float32) * 0.5
     e = np.exp(z - z.max(0, keepdims=True))
     return (e / e.sum(0, keepdims=True)).astype(np.float32)

@@ -1,0 +1,85 @@
+"""GPU parity tests of the instance-labelling post-processing (lu_postprocess through postprocess.PostProcessor) --
+bit-exact against the golden vectors made by executing the reference's own statements, and against the pinned oracle
+on seeded inputs at the benchmark frame size."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import postprocess_oracle as P
+from tests.test_postprocess_oracle import golden_cases
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize('case', list(golden_cases()), ids=lambda c: c[0])
+def test_matches_reference_vectors(case):
+    from lstm_unet_b200.postprocess import PostProcessor
+    name, sm, want, num, kw = case
+    pp = PostProcessor(**kw)
+    got = pp(sm).numpy()
+    assert got.dtype == np.uint16 and got.shape == want.shape
+    assert pp.info()[0, 0] == num and pp.info()[0, 1] == want.max()
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize('kind,H,W,n', [('cells', 512, 512, 4), ('noise', 256, 320, 3), ('cells', 1024, 1024, 1),
+                                        ('noise', 130, 70, 8), ('full', 300, 200, 1), ('empty', 64, 64, 2)])
+def test_matches_oracle_large_and_batched(kind, H, W, n):
+    from lstm_unet_b200.postprocess import PostProcessor
+    sms = np.stack([P.synthetic_softmax(H, W, 50 + i, kind) for i in range(n)])
+    kw = dict(edge_dist=3, min_cell_size=3, max_cell_size=(10 ** 7 if kind == 'full' else 200), FOV=2)
+    want = np.stack([P.postprocess_frame(s, **kw) for s in sms])
+    pp = PostProcessor(**kw)
+    dev = torch.from_numpy(sms).cuda()
+    got = pp(dev).numpy()
+    assert np.array_equal(got, want)
+    # the same frames again through the same workspace, and in the other layout: no state leaks between calls
+    assert np.array_equal(pp(dev).numpy(), want)
+    last = PostProcessor(data_format='NHWC', **kw)(dev.permute(0, 2, 3, 1).contiguous()).numpy()
+    assert np.array_equal(last, want)
+
+
+def test_sequential_pass_on_device():
+    from lstm_unet_b200.postprocess import PostProcessor
+    kw = dict(edge_dist=4, min_cell_size=1, max_cell_size=10000)
+    flagged = 0
+    for seed in range(8):
+        sm = P.synthetic_softmax(48, 48, 100 + seed, 'noise')
+        pp = PostProcessor(**kw)
+        got = pp(sm).numpy()
+        flagged += int(pp.info()[0, 2])
+        assert np.array_equal(got, P.postprocess_frame(sm, **kw)), seed
+    assert flagged > 0
+
+
+def test_repeatable_under_contention():
+    """the union-find and the atomics must give the same labels on every run (the roots are minima, not winners)"""
+    from lstm_unet_b200.postprocess import PostProcessor
+    sms = torch.from_numpy(np.stack([P.synthetic_softmax(384, 384, 70 + i, 'noise') for i in range(6)])).cuda()
+    pp = PostProcessor(edge_dist=2, min_cell_size=2, max_cell_size=500)
+    first = pp(sms).numpy().copy()
+    for _ in range(5):
+        assert np.array_equal(pp(sms).numpy(), first)
+
+
+def test_model_softmax_to_labels_stays_on_device():
+    """Inference2D's frame loop: model soft-max (device) -> labels; equals the oracle applied to the soft-max the
+    model produced"""
+    from lstm_unet_b200.Networks import ULSTMnet2D
+    from lstm_unet_b200.postprocess import PostProcessor
+    from oracle import lstm_unet_oracle as O
+    net = {'down_conv_kernels': [[(3, 16), (3, 16)], [(3, 32), (3, 32)]], 'lstm_kernels': [[(5, 16)], [(5, 32)]],
+           'up_conv_kernels': [[(3, 32), (3, 32)], [(3, 16), (3, 16), (1, 3)]]}
+    params = O.init_params(net, seed=3, randomize_bn=True)
+    m = ULSTMnet2D(net, 'NCHW', True, precision='bf16')
+    m.set_weights_dict({k: v.numpy().copy() for k, v in params.items()})
+    x = np.random.default_rng(0).standard_normal((2, 2, 1, 64, 72)).astype(np.float32) * 3
+    _, softmax = m(x, training=False)
+    pp = PostProcessor(edge_dist=2, min_cell_size=1, max_cell_size=1000)
+    labels = pp(softmax).numpy()
+    assert labels.shape == (2, 2, 64, 72)
+    sm = softmax.numpy()
+    for b in range(2):
+        for t in range(2):
+            assert np.array_equal(labels[b, t], P.postprocess_frame(sm[b, t], edge_dist=2, min_cell_size=1,
+                                                                    max_cell_size=1000))
