@@ -92,6 +92,12 @@ int lu_params_changed(lu_handle h, void* stream);
 int lu_forward(lu_handle h, const float* dev_x, int32_t T, int32_t training, float* dev_logits,
                float* dev_softmax, void* stream);
 
+/* Launch-bound shapes (Inference2D's per-frame call, B=1, T=1: Inference2D.py:59): replay the inference forward as an
+ * instantiated CUDA graph (one per T and recurrent-state ping-pong parity; inputs / outputs pass through fixed staging
+ * buffers of the workspace).  Available when batch*max_t <= 8 and the handle was not created for training;
+ * *effective returns whether it is on.  Results are identical to the plain launches. */
+int lu_set_graph_mode(lu_handle h, int32_t enable, int32_t* effective);
+
 /* reset_states_per_batch (Networks.py:77-84,279-281): h,c *= mask[b]; mask is (B,) fp32 on the device */
 int lu_reset_states(lu_handle h, const float* dev_mask, void* stream);
 /* get_states / set_states (Networks.py:86-98,283-291): one (B,F,H,W)/(B,H,W,F) fp32 tensor per call;
@@ -143,6 +149,16 @@ int lu_post_workspace_bytes(int32_t frames, int32_t H, int32_t W, size_t* bytes)
 int lu_postprocess(const float* dev_softmax, int32_t frames, int32_t H, int32_t W, const lu_post_params* params,
                    uint16_t* dev_labels, int32_t* dev_info, void* dev_ws, size_t ws_bytes, void* stream);
 int lu_post_launch_count(int64_t* launches, int32_t reset);
+
+/* ---- per-step metrics of the reference's train / validation step (train2D.py:97-102,111-116): the SEG measure
+ * (losses.py:29-88: tf.py_function with SciPy labelling and Python loops on the host) and the sparse categorical
+ * accuracy, computed on the device from the labels and logits that are already there.
+ * dev_labels: (frames,1,H,W) == (frames,H,W,1) fp32 in {-1,0,1,2}; dev_logits: (frames,3,H,W) [channels_first] or
+ * (frames,H,W,3).  dev_result4 (4 doubles): sum of the truth objects' scores, truth objects, correctly classified
+ * pixels, pixels -- SEG = r[0]/r[1] (NaN without objects, like np.mean of nothing), accuracy = r[2]/r[3]. */
+int lu_seg_workspace_bytes(int32_t frames, int32_t H, int32_t W, size_t* bytes);
+int lu_seg_measure(const float* dev_labels, const float* dev_logits, int32_t frames, int32_t H, int32_t W,
+                   int32_t channels_first, double* dev_result4, void* dev_ws, size_t ws_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -199,7 +199,8 @@ class Adam:
 
 class ULSTMnet2D:
     def __init__(self, net_params=DEFAULT_NET_DOWN_PARAMS, data_format='NCHW', pad_image=True, *, precision='bf16',
-                 engine='tcgen05', gate='hard_sigmoid', a_mode='halo', train=False, seed=0, device=None):
+                 engine='tcgen05', gate='hard_sigmoid', a_mode='halo', train=False, seed=0, device=None,
+                 cuda_graph='auto'):
         # Networks.py:188-193: same ValueErrors, raised before anything touches the device
         _lib.make_config(net_params, data_format, pad_image)
         self.net_params = net_params
@@ -208,6 +209,10 @@ class ULSTMnet2D:
         self.channel_axis = 1 if data_format[1] == 'C' else -1
         self.pad_image = pad_image
         self.precision, self.engine, self.gate, self.a_mode, self.train_capable = precision, engine, gate, a_mode, train
+        # 'auto': the inference forward of launch-bound shapes (B*T <= 2, Inference2D's per-frame call) is replayed as a
+        # CUDA graph; True / False force it where the library allows it (B*T <= 8, not a training model)
+        self.cuda_graph = cuda_graph
+        self.graph_active = False
         self.seed, self._device = seed, device
         n = len(net_params['down_conv_kernels'])
         self.DownLayers = [DownBlock2D(c, l, 2 if i < n - 1 else 1, data_format, self, i)
@@ -245,6 +250,8 @@ class ULSTMnet2D:
                                precision=self.precision, engine=self.engine, gate=self.gate, a_mode=self.a_mode,
                                train=self.train_capable)
         sess = LuSession(self._lib, be, cfg)
+        want_graph = (B * T <= 2) if self.cuda_graph == 'auto' else bool(self.cuda_graph)
+        self.graph_active = sess.set_graph_mode(want_graph and not self.train_capable)
         if old is not None:                       # longer unroll than before: carry weights and states over
             sess.params.copy_(old.params)
             sess.params_changed()

@@ -58,6 +58,7 @@ def bind(lib):
         'lu_bind_params': [vp, vp],
         'lu_params_changed': [vp, vp],
         'lu_forward': [vp, vp, i32, i32, vp, vp, vp],
+        'lu_set_graph_mode': [vp, i32, P(i32)],
         'lu_reset_states': [vp, vp, vp],
         'lu_state_shape': [vp, i32, i32, P(i64)],
         'lu_get_state': [vp, i32, i32, i32, vp, vp],
@@ -72,6 +73,8 @@ def bind(lib):
         'lu_post_workspace_bytes': [i32, i32, i32, P(ctypes.c_size_t)],
         'lu_postprocess': [vp, i32, i32, i32, P(lu_post_params), vp, vp, vp, ctypes.c_size_t, vp],
         'lu_post_launch_count': [P(i64), i32],
+        'lu_seg_workspace_bytes': [i32, i32, i32, P(ctypes.c_size_t)],
+        'lu_seg_measure': [vp, vp, i32, i32, i32, i32, vp, vp, ctypes.c_size_t, vp],
     }
     for name, args in sigs.items():
         fn = getattr(lib, name)
@@ -82,9 +85,10 @@ def bind(lib):
 
 EXPORTED_SYMBOLS = ['lu_last_error', 'lu_version', 'lu_is_cuda_build', 'lu_create', 'lu_destroy', 'lu_workspace_bytes',
                     'lu_bind_workspace', 'lu_param_count', 'lu_param_info', 'lu_bind_params', 'lu_params_changed',
-                    'lu_forward', 'lu_reset_states', 'lu_state_shape', 'lu_get_state', 'lu_set_state',
+                    'lu_forward', 'lu_set_graph_mode', 'lu_reset_states', 'lu_state_shape', 'lu_get_state', 'lu_set_state',
                     'lu_loss_backward', 'lu_adam_step', 'lu_debug_buffer', 'lu_launch_count', 'lu_forward_flops', 'lu_lstm_flops',
-                    'lu_lstm_kernel_time', 'lu_post_workspace_bytes', 'lu_postprocess', 'lu_post_launch_count']
+                    'lu_lstm_kernel_time', 'lu_post_workspace_bytes', 'lu_postprocess', 'lu_post_launch_count',
+                    'lu_seg_workspace_bytes', 'lu_seg_measure']
 
 _LIB = None
 

@@ -143,6 +143,20 @@ struct lu_handle_s {
   std::vector<int> gidx;          // activation buffer -> its gradient twin (cfg.train)
   int g_logits_buf = -1;
   size_t tr_off_dwp = 0, tr_dwp_bytes = 0;
+  // CUDA-graph replay of the inference forward for launch-bound shapes (Inference2D's B=1, T=1 frame loop): one
+  // instantiated graph per (T, h ping-pong parity); inputs / outputs go through fixed staging buffers in the workspace
+  int graph_mode = 0;
+  bool graph_ok = false;
+  size_t off_gx = 0, off_glogits = 0, off_gsoftmax = 0, g_x_bytes = 0, g_out_bytes = 0;
+  struct FwdGraph { int T, hcur; int64_t launches;
+#ifndef LU_HOST_EMU
+    cudaGraphExec_t exec;
+#endif
+  };
+  std::vector<FwdGraph> graphs;
+#ifndef LU_HOST_EMU
+  cudaStream_t cap_stream = nullptr;
+#endif
   // optional CUDA-event timing of every ConvLSTM launch (bench.py roofline)
   bool time_lstm = false;
   size_t ev_used = 0;
@@ -593,6 +607,14 @@ static void layout_workspace(lu_handle_s* h) {
   for (auto& cv : h->convs)
     if (cv.off_raw == (size_t)-1) cv.off_raw = h->off_raw_scratch;
   train_layout(h, off);
+  h->graph_ok = !c.train && N <= 8;
+  if (h->graph_ok) {
+    h->g_x_bytes = (size_t)N * c.in_channels * c.height * c.width * 4;
+    h->g_out_bytes = (size_t)N * h->convs[h->logits_conv].cout * c.height * c.width * 4;
+    h->off_gx = take(h->g_x_bytes);
+    h->off_glogits = take(h->g_out_bytes);
+    h->off_gsoftmax = take(h->g_out_bytes);
+  }
   h->ws_bytes = off;
 }
 
@@ -782,7 +804,18 @@ int lu_create(const lu_config* cfg, lu_handle* out) {
 }
 
 int lu_destroy(lu_handle h) {
-  if (h) { train_destroy(h); delete h; }
+  if (h) {
+    for (size_t i = 0; i < h->graphs.size(); ++i) {
+#ifndef LU_HOST_EMU
+      cudaGraphExecDestroy(h->graphs[i].exec);
+#endif
+    }
+    h->graphs.clear();
+#ifndef LU_HOST_EMU
+    if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
+#endif
+    train_destroy(h); delete h;
+  }
   return 0;
 }
 
@@ -797,6 +830,12 @@ int lu_bind_workspace(lu_handle h, void* dev_ws, size_t bytes, void* stream) {
   LU_REQUIRE(bytes >= h->ws_bytes, "workspace too small: %zu < %zu", bytes, h->ws_bytes);
   LU_REQUIRE(((uintptr_t)dev_ws & 1023) == 0, "workspace must be 1024-byte aligned");
   h->ws = (uint8_t*)dev_ws;
+  for (size_t i = 0; i < h->graphs.size(); ++i) {      // instantiated graphs point into the previous workspace
+#ifndef LU_HOST_EMU
+    cudaGraphExecDestroy(h->graphs[i].exec);
+#endif
+  }
+  h->graphs.clear();
 #ifndef LU_HOST_EMU
   {
     int dev = 0;
@@ -989,12 +1028,76 @@ static int run_lstm_layer(lu_handle_s* h, ConvPlan& cv, int T, int training, voi
   return 0;
 }
 
+static int forward_body(lu_handle h, const float* dev_x, int32_t T, int32_t training, float* dev_logits,
+                        float* dev_softmax, void* stream);
+
+int lu_set_graph_mode(lu_handle h, int32_t enable, int32_t* effective) {
+  LU_REQUIRE(h, "null handle");
+  h->graph_mode = (enable && h->graph_ok) ? 1 : 0;
+#ifdef LU_HOST_EMU
+  h->graph_mode = 0;
+#endif
+  if (effective) *effective = h->graph_mode;
+  return 0;
+}
+
 int lu_forward(lu_handle h, const float* dev_x, int32_t T, int32_t training, float* dev_logits, float* dev_softmax,
                void* stream) {
   LU_REQUIRE(h && h->bound && h->dparams, "bind workspace and parameters first");
   LU_REQUIRE(dev_x && dev_logits && dev_softmax, "null tensor");
   LU_REQUIRE(T >= 1 && T <= h->cfg.max_t, "T=%d outside [1,%d]", T, h->cfg.max_t);
   if (!h->packed && lu_params_changed(h, stream)) return 1;
+#ifndef LU_HOST_EMU
+  if (h->graph_mode && !training && !h->time_lstm) {
+    // replay path: stage the input, launch the instantiated graph of this (T, state parity), copy the outputs out
+    const lu_config& c = h->cfg;
+    float* gx = reinterpret_cast<float*>(h->ws + h->off_gx);
+    float* gl = reinterpret_cast<float*>(h->ws + h->off_glogits);
+    float* gs = reinterpret_cast<float*>(h->ws + h->off_gsoftmax);
+    lu_handle_s::FwdGraph* g = nullptr;
+    for (auto& e : h->graphs) if (e.T == T && e.hcur == h->hcur) g = &e;
+    if (!g) {
+      if (!h->cap_stream) {
+        cudaError_t e = cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking);
+        LU_REQUIRE(e == cudaSuccess, "cudaStreamCreate: %s", cudaGetErrorString(e));
+      }
+      const int hcur0 = h->hcur; const int64_t l0 = h->launches;
+      cudaError_t e = cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal);
+      LU_REQUIRE(e == cudaSuccess, "cudaStreamBeginCapture: %s", cudaGetErrorString(e));
+      const int rc = forward_body(h, gx, T, 0, gl, gs, h->cap_stream);
+      cudaGraph_t graph = nullptr;
+      e = cudaStreamEndCapture(h->cap_stream, &graph);
+      h->hcur = hcur0;
+      lu_handle_s::FwdGraph ng; ng.T = T; ng.hcur = hcur0; ng.launches = h->launches - l0; ng.exec = nullptr;
+      h->launches = l0;
+      if (rc) { if (graph) cudaGraphDestroy(graph); return 1; }
+      LU_REQUIRE(e == cudaSuccess && graph, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
+      e = cudaGraphInstantiate(&ng.exec, graph, 0);
+      cudaGraphDestroy(graph);
+      LU_REQUIRE(e == cudaSuccess, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
+      h->graphs.push_back(ng);
+      g = &h->graphs.back();
+    }
+    const size_t frac_x = (size_t)c.batch * T * c.in_channels * c.height * c.width * 4;
+    const size_t frac_o = (size_t)c.batch * T * h->convs[h->logits_conv].cout * c.height * c.width * 4;
+    cudaMemcpyAsync(gx, dev_x, frac_x, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+    cudaError_t e = cudaGraphLaunch(g->exec, (cudaStream_t)stream);
+    LU_REQUIRE(e == cudaSuccess, "cudaGraphLaunch: %s", cudaGetErrorString(e));
+    cudaMemcpyAsync(dev_logits, gl, frac_o, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+    cudaMemcpyAsync(dev_softmax, gs, frac_o, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+    h->launches += g->launches;
+    h->hcur ^= 1;
+    h->last_T = T; h->last_training = 0;
+    e = cudaGetLastError();
+    LU_REQUIRE(e == cudaSuccess, "forward (graph): %s", cudaGetErrorString(e));
+    return 0;
+  }
+#endif
+  return forward_body(h, dev_x, T, training, dev_logits, dev_softmax, stream);
+}
+
+static int forward_body(lu_handle h, const float* dev_x, int32_t T, int32_t training, float* dev_logits,
+                        float* dev_softmax, void* stream) {
   const lu_config& c = h->cfg;
   const int N = c.batch * T;
   {

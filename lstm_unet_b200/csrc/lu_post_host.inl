@@ -4,9 +4,9 @@
 static int64_t g_post_launches = 0;
 
 struct PostLayout {
-  size_t cls, parA, parB, key, area, cc, lab, add, bflag, larea, present, newlab, bbox, info, slab, total;
+  size_t cls, parA, parB, key, area, cc, lab, add, bflag, rowcnt, larea, present, newlab, bbox, info, slab, total;
   size_t zero_begin, zero_end;     // bflag .. info: cleared at the start of every call (bbox with the 0x7f pattern)
-  int WB, NB, KMAX, G;
+  int WB, HB, NB, KMAX, G;
 };
 
 static int post_layout(int frames, int H, int W, PostLayout* L) {
@@ -14,10 +14,11 @@ static int post_layout(int frames, int H, int W, PostLayout* L) {
   LU_REQUIRE((int64_t)H * W < (1ll << 30) && (int64_t)frames * H * W < (1ll << 40), "frame too large");
   const size_t HW = (size_t)H * W, N = (size_t)frames;
   L->WB = (W + 1) / 2;
-  L->NB = L->WB * ((H + 1) / 2);
+  L->HB = (H + 1) / 2;
+  L->NB = L->WB * L->HB;
   L->KMAX = L->NB + 1;
-  int g = 296 / frames;
-  L->G = g < 2 ? 2 : (g > 64 ? 64 : g);
+  int g = 1184 / frames;          // flood CTAs per frame: about 8 resident 128-thread CTAs per SM over the batch
+  L->G = g < 4 ? 4 : (g > 148 ? 148 : g);
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
   L->cls = take(N * HW);
@@ -25,10 +26,10 @@ static int post_layout(int frames, int H, int W, PostLayout* L) {
   L->cc = take(N * HW * 4); L->lab = take(N * HW * 4); L->add = take(N * HW * 4);
   L->larea = take(N * L->KMAX * 4); L->newlab = take(N * L->KMAX * 4);
   L->zero_begin = off;
-  L->bflag = take(N * L->NB * 4); L->present = take(N * L->KMAX * 4); L->info = take(N * 4 * 4);
+  L->bflag = take(N * L->NB); L->rowcnt = take(N * L->HB * 4); L->present = take(N * L->KMAX * 4); L->info = take(N * 4 * 4);
   L->zero_end = off;
   L->bbox = take(N * L->KMAX * 16);
-  L->slab = take(N * L->G * HW);
+  L->slab = take(N * LU_PP_SLABS * HW);
   L->total = off;
   return 0;
 }
@@ -82,7 +83,7 @@ extern "C" int lu_postprocess(const float* dev_softmax, int32_t frames, int32_t 
   LuPost q;
   memset(&q, 0, sizeof q);
   q.sm = dev_softmax; q.chw = pp->channels_first ? 1 : 0;
-  q.N = frames; q.H = H; q.W = W; q.HW = H * W; q.WB = L.WB; q.NB = L.NB; q.KMAX = L.KMAX; q.G = L.G;
+  q.N = frames; q.H = H; q.W = W; q.HW = H * W; q.WB = L.WB; q.HB = L.HB; q.NB = L.NB; q.KMAX = L.KMAX; q.G = L.G;
   q.edge_thresh = pp->edge_thresh; q.d2lim = pp->edge_d2_limit;
   q.rad = 0;
   while ((q.rad + 1) * (q.rad + 1) < q.d2lim) q.rad++;
@@ -90,18 +91,17 @@ extern "C" int lu_postprocess(const float* dev_softmax, int32_t frames, int32_t 
   q.cls = ws + L.cls;
   q.parA = (int32_t*)(ws + L.parA); q.parB = (int32_t*)(ws + L.parB); q.key = (int32_t*)(ws + L.key);
   q.area = (int32_t*)(ws + L.area); q.cc = (int32_t*)(ws + L.cc); q.lab = (int32_t*)(ws + L.lab); q.add = (int32_t*)(ws + L.add);
-  q.bflag = (int32_t*)(ws + L.bflag); q.larea = (int32_t*)(ws + L.larea); q.present = (int32_t*)(ws + L.present);
+  q.bflag = ws + L.bflag; q.rowcnt = (int32_t*)(ws + L.rowcnt); q.larea = (int32_t*)(ws + L.larea); q.present = (int32_t*)(ws + L.present);
   q.newlab = (int32_t*)(ws + L.newlab); q.bbox = (int32_t*)(ws + L.bbox); q.info = (int32_t*)(ws + L.info);
   q.slab = ws + L.slab; q.out = dev_labels;
 
   LU_MEMSET(ws + L.zero_begin, 0, L.zero_end - L.zero_begin, stream);
   LU_MEMSET(ws + L.bbox, 0x7f, (size_t)frames * L.KMAX * 16, stream);
   const int64_t npix = (int64_t)frames * q.HW;
-  const int64_t nseg = (int64_t)frames * H * ((W + LU_PP_SEG - 1) / LU_PP_SEG);
-  post_pf(nseg, stream, LuPpClassify{q});
+  post_pf(npix, stream, LuPpClassify{q, npix});
   post_pf(npix, stream, LuPpMergeBg{q});
   post_pf(npix, stream, LuPpFlattenBg{q});
-  post_pf(nseg, stream, LuPpFill{q});
+  post_pf(npix, stream, LuPpFill{q, npix});
   post_pf(npix, stream, LuPpMergeFg{q});
   post_pf(npix, stream, LuPpFlattenFg{q});
   post_pf(npix, stream, LuPpMarkBlocks{q});
@@ -111,20 +111,24 @@ extern "C" int lu_postprocess(const float* dev_softmax, int32_t frames, int32_t 
   const LuCta one{0, 1};
   for (int n = 0; n < frames; ++n) lu_pp_rank_cta(one, q, n, sums);
 #else
-  lu_pp_rank_kernel<<<frames, 1024, 0, (cudaStream_t)stream>>>(q);
+  lu_pp_rank_kernel<<<frames, 256, 0, (cudaStream_t)stream>>>(q);
 #endif
   g_post_launches++;
+  post_pf(npix, stream, LuPpRootLabel{q});
   post_pf(npix, stream, LuPpAssign{q});
   post_pf(npix, stream, LuPpEdges{q});
 #ifdef LU_HOST_EMU
   for (int n = 0; n < frames; ++n)
     for (int g = 0; g < q.G; ++g) lu_pp_holes_cta(one, q, g, n, small.data(), &changed);
+  for (int n = 0; n < frames; ++n)
+    for (int g = 0; g < LU_PP_SLABS; ++g) lu_pp_holes_big_cta(one, q, g, n, small.data(), &changed);
   for (int n = 0; n < frames; ++n) lu_pp_holes_seq_cta(one, q, n, small.data(), &changed);
 #else
   lu_pp_holes_kernel<<<dim3(q.G, frames), LU_PP_CTA, 0, (cudaStream_t)stream>>>(q);
+  lu_pp_holes_big_kernel<<<dim3(LU_PP_SLABS, frames), 1024, 0, (cudaStream_t)stream>>>(q);
   lu_pp_holes_seq_kernel<<<frames, 256, 0, (cudaStream_t)stream>>>(q);
 #endif
-  g_post_launches += 2;
+  g_post_launches += 3;
   post_pf(npix, stream, LuPpCombine{q});
 #ifdef LU_HOST_EMU
   for (int n = 0; n < frames; ++n) lu_pp_relabel_cta(one, q, n, sums);
@@ -137,6 +141,65 @@ extern "C" int lu_postprocess(const float* dev_softmax, int32_t frames, int32_t 
 #ifndef LU_HOST_EMU
   cudaError_t e = cudaGetLastError();
   LU_REQUIRE(e == cudaSuccess, "post-processing launch failed: %s", cudaGetErrorString(e));
+#endif
+  return 0;
+}
+
+// ---- SEG measure + accuracy (losses.py:29-88, train2D.py:97-102) ---------------------------------------------------------
+struct SegLayout { size_t cls, parG, parS, areaG, areaS, score, keys, cnt, total; int cap; };
+static int seg_layout(int frames, int H, int W, SegLayout* L) {
+  LU_REQUIRE(frames > 0 && H > 0 && W > 0, "SEG measure needs frames, H, W > 0");
+  LU_REQUIRE((int64_t)H * W < (1ll << 30), "frame too large");
+  const size_t HW = (size_t)H * W, N = (size_t)frames;
+  int cap = 64;
+  while ((size_t)cap < HW) cap <<= 1;
+  L->cap = cap;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+  L->cls = take(N * HW);
+  L->parG = take(N * HW * 4); L->parS = take(N * HW * 4); L->areaG = take(N * HW * 4); L->areaS = take(N * HW * 4);
+  L->score = take(N * HW * 4);
+  L->keys = take(N * (size_t)cap * 8); L->cnt = take(N * (size_t)cap * 4);
+  L->total = off;
+  return 0;
+}
+extern "C" int lu_seg_workspace_bytes(int32_t frames, int32_t H, int32_t W, size_t* bytes) {
+  SegLayout L;
+  if (seg_layout(frames, H, W, &L)) return 1;
+  LU_REQUIRE(bytes, "null argument");
+  *bytes = L.total;
+  return 0;
+}
+extern "C" int lu_seg_measure(const float* dev_labels, const float* dev_logits, int32_t frames, int32_t H, int32_t W,
+                              int32_t channels_first, double* dev_result4, void* dev_ws, size_t ws_bytes, void* stream) {
+  LU_REQUIRE(dev_labels && dev_logits && dev_result4 && dev_ws, "null argument");
+  SegLayout L;
+  if (seg_layout(frames, H, W, &L)) return 1;
+  LU_REQUIRE(ws_bytes >= L.total, "workspace too small: %zu < %zu", ws_bytes, L.total);
+  LU_REQUIRE(((uintptr_t)dev_ws & 255) == 0, "workspace must be 256-byte aligned");
+  uint8_t* ws = (uint8_t*)dev_ws;
+  LuSeg q;
+  memset(&q, 0, sizeof q);
+  q.labels = dev_labels; q.logits = dev_logits; q.chw = channels_first ? 1 : 0;
+  q.N = frames; q.H = H; q.W = W; q.HW = H * W; q.cap = L.cap;
+  q.cls = ws + L.cls;
+  q.parG = (int32_t*)(ws + L.parG); q.parS = (int32_t*)(ws + L.parS);
+  q.areaG = (int32_t*)(ws + L.areaG); q.areaS = (int32_t*)(ws + L.areaS);
+  q.score = (float*)(ws + L.score); q.keys = (long long*)(ws + L.keys); q.cnt = (int32_t*)(ws + L.cnt);
+  q.result = dev_result4;
+  LU_MEMSET(ws + L.keys, 0xff, (size_t)frames * L.cap * 8, stream);
+  LU_MEMSET(ws + L.cnt, 0, (size_t)frames * L.cap * 4, stream);
+  LU_MEMSET(dev_result4, 0, 4 * sizeof(double), stream);
+  const int64_t npix = (int64_t)frames * q.HW;
+  post_pf(npix, stream, LuSegClassify{q, npix});
+  post_pf(npix, stream, LuSegMerge{q});
+  post_pf(npix, stream, LuSegFlatten{q});
+  post_pf(npix, stream, LuSegPairs{q, npix});
+  post_pf((int64_t)frames * L.cap, stream, LuSegScore{q});
+  post_pf(npix, stream, LuSegReduce{q, npix});
+#ifndef LU_HOST_EMU
+  cudaError_t e = cudaGetLastError();
+  LU_REQUIRE(e == cudaSuccess, "SEG measure launch failed: %s", cudaGetErrorString(e));
 #endif
   return 0;
 }

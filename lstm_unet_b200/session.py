@@ -113,6 +113,11 @@ class LuSession:
         self._check(self.lib.lu_forward(self.h, x_ptr, int(T), 1 if training else 0, logits_ptr, softmax_ptr,
                                         self.be.stream()))
 
+    def set_graph_mode(self, enable):
+        eff = ctypes.c_int32()
+        self._check(self.lib.lu_set_graph_mode(self.h, 1 if enable else 0, ctypes.byref(eff)))
+        return bool(eff.value)
+
     def reset_states(self, mask_ptr):
         self._check(self.lib.lu_reset_states(self.h, mask_ptr, self.be.stream()))
 

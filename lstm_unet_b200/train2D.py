@@ -1,7 +1,7 @@
 """Mirror of the hot-path part of the reference's ``train2D.py`` (train2D.py:33-118,145-161,192-220): same call
 order -- providers, model construction with pad_image=False, Adam, train_step, reset_states_per_batch, validation
-with swapped recurrent states.  TensorBoard, checkpoint manager, AWS polling and the seg_measure metric are out of
-scope.  Usage, as in the reference: set the module global ``params`` and call ``train()``."""
+with swapped recurrent states, and the per-step SEG measure / accuracy metrics (train2D.py:97-102,111-116) computed on the
+device.  TensorBoard, checkpoint manager and AWS polling are out of scope.  Usage, as in the reference: set the module global ``params`` and call ``train()``."""
 from . import Networks as Nets
 from . import losses
 
@@ -23,15 +23,21 @@ def train(num_iterations=None, allreduce=None, log=log_print):
                              precision=getattr(params, 'precision', 'bf16'), train=True)
     ce_loss = losses.WeightedCELoss(params.channel_axis + 1, params.class_weights)
     optimizer = Nets.Adam(lr=params.learning_rate)
+    seg_measure = losses.seg_measure(params.channel_axis + 1, three_d=False)     # train2D.py:51
+    metrics = {'train': {'SEG': [], 'accuracy': []}, 'val': {'SEG': [], 'accuracy': []}}
     step = 0
 
     def train_step(image, label):
         softmax, predictions, loss = model.train_step(image, label, params.class_weights, optimizer, allreduce)
+        metrics['train']['SEG'].append(seg_measure(label, predictions))          # train2D.py:97-102
+        metrics['train']['accuracy'].append(seg_measure.last_accuracy)
         return softmax, predictions, loss
 
     def val_step(image, label):
         predictions, softmax = model(image, False)
         t_loss = ce_loss(label, predictions)
+        metrics['val']['SEG'].append(seg_measure(label, predictions))            # train2D.py:111-116
+        metrics['val']['accuracy'].append(seg_measure.last_accuracy)
         return softmax, predictions, t_loss
 
     losses_seen = []
@@ -55,4 +61,5 @@ def train(num_iterations=None, allreduce=None, log=log_print):
             val_states = model.get_states()
             model.set_states(train_states)
     train.model = model
+    train.metrics = metrics
     return losses_seen

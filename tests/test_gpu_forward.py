@@ -157,3 +157,46 @@ def test_unroll_length_may_change_and_grow():
         assert tuple(logits.shape) == (2, T, 3, 16, 24)
         assert rel_err(logits.numpy(), ref_l.numpy()) < 1e-3, T
     model.close()
+
+
+@pytest.mark.parametrize("precision", ['bf16', 'bf16x3'])
+def test_cuda_graph_replay_is_bitwise_the_plain_forward(precision):
+    """Inference2D's frame loop (B=1, T=1, stateful) replayed as CUDA graphs (lu_set_graph_mode): same bits as the
+    plain launches over a sequence that alternates the recurrent-state ping-pong parity, with a state reset and a
+    set_states in between, and with T=2 calls mixed in."""
+    from lstm_unet_b200.Networks import ULSTMnet2D
+    params = O.init_params(NET_WIDE, seed=5, randomize_bn=True)
+    rng = np.random.default_rng(7)
+    frames = [rng.standard_normal((1, 1, 1, 40, 56)).astype(np.float32) for _ in range(7)]
+    pair = rng.standard_normal((1, 2, 1, 40, 56)).astype(np.float32)
+    outs = {}
+    for mode in (False, True):
+        m = ULSTMnet2D(NET_WIDE, 'NCHW', True, precision=precision, cuda_graph=mode)
+        m.set_weights_dict({k: v.numpy().copy() for k, v in params.items()})
+        got = []
+        m(pair, False)                                   # builds the session with max_t = 2
+        assert m.graph_active == mode
+        for i, f in enumerate(frames):
+            lg, sm = m(f, False)
+            got.append((lg.numpy().copy(), sm.numpy().copy()))
+            if i == 2:
+                m.reset_states_per_batch(np.zeros(1, np.float32))
+            if i == 4:
+                st = m.get_states()
+                m.set_states(st)
+                lg2, _ = m(pair, False)
+                got.append((lg2.numpy().copy(),))
+        n0 = m.launch_count(reset=True)
+        m(frames[0], False)
+        assert m.launch_count() > 0 and n0 > 0
+        outs[mode] = got
+        m.close()
+    for a, b in zip(outs[False], outs[True]):
+        for u, v in zip(a, b):
+            assert np.array_equal(u, v)
+    auto = ULSTMnet2D(NET_WIDE, 'NCHW', True, precision=precision)
+    auto(frames[0], False)
+    assert auto.graph_active                            # B*T = 1: on by default
+    big = ULSTMnet2D(NET_WIDE, 'NCHW', True, precision=precision)
+    big(np.zeros((2, 2, 1, 40, 56), np.float32), False)
+    assert not big.graph_active
