@@ -591,7 +591,9 @@ static void layout_workspace(lu_handle_s* h) {
         cv.off_save_c = take(pn * cv.fpad * 4);
       }
     } else {
-      cv.raw_cpad = cv.npad;
+      // fp32 pre-activation output: all packed columns for a BN conv, the 16-column chunks that hold real channels for
+      // the logits conv (3 classes: 64 B per pixel instead of 256 B)
+      cv.raw_cpad = cv.has_bn ? cv.npad : ceil_to(cv.cout, 16);
       const size_t rb = (size_t)N * cv.Hout * cv.Wout * cv.raw_cpad * 4;
       cv.off_bscale = take((size_t)cv.npad * 4);
       cv.off_bshift = take((size_t)cv.npad * 4);

@@ -16,6 +16,7 @@
 #define LU_HDI inline
 #else
 #include <cuda_runtime.h>
+#include <cuda_bf16.h>
 #define LU_HD __host__ __device__
 #define LU_HDI __host__ __device__ __forceinline__
 #endif
@@ -41,10 +42,14 @@ LU_HDI float lu_u2f(uint32_t u) {
 #endif
 }
 LU_HDI uint16_t lu_f2bf(float f) {
+#ifdef __CUDA_ARCH__
+  return __bfloat16_as_ushort(__float2bfloat16_rn(f));     // cvt.rn.bf16.f32: same RNE result for every finite value
+#else
   uint32_t u = lu_f2u(f);
   if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);   // NaN
   u += 0x7fffu + ((u >> 16) & 1u);
   return (uint16_t)(u >> 16);
+#endif
 }
 LU_HDI float lu_bf2f(uint16_t h) { return lu_u2f(((uint32_t)h) << 16); }
 // split v into hi + lo bf16 parts (lo = bf16(v - hi)); used by the bf16x3 precision mode

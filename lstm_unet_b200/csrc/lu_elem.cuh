@@ -87,10 +87,10 @@ struct LuPrepPatches {
       for (int dx = 0; dx < pw; ++dx) {
         const int px = xx + dx - c;
         if (px < 0 || px >= Wp) continue;
-        uint16_t h, l; lu_split(row[lu_reflect(px - pad_x0, W)], h, l);
+        const float v = row[lu_reflect(px - pad_x0, W)];
         const int t = dy * pw + dx;
-        r[t] = h;
-        if (x3) r[32 + t] = l;
+        if (x3) { uint16_t h, l; lu_split(v, h, l); r[t] = h; r[32 + t] = l; }
+        else r[t] = lu_f2bf(v);
       }
     }
     uint16_t* o = out + p * 64;
@@ -137,7 +137,8 @@ struct LuUpsample2x {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float top = 0.75f * v00[j] + 0.25f * v01[j], bot = 0.75f * v10[j] + 0.25f * v11[j];
-      lu_split(0.75f * top + 0.25f * bot, hi[j], lo[j]);
+      if (planes == 2) lu_split(0.75f * top + 0.25f * bot, hi[j], lo[j]);
+      else hi[j] = lu_f2bf(0.75f * top + 0.25f * bot);
     }
     uint16_t* o = out + (((n * 2 * h + oy) * 2 * w) + ox) * (int64_t)ct + c;
     lu_store8_bf16(o, hi);
@@ -195,7 +196,8 @@ struct LuBnApply {
     for (int j = 0; j < 8; ++j) {
       float a = 0.f;
       if (c + j < raw_cpad) { a = raw[p * raw_cpad + c + j] * scale[c + j] + shift[c + j]; a = a > 0.f ? a : alpha * a; }
-      lu_split(a, hi[j], lo[j]);
+      if (planes == 2) lu_split(a, hi[j], lo[j]);
+      else hi[j] = lu_f2bf(a);
     }
     uint16_t* o = out + p * (int64_t)(out_cpad * planes) + c;
     lu_store8_bf16(o, hi);
