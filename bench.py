@@ -417,6 +417,115 @@ def run_postprocess(args):
         dist.destroy_process_group()
 
 
+def run_augment(args):
+    """--mode augment: the training reader's per-frame augmentation chain (DataHandeling.py:330-380:
+    contrast / brightness, cv2.warpAffine + scipy map_coordinates elastic warp of image and segmentation,
+    _fix_transformed_segmentation, flips, rot90) for one batch of sequences on the device.  value: crops resident in
+    HBM; e2e: host crops in (pinned), device batch out + a 4-byte checksum read back (the batch feeds the model on the
+    device); cpu_baseline: the oracle (pinned to vectors made by the reference's helpers) on a few frames."""
+    import torch
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    import __graft_entry__ as ge
+    ge.build()
+    from lstm_unet_b200.augment import SequenceAugmenter, random_affine
+    from lstm_unet_b200 import _lib
+    from oracle import augment_oracle as A
+    B, T, H, W = args.batch, args.unroll, args.size, args.size
+    rs = np.random.RandomState(7 + rank)
+    imgs, segs = A.synthetic_sequence(T, H, W, 11 + rank)
+    aug = SequenceAugmenter()
+    affine = random_affine((H, W), W * 0.08, rs)
+    rand2 = np.stack([rs.rand(H, W), rs.rand(H, W)])
+    contrast = (rs.rand(T) + 0.5).astype(np.float32)
+    brightness = ((rs.rand(T) - 0.5) * 0.2 * imgs.max()).astype(np.float32)
+    coords = aug.elastic_coords(rand2, W * 2, W * 0.15)
+    img_pin, seg_pin = torch.from_numpy(imgs).pin_memory(), torch.from_numpy(segs).pin_memory()
+    img_dev, seg_dev = img_pin.cuda(), seg_pin.cuda()
+    out_i = torch.empty(B * T * H * W, dtype=torch.float32, device='cuda')
+    out_s = torch.empty_like(out_i)
+
+    def step(src_i, src_s):
+        for b in range(B):          # one launch sequence per sample's sequence chunk, written into its batch slice
+            sl = slice(b * T * H * W, (b + 1) * T * H * W)
+            aug.augment(src_i, src_s, contrast, brightness, affine, coords, (1, 0), 1, out_img=out_i[sl], out_seg=out_s[sl])
+    step(img_dev, seg_dev)
+    torch.cuda.synchronize()
+    if rank == 0:
+        ref_i, ref_s = A.augment_frame(imgs[0], segs[0], contrast[0], brightness[0], affine,
+                                       A.elastic_coords(rand2, W * 2, W * 0.15), (1, 0), 1)
+        got_s = out_s[:H * W].reshape(H, W).cpu().numpy()
+        got_i = out_i[:H * W].reshape(H, W).cpu().numpy()
+        assert (got_s != ref_s).mean() < 1e-4 and np.allclose(got_i, ref_i, rtol=1e-5, atol=1e-2), 'augmentation differs from the oracle'
+    for _ in range(args.warmup):
+        step(img_dev, seg_dev)
+    torch.cuda.synchronize()
+    lib = _lib.load_library()
+    lib.lu_post_launch_count(None, 1)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step(img_dev, seg_dev)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    import ctypes
+    nl = ctypes.c_int64()
+    lib.lu_post_launch_count(ctypes.byref(nl), 0)
+    clocks = sampler.stop() if rank == 0 else None
+    e2e_steps = max(2, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        img_dev.copy_(img_pin, non_blocking=True)
+        seg_dev.copy_(seg_pin, non_blocking=True)
+        step(img_dev, seg_dev)
+        chk = float(out_i[:16].sum())
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    if rank != 0:
+        return
+    n = B * T
+    alg = n * H * W * 16.0           # image + segmentation read and written once, fp32
+    hbm, src = 6550.0, 'fallback'
+    pk = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(pk):
+        with open(pk) as f:
+            hbm = json.load(f).get('hbm_gbs', hbm)
+        src = 'measured hbm_gbs'
+    ach = alg * args.steps / (ms * 1e-3) / 1e9
+    line = {'metric': 'frames/sec (%dx%d crop: elastic + affine + photometric augmentation)' % (H, W), 'value': n * args.steps * world / (ms * 1e-3),
+            'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32/f64', 'data': 'synthetic',
+            'config': {'workload': 'SURVEY 8f row 4: DataHandeling.py:330-380 augmentation of a batch of %d sequences x %d frames, %dx%d crops, '
+                                   'elastic_augmentation=True, randomize=True' % (B, T, H, W),
+                       'l2_policy': 'batch + scratch (%.0f MB) exceed the 126 MB L2 at the default size' % (n * H * W * 40 / 1e6)},
+            'e2e': {'value': n * e2e_steps * world / (e2e_ms * 1e-3), 'unit': 'frames/s', 'h2d_bytes_per_step': int(imgs.nbytes + segs.nbytes),
+                    'd2h_bytes_per_step': 4, 'steps': e2e_steps, 'ms_per_step': e2e_ms / e2e_steps},
+            'gpu_launches': int(nl.value), 'clocks': clocks,
+            'roofline': {'bound': 'hbm', 'achieved': ach, 'peak': hbm, 'unit': 'GB/s', 'frac': ach / hbm, 'traffic': None,
+                         'peak_source': src, 'kernel': 'whole lu_augment_sequence chain (%d launches per batch); algorithmic bytes = 16 B/pixel' % (nl.value // max(1, args.steps))}}
+    if world == 1 and not args.no_cpu:
+        cref = A.elastic_coords(rand2, W * 2, W * 0.15)
+        k = 3
+        t0 = time.perf_counter()
+        for i in range(k):
+            A.augment_frame(imgs[i % T], segs[i % T], contrast[i % T], brightness[i % T], affine, cref, (1, 0), 1)
+        dt = time.perf_counter() - t0
+        line['cpu_baseline'] = {'value': k / dt, 'unit': 'frames/s', 'cores': 1, 'kind': 'port',
+                                'sample': 'oracle/augment_oracle.augment_frame (numpy restatement of the reference chain, pinned to vectors '
+                                          'made by the reference\'s helpers; slower than cv2 / scipy themselves) on %d frames' % k}
+    emit(line)
+
+
 def main():
     # stdout carries exactly ONE JSON line: libraries that print to fd 1 (NCCL's version banner) are sent to stderr
     global _REAL_STDOUT
@@ -428,7 +537,7 @@ def main():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--mode', default='infer', choices=['infer', 'train', 'stream', 'postprocess'],
+    ap.add_argument('--mode', default='infer', choices=['infer', 'train', 'stream', 'postprocess', 'augment'],
                     help="infer = C2 (default, headline); train = C3/C4 full train step; stream = Inference2D's real per-frame call (B=1, T=1)")
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'bf16x3'])
     ap.add_argument('--a-mode', dest='a_mode', default='halo', choices=['halo', 'direct'])
@@ -446,6 +555,8 @@ def main():
         run_reference(args)
     elif args.mode == 'postprocess':
         run_postprocess(args)
+    elif args.mode == 'augment':
+        run_augment(args)
     else:
         run_ours(args)
 

@@ -160,6 +160,32 @@ int lu_seg_workspace_bytes(int32_t frames, int32_t H, int32_t W, size_t* bytes);
 int lu_seg_measure(const float* dev_labels, const float* dev_logits, int32_t frames, int32_t H, int32_t W,
                    int32_t channels_first, double* dev_result4, void* dev_ws, size_t ws_bytes, void* stream);
 
+/* ---- training-reader augmentation on the device (CTCRAMReaderSequence2D._load_and_enqueue, DataHandeling.py:262-395,
+ * and its static helpers :150-261): contrast / brightness, cv2.warpAffine + scipy map_coordinates elastic warp of image
+ * and segmentation, _fix_transformed_segmentation, flips, rot90 -- one call per sequence chunk, results written where
+ * the caller points (its slice of the (B,T,1,H,W) batch tensors).  Random numbers stay on the host (np.random, same
+ * draws as the reference). */
+typedef struct lu_aug_params {
+  int32_t frames, H, W;
+  int32_t randomize;        /* contrast / brightness on (self.randomize, :330-336) */
+  int32_t elastic;          /* affine + elastic warp on (self.elastic_augmentation, :338-366) */
+  int32_t flip0, flip1;     /* cv2.flip(., 0) / cv2.flip(., 1) (:369-374) */
+  int32_t rot90;            /* np.rot90(., k) (:375-377); odd k needs H == W like the reference's fixed queue shapes */
+  double affine[6];         /* the 2x3 matrix cv2.getAffineTransform returned (:150-168); inverted like cv2.warpAffine */
+} lu_aug_params;
+int lu_aug_workspace_bytes(int32_t frames, int32_t H, int32_t W, size_t* bytes);
+/* dev_img / dev_seg: (frames,H,W) fp32 crops (seg: instance labels, -1 = not annotated); dev_contrast / dev_brightness:
+ * (frames) fp32; dev_coords: (2,H,W) float64 from lu_elastic_coords (NULL without elastic); outputs (frames,H,W) fp32:
+ * image, and segmentation in {-1, 0, 1, 2} */
+int lu_augment_sequence(const float* dev_img, const float* dev_seg, const float* dev_contrast, const float* dev_brightness,
+                        const double* dev_coords, const lu_aug_params* params, float* dev_img_out, float* dev_seg_out,
+                        void* dev_ws, size_t ws_bytes, void* stream);
+/* _get_indices4elastic_transform (:183-193): dev_rand (2,H,W) float64 uniform [0,1) (x field first), dev_weights the
+ * 2*lw+1 normalised taps of scipy's gaussian_filter(sigma, truncate=4), dev_tmp (2,H,W) scratch -> dev_coords (2,H,W) =
+ * (y + dy, x + dx) */
+int lu_elastic_coords(const double* dev_rand, const double* dev_weights, int32_t lw, int32_t H, int32_t W, double alpha,
+                      double* dev_tmp, double* dev_coords, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -34,6 +34,11 @@ class lu_post_params(ctypes.Structure):
                 ('max_cell_size', _I32), ('fov', _I32), ('channels_first', _I32)]
 
 
+class lu_aug_params(ctypes.Structure):
+    _fields_ = [('frames', _I32), ('H', _I32), ('W', _I32), ('randomize', _I32), ('elastic', _I32), ('flip0', _I32),
+                ('flip1', _I32), ('rot90', _I32), ('affine', ctypes.c_double * 6)]
+
+
 LIB_NAME = 'liblstm_unet_b200.so'
 
 
@@ -75,6 +80,9 @@ def bind(lib):
         'lu_post_launch_count': [P(i64), i32],
         'lu_seg_workspace_bytes': [i32, i32, i32, P(ctypes.c_size_t)],
         'lu_seg_measure': [vp, vp, i32, i32, i32, i32, vp, vp, ctypes.c_size_t, vp],
+        'lu_aug_workspace_bytes': [i32, i32, i32, P(ctypes.c_size_t)],
+        'lu_augment_sequence': [vp, vp, vp, vp, vp, P(lu_aug_params), vp, vp, vp, ctypes.c_size_t, vp],
+        'lu_elastic_coords': [vp, vp, i32, i32, i32, ctypes.c_double, vp, vp, vp],
     }
     for name, args in sigs.items():
         fn = getattr(lib, name)
@@ -88,7 +96,8 @@ EXPORTED_SYMBOLS = ['lu_last_error', 'lu_version', 'lu_is_cuda_build', 'lu_creat
                     'lu_forward', 'lu_set_graph_mode', 'lu_reset_states', 'lu_state_shape', 'lu_get_state', 'lu_set_state',
                     'lu_loss_backward', 'lu_adam_step', 'lu_debug_buffer', 'lu_launch_count', 'lu_forward_flops', 'lu_lstm_flops',
                     'lu_lstm_kernel_time', 'lu_post_workspace_bytes', 'lu_postprocess', 'lu_post_launch_count',
-                    'lu_seg_workspace_bytes', 'lu_seg_measure']
+                    'lu_seg_workspace_bytes', 'lu_seg_measure', 'lu_aug_workspace_bytes', 'lu_augment_sequence',
+                    'lu_elastic_coords']
 
 _LIB = None
 

@@ -12,6 +12,7 @@
 #include "lu_elem.cuh"
 #include "lu_train.cuh"
 #include "lu_post.cuh"
+#include "lu_aug.cuh"
 
 #ifdef LU_HOST_EMU
 #define LU_MEMSET(p, v, n, s) memset((p), (v), (n))
@@ -1281,4 +1282,5 @@ int lu_adam_step(lu_handle h, const float* dev_grads, float* dev_m, float* dev_v
 }  // extern "C"
 
 #include "lu_post_host.inl"
+#include "lu_aug_host.inl"
 

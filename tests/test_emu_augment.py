@@ -1,0 +1,89 @@
+"""CPU tests of the device augmentation (lu_augment_sequence / lu_elastic_coords) through the TEST-ONLY host build:
+against the vectors made by the reference's own helpers and against the oracle on seeded inputs.  Segmentations are
+bit-exact; images agree to float32 rounding of the frame mean (the one value summed in a different order)."""
+import numpy as np
+import pytest
+
+from oracle import augment_oracle as A
+from tests.emu_backend import NumpyBackend, build_emu
+from tests.test_augment_oracle import augment_cases
+
+
+def emu_augmenter():
+    from lstm_unet_b200 import _lib
+    from lstm_unet_b200.augment import SequenceAugmenter
+    lib = _lib.load_library(build_emu())
+    assert lib.lu_is_cuda_build() == 0
+    return SequenceAugmenter(_lib_override=lib, _backend=NumpyBackend())
+
+
+@pytest.mark.parametrize('case', list(augment_cases()), ids=lambda c: c[0])
+def test_emu_matches_reference_vectors(case):
+    name, c = case
+    aug = emu_augmenter()
+    flip, rot = (int(c['flip_rot'][0]), int(c['flip_rot'][1])), int(c['flip_rot'][2])
+    coords = c['coords'].reshape(-1).copy() if 'coords' in c else None
+    img, seg = aug.augment(c['img'], c['seg'], c['contrast'], c['brightness'], c.get('affine'), coords, flip, rot)
+    assert img.shape == c['out_img'].shape
+    assert np.array_equal(seg, c['out_seg'])
+    np.testing.assert_allclose(img, c['out_img'], rtol=2e-6, atol=2e-4)
+
+
+@pytest.mark.parametrize('case', [c for c in augment_cases() if 'rand2' in c[1]], ids=lambda c: c[0])
+def test_emu_elastic_field_matches_reference_vectors(case):
+    name, c = case
+    H, W = c['img'].shape[1:]
+    coords = emu_augmenter().elastic_coords(c['rand2'], W * 2, W * 0.15).reshape(2, H, W)
+    np.testing.assert_allclose(coords, c['coords'], rtol=0, atol=1e-10)
+
+
+def test_emu_not_randomized_is_exact_and_errors():
+    aug = emu_augmenter()
+    imgs, segs = A.synthetic_sequence(2, 24, 30, 9)
+    img, seg = aug.augment(imgs, segs, randomize=False, flip=(1, 1))
+    for t in range(2):
+        ri, rs = A.augment_frame(imgs[t], segs[t], 1, 0, None, None, (1, 1), 0, randomize=False)
+        assert np.array_equal(img[t], ri) and np.array_equal(seg[t], rs)
+    with pytest.raises(ValueError):
+        aug.augment(imgs, segs, randomize=False, rot90=1)          # odd rotation of a non-square crop
+
+
+def test_reader_mirror_batches_match_oracle_chain():
+    """data.CTCRAMReaderSequence2D: the draws of a sequence (recorded in ``last_draws``) pushed through the oracle give
+    the frames the reader hands out; batch layout, is_last semantics and the unroll windows follow DataHandeling.py:452-492"""
+    from lstm_unet_b200.data import CTCRAMReaderSequence2D
+    seqs = []
+    for s in range(2):
+        imgs, segs = A.synthetic_sequence(9, 40, 44, 20 + s, unlabeled_every=4)
+        seqs.append({'images': imgs, 'segs': segs, 'full_seg': np.ones(9)})
+    rd = CTCRAMReaderSequence2D(sequences=seqs, image_crop_size=(32, 32), unroll_len=2, batch_size=1, seed=3,
+                                elastic_seed=5, _augmenter=emu_augmenter())
+    rd.start_queues()
+    image, seg, full, is_last = rd.get_batch()
+    assert image.shape == (1, 2, 1, 32, 32) and seg.shape == (1, 2, 1, 32, 32) and full.shape == (1, 2) and is_last.shape == (1,)
+    d = rd.last_draws
+    src = seqs[d['key']]
+    coords = A.elastic_coords(d['rand2'], 32 * 2, 32 * 0.15)
+    n = len(d['idx'])
+    assert n % 2 == 0 and n >= 2
+    frames = [(image, seg, is_last)]
+    for _ in range(n // 2 - 1):
+        i2, s2, _, l2 = rd.get_batch()
+        frames.append((i2, s2, l2))
+    for w, (im, sg, last) in enumerate(frames):
+        assert last[0] == (0.0 if w == n // 2 - 1 else 1.0)          # 0 = the window that ends the sequence
+        for k in range(2):
+            t = 2 * w + k
+            f = d['idx'][t]
+            ys, xs = slice(d['crop_y'], d['crop_y'] + 32), slice(d['crop_x'], d['crop_x'] + 32)
+            ri, rs = A.augment_frame(src['images'][f][ys, xs], src['segs'][f][ys, xs], d['contrast'][t], d['brightness'][t],
+                                     d['affine'], coords, d['flip'], d['rotate'])
+            assert np.array_equal(sg[0, k, 0], rs)
+            np.testing.assert_allclose(im[0, k, 0], ri, rtol=2e-6, atol=2e-4)
+    # channels-last layout and the non-randomized path
+    rd2 = CTCRAMReaderSequence2D(sequences=seqs, image_crop_size=(40, 44), unroll_len=3, batch_size=2, seed=1,
+                                 data_format='NHWC', randomize=False, elastic_augmentation=False, _augmenter=emu_augmenter())
+    image, seg, full, is_last = rd2.get_batch()
+    assert image.shape == (2, 3, 40, 44, 1)
+    assert np.array_equal(image[1, 0, :, :, 0], seqs[rd2.last_draws['key']]['images'][0])      # slot 1 was produced last
+    assert set(np.unique(seg)) <= {-1.0, 0.0, 1.0, 2.0}
