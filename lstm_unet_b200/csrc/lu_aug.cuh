@@ -99,17 +99,29 @@ LU_HDI int lu_ni_reflect_index(long long i, int n) {
   return (int)i;
 }
 
-// item = (frame, chunk of 1024 pixels): frame sum of the image and number of annotated segmentation pixels
+// sum of `v` over the 32-group of items, returned to its first item (others get 0); all items of the group must call
+LU_HDI double lu_group_sum(double v) {
+#ifdef __CUDA_ARCH__
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return (threadIdx.x & 31) == 0 ? v : 0.0;
+#else
+  return v;
+#endif
+}
+// item = (frame, chunk of 1024 pixels, lane): each item strides through its chunk (coalesced across the 32 lanes of a
+// chunk); one atomic per chunk: frame sum of the image and number of annotated segmentation pixels
 struct LuAugStats {
   LuAug q;
   LU_HD void operator()(int64_t i) const {
     const int chunks = (q.HW + 1023) / 1024;
-    const int f = (int)(i / chunks), c = (int)(i % chunks);
-    const int p0 = c * 1024, p1 = p0 + 1024 < q.HW ? p0 + 1024 : q.HW;
-    double s = 0; int ann = 0;
-    for (int p = p0; p < p1; ++p) { s += (double)q.img[(int64_t)f * q.HW + p]; ann += q.seg[(int64_t)f * q.HW + p] != -1.0f; }
-    lu_atomic_add(q.sums + 2 * f, s);
-    if (ann) lu_atomic_add(q.sums + 2 * f + 1, (double)ann);
+    const int lane = (int)(i & 31); const int64_t r = i >> 5;
+    const int f = (int)(r / chunks), c = (int)(r % chunks);
+    const int p1 = (c + 1) * 1024 < q.HW ? (c + 1) * 1024 : q.HW;
+    double s = 0, ann = 0;
+    for (int p = c * 1024 + lane; p < p1; p += 32) { s += (double)q.img[(int64_t)f * q.HW + p]; ann += q.seg[(int64_t)f * q.HW + p] != -1.0f ? 1.0 : 0.0; }
+    s = lu_group_sum(s); ann = lu_group_sum(ann);
+    if (s != 0.0) lu_atomic_add(q.sums + 2 * f, s);
+    if (ann != 0.0) lu_atomic_add(q.sums + 2 * f + 1, ann);
   }
 };
 // item = pixel: contrast about the frame mean, brightness (DataHandeling.py:215-240, float32 like numpy)

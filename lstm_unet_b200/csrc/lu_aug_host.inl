@@ -53,7 +53,7 @@ extern "C" int lu_augment_sequence(const float* dev_img, const float* dev_seg, c
   q.out_img = dev_img_out; q.out_seg = dev_seg_out;
   const int64_t npix = (int64_t)q.frames * q.HW;
   LU_MEMSET(q.sums, 0, (size_t)q.frames * 16, stream);
-  post_pf((int64_t)q.frames * ((q.HW + 1023) / 1024), stream, LuAugStats{q});
+  post_pf((int64_t)q.frames * ((q.HW + 1023) / 1024) * 32, stream, LuAugStats{q});
   post_pf(npix, stream, LuAugAdjust{q});
   if (q.elastic) {
     post_pf(npix, stream, LuAugWarp{q});

@@ -295,6 +295,13 @@ __device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* 
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_5d_mc(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2,
+                                               int c3, int c4, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5, %6, %7}], [%2], %8;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "h"(mask)
+      : "memory");
+}
 __device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
                : "memory");
@@ -644,8 +651,14 @@ __device__ __forceinline__ uint32_t desc_lo_mn(uint32_t addr, uint32_t lbo_bytes
 }
 }  // namespace lutc
 
+// CL == 2: the two CTAs of a cluster run two tasks that differ only in their taps (same channel rows, column slab and
+// pixel range).  Every operand box of a stage is fetched from L2 by ONE of them and multicast into both CTAs' shared
+// memory (half the L2->SM traffic per MMA); a stage is released by both MMA issuers (multicast tcgen05.commit).  A task
+// with ntaps == 0 is a partner that only takes part in the staging.
+template <int CL>
 __global__ void __launch_bounds__(256, 1) lu_wgrad_tc_kernel(const __grid_constant__ LuWgParams P) {
   using namespace lutc;
+  const int crank = (CL == 2) ? (int)cluster_ctarank() : 0;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t pad = ((raw_addr + 1023u) & ~1023u) - raw_addr;
@@ -668,7 +681,7 @@ __global__ void __launch_bounds__(256, 1) lu_wgrad_tc_kernel(const __grid_consta
 
   if (warp == 0 && lane == 0) { prefetch_tmap(&P.tmA[st0.src]); prefetch_tmap(&P.tmY); }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < nS; ++i) { mbar_init(full + 8u * i, 1); mbar_init(empty + 8u * i, 1); }
+    for (int i = 0; i < nS; ++i) { mbar_init(full + 8u * i, 1); mbar_init(empty + 8u * i, CL); }
     mbar_init(done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -677,7 +690,7 @@ __global__ void __launch_bounds__(256, 1) lu_wgrad_tc_kernel(const __grid_consta
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
-  __syncthreads();
+  if (CL == 1) __syncthreads(); else cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -694,14 +707,23 @@ __global__ void __launch_bounds__(256, 1) lu_wgrad_tc_kernel(const __grid_consta
         const uint32_t base = s0 + (uint32_t)s * P.stage_bytes;
         mbar_expect_tx(full + 8u * s, bytes);
         const int fa = frame * v.frame_mul + v.frame_add;
-        tma_load_5d(base, &P.tmA[st0.src], full + 8u * s, st0.c, x0 + st0.dx, st0.plane, y0 + st0.dy, fa);
-        if (tk.stage1 >= 0)
-          tma_load_5d(base + (uint32_t)P.a_win_bytes, &P.tmA[st1.src], full + 8u * s, st1.c, x0 + st1.dx, st1.plane, y0 + st1.dy, fa);
+        int box = 0;                                   // boxes alternate between the two CTAs of a cluster
+        if (CL == 1) tma_load_5d(base, &P.tmA[st0.src], full + 8u * s, st0.c, x0 + st0.dx, st0.plane, y0 + st0.dy, fa);
+        else if ((box & 1) == crank) tma_load_5d_mc(base, &P.tmA[st0.src], full + 8u * s, st0.c, x0 + st0.dx, st0.plane, y0 + st0.dy, fa, (uint16_t)3);
+        ++box;
+        if (tk.stage1 >= 0) {
+          if (CL == 1) tma_load_5d(base + (uint32_t)P.a_win_bytes, &P.tmA[st1.src], full + 8u * s, st1.c, x0 + st1.dx, st1.plane, y0 + st1.dy, fa);
+          else if ((box & 1) == crank) tma_load_5d_mc(base + (uint32_t)P.a_win_bytes, &P.tmA[st1.src], full + 8u * s, st1.c, x0 + st1.dx, st1.plane, y0 + st1.dy, fa, (uint16_t)3);
+          ++box;
+        }
         const int fy = frame * P.dy_frame_mul + P.dy_frame_add;
         for (int dp = 0; dp < nyp; ++dp)
-          for (int c = 0; c < tk.nch; ++c)
-            tma_load_5d(base + b_off + (uint32_t)(dp * tk.nch + c) * 16384u, &P.tmY, full + 8u * s,
-                        tk.ychan[c] + dp * P.dy_cpad, x0, 0, y0, fy);
+          for (int c = 0; c < tk.nch; ++c) {
+            const uint32_t dst = base + b_off + (uint32_t)(dp * tk.nch + c) * 16384u;
+            if (CL == 1) tma_load_5d(dst, &P.tmY, full + 8u * s, tk.ychan[c] + dp * P.dy_cpad, x0, 0, y0, fy);
+            else if ((box & 1) == crank) tma_load_5d_mc(dst, &P.tmY, full + 8u * s, tk.ychan[c] + dp * P.dy_cpad, x0, 0, y0, fy, (uint16_t)3);
+            ++box;
+          }
       }
       __syncwarp();
       if (++s == nS) { s = 0; ph ^= 1u; }
@@ -732,7 +754,8 @@ __global__ void __launch_bounds__(256, 1) lu_wgrad_tc_kernel(const __grid_consta
                        idesc, (first && dp == 0 && j == 0) ? 0u : 1u);
           }
         }
-        tc_commit(empty + 8u * s);
+        if (CL == 2) tc_commit_mc(empty + 8u * s, (uint16_t)3);      // the stage is shared by the cluster
+        else tc_commit(empty + 8u * s);
       }
       __syncwarp();
       first = 0;
@@ -769,7 +792,7 @@ __global__ void __launch_bounds__(256, 1) lu_wgrad_tc_kernel(const __grid_consta
     }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CL == 1) __syncthreads(); else cluster_sync_all();       // no CTA may exit while its peer can still multicast into it
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");

@@ -192,7 +192,7 @@ static void run_colsum(lu_handle_s* h, int gbuf, int frames_used, float* dst, in
 
 #ifndef LU_HOST_EMU
 // ---- tcgen05 weight gradient: task list for one forward conv (see lu_wgrad_tc_kernel) --------------------------------
-static void build_wg_tasks(lu_handle_s* h, const ConvPlan& f, int frames, int only_src, std::vector<LuWgTask>& out) {
+static void build_wg_tasks(lu_handle_s* h, const ConvPlan& f, int frames, int only_src, int pair, std::vector<LuWgTask>& out) {
   const bool x3 = h->planes == 2;
   const int tiles = frames * ((f.Hout + LU_TILE_H - 1) / LU_TILE_H) * ((f.Wout + LU_TILE_W - 1) / LU_TILE_W);
   // K block index of the first tap of every stage
@@ -239,8 +239,15 @@ static void build_wg_tasks(lu_handle_s* h, const ConvPlan& f, int frames, int on
   std::vector<std::pair<int, int>> slabs;      // (first chunk, number of chunks)
   const int n_chunks = f.kind == LU_EPI_LSTM ? f.npad / 64 : ceil_to(f.cout, 64) / 64;
   for (int c = 0; c < n_chunks; c += nch_max) slabs.push_back({c, (n_chunks - c) < nch_max ? (n_chunks - c) : nch_max});
+  // taps of a base are spread evenly over its tasks (at most 4 accumulators each); pair: an even number of tasks,
+  // consecutive ones forming the 2-CTA clusters that share every operand box
+  auto n_tasks_of = [&](size_t ntaps) {
+    int n = (int)((ntaps + 3) / 4);
+    if (pair && (n & 1)) ++n;
+    return n;
+  };
   int base_tasks = 0;
-  for (auto& b : bases) base_tasks += (int)((b.taps.size() + 3) / 4) * (int)slabs.size();
+  for (auto& b : bases) base_tasks += n_tasks_of(b.taps.size()) * (int)slabs.size();
   // enough tasks to fill the machine, and pixel ranges small enough (~256 tiles = 32k pixels) that the range's
   // activations + gradients stay L2-resident while the wave of tasks sharing it runs
   int split = (4 * h->num_sms + base_tasks - 1) / (base_tasks > 0 ? base_tasks : 1);
@@ -252,12 +259,15 @@ static void build_wg_tasks(lu_handle_s* h, const ConvPlan& f, int frames, int on
   // rows / taps / column slabs), so activations and upstream gradients are fetched from DRAM once per range instead of
   // once per task (measured before the reorder: 84 GB of DRAM reads for a 6 GB working set).
   for (int sp = 0; sp < split; ++sp)
-    for (auto& b : bases)
-      for (size_t t0 = 0; t0 < b.taps.size(); t0 += 4)
-        for (auto& sl : slabs) {
+    for (auto& b : bases) {
+      const int nt = n_tasks_of(b.taps.size());
+      const int per = (int)b.taps.size() / nt, extra = (int)b.taps.size() % nt;
+      for (auto& sl : slabs) {
+        size_t t0 = 0;
+        for (int ti_ = 0; ti_ < nt; ++ti_) {
           LuWgTask tk; memset(&tk, 0, sizeof tk);
           tk.stage0 = (int16_t)b.s0; tk.stage1 = (int16_t)b.s1; tk.a_is_lo = (int16_t)b.a_is_lo;
-          tk.ntaps = (int16_t)((b.taps.size() - t0) < 4 ? (b.taps.size() - t0) : 4);
+          tk.ntaps = (int16_t)(per + (ti_ < extra ? 1 : 0));
           for (int i = 0; i < tk.ntaps; ++i) {
             const int ti = b.taps[t0 + i];
             tk.off[i] = f.taps[f.astages[b.s0].tap_begin + ti];
@@ -270,8 +280,11 @@ static void build_wg_tasks(lu_handle_s* h, const ConvPlan& f, int frames, int on
             tk.ychan[c] = f.kind == LU_EPI_LSTM ? (ci % 4) * f.fpad + (ci / 4) * 64 : ci * 64;
           }
           tk.tile0 = (int)((int64_t)tiles * sp / split); tk.tile1 = (int)((int64_t)tiles * (sp + 1) / split);
+          t0 += tk.ntaps;
           if (tk.tile1 > tk.tile0) out.push_back(tk);
         }
+      }
+    }
 }
 #endif
 
@@ -287,6 +300,10 @@ static int run_wgrad(lu_handle_s* h, ConvPlan& f, int gbuf, int T, float* grads,
   const char* wg_env = getenv("LU_WGRAD_ENGINE");
   const bool use_tc = h->cfg.engine == LU_ENGINE_TCGEN05 && h->cfg.a_mode == LU_AMODE_HALO &&
                       !(wg_env && strcmp(wg_env, "simt") == 0);
+  // 2-CTA clusters sharing the operand staging (LU_WGRAD_CLUSTER=1 switches back to independent CTAs)
+  static int wg_cluster_env = -1;
+  if (wg_cluster_env < 0) { const char* ce = getenv("LU_WGRAD_CLUSTER"); wg_cluster_env = ce ? atoi(ce) : 2; }
+  const int wg_pair = wg_cluster_env == 2 ? 1 : 0;
   for (int pass = 0; pass < n_launch; ++pass) {
     LuWgradMirror w; memset(&w, 0, sizeof w);
     for (int i = 0; i < f.n_views; ++i) {
@@ -317,7 +334,7 @@ static int run_wgrad(lu_handle_s* h, ConvPlan& f, int gbuf, int T, float* grads,
       LuWgTask* dtasks = reinterpret_cast<LuWgTask*>(h->ws + f.off_wg_tasks) + (size_t)pass * LU_WG_MAX_TASKS;
       if (f.wg_cached_T[pass] != T) {
         std::vector<LuWgTask> tasks;
-        build_wg_tasks(h, f, w.frames, w.only_src, tasks);
+        build_wg_tasks(h, f, w.frames, w.only_src, wg_pair, tasks);
         LU_REQUIRE(tasks.size() <= (size_t)LU_WG_MAX_TASKS, "too many weight-gradient tasks (%zu)", tasks.size());
         if (!tasks.empty()) {
           cudaError_t e = cudaMemcpyAsync(dtasks, tasks.data(), tasks.size() * sizeof(LuWgTask), cudaMemcpyHostToDevice, (cudaStream_t)stream);
@@ -347,12 +364,29 @@ static int run_wgrad(lu_handle_s* h, ConvPlan& f, int gbuf, int T, float* grads,
       LU_REQUIRE(wp.n_stages >= 1, "weight-gradient stage does not fit shared memory");
       static bool attr = false;
       if (!attr) {
-        e = cudaFuncSetAttribute(lu_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+        e = cudaFuncSetAttribute(lu_wgrad_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+        LU_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        e = cudaFuncSetAttribute(lu_wgrad_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
         LU_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         attr = true;
       }
       h->launches++;
-      lu_wgrad_tc_kernel<<<(unsigned)n_tasks, 256, wp.n_stages * wp.stage_bytes + 1024 + 256, (cudaStream_t)stream>>>(wp);
+      const size_t wg_smem = (size_t)wp.n_stages * wp.stage_bytes + 1024 + 256;
+      if (wg_pair) {
+        LU_REQUIRE((n_tasks & 1) == 0, "paired weight-gradient task list has odd length %d", n_tasks);
+        cudaLaunchConfig_t lc;
+        memset(&lc, 0, sizeof lc);
+        lc.gridDim = dim3((unsigned)n_tasks); lc.blockDim = dim3(256); lc.dynamicSmemBytes = wg_smem;
+        lc.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        lc.attrs = at; lc.numAttrs = 1;
+        e = cudaLaunchKernelEx(&lc, lu_wgrad_tc_kernel<2>, wp);
+        LU_REQUIRE(e == cudaSuccess, "wgrad cluster launch (%s) failed: %s", f.name.c_str(), cudaGetErrorString(e));
+      } else {
+        lu_wgrad_tc_kernel<1><<<(unsigned)n_tasks, 256, wg_smem, (cudaStream_t)stream>>>(wp);
+      }
       e = cudaGetLastError();
       LU_REQUIRE(e == cudaSuccess, "wgrad launch (%s) failed: %s", f.name.c_str(), cudaGetErrorString(e));
       continue;
