@@ -233,8 +233,15 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
 
     # end to end through the public API with host buffers: pinned H2D of the frames + D2H of the soft-max
+    post = None
+    if args.post and not training:
+        from lstm_unet_b200.postprocess import PostProcessor
+        post = PostProcessor()
+
     def e2e_once():
         out = run(x_host, training)
+        if post is not None:
+            return post(out[1]).numpy()
         # inference: D2H of the soft-max (Inference2D.py:60); training: D2H of the loss (train2D.py:103 -> metrics)
         return out[1].numpy() if not training else np.asarray(float(out[0]), dtype=np.float32)
     for _ in range(2):
@@ -278,7 +285,8 @@ def run_ours(args):
                    'a_mode': args.a_mode, 'step_tflop': flops_step / 1e12, 'cuda_graph': bool(model.graph_active)},
         'e2e': {'value': e2e_value, 'unit': 'frames/s',
                 'h2d_bytes_per_step': int(x_host.nbytes) * (2 if training else 1),
-                'd2h_bytes_per_step': int(sm.nbytes), 'steps': e2e_steps, 'ms_per_step': e2e_wall_ms / e2e_steps},
+                'd2h_bytes_per_step': int(sm.nbytes), 'steps': e2e_steps, 'ms_per_step': e2e_wall_ms / e2e_steps,
+                'labelled_on_device': post is not None},
         'gpu_launches': int(launches),
         'clocks': clocks,
         'roofline': {'bound': 'tensor', 'achieved': lstm_tflops, 'peak': sustained, 'unit': 'TFLOP/s',
@@ -545,6 +553,7 @@ def main():
     ap.add_argument('--unroll', type=int, default=8)
     ap.add_argument('--size', type=int, default=512)
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--post', action='store_true', help='e2e leg: label every step on the device (postprocess.PostProcessor) and read back the uint16 labels instead of the soft-max (Inference2D.py:59-124)')
     ap.add_argument('--cuda-graph', dest='cuda_graph', default='auto', choices=['auto', 'on', 'off'],
                     help='replay the inference forward as a CUDA graph (auto: launch-bound shapes, B*T <= 2)')
     args = ap.parse_args()

@@ -300,9 +300,12 @@ static int run_wgrad(lu_handle_s* h, ConvPlan& f, int gbuf, int T, float* grads,
   const char* wg_env = getenv("LU_WGRAD_ENGINE");
   const bool use_tc = h->cfg.engine == LU_ENGINE_TCGEN05 && h->cfg.a_mode == LU_AMODE_HALO &&
                       !(wg_env && strcmp(wg_env, "simt") == 0);
-  // 2-CTA clusters sharing the operand staging (LU_WGRAD_CLUSTER=1 switches back to independent CTAs)
+  // LU_WGRAD_CLUSTER=2: 2-CTA clusters sharing the operand staging by multicast.  Measured on B200 (round 1): no gain
+  // (level-1 ConvLSTM launch 26.9 vs 27.3 ms, whole step 280.5 vs 276.7 ms) -- the kernel is bound by shared-memory
+  // bandwidth at the MMA operand fetch (M = N = 128: 8 KB per 64-clock MMA = 128 B/clk/SM), not by L2->SM traffic;
+  // the default stays independent CTAs.  The way past that bound is cta_group::2 (each SM then supplies half of B).
   static int wg_cluster_env = -1;
-  if (wg_cluster_env < 0) { const char* ce = getenv("LU_WGRAD_CLUSTER"); wg_cluster_env = ce ? atoi(ce) : 2; }
+  if (wg_cluster_env < 0) { const char* ce = getenv("LU_WGRAD_CLUSTER"); wg_cluster_env = ce ? atoi(ce) : 1; }
   const int wg_pair = wg_cluster_env == 2 ? 1 : 0;
   for (int pass = 0; pass < n_launch; ++pass) {
     LuWgradMirror w; memset(&w, 0, sizeof w);
