@@ -57,14 +57,37 @@ def launch_table(path, step_index=4):
 for src, dst in [('bench_infer.json', '%s_bench_n1_infer.json'), ('bench_train.json', '%s_bench_n1_train.json'),
                  ('bench_ref.json', '%s_bench_n1_reference_arm.json'), ('launches_infer.csv', '%s_launches_bench_steps1.csv'),
                  ('launches_train.csv', '%s_launches_train_steps1.csv'), ('bench_n2.json', '%s_bench_n2_infer.json'),
-                 ('bench_train_n2.json', '%s_bench_n2_train.json')]:
+                 ('bench_train_n2.json', '%s_bench_n2_train.json'), ('bench_infer_post.json', '%s_bench_n1_infer_labelled.json'),
+                 ('bench_stream.json', '%s_bench_n1_stream.json'), ('bench_post.json', '%s_bench_n1_postprocess.json'),
+                 ('bench_aug.json', '%s_bench_n1_augment.json'), ('metrics_timing.json', '%s_metrics_timing.json'),
+                 ('launches_post.csv', '%s_launches_postprocess_steps1.csv'), ('launches_aug.csv', '%s_launches_augment_steps1.csv')]:
     if os.path.exists(os.path.join(G, src)):
         shutil.copy(os.path.join(G, src), os.path.join(P, dst % TAG))
 for rep, out in [('prof_lstm_l1.ncu-rep', '%s_ncu_prof_lstm_l1.txt'), ('prof_wgrad_l1.ncu-rep', '%s_ncu_prof_wgrad_l1.txt'),
-                 ('prof_conv_d0_c.ncu-rep', '%s_ncu_prof_conv_d0.txt')]:
+                 ('prof_conv_d0_c.ncu-rep', '%s_ncu_prof_conv_d0.txt'), ('prof_pp_edges.ncu-rep', '%s_ncu_prof_pp_edges.txt'),
+                 ('prof_pp_flatten.ncu-rep', '%s_ncu_prof_pp_flatten_bg.txt')]:
     if os.path.exists(os.path.join(G, rep)):
         ncu_summary(os.path.join(G, rep), os.path.join(P, out % TAG))
 print('## inference step')
 launch_table(os.path.join(G, 'launches_infer.csv'))
 print('\n## train step')
 launch_table(os.path.join(G, 'launches_train.csv'))
+
+
+def tail_table(path, pattern, count):
+    lines = [l for l in open(path) if not l.startswith('==')]
+    rows = list(csv.DictReader(lines))
+    names = [(r['Kernel Name'], float(r['Metric Value'].replace(',', ''))) for r in rows if re.search(pattern, r['Kernel Name'])][-count:]
+    print('| kernel | us |\n|---|---|')
+    for n, v in names:
+        m = re.search(r'(Lu\w+|lu_pp_\w+)', n)
+        print('| `%s` | %.1f |' % (m.group(1) if m else n[:40], v / 1e3))
+    print('| total | %.1f |' % (sum(v for _, v in names) / 1e3))
+
+
+if os.path.exists(os.path.join(G, 'launches_post.csv')):
+    print('\n## post-processing call (32 frames)')
+    tail_table(os.path.join(G, 'launches_post.csv'), r'LuPp|lu_pp_', 19)
+if os.path.exists(os.path.join(G, 'launches_aug.csv')):
+    print('\n## augmentation of one sequence chunk (8 frames)')
+    tail_table(os.path.join(G, 'launches_aug.csv'), r'LuAug', 5)
