@@ -244,8 +244,8 @@ def run_ours(args):
             return post(out[1]).numpy()
         # inference: D2H of the soft-max (Inference2D.py:60); training: D2H of the loss (train2D.py:103 -> metrics)
         return out[1].numpy() if not training else np.asarray(float(out[0]), dtype=np.float32)
-    for _ in range(2):
-        e2e_once()
+    for _ in range(4):          # >= 3: the .numpy() read-back cycles through a ring of three pinned host buffers, each
+        e2e_once()              # allocated (cudaHostAlloc, tens of ms for 100 MB) the first time it is used
     barrier()
     t0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -367,7 +367,7 @@ def run_postprocess(args):
     def e2e_once():
         dev_buf.copy_(sm_host, non_blocking=True)
         return pp(dev_buf).numpy()
-    for _ in range(2):
+    for _ in range(4):          # the pinned read-back ring has three buffers
         e2e_once()
     barrier()
     e2e_steps = max(2, min(args.steps, 10))

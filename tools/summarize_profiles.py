@@ -65,7 +65,8 @@ for src, dst in [('bench_infer.json', '%s_bench_n1_infer.json'), ('bench_train.j
         shutil.copy(os.path.join(G, src), os.path.join(P, dst % TAG))
 for rep, out in [('prof_lstm_l1.ncu-rep', '%s_ncu_prof_lstm_l1.txt'), ('prof_wgrad_l1.ncu-rep', '%s_ncu_prof_wgrad_l1.txt'),
                  ('prof_conv_d0_c.ncu-rep', '%s_ncu_prof_conv_d0.txt'), ('prof_pp_edges.ncu-rep', '%s_ncu_prof_pp_edges.txt'),
-                 ('prof_pp_flatten.ncu-rep', '%s_ncu_prof_pp_flatten_bg.txt')]:
+                 ('prof_pp_flatten.ncu-rep', '%s_ncu_prof_pp_flatten_bg.txt'), ('prof_upsample.ncu-rep', '%s_ncu_prof_upsample.txt'),
+                 ('prof_dgrad_l1.ncu-rep', '%s_ncu_prof_dgrad_l1.txt'), ('prof_cellbwd.ncu-rep', '%s_ncu_prof_lstm_cell_bwd.txt')]:
     if os.path.exists(os.path.join(G, rep)):
         ncu_summary(os.path.join(G, rep), os.path.join(P, out % TAG))
 print('## inference step')
