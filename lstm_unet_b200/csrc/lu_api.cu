@@ -1123,7 +1123,7 @@ static int forward_body(lu_handle h, const float* dev_x, int32_t T, int32_t trai
       LuUpsample2x up;
       up.in = reinterpret_cast<const uint16_t*>(h->ws + s.off); up.out = reinterpret_cast<uint16_t*>(h->ws + d.off);
       up.h = s.H; up.w = s.W; up.cpad = s.cpad; up.planes = s.planes;
-      pf(h, (int64_t)N * d.H * d.W * (d.cpad / 8), stream, up);
+      pf(h, (int64_t)N * s.H * s.W * (s.cpad / 8), stream, up);     // one item per INPUT pixel and 8 channels
     }
     for (int ci : h->conv_of_up[u])
       if (run_conv_layer(h, h->convs[ci], T, training, stream)) return 1;

@@ -104,45 +104,47 @@ struct LuPrepPatches {
 struct LuUpsample2x {
   const uint16_t* in; uint16_t* out;
   int h, w, cpad, planes;
-  LU_HD void operator()(int64_t i) const {        // item = (n, oy, ox, group of 8 channels)
-    const int cg = cpad / 8;
-    const int c = (int)(i % cg) * 8; int64_t p = i / cg;
-    const int ox = (int)(p % (2 * w)); p /= (2 * w);
-    const int oy = (int)(p % (2 * h)); const int64_t n = p / (2 * h);
-    // out[2i] = .25 in[i-1] + .75 in[i]; out[2i+1] = .75 in[i] + .25 in[i+1] (edge clamped)
-    const int iy = oy >> 1, ix = ox >> 1;
-    const int y1 = (oy & 1) ? (iy + 1 < h ? iy + 1 : h - 1) : (iy > 0 ? iy - 1 : 0);
-    const int x1 = (ox & 1) ? (ix + 1 < w ? ix + 1 : w - 1) : (ix > 0 ? ix - 1 : 0);
+  LU_HD void load(const uint16_t* b, int y, int x, float* v) const {
     const int ct = cpad * planes;
-    const uint16_t* b = in + n * (int64_t)h * w * ct + c;
-    float v00[8], v01[8], v10[8], v11[8];
-    lu_load8_bf16(b + ((int64_t)iy * w + ix) * ct, v00); lu_load8_bf16(b + ((int64_t)iy * w + x1) * ct, v01);
-    lu_load8_bf16(b + ((int64_t)y1 * w + ix) * ct, v10); lu_load8_bf16(b + ((int64_t)y1 * w + x1) * ct, v11);
+    lu_load8_bf16(b + ((int64_t)y * w + x) * ct, v);
     if (planes == 2) {
       float t[8];
-      lu_load8_bf16(b + ((int64_t)iy * w + ix) * ct + cpad, t);
+      lu_load8_bf16(b + ((int64_t)y * w + x) * ct + cpad, t);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v00[j] += t[j];
-      lu_load8_bf16(b + ((int64_t)iy * w + x1) * ct + cpad, t);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v01[j] += t[j];
-      lu_load8_bf16(b + ((int64_t)y1 * w + ix) * ct + cpad, t);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v10[j] += t[j];
-      lu_load8_bf16(b + ((int64_t)y1 * w + x1) * ct + cpad, t);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v11[j] += t[j];
+      for (int j = 0; j < 8; ++j) v[j] += t[j];
     }
-    uint16_t hi[8], lo[8];
+  }
+  // item = (n, iy, ix, group of 8 channels): the 2x2 output quad of one input pixel from its 3x3 neighbourhood
+  // (9 loads for 4 outputs).  out[2i] = .25 in[i-1] + .75 in[i]; out[2i+1] = .75 in[i] + .25 in[i+1] (edge clamped)
+  LU_HD void operator()(int64_t i) const {
+    const int cg = cpad / 8;
+    const int c = (int)(i % cg) * 8; int64_t p = i / cg;
+    const int ix = (int)(p % w); p /= w;
+    const int iy = (int)(p % h); const int64_t n = p / h;
+    const int ym = iy > 0 ? iy - 1 : 0, yp = iy + 1 < h ? iy + 1 : h - 1;
+    const int xm = ix > 0 ? ix - 1 : 0, xp = ix + 1 < w ? ix + 1 : w - 1;
+    const int ct = cpad * planes;
+    const uint16_t* b = in + n * (int64_t)h * w * ct + c;
+    float v[3][3][8];
+    load(b, ym, xm, v[0][0]); load(b, ym, ix, v[0][1]); load(b, ym, xp, v[0][2]);
+    load(b, iy, xm, v[1][0]); load(b, iy, ix, v[1][1]); load(b, iy, xp, v[1][2]);
+    load(b, yp, xm, v[2][0]); load(b, yp, ix, v[2][1]); load(b, yp, xp, v[2][2]);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float top = 0.75f * v00[j] + 0.25f * v01[j], bot = 0.75f * v10[j] + 0.25f * v11[j];
-      if (planes == 2) lu_split(0.75f * top + 0.25f * bot, hi[j], lo[j]);
-      else hi[j] = lu_f2bf(0.75f * top + 0.25f * bot);
-    }
-    uint16_t* o = out + (((n * 2 * h + oy) * 2 * w) + ox) * (int64_t)ct + c;
-    lu_store8_bf16(o, hi);
-    if (planes == 2) lu_store8_bf16(o + cpad, lo);
+    for (int qy = 0; qy < 2; ++qy)
+#pragma unroll
+      for (int qx = 0; qx < 2; ++qx) {
+        const int fy = qy ? 2 : 0, fx = qx ? 2 : 0;          // the "far" row / column of this output
+        uint16_t hi[8], lo[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float top = 0.75f * v[1][1][j] + 0.25f * v[1][fx][j], bot = 0.75f * v[fy][1][j] + 0.25f * v[fy][fx][j];
+          if (planes == 2) lu_split(0.75f * top + 0.25f * bot, hi[j], lo[j]);
+          else hi[j] = lu_f2bf(0.75f * top + 0.25f * bot);
+        }
+        uint16_t* o = out + (((n * 2 * h + 2 * iy + qy) * 2 * w) + 2 * ix + qx) * (int64_t)ct + c;
+        lu_store8_bf16(o, hi);
+        if (planes == 2) lu_store8_bf16(o + cpad, lo);
+      }
   }
 };
 
