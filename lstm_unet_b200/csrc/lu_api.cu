@@ -711,7 +711,7 @@ static int launch_conv(lu_handle_s* h, ConvPlan& cv, int frames, const int* mul,
 #ifdef LU_HOST_EMU
   LU_FAIL("the tcgen05 engine does not exist in the host test build");
 #else
-  static bool attr_set[7] = {false, false, false, false, false, false, false};
+  static bool attr_set[9] = {false, false, false, false, false, false, false, false, false};
   LuTcParams tp;
   memset(&tp, 0, sizeof tp);
   for (int i = 0; i < cv.n_views; ++i) tp.tmA[i] = cv.tmA[i];
@@ -724,7 +724,13 @@ static int launch_conv(lu_handle_s* h, ConvPlan& cv, int frames, const int* mul,
   // thread-block clusters of 2 (weight multicast) for the ConvLSTM launches; LU_CLUSTER=1 disables
   static int cluster_env = -1;
   if (cluster_env < 0) { const char* ce = getenv("LU_CLUSTER"); cluster_env = ce ? atoi(ce) : 2; }
-  const bool cl2 = cluster_env == 2 && epi.kind == LU_EPI_LSTM && cv.ptab_ok && (h->num_sms % 2 == 0);
+  // ... and for the conv / data-gradient launches whose weight stream is large (K >= 2048, N tile >= 128): without
+  // the multicast every CTA pulls the whole K x N weight panel from L2 for every tile (measured on the level-1
+  // data gradient: 70 % tensor-pipe activity at ~14 TB/s of L2->SM weight traffic).  LU_CLUSTER_WIDE=0 disables.
+  static int wide_env = -1;
+  if (wide_env < 0) { const char* ce = getenv("LU_CLUSTER_WIDE"); wide_env = ce ? atoi(ce) : 1; }
+  const bool wide = wide_env == 1 && epi.kind != LU_EPI_LSTM && cv.ktot >= 2048 && cv.BN >= 128 && m_tiles >= 2 * h->num_sms;
+  const bool cl2 = cluster_env == 2 && (epi.kind == LU_EPI_LSTM || wide) && cv.ptab_ok && (h->num_sms % 2 == 0);
   tp.num_mt = (int)m_tiles;
   tp.total_tiles = cl2 ? (int)(((m_tiles + 1) / 2) * cv.n_tiles_n) : (int)(m_tiles * cv.n_tiles_n);
   tp.tmBh = cv.tmBh;
@@ -734,12 +740,13 @@ static int launch_conv(lu_handle_s* h, ConvPlan& cv, int frames, const int* mul,
     memcpy(tp.tap_tab, cv.ptaps.data(), cv.ptaps.size() * sizeof(uint16_t));
   }
   int grid = tp.total_tiles * (cl2 ? 2 : 1) < h->num_sms ? tp.total_tiles * (cl2 ? 2 : 1) : h->num_sms;
-  const int ei = cl2 ? 6 : epi.kind * 2 + (cv.ptab_ok ? 1 : 0);
+  const int ei = cl2 ? (epi.kind == LU_EPI_LSTM ? 6 : (epi.kind == LU_EPI_GRAD ? 7 : 8)) : epi.kind * 2 + (cv.ptab_ok ? 1 : 0);
   typedef void (*KernelFn)(const LuTcParams);
-  static const KernelFn kfn[7] = {lu_conv_tc_kernel<LU_EPI_CONV, false, 1>, lu_conv_tc_kernel<LU_EPI_CONV, true, 1>,
+  static const KernelFn kfn[9] = {lu_conv_tc_kernel<LU_EPI_CONV, false, 1>, lu_conv_tc_kernel<LU_EPI_CONV, true, 1>,
                                   lu_conv_tc_kernel<LU_EPI_LSTM, false, 1>, lu_conv_tc_kernel<LU_EPI_LSTM, true, 1>,
                                   lu_conv_tc_kernel<LU_EPI_GRAD, false, 1>, lu_conv_tc_kernel<LU_EPI_GRAD, true, 1>,
-                                  lu_conv_tc_kernel<LU_EPI_LSTM, true, 2>};
+                                  lu_conv_tc_kernel<LU_EPI_LSTM, true, 2>, lu_conv_tc_kernel<LU_EPI_GRAD, true, 2>,
+                                  lu_conv_tc_kernel<LU_EPI_CONV, true, 2>};
   if (!attr_set[ei]) {
     cudaError_t e = cudaFuncSetAttribute(kfn[ei], cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     LU_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));

@@ -158,23 +158,6 @@ struct LuPpClassify {
   }
 };
 
-// item = group of 32 pixels: a run that continues from the previous group is linked straight to the first pixel of the
-// whole run in this row (the classify / fill kernels could only link it to the pixel on its left), so that every later
-// find() crosses a row in two hops instead of two per group
-struct LuPpRowCompress {
-  int32_t* par; int HW; int64_t n_items;
-  LU_HD void operator()(int64_t g) const {
-    const int64_t i = g * 32;
-    if (i >= n_items) return;
-    const int p = (int)(i % HW);
-    int32_t* base = par + (i - p);
-    int r = base[p];
-    if (r == p) return;
-    for (;;) { const int up = lu_ld_volatile(base + r); if (up == r) break; r = up; }
-    base[p] = r;
-  }
-};
-
 // item = pixel: vertical links of the 4-connected background.  A pixel whose left and upper-left neighbours are
 // background too leaves the link to its left neighbour (same runs).
 struct LuPpMergeBg {
@@ -318,11 +301,11 @@ struct LuPpEdges {
     }
     q.lab[i] = l;
     if (l > 0) {                       // a (possibly stale) read first: interior pixels skip the atomics
-      int32_t* b = q.bbox + (n * q.KMAX + l) * 4;           // (L2 reads: a stale L1 line would keep every SM on the atomics)
-      if (y < lu_ld_volatile(b + 0)) lu_atomic_min_i(b + 0, y);
-      if (-y < lu_ld_volatile(b + 1)) lu_atomic_min_i(b + 1, -y);
-      if (x < lu_ld_volatile(b + 2)) lu_atomic_min_i(b + 2, x);
-      if (-x < lu_ld_volatile(b + 3)) lu_atomic_min_i(b + 3, -x);
+      int32_t* b = q.bbox + (n * q.KMAX + l) * 4;
+      if (y < b[0]) lu_atomic_min_i(b + 0, y);
+      if (-y < b[1]) lu_atomic_min_i(b + 1, -y);
+      if (x < b[2]) lu_atomic_min_i(b + 2, x);
+      if (-x < b[3]) lu_atomic_min_i(b + 3, -x);
     }
   }
 };

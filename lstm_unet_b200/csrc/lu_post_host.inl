@@ -99,11 +99,9 @@ extern "C" int lu_postprocess(const float* dev_softmax, int32_t frames, int32_t 
   LU_MEMSET(ws + L.bbox, 0x7f, (size_t)frames * L.KMAX * 16, stream);
   const int64_t npix = (int64_t)frames * q.HW;
   post_pf(npix, stream, LuPpClassify{q, npix});
-  post_pf((npix + 31) / 32, stream, LuPpRowCompress{q.parA, q.HW, npix});
   post_pf(npix, stream, LuPpMergeBg{q});
   post_pf(npix, stream, LuPpFlattenBg{q});
   post_pf(npix, stream, LuPpFill{q, npix});
-  post_pf((npix + 31) / 32, stream, LuPpRowCompress{q.parB, q.HW, npix});
   post_pf(npix, stream, LuPpMergeFg{q});
   post_pf(npix, stream, LuPpFlattenFg{q});
   post_pf(npix, stream, LuPpMarkBlocks{q});
@@ -194,8 +192,6 @@ extern "C" int lu_seg_measure(const float* dev_labels, const float* dev_logits, 
   LU_MEMSET(dev_result4, 0, 4 * sizeof(double), stream);
   const int64_t npix = (int64_t)frames * q.HW;
   post_pf(npix, stream, LuSegClassify{q, npix});
-  post_pf((npix + 31) / 32, stream, LuPpRowCompress{q.parG, q.HW, npix});
-  post_pf((npix + 31) / 32, stream, LuPpRowCompress{q.parS, q.HW, npix});
   post_pf(npix, stream, LuSegMerge{q});
   post_pf(npix, stream, LuSegFlatten{q});
   post_pf(npix, stream, LuSegPairs{q, npix});
