@@ -69,4 +69,13 @@ def inference(frames=None, on_frame=None, model=None, on_labels=None):
                 if cv2 is not None:
                     os.makedirs(out_dir, exist_ok=True)
                     cv2.imwrite(os.path.join(out_dir, 'mask{time:03d}.tif'.format(time=t)), labels_out)
+                    if getattr(params, 'save_intermediate', False):          # Inference2D.py:105-112,127-130
+                        vis_dir = getattr(params, 'save_intermediate_vis_path', os.path.join(out_dir, 'Softmax'))
+                        lab_dir = getattr(params, 'save_intermediate_label_path', os.path.join(out_dir, 'Labels'))
+                        os.makedirs(vis_dir, exist_ok=True)
+                        os.makedirs(lab_dir, exist_ok=True)
+                        sm_hwc = image_softmax_np if params.data_format != 'NCHW' else np.transpose(image_softmax_np, (1, 2, 0))
+                        vis = np.flip(np.round(sm_hwc * (2 ** 16 - 1)).astype(np.uint16), 2)
+                        cv2.imwrite(os.path.join(vis_dir, 'softmax{time:03d}.tif'.format(time=t)), vis)
+                        cv2.imwrite(os.path.join(lab_dir, 'mask{time:03d}.tif'.format(time=t)), labels_out)
     return outputs

@@ -1,7 +1,12 @@
 """Mirror of the hot-path part of the reference's ``train2D.py`` (train2D.py:33-118,145-161,192-220): same call
 order -- providers, model construction with pad_image=False, Adam, train_step, reset_states_per_batch, validation
 with swapped recurrent states, and the per-step SEG measure / accuracy metrics (train2D.py:97-102,111-116) computed on the
-device.  TensorBoard, checkpoint manager and AWS polling are out of scope.  Usage, as in the reference: set the module global ``params`` and call ``train()``."""
+device, and the final export for inference (train2D.py:232-240: ``model.ckpt`` as a TF2 tensor bundle +
+``model_params.pickle``, what ``Inference2D.inference`` loads).  TensorBoard, the periodic checkpoint manager and AWS
+polling are out of scope.  Usage, as in the reference: set the module global ``params`` and call ``train()``."""
+import os
+import pickle
+
 from . import Networks as Nets
 from . import losses
 
@@ -62,4 +67,13 @@ def train(num_iterations=None, allreduce=None, log=log_print):
             model.set_states(train_states)
     train.model = model
     train.metrics = metrics
+    if not getattr(params, 'dry_run', True):                 # train2D.py:232-240
+        save_dir = os.path.expanduser(params.experiment_save_dir)
+        os.makedirs(save_dir, exist_ok=True)
+        model_fname = os.path.join(save_dir, 'model.ckpt')
+        model.save_weights(model_fname, save_format='tf')
+        with open(os.path.join(save_dir, 'model_params.pickle'), 'wb') as fobj:
+            pickle.dump({'name': model.__class__.__name__, 'params': (params.net_kernel_params,)}, fobj,
+                        protocol=pickle.HIGHEST_PROTOCOL)
+        log('Saved Model to file: {}'.format(model_fname))
     return losses_seen

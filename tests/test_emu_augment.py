@@ -87,3 +87,31 @@ def test_reader_mirror_batches_match_oracle_chain():
     assert image.shape == (2, 3, 40, 44, 1)
     assert np.array_equal(image[1, 0, :, :, 0], seqs[rd2.last_draws['key']]['images'][0])      # slot 1 was produced last
     assert set(np.unique(seg)) <= {-1.0, 0.0, 1.0, 2.0}
+
+
+def test_emu_randomized_sweep_against_oracle():
+    """seeded sweep over crop shapes, affine strengths, flips / rotations, with and without the elastic warp"""
+    from lstm_unet_b200.augment import random_affine
+    rng = np.random.RandomState(31)
+    aug = emu_augmenter()
+    for trial in range(10):
+        square = trial % 2 == 0
+        H = int(rng.randint(8, 40)); W = H if square else int(rng.randint(8, 40))
+        T = int(rng.randint(1, 4))
+        imgs, segs = A.synthetic_sequence(T, H, W, 300 + trial, unlabeled_every=2 if trial % 3 == 0 else 0)
+        elastic = trial % 4 != 3
+        affine = coords_dev = coords = None
+        if elastic:
+            affine = random_affine((H, W), W * rng.uniform(0.02, 0.2), rng)
+            rand2 = np.stack([rng.rand(H, W), rng.rand(H, W)])
+            coords = A.elastic_coords(rand2, W * 2, W * 0.15)
+            coords_dev = aug.elastic_coords(rand2, W * 2, W * 0.15)
+            np.testing.assert_allclose(coords_dev.reshape(2, H, W), coords, rtol=0, atol=1e-10)
+        contrast = (rng.rand(T) + 0.5).astype(np.float32)
+        brightness = ((rng.rand(T) - 0.5) * 0.2 * imgs.max()).astype(np.float32)
+        flip, rot = (int(rng.randint(0, 2)), int(rng.randint(0, 2))), int(rng.randint(0, 4)) if square else 2 * int(rng.randint(0, 2))
+        img, seg = aug.augment(imgs, segs, contrast, brightness, affine, coords_dev, flip, rot)
+        for t in range(T):
+            ri, rs = A.augment_frame(imgs[t], segs[t], contrast[t], brightness[t], affine, coords, flip, rot)
+            assert np.array_equal(seg[t], rs), (trial, t)
+            np.testing.assert_allclose(img[t], ri, rtol=2e-6, atol=2e-4)

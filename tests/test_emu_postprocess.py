@@ -93,3 +93,24 @@ def test_bad_arguments_raise():
         emu_post()(np.zeros((4, 8, 8), np.float32))
     with pytest.raises(LuError):
         emu_post(FOV=9)(np.zeros((3, 8, 8), np.float32))
+
+
+def test_emu_randomized_sweep_against_oracle():
+    """seeded sweep over frame shapes, map statistics and parameters (incl. non-integer edge distances, FOV, degenerate
+    1-pixel-wide frames): every label image equals the oracle's"""
+    rng = np.random.default_rng(2024)
+    flagged = 0
+    for trial in range(60):
+        H, W = int(rng.integers(1, 60)), int(rng.integers(2, 60))
+        kind = ('noise', 'cells')[trial % 2] if min(H, W) >= 8 else 'noise'
+        sm = P.synthetic_softmax(H, W, 5000 + trial, kind)
+        if trial % 7 == 0:                       # exact ties in the arg-max and at the edge threshold
+            sm = np.round(sm * 4) / 4
+            sm = (sm / np.maximum(sm.sum(0, keepdims=True), 1e-6)).astype(np.float32)
+        kw = dict(edge_dist=float(rng.choice([0, 1, 1.5, 2, 2.5, 3, 5])), min_cell_size=int(rng.integers(0, 6)),
+                  max_cell_size=int(rng.choice([20, 100, 10 ** 6])), FOV=int(rng.integers(0, max(1, min(W - 1, 4)))))
+        pp = emu_post(**kw)
+        got = pp(sm)
+        flagged += int(pp.info()[0, 2])
+        assert np.array_equal(got, P.postprocess_frame(sm, **kw)), (trial, H, W, kind, kw)
+    assert flagged > 0

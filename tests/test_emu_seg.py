@@ -45,3 +45,18 @@ def test_emu_seg_nan_without_objects_and_bad_shapes():
     from lstm_unet_b200 import losses
     with pytest.raises(ValueError):
         losses.seg_measure(2, three_d=True)
+
+
+def test_emu_seg_randomized_sweep():
+    rng = np.random.default_rng(77)
+    for trial in range(25):
+        B, T = int(rng.integers(1, 3)), int(rng.integers(1, 4))
+        H, W = int(rng.integers(1, 50)), int(rng.integers(1, 50))
+        labels, logits = S.synthetic_pair(B, T, H, W, 900 + trial, ('noise', 'blobs')[trial % 2] if min(H, W) > 6 else 'noise')
+        if trial % 5 == 0:
+            logits = np.round(logits)              # arg-max ties
+        want, acc = S.seg_measure(labels, logits), S.accuracy(labels, logits)
+        calc = emu_metrics()
+        got = calc(labels, logits)
+        assert (np.isnan(want) and np.isnan(got)) or got == pytest.approx(want, rel=1e-6, abs=1e-7), (trial, B, T, H, W)
+        assert calc.last_accuracy == pytest.approx(acc, rel=1e-12, abs=1e-15)

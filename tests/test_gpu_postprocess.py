@@ -83,3 +83,32 @@ def test_model_softmax_to_labels_stays_on_device():
         for t in range(2):
             assert np.array_equal(labels[b, t], P.postprocess_frame(sm[b, t], edge_dist=2, min_cell_size=1,
                                                                     max_cell_size=1000))
+
+
+def test_train_export_then_inference_with_labels(tmp_path):
+    """train2D.train exports model.ckpt (TF2 tensor bundle) + model_params.pickle (train2D.py:232-240); Inference2D.inference
+    loads them, streams frames, labels every frame on the device and writes the uint16 masks (Inference2D.py:27-35,59-126)"""
+    import cv2
+    from lstm_unet_b200 import Params, train2D, Inference2D
+    net = {'down_conv_kernels': [[(3, 16), (3, 16)], [(3, 32), (3, 32)]], 'lstm_kernels': [[(5, 16)], [(5, 32)]],
+           'up_conv_kernels': [[(3, 32), (3, 32)], [(3, 16), (3, 16), (1, 3)]]}
+    p = Params.CTCParams({'net_kernel_params': net, 'crop_size': (32, 32), 'batch_size': 2, 'unroll_len': 2, 'dry_run': False,
+                          'learning_rate': 1e-3, 'validation_interval': 100, 'print_to_console_interval': 100,
+                          'save_checkpoint_dir': str(tmp_path / 'ckpt'), 'save_log_dir': str(tmp_path / 'log')})
+    train2D.params = p
+    train2D.train(num_iterations=2, log=lambda *a: None)
+    save_dir = p.experiment_save_dir
+    import os
+    assert os.path.exists(os.path.join(save_dir, 'model.ckpt.index')) and os.path.exists(os.path.join(save_dir, 'model_params.pickle'))
+    frames = [np.random.default_rng(i).standard_normal((40, 48)).astype(np.float32) * 2 for i in range(3)]
+    ip = Params.CTCInferenceParams({'model_path': save_dir, 'pre_sequence_frames': 1, 'dry_run': False, 'min_cell_size': 1,
+                                    'max_cell_size': 10000, 'output_path': str(tmp_path / 'out'), 'save_intermediate': True})
+    Inference2D.params = ip
+    got = []
+    outs = Inference2D.inference(frames, on_labels=lambda t, lab: got.append((t, lab.copy())))
+    assert len(outs) == 3 and [t for t, _ in got] == [0, 1, 2]
+    for (t, lab), sm in zip(got, outs):
+        assert lab.dtype == np.uint16 and lab.shape == (40, 48)
+        assert np.array_equal(lab, P.postprocess_frame(sm, edge_dist=2, min_cell_size=1, max_cell_size=10000))
+        disk = cv2.imread(str(tmp_path / 'out' / ('mask%03d.tif' % t)), -1)
+        assert disk is not None and np.array_equal(disk, lab)
