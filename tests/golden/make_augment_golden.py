@@ -4,8 +4,8 @@ DataHandeling.py imports TensorFlow (queues) and utils (-> Networks -> Keras) at
 the training reader's augmentation lives in static methods of ``CTCRAMReaderSequence2D`` that only use numpy, OpenCV and
 SciPy.  This script imports the module from /root/reference with permissive stand-ins registered as ``tensorflow`` and
 ``utils`` and then replays, statement for statement, the per-frame part of ``_load_and_enqueue``
-(DataHandeling.py:330-380) by calling those static methods as they stand -- with explicit, seeded parameters in place of
-the reader's np.random draws.  Nothing is copied into this repository.  Run in the build container only."""
+(DataHandeling.py:330-377): the statements themselves are read from the file and executed (np.random seeded, so the
+contrast / brightness factors they draw are known), calling the reference's static helpers.  Nothing is copied into this repository.  Run in the build container only."""
 import os
 import sys
 import types
@@ -41,36 +41,38 @@ def reference_reader():
     return DataHandeling.CTCRAMReaderSequence2D
 
 
-def reference_frame(R, img_crop, seg_crop, contrast, brightness, affine_matrix, indices, flip, rotate, randomize=True):
-    """the body of the frame loop of _load_and_enqueue, calling the reference's helpers"""
-    img_crop, seg_crop = img_crop.copy(), seg_crop.copy()
-    if randomize:
-        img_crop = R._adjust_contrast_(img_crop, contrast)
-        img_crop = R._adjust_brightness_(img_crop, brightness)
-    if affine_matrix is not None:
-        img_crop = R._get_transformed_image_(img_crop, affine_matrix, indices)
-        if not np.equal(seg_crop, -1).all():
-            seg_not_valid = np.equal(seg_crop, -1)
-            labeled_gt = seg_crop
-            labeled_gt[:, 0] = 0
-            labeled_gt[:, -1] = 0
-            labeled_gt[-1, :] = 0
-            labeled_gt[0, :] = 0
-            trans_seg = R._get_transformed_image_(labeled_gt.astype(np.float32), affine_matrix, indices, seg=True)
-            trans_not_valid = R._get_transformed_image_(seg_not_valid.astype(np.float32), affine_matrix, indices, seg=True)
-            trans_seg_fix = R._fix_transformed_segmentation(trans_seg)
-            trans_not_valid = np.logical_or(np.greater(trans_not_valid, 0.5), np.equal(trans_seg, -1))
-            seg_crop = trans_seg_fix
-            seg_crop[trans_not_valid] = -1
-    else:
-        seg_crop = R._fix_transformed_segmentation(seg_crop)
-    if flip[0]:
-        img_crop, seg_crop = cv2.flip(img_crop, 0), cv2.flip(seg_crop, 0)
-    if flip[1]:
-        img_crop, seg_crop = cv2.flip(img_crop, 1), cv2.flip(seg_crop, 1)
-    if rotate > 0:
-        img_crop, seg_crop = np.rot90(img_crop, rotate), np.rot90(seg_crop, rotate)
-    return np.ascontiguousarray(img_crop), np.ascontiguousarray(seg_crop)
+def _frame_statements():
+    """the per-frame statements of _load_and_enqueue (from the contrast draw to the rot90), compiled as they stand"""
+    src = open(os.path.join(REF, 'DataHandeling.py')).read().split('\n')
+    first = next(i for i, l in enumerate(src) if l.strip() == '# contrast factor between [0.5, 1.5]') - 1
+    assert src[first].strip() == 'if self.randomize:'
+    last = next(i for i in range(first, len(src)) if src[i].strip() == 'if self.return_dist:')
+    import textwrap
+    return compile(textwrap.dedent('\n'.join(src[first:last])), 'DataHandeling.py[%d:%d]' % (first + 1, last), 'exec')
+
+
+_FRAME_CODE = None
+
+
+def reference_frame(R, img_crop, seg_crop, np_seed, img_max, affine_matrix, indices, flip, rotate, randomize=True):
+    """Executes the reference's own frame-loop statements (DataHandeling.py:330-377).  The contrast / brightness factors
+    are drawn by those statements from np.random, seeded here; returns them with the augmented frame."""
+    global _FRAME_CODE
+    if _FRAME_CODE is None:
+        _FRAME_CODE = _frame_statements()
+    self = types.SimpleNamespace(randomize=randomize, elastic_augmentation=affine_matrix is not None,
+                                 _adjust_contrast_=R._adjust_contrast_, _adjust_brightness_=R._adjust_brightness_,
+                                 _get_transformed_image_=R._get_transformed_image_,
+                                 _fix_transformed_segmentation=R._fix_transformed_segmentation)
+    np.random.seed(np_seed)
+    ns = {'np': np, 'cv2': cv2, 'self': self, 'img_crop': img_crop.copy(), 'seg_crop': seg_crop.copy(), 'img_max': img_max,
+          'affine_matrix': affine_matrix, 'indices': indices, 'flip': flip, 'rotate': rotate, 'file_idx': 0,
+          'sequence_folder': 'synthetic'}
+    exec(_FRAME_CODE, ns)
+    np.random.seed(np_seed)                      # the two draws the statements made, in their order
+    contrast = np.random.rand() + 0.5
+    brightness = (np.random.rand() - 0.5) * 0.2 * img_max
+    return np.ascontiguousarray(ns['img_crop']), np.ascontiguousarray(ns['seg_crop']), contrast, brightness
 
 
 CASES = [  # name, T, H, W, seed, elastic, flip, rot
@@ -108,9 +110,10 @@ def main():
             out[name + '/coords'] = np.stack([indices[0].reshape(H, W), indices[1].reshape(H, W)])
         else:
             affine = indices = None
-        contrast = (rng.rand(T) + 0.5).astype(np.float32)
-        brightness = ((rng.rand(T) - 0.5) * 0.2 * imgs.max()).astype(np.float32)
-        res = [reference_frame(R, imgs[t], segs[t], contrast[t], brightness[t], affine, indices, flip, rot) for t in range(T)]
+        img_max = imgs.max()
+        res = [reference_frame(R, imgs[t], segs[t], 1000 * seed + t, img_max, affine, indices, flip, rot) for t in range(T)]
+        contrast = np.array([r[2] for r in res], np.float32)
+        brightness = np.array([r[3] for r in res], np.float32)
         names.append(name)
         out[name + '/img'] = imgs
         out[name + '/seg'] = segs.astype(np.float32)
