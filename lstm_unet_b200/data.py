@@ -164,7 +164,11 @@ class CTCRAMReaderSequence2D:
     def _produce(self, slot):
         d, seq = self._draw_sequence()
         sub = self.sub_seq_size
-        while not d['idx']:                                  # sequence shorter than one unroll window
+        tries = 0
+        while not d['idx']:                                  # sequence shorter than one unroll window: draw another
+            tries += 1
+            if tries > 64:
+                raise ValueError('no sequence is long enough for unroll_len=%d' % self.unroll_len)
             d, seq = self._draw_sequence()
         ys, xs = slice(d['crop_y'], d['crop_y'] + sub[0]), slice(d['crop_x'], d['crop_x'] + sub[1])
         img = np.ascontiguousarray(seq['images'][d['idx'], ys, xs], dtype=np.float32)

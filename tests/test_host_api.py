@@ -58,6 +58,18 @@ def test_no_cpu_fallback():
     m = ULSTMnet2D()
     with pytest.raises(RuntimeError):
         m(np.zeros((1, 1, 1, 16, 16), np.float32), False)
+    # the steps either side of the model have no CPU path either
+    from lstm_unet_b200.postprocess import PostProcessor
+    from lstm_unet_b200.augment import SequenceAugmenter
+    from lstm_unet_b200 import losses
+    from lstm_unet_b200.data import CTCRAMReaderSequence2D
+    for make in (PostProcessor, SequenceAugmenter, lambda: losses.seg_measure(2)):
+        with pytest.raises(RuntimeError):
+            make()
+    rd = CTCRAMReaderSequence2D(sequences=[{'images': np.zeros((4, 16, 16)), 'segs': np.zeros((4, 16, 16))}],
+                                image_crop_size=(16, 16), unroll_len=2, batch_size=1)
+    with pytest.raises(RuntimeError):
+        rd.get_batch()
 
 
 def test_reference_surface_names():
