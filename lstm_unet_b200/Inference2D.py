@@ -30,9 +30,12 @@ def inference(frames=None, on_frame=None, model=None, on_labels=None):
         model = model_cls(*model_dict['params'], data_format=params.data_format, pad_image=True,
                           precision=getattr(params, 'precision', 'bf16'))
         model.load_weights(os.path.join(params.model_path, 'model.ckpt'))
-    frames = list(frames if frames is not None else params.data_reader)
     pre = params.pre_sequence_frames
-    sequence = frames[:pre][::-1] + frames
+    if frames is not None:                # in-memory frames: the warm-up prefix is built here
+        frames = list(frames)
+        sequence = frames[:pre][::-1] + frames
+    else:                                 # Inference2D.py:42-43: the reader's dataset already starts with the prefix
+        sequence = params.data_reader(params.sequence_path, params.filename_format, pre_sequence_frames=pre).dataset
     outputs = []
     last_labels = []
     post = None

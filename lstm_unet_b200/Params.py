@@ -140,7 +140,7 @@ class CTCInferenceParams(ParamsBase):
     output_path = './tmp/output/PhC-C2DL-PSC/01'
     sequence_path = os.path.join(ROOT_TEST_DATA_DIR, 'PhC-C2DL-PSC/01/')
     filename_format = 't*.tif'
-    data_reader = None           # an iterable of 2-D float frames (the reference's CTCInferenceReader is out of scope)
+    data_reader = DataHandeling.CTCInferenceReader
     data_format = 'NCHW'
     FOV = 0
     min_cell_size = 10

@@ -211,3 +211,35 @@ class CTCRAMReaderSequence2D:
         full_seg = np.stack([p[2] for p in parts])
         is_last = np.stack([p[3][-1] for p in parts]).astype(np.float32)
         return image, seg, full_seg, is_last
+
+
+class CTCInferenceReader:
+    """Mirror of DataHandeling.CTCInferenceReader (DataHandeling.py:1572-1596): ``.dataset`` iterates the frames of a
+    sequence folder -- the first ``pre_sequence_frames`` played in reverse, then all frames in order -- as float32 images,
+    z-scored per frame.  Host I/O (OpenCV); an iterable instead of a tf.data.Dataset."""
+
+    def __init__(self, data_path, filename_format='t*.tif', normalize=True, pre_sequence_frames=0):
+        import glob
+        import os
+        file_list = glob.glob(os.path.join(data_path, filename_format))
+        if len(file_list) == 0:
+            raise ValueError('Could not read images from: {}'.format(os.path.join(data_path, filename_format)))
+        file_list.sort()
+        self.file_list = file_list[:pre_sequence_frames][::-1] + file_list
+        self.normalize = normalize
+
+    def _gen(self):
+        import cv2
+        for file in self.file_list:
+            img = cv2.imread(file, -1)
+            if img is None:
+                raise ValueError('Could not read image: {}'.format(file))
+            img = img.astype(np.float32)
+            if self.normalize:
+                img = (img - img.mean())
+                img = img / (img.std())
+            yield img
+
+    @property
+    def dataset(self):
+        return self._gen()

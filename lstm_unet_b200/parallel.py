@@ -18,8 +18,11 @@ def shard_range(global_batch, rank, world):
 def all_reduce_mean_(flat):
     """In-place mean all-reduce of a flat gradient tensor (one collective per step)."""
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-        flat.div_(dist.get_world_size())
+        if dist.get_backend() == 'nccl':
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG)          # one pass: NCCL averages inside the collective
+        else:
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM)          # gloo (CPU tests) has no AVG
+            flat.div_(dist.get_world_size())
     return flat
 
 

@@ -112,3 +112,16 @@ def test_train_export_then_inference_with_labels(tmp_path):
         assert np.array_equal(lab, P.postprocess_frame(sm, edge_dist=2, min_cell_size=1, max_cell_size=10000))
         disk = cv2.imread(str(tmp_path / 'out' / ('mask%03d.tif' % t)), -1)
         assert disk is not None and np.array_equal(disk, lab)
+    # the same through the sequence reader (Inference2D.py:42-43): TIFF frames on disk, z-scored by the reader
+    seq_dir = tmp_path / 'seq'
+    os.makedirs(seq_dir)
+    raws = [np.random.default_rng(10 + i).integers(0, 3000, size=(40, 48)).astype(np.uint16) for i in range(3)]
+    for i, a in enumerate(raws):
+        cv2.imwrite(str(seq_dir / ('t%03d.tif' % i)), a)
+    ip2 = Params.CTCInferenceParams({'model_path': save_dir, 'pre_sequence_frames': 2, 'dry_run': False, 'min_cell_size': 1,
+                                     'max_cell_size': 10000, 'output_path': str(tmp_path / 'out2'), 'sequence_path': str(seq_dir)})
+    Inference2D.params = ip2
+    outs2 = Inference2D.inference()
+    assert len(outs2) == 3 and len(Inference2D.last_labels) == 3
+    for lab, sm in zip(Inference2D.last_labels, outs2):
+        assert np.array_equal(lab, P.postprocess_frame(sm, edge_dist=2, min_cell_size=1, max_cell_size=10000))

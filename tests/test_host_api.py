@@ -88,3 +88,22 @@ def test_reference_surface_names():
     assert callable(train2D.train) and callable(Inference2D.inference) and callable(losses.WeightedCELoss)
     with pytest.raises(ValueError):
         Networks.ULSTMnet2D({'down_conv_kernels': [[(3, 4)]], 'lstm_kernels': [], 'up_conv_kernels': [[(1, 3)]]})
+
+
+def test_inference_reader_mirror(tmp_path):
+    """data.CTCInferenceReader (DataHandeling.py:1572-1596): sorted files, reversed warm-up prefix, per-frame z-score"""
+    import cv2
+    from lstm_unet_b200.data import CTCInferenceReader
+    rng = np.random.default_rng(0)
+    raw = [rng.integers(0, 4000, size=(12, 10)).astype(np.uint16) for _ in range(4)]
+    for i, a in enumerate(raw):
+        cv2.imwrite(str(tmp_path / ('t%03d.tif' % i)), a)
+    frames = list(CTCInferenceReader(str(tmp_path), 't*.tif', pre_sequence_frames=2).dataset)
+    order = [1, 0, 0, 1, 2, 3]
+    assert len(frames) == 6
+    for f, k in zip(frames, order):
+        a = raw[k].astype(np.float32)
+        want = (a - a.mean()) / a.std()
+        assert f.dtype == np.float32 and np.allclose(f, want, rtol=1e-6, atol=1e-6)
+    with pytest.raises(ValueError):
+        CTCInferenceReader(str(tmp_path), 'nothing*.tif')
