@@ -1115,7 +1115,7 @@ static int forward_body(lu_handle h, const float* dev_x, int32_t T, int32_t trai
     pp.x = dev_x; pp.out = reinterpret_cast<uint16_t*>(h->ws + h->off_patches);
     pp.H = c.height; pp.W = c.width; pp.Hp = h->Hp; pp.Wp = h->Wp; pp.pad_y0 = h->pad_y0; pp.pad_x0 = h->pad_x0;
     pp.pw = h->pw; pp.x3 = h->planes == 2;
-    pf(h, (int64_t)N * h->Hp * h->Wp, stream, pp);
+    pf(h, (int64_t)N * h->Hp * h->Wp * 8, stream, pp);     // 8 items (16-byte channel groups) per pixel
   }
   for (int l = 0; l < h->L; ++l) {
     for (int ci : h->lstm_of_level[l])
