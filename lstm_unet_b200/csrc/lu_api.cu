@@ -88,6 +88,7 @@ struct ConvPlan {
   size_t off_bscale = 0, off_bshift = 0, off_sums = 0, off_save_mean = 0, off_save_invstd = 0;
   int ktot = 0;
   int nA = 2, nB = 4, a_bytes = 0, b_bytes = 0, smem = 0, b_group = 1;
+  bool b_resident = false;              // the whole weight panel of the (single) N tile stays in shared memory
   bool ptab_ok = false;                 // staging tables fit the kernel-parameter copies
   std::vector<LuAStage> pstages;        // stages with tap_begin remapped into the de-duplicated tap list
   std::vector<uint16_t> ptaps;
@@ -416,6 +417,14 @@ static int finish_tables(lu_handle_s* h, ConvPlan& cv) {
   cv.nB = (budget - cv.nA * cv.a_bytes) / cv.b_bytes;
   if (cv.nB > 8) cv.nB = 8;
   LU_REQUIRE(cv.nB >= 2, "shared memory budget exceeded for %s", cv.name.c_str());
+  // Narrow convolutions (one N tile, small K -- the 32/64-channel decoder tail, the logits conv): every tile would
+  // re-stream the same few tens of KB of weights from L2; instead the panel is loaded once per CTA and stays resident,
+  // and the shared memory it does not need goes to deeper activation prefetch.
+  cv.b_resident = false;
+  if (cv.kind != LU_EPI_LSTM && cv.n_tiles_n == 1 && ngrp <= 8 && (size_t)ngrp * cv.b_bytes <= 96 * 1024) {
+    const int na = (budget - ngrp * cv.b_bytes) / cv.a_bytes;
+    if (na >= 3) { cv.b_resident = true; cv.nB = ngrp; cv.nA = na > 8 ? 8 : na; }
+  }
   cv.smem = cv.nA * cv.a_bytes + cv.nB * cv.b_bytes + 1024 + 512 + 6144;
   return 0;
 }
@@ -734,6 +743,9 @@ static int launch_conv(lu_handle_s* h, ConvPlan& cv, int frames, const int* mul,
   tp.num_mt = (int)m_tiles;
   tp.total_tiles = cl2 ? (int)(((m_tiles + 1) / 2) * cv.n_tiles_n) : (int)(m_tiles * cv.n_tiles_n);
   tp.tmBh = cv.tmBh;
+  static int resident_env = -1;
+  if (resident_env < 0) { const char* ce = getenv("LU_B_RESIDENT"); resident_env = ce ? atoi(ce) : 1; }
+  tp.b_resident = (cv.b_resident && !cl2 && resident_env == 1) ? 1 : 0;
   tp.tables_in_params = cv.ptab_ok ? 1 : 0;
   if (cv.ptab_ok) {
     memcpy(tp.st_tab, cv.pstages.data(), cv.pstages.size() * sizeof(LuAStage));
@@ -1115,7 +1127,7 @@ static int forward_body(lu_handle h, const float* dev_x, int32_t T, int32_t trai
     pp.x = dev_x; pp.out = reinterpret_cast<uint16_t*>(h->ws + h->off_patches);
     pp.H = c.height; pp.W = c.width; pp.Hp = h->Hp; pp.Wp = h->Wp; pp.pad_y0 = h->pad_y0; pp.pad_x0 = h->pad_x0;
     pp.pw = h->pw; pp.x3 = h->planes == 2;
-    pf(h, (int64_t)N * h->Hp * h->Wp * 8, stream, pp);     // 8 items (16-byte channel groups) per pixel
+    pf(h, (int64_t)N * h->Hp * h->Wp, stream, pp);
   }
   for (int l = 0; l < h->L; ++l) {
     for (int ci : h->lstm_of_level[l])

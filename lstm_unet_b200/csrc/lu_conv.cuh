@@ -234,6 +234,7 @@ struct LuTcParams {
   LuConvParams cp;
   int32_t n_a_stages, n_b_stages, a_stage_bytes, b_stage_bytes;
   int32_t b_group;               // K blocks per weight stage (one mbarrier wait / commit per group)
+  int32_t b_resident;            // 1: n_b_stages holds the whole weight panel; loaded for the CTA's first tile only
   uint32_t idesc;
   int32_t total_tiles;           // work items: tiles (cluster 1) or pairs of M tiles sharing an N tile (cluster 2)
   int32_t num_mt;                // number of M tiles (frames * tiles per frame)
@@ -462,6 +463,7 @@ __global__ void __launch_bounds__(lutc::kThreads, 1) lu_conv_tc_kernel(const __g
     for (int tile = item0; tile < P.total_tiles; tile += item_step) {
       int nt, mt; bool dummy;
       decode(tile, nt, mt, dummy);
+      if (P.b_resident && tile != item0) continue;               // the panel of the first tile stays in shared memory
       for (int kb = 0; kb < nkb; kb += G) {
         const int g = (nkb - kb) < G ? (nkb - kb) : G;
         mbar_wait(empty_b + 8u * sb, ph ^ 1u);               // cluster 2: released by BOTH CTAs' MMA issuers
@@ -491,6 +493,8 @@ __global__ void __launch_bounds__(lutc::kThreads, 1) lu_conv_tc_kernel(const __g
       const uint32_t b_hi = desc_hi(1024u);
       const uint32_t bn_bytes16 = (uint32_t)BN * 8u;            // one K block of weights, in 16-byte units
       const uint32_t idesc = P.idesc;
+      const bool resident = P.b_resident != 0;
+      bool first_tile = true;
       for (int tile = item0; tile < P.total_tiles; tile += item_step) {
         mbar_wait(tmem_empty + 8u * acc, phacc ^ 1u);
         tc_fence_after();
@@ -510,8 +514,10 @@ __global__ void __launch_bounds__(lutc::kThreads, 1) lu_conv_tc_kernel(const __g
             // tap offset in rows of 128 bytes -> 16-byte units
             const uint32_t off8 = (PTAB ? (uint32_t)P.tap_tab[tb + t] : (uint32_t)cp.taps[tb + t]) * 8u;
             if (gi == 0) {
-              mbar_wait(full_b + 8u * sb, phb);
-              tc_fence_after();
+              if (!resident || first_tile) {
+                mbar_wait(full_b + 8u * sb, phb);
+                tc_fence_after();
+              }
               b_lo = desc_lo(sB + (uint32_t)sb * P.b_stage_bytes);
             }
 #pragma unroll
@@ -521,7 +527,7 @@ __global__ void __launch_bounds__(lutc::kThreads, 1) lu_conv_tc_kernel(const __g
             b_lo += bn_bytes16;
             if (++gi == G) {
               if (CL == 2) tc_commit_mc(empty_b + 8u * sb, (uint16_t)3);   // weight stage is shared by the cluster
-              else tc_commit(empty_b + 8u * sb);                // frees the weight stage once its MMAs retire
+              else if (!resident) tc_commit(empty_b + 8u * sb);  // frees the weight stage once its MMAs retire
               gi = 0;
               if (++sb == nB) { sb = 0; phb ^= 1u; }
             }
@@ -531,9 +537,10 @@ __global__ void __launch_bounds__(lutc::kThreads, 1) lu_conv_tc_kernel(const __g
         }
         if (gi != 0) {                                          // partial last weight group of the tile
           if (CL == 2) tc_commit_mc(empty_b + 8u * sb, (uint16_t)3);
-          else tc_commit(empty_b + 8u * sb);
+          else if (!resident) tc_commit(empty_b + 8u * sb);
           if (++sb == nB) { sb = 0; phb ^= 1u; }
         }
+        first_tile = false;
         tc_commit(tmem_full + 8u * acc);                        // accumulator complete -> epilogue
         if (++acc == 2) { acc = 0; phacc ^= 1u; }
       }

@@ -72,31 +72,30 @@ LU_HDI int lu_reflect(int i, int n) {     // tf.pad REFLECT index (no edge repea
 struct LuPrepPatches {
   const float* x; uint16_t* out;
   int H, W, Hp, Wp, pad_y0, pad_x0, pw, x3;
-  // item = (pixel of the padded frame, group of 8 channels): 16 bytes of the pixel's 128-byte patch row; the 8 threads of
-  // a pixel store one contiguous row.  Groups 0-3 hold the taps (hi parts), groups 4-7 their lo parts (bf16x3) or zeros.
-  LU_HD void operator()(int64_t i) const {
-    const int g = (int)(i & 7); const int64_t p = i >> 3;
+  LU_HD void operator()(int64_t p) const {        // item = one pixel of the padded frame: 64 channels = 128 bytes
     const int xx = (int)(p % Wp); int64_t q = p / Wp;
     const int yy = (int)(q % Hp); const int64_t n = q / Hp;
-    uint16_t r[8];
+    uint16_t r[64];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) r[j] = 0;
-    const bool lo_part = g >= 4;
-    if (!lo_part || x3) {
-      const int c = (pw - 1) / 2;
-      const float* img = x + n * (int64_t)H * W;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int t = (g & 3) * 8 + j;
-        if (t >= pw * pw) continue;
-        const int py = yy + t / pw - c, px = xx + t % pw - c;
-        if (py < 0 || py >= Hp || px < 0 || px >= Wp) continue;
-        const float v = img[(int64_t)lu_reflect(py - pad_y0, H) * W + lu_reflect(px - pad_x0, W)];
-        if (x3) { uint16_t hh, ll; lu_split(v, hh, ll); r[j] = lo_part ? ll : hh; }
-        else r[j] = lu_f2bf(v);
+    for (int j = 0; j < 64; ++j) r[j] = 0;
+    const int c = (pw - 1) / 2;
+    const float* img = x + n * (int64_t)H * W;
+    for (int dy = 0; dy < pw; ++dy) {
+      const int py = yy + dy - c;
+      if (py < 0 || py >= Hp) continue;
+      const float* row = img + (int64_t)lu_reflect(py - pad_y0, H) * W;
+      for (int dx = 0; dx < pw; ++dx) {
+        const int px = xx + dx - c;
+        if (px < 0 || px >= Wp) continue;
+        const float v = row[lu_reflect(px - pad_x0, W)];
+        const int t = dy * pw + dx;
+        if (x3) { uint16_t h, l; lu_split(v, h, l); r[t] = h; r[32 + t] = l; }
+        else r[t] = lu_f2bf(v);
       }
     }
-    lu_store8_bf16(out + p * 64 + g * 8, r);
+    uint16_t* o = out + p * 64;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) lu_store8_bf16(o + g * 8, r + g * 8);
   }
 };
 
