@@ -1,5 +1,5 @@
 #!/bin/bash
-# end-of-iteration evidence run: tests, smoke, every bench mode, launch lists, ncu --set full of the dominant kernels
+# end-of-iteration evidence run: tests, smoke, every bench mode, launch lists (ncu --set full captures: tools/gpu_final2.sh)
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.max.sm,power.limit --format=csv,noheader
 timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
@@ -16,6 +16,3 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --lo
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_train.csv python bench.py --mode train --steps 1 --warmup 3 --no-cpu > /dev/null 2>&1; echo "ncu list train rc=$?"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_post.csv python bench.py --mode postprocess --steps 1 --warmup 3 --no-cpu > /dev/null 2>&1; echo "ncu list post rc=$?"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_aug.csv python bench.py --mode augment --steps 1 --warmup 3 --no-cpu > /dev/null 2>&1; echo "ncu list aug rc=$?"
-timeout 1500 ncu --set full --clock-control none --import-source on -k regex:lu_conv_tc_kernel -s 110 -c 1 -o gpurun_out/prof_lstm_l1 python bench.py --steps 1 --warmup 3 --no-cpu > /dev/null 2>&1; echo "ncu full lstm rc=$?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:LuPpEdges -s 3 -c 1 -o gpurun_out/prof_pp_edges python bench.py --mode postprocess --steps 1 --warmup 3 --no-cpu > /dev/null 2>&1; echo "ncu full pp rc=$?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:LuPpFlattenBg -s 3 -c 1 -o gpurun_out/prof_pp_flatten python bench.py --mode postprocess --steps 1 --warmup 3 --no-cpu > /dev/null 2>&1; echo "ncu full pp2 rc=$?"
