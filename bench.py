@@ -185,7 +185,10 @@ def run_ours(args):
         # config 3/4: full train step = forward(training=True) + weighted CE + backward + (N>1: one NCCL all-reduce of
         # the flat gradients) + Keras Adam; same initial weights on every rank (seed 0), batch-sharded data
         from lstm_unet_b200.Networks import Adam
-        from lstm_unet_b200.parallel import all_reduce_mean_
+        from lstm_unet_b200.parallel import all_reduce_mean_, OverlappedAllReduce
+        reducer = None
+        if world > 1:
+            reducer = OverlappedAllReduce() if args.allreduce == 'overlapped' else all_reduce_mean_
         lab_host = rng.integers(-1, 3, size=(B, T, 1, H, W)).astype(np.float32)
         lab_dev = torch.from_numpy(lab_host).cuda()
         opt = Adam(lr=1e-5)
@@ -195,7 +198,7 @@ def run_ours(args):
         class _Step:
             def __call__(self, x, tr):
                 lab = lab_dev if x.__class__ is not np.ndarray else lab_host
-                sm, lg, loss = fwd.train_step(x, lab, cw, opt, all_reduce_mean_ if world > 1 else None)
+                sm, lg, loss = fwd.train_step(x, lab, cw, opt, reducer)
                 return loss, sm
         step_fn = _Step()
     else:
@@ -279,7 +282,7 @@ def run_ours(args):
         'config': {'workload': '%s: ConvLSTM-UNet (CTCParams net, 74.6M params) %s, %dx%d, T=%d, batch %d per GPU, '
                                'pad_image=%s, stateful' % ('C3' if training else 'C2', 'full train step (fwd+loss+bwd+Adam)' if training
                                                            else 'inference forward', H, W, T, B, not training),
-                   'global_batch': B * world, 'parallelism': ('data parallel x%d: batch-sharded, one NCCL all-reduce of the 74.6M fp32 gradients per step'
+                   'global_batch': B * world, 'parallelism': ('data parallel x%d: batch-sharded, NCCL mean all-reduce of the 74.6M fp32 gradients per step (started per block from inside the backward)'
                                    if training else 'batch-sharded replicas x%d (no data-path collective)') % world,
                    'l2_policy': 'inputs+activations per step (>6 GB) exceed the 126 MB L2; no flush needed',
                    'a_mode': args.a_mode, 'step_tflop': flops_step / 1e12, 'cuda_graph': bool(model.graph_active)},
@@ -553,6 +556,8 @@ def main():
     ap.add_argument('--unroll', type=int, default=8)
     ap.add_argument('--size', type=int, default=512)
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--allreduce', default='overlapped', choices=['overlapped', 'single'],
+                    help='train mode, N>1: gradient exchange started per block from inside the backward, or one collective after it')
     ap.add_argument('--post', action='store_true', help='e2e leg: label every step on the device (postprocess.PostProcessor) and read back the uint16 labels instead of the soft-max (Inference2D.py:59-124)')
     ap.add_argument('--cuda-graph', dest='cuda_graph', default='auto', choices=['auto', 'on', 'off'],
                     help='replay the inference forward as a CUDA graph (auto: launch-bound shapes, B*T <= 2)')

@@ -111,6 +111,12 @@ int lu_set_state(lu_handle h, int32_t level, int32_t layer, int32_t which, const
  * trainable prefix of the parameter buffer. */
 int lu_loss_backward(lu_handle h, const float* dev_labels, const float* class_weights3, float* dev_loss,
                      float* dev_grads, void* stream);
+/* Data-parallel training: `fn(offset, count, user)` is called on the host, from inside lu_loss_backward, as
+ * soon as every launch that writes dev_grads[offset, offset+count) has been enqueued -- one call per Up / Down block,
+ * decoder first.  The caller can start the all-reduce of that range on another stream (ordered after `stream` at that
+ * point) while the rest of the backward runs.  NULL switches it off. */
+typedef void (*lu_grad_bucket_fn)(int64_t offset, int64_t count, void* user);
+int lu_set_grad_bucket_callback(lu_handle h, lu_grad_bucket_fn fn, void* user);
 /* optimizer.apply_gradients with Keras Adam (train2D.py:61,93): step is 1-based; m,v are flat fp32 buffers */
 int lu_adam_step(lu_handle h, const float* dev_grads, float* dev_m, float* dev_v, float lr, float beta1,
                  float beta2, float eps, int64_t step, void* stream);

@@ -486,6 +486,11 @@ class ULSTMnet2D:
         """One train2D.train_step: returns (softmax, logits, loss).  `allreduce(flat_grads)` is the single data-parallel
         exchange (parallel.all_reduce_mean_)."""
         logits, softmax = self(image, True)
+        if allreduce is not None and hasattr(allreduce, 'begin'):     # parallel.OverlappedAllReduce: buckets from the backward
+            import torch
+            if getattr(self, '_grads', None) is None:
+                self._grads = torch.zeros(self._need_session().n_trainable, dtype=torch.float32, device=self._be.device)
+            allreduce.begin(self._need_session(), self._grads)
         loss, grads = self.backward(label, class_weights)
         if allreduce is not None:
             allreduce(grads)

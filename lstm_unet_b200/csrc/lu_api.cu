@@ -159,6 +159,10 @@ struct lu_handle_s {
 #ifndef LU_HOST_EMU
   cudaStream_t cap_stream = nullptr;
 #endif
+  // data-parallel training: called on the host as soon as the launches that finalise the gradients of one block of
+  // parameters (one Up / Down block = one contiguous range of the flat gradient buffer) have been enqueued
+  lu_grad_bucket_fn bucket_fn = nullptr;
+  void* bucket_user = nullptr;
   // optional CUDA-event timing of every ConvLSTM launch (bench.py roofline)
   bool time_lstm = false;
   size_t ev_used = 0;
@@ -1286,6 +1290,12 @@ int lu_debug_buffer(lu_handle h, const char* name, int32_t kind, float* out, int
     return 0;
   }
   LU_FAIL("no conv named %s", name);
+}
+
+int lu_set_grad_bucket_callback(lu_handle h, lu_grad_bucket_fn fn, void* user) {
+  LU_REQUIRE(h, "null handle");
+  h->bucket_fn = fn; h->bucket_user = user;
+  return 0;
 }
 
 int lu_loss_backward(lu_handle h, const float* dev_labels, const float* class_weights3, float* dev_loss, float* dev_grads,

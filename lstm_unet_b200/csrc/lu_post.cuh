@@ -16,12 +16,12 @@
 //                      and then a one-CTA-per-frame pass redoes the loop in the reference's order (:80-91)
 //   field of view, size filter on the core area, consecutive renumbering, uint16 output        (:94-124)
 //
-// Pixel kernels are index functors (lu_parallel_for_impl) and the CTA kernels are written as phase-separated strided
-// loops, so the TEST-ONLY host build (LU_HOST_EMU) runs the same code with one "thread" per CTA.
+// Pixel kernels are index functors (lu_parallel_for_impl; run links and small reductions use warp ballots / shuffles over
+// the 32 consecutive items of a warp, with a serial equivalent in the host build) and the CTA kernels are written as
+// phase-separated strided loops, so the TEST-ONLY host build (LU_HOST_EMU) runs the same code with one "thread" per CTA.
 #pragma once
 #include "lu_elem.cuh"
 
-#define LU_PP_SEG 32             // pixels of a row handled by one item of the run-linking kernels
 #define LU_PP_EMPTY 0x7f7f7f7f   // memset(0x7f) pattern: "no pixel yet" in the bounding boxes / block keys
 #define LU_PP_SMEM_CROP 24576    // crops up to this many pixels are flooded in shared memory
 #define LU_PP_CTA 128

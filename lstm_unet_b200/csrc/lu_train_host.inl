@@ -495,6 +495,19 @@ static int train_loss_only(lu_handle_s* h, const float* labels, const float* cw,
   return 0;
 }
 
+// the contiguous range of the flat gradient buffer that holds the trainable tensors whose names start with `prefix`
+static void notify_bucket(lu_handle_s* h, const char* prefix) {
+  if (!h->bucket_fn) return;
+  int64_t lo = -1, hi = -1;
+  const size_t n = strlen(prefix);
+  for (auto& p : h->params) {
+    if (!p.trainable || p.name.compare(0, n, prefix) != 0) continue;
+    if (lo < 0 || p.offset < lo) lo = p.offset;
+    if (p.offset + p.count > hi) hi = p.offset + p.count;
+  }
+  if (lo >= 0) h->bucket_fn(lo, hi - lo, h->bucket_user);
+}
+
 static int train_loss_backward(lu_handle_s* h, const float* labels, const float* cw, float* loss_out, float* grads,
                                void* stream) {
   LU_REQUIRE(h && h->bound && h->dparams, "bind workspace and parameters first");
@@ -520,6 +533,7 @@ static int train_loss_backward(lu_handle_s* h, const float* labels, const float*
       pf(h, (int64_t)h->cfg.batch * T * s.H * s.W * (s.cpad / 8), stream, ub);
       gwritten[gs] = 1;
     }
+    { char pre[64]; snprintf(pre, sizeof pre, "UpLayers/%d/", u); notify_bucket(h, pre); }
   }
   for (int l = h->L - 1; l >= 0; --l) {
     const std::vector<int>& cl = h->conv_of_level[l];
@@ -528,6 +542,7 @@ static int train_loss_backward(lu_handle_s* h, const float* labels, const float*
     const std::vector<int>& ll = h->lstm_of_level[l];
     for (int j = (int)ll.size() - 1; j >= 0; --j)
       if (bwd_lstm_layer(h, h->convs[ll[j]], T, grads, gwritten, stream)) return 1;
+    { char pre[64]; snprintf(pre, sizeof pre, "DownLayers/%d/", l); notify_bucket(h, pre); }
   }
 #ifndef LU_HOST_EMU
   cudaError_t e = cudaGetLastError();

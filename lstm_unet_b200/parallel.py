@@ -32,3 +32,53 @@ def max_over_ranks(value, device='cpu'):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
     return float(value)
+
+
+class OverlappedAllReduce:
+    """Mean all-reduce of the flat gradient buffer, started block by block from inside the backward.
+
+    ``lu_loss_backward`` reports every Up / Down block whose gradient range is final (decoder first); each range is
+    all-reduced on a side stream ordered after the compute stream at that point, so the exchange of the large bottleneck
+    block overlaps the backward of the encoder.  Pass an instance as ``allreduce=`` to ``ULSTMnet2D.train_step``: it is
+    armed with ``begin(session, grads)`` before the backward and called like ``all_reduce_mean_`` after it (which then only
+    joins the side stream).  On CPU tensors (gloo, the tests) the ranges are reduced synchronously."""
+
+    def __init__(self):
+        self.side = None
+        self.ranges = []
+        self._grads = None
+
+    def active(self):
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+    def begin(self, session, grads):
+        self._grads = grads
+        self.ranges = []
+        if not self.active():
+            session.set_grad_bucket_callback(None)
+            return
+        if grads.is_cuda and self.side is None:
+            self.side = torch.cuda.Stream(device=grads.device)
+        session.set_grad_bucket_callback(self._on_bucket)
+
+    def _on_bucket(self, offset, count):
+        g = self._grads[offset:offset + count]
+        self.ranges.append((offset, count))
+        if g.is_cuda:
+            self.side.wait_stream(torch.cuda.current_stream(g.device))
+            with torch.cuda.stream(self.side):
+                all_reduce_mean_(g)
+        else:
+            all_reduce_mean_(g)
+
+    def __call__(self, flat):
+        if not self.active():
+            return flat
+        covered = sum(c for _, c in self.ranges)
+        if not self.ranges:                    # no bucket was reported (callback not armed): one collective, as before
+            all_reduce_mean_(flat)
+        elif covered != flat.numel():
+            raise RuntimeError('gradient buckets cover %d of %d elements' % (covered, flat.numel()))
+        if flat.is_cuda and self.side is not None:
+            torch.cuda.current_stream(flat.device).wait_stream(self.side)
+        return flat

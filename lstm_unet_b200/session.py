@@ -137,6 +137,12 @@ class LuSession:
         cw = (ctypes.c_float * 3)(*[float(v) for v in class_weights])
         self._check(self.lib.lu_loss_backward(self.h, labels_ptr, cw, loss_ptr, grads_ptr, self.be.stream()))
 
+    def set_grad_bucket_callback(self, fn):
+        """fn(offset, count) or None; see lu_set_grad_bucket_callback."""
+        self._bucket_cb = _lib.GRAD_BUCKET_FN(lambda off, cnt, user: fn(int(off), int(cnt))) if fn is not None else None
+        cb = ctypes.cast(self._bucket_cb, ctypes.c_void_p) if self._bucket_cb is not None else None
+        self._check(self.lib.lu_set_grad_bucket_callback(self.h, cb, None))
+
     def adam_step(self, grads_ptr, m_ptr, v_ptr, lr, step, b1=0.9, b2=0.999, eps=1e-7):
         self._check(self.lib.lu_adam_step(self.h, grads_ptr, m_ptr, v_ptr, lr, b1, b2, eps, int(step), self.be.stream()))
 

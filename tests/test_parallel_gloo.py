@@ -47,7 +47,17 @@ def _worker(rank, world, port, out_dir):
     g = torch.from_numpy(grads)
     all_reduce_mean_(g)
     t = max_over_ranks(1.0 + rank)
-    np.savez(os.path.join(out_dir, 'rank%d.npz' % rank), logits=logits, grads=g.numpy(), loss=loss, t=t)
+    # the same exchange started block by block from inside the backward (parallel.OverlappedAllReduce)
+    from lstm_unet_b200.parallel import OverlappedAllReduce
+    grads2 = np.zeros(sess.n_trainable, dtype=np.float32)
+    g2 = torch.from_numpy(grads2)
+    ov = OverlappedAllReduce()
+    ov.begin(sess, g2)
+    sess.loss_backward(lab_r.ctypes.data, CW, loss.ctypes.data, grads2.ctypes.data)
+    ov(g2)
+    sess.set_grad_bucket_callback(None)
+    np.savez(os.path.join(out_dir, 'rank%d.npz' % rank), logits=logits, grads=g.numpy(), loss=loss, t=t, grads_overlapped=g2.numpy(),
+             n_buckets=len(ov.ranges))
     dist.destroy_process_group()
 
 
@@ -57,6 +67,8 @@ def test_two_rank_sharding_and_gradient_allreduce(tmp_path):
     r = [np.load(tmp_path / ('rank%d.npz' % i)) for i in range(world)]
     assert float(r[0]['t']) == 2.0 and float(r[1]['t']) == 2.0          # max over ranks
     np.testing.assert_array_equal(r[0]['grads'], r[1]['grads'])         # identical after the all-reduce
+    np.testing.assert_array_equal(r[0]['grads_overlapped'], r[0]['grads'])   # bucketed exchange == one collective
+    assert int(r[0]['n_buckets']) == 2                                  # one Up block + one Down block in this net
     from oracle import lstm_unet_oracle as O
     from tests.emu_backend import emu_session, emu_forward
     params = O.init_params(NET, seed=3, randomize_bn=True)
