@@ -13,89 +13,60 @@ ROOT_TEST_DATA_DIR = '~/CellTrackingChallenge/Test/'
 ROOT_SAVE_DIR = '~/LSTM-UNet-Outputs/'
 
 
+def _with_defaults(**defaults):
+    """Class decorator: the reference declares its configuration as class attributes (Params.py:28-95, 153-175); the
+    same names and values are attached here from one table per class."""
+    def attach(cls):
+        for name, value in defaults.items():
+            setattr(cls, name, value)
+        return cls
+    return attach
+
+
+def _ctc_net_kernel_params():
+    """Params.py:49-69: 3x3 conv pairs and one 5x5 ConvLSTM per encoder level, 3x3 conv pairs + the 1x1 logits conv in
+    the decoder."""
+    enc, dec = (128, 256, 256, 512), (256, 128, 64, 32)
+    up = [[(3, f), (3, f)] for f in dec]
+    up[-1].append((1, 3))
+    return {'down_conv_kernels': [[(3, f), (3, f)] for f in enc], 'lstm_kernels': [[(5, f)] for f in enc],
+            'up_conv_kernels': up}
+
+
 class ParamsBase(object):
     aws = False
 
     def _override_params_(self, params_dict: dict):
-        this_dict = {}
+        """Params.py:16-25: every key becomes an instance attribute; unknown keys are reported, not rejected."""
+        known = set()
         for klass in type(self).__mro__:
-            this_dict.update(klass.__dict__)
-        for key, val in params_dict.items():
-            if key not in this_dict:
+            known.update(vars(klass))
+        for key in params_dict:
+            if key not in known:
                 print('Warning!: Parameter:{} not in defualt parameters'.format(key))
-            setattr(self, key, val)
+            setattr(self, key, params_dict[key])
 
 
+@_with_defaults(
+    # general / data (Params.py:30-46)
+    experiment_name='MyRun_SIM', gpu_id=0, data_provider_class=DataHandeling.SyntheticSequenceProvider,
+    root_data_dir=ROOT_DATA_DIR, train_sequence_list=[('Fluo-N2DH-SIM+', '01'), ('Fluo-N2DH-SIM+', '02')],
+    val_sequence_list=[('Fluo-N2DH-SIM+', '01'), ('Fluo-N2DH-SIM+', '02')], crop_size=(128, 128), batch_size=5,
+    unroll_len=4, data_format='NCHW', train_q_capacity=200, val_q_capacity=200, num_val_threads=2, num_train_threads=8,
+    # network (Params.py:48-69)
+    net_model=Nets.ULSTMnet2D, net_kernel_params=_ctc_net_kernel_params(),
+    # training (Params.py:71-76)
+    class_weights=[0.15, 0.25, 0.6], learning_rate=1e-5, num_iterations=1000000, validation_interval=1000,
+    print_to_console_interval=10,
+    # save / restore, TensorBoard (Params.py:78-91)
+    load_checkpoint=False, load_checkpoint_path='', continue_run=False, save_checkpoint_dir=ROOT_SAVE_DIR,
+    save_checkpoint_iteration=5000, save_checkpoint_every_N_hours=24, save_checkpoint_max_to_keep=5,
+    tb_sub_folder='LSTMUNet', write_to_tb_interval=500, save_log_dir=ROOT_SAVE_DIR,
+    # debugging (the reference defaults dry_run to False; nothing is written here unless asked)
+    dry_run=True, profile=False,
+    # B200 backend (not in the reference)
+    precision='bf16')
 class CTCParams(ParamsBase):
-    # --------General-------------
-    experiment_name = 'MyRun_SIM'
-    gpu_id = 0
-
-    #  ------- Data -------
-    data_provider_class = DataHandeling.SyntheticSequenceProvider
-    root_data_dir = ROOT_DATA_DIR
-    train_sequence_list = [('Fluo-N2DH-SIM+', '01'), ('Fluo-N2DH-SIM+', '02')]
-    val_sequence_list = [('Fluo-N2DH-SIM+', '01'), ('Fluo-N2DH-SIM+', '02')]
-    crop_size = (128, 128)
-    batch_size = 5
-    unroll_len = 4
-    data_format = 'NCHW'
-    train_q_capacity = 200
-    val_q_capacity = 200
-    num_val_threads = 2
-    num_train_threads = 8
-
-    # -------- Network Architecture ----------
-    net_model = Nets.ULSTMnet2D
-    net_kernel_params = {
-        'down_conv_kernels': [
-            [(3, 128), (3, 128)],
-            [(3, 256), (3, 256)],
-            [(3, 256), (3, 256)],
-            [(3, 512), (3, 512)],
-        ],
-        'lstm_kernels': [
-            [(5, 128)],
-            [(5, 256)],
-            [(5, 256)],
-            [(5, 512)],
-        ],
-        'up_conv_kernels': [
-            [(3, 256), (3, 256)],
-            [(3, 128), (3, 128)],
-            [(3, 64), (3, 64)],
-            [(3, 32), (3, 32), (1, 3)],
-        ],
-    }
-
-    # -------- Training ----------
-    class_weights = [0.15, 0.25, 0.6]
-    learning_rate = 1e-5
-    num_iterations = 1000000
-    validation_interval = 1000
-    print_to_console_interval = 10
-
-    # ---------Save and Restore ----------
-    load_checkpoint = False
-    load_checkpoint_path = ''
-    continue_run = False
-    save_checkpoint_dir = ROOT_SAVE_DIR
-    save_checkpoint_iteration = 5000
-    save_checkpoint_every_N_hours = 24
-    save_checkpoint_max_to_keep = 5
-
-    # ---------Tensorboard-------------
-    tb_sub_folder = 'LSTMUNet'
-    write_to_tb_interval = 500
-    save_log_dir = ROOT_SAVE_DIR
-
-    # ---------Debugging-------------
-    dry_run = True
-    profile = False
-
-    # --------- B200 backend (not in the reference) ---------
-    precision = 'bf16'
-
     def __init__(self, params_dict=None):
         self._override_params_(params_dict or {})
         if isinstance(self.gpu_id, list):
@@ -134,24 +105,14 @@ class CTCParams(ParamsBase):
         return self._val_provider
 
 
+@_with_defaults(
+    gpu_id=0, model_path='./Models/LSTMUNet2D/PhC-C2DL-PSC/', output_path='./tmp/output/PhC-C2DL-PSC/01',
+    sequence_path=os.path.join(ROOT_TEST_DATA_DIR, 'PhC-C2DL-PSC/01/'), filename_format='t*.tif',
+    data_reader=DataHandeling.CTCInferenceReader, data_format='NCHW',
+    # instance labelling (Params.py:164-168; read by postprocess.PostProcessor)
+    FOV=0, min_cell_size=10, max_cell_size=100, edge_dist=2, pre_sequence_frames=4,
+    dry_run=True, save_intermediate=False, save_intermediate_path='./tmp/output/PhC-C2DL-PSC/01', precision='bf16')
 class CTCInferenceParams(ParamsBase):
-    gpu_id = 0
-    model_path = './Models/LSTMUNet2D/PhC-C2DL-PSC/'
-    output_path = './tmp/output/PhC-C2DL-PSC/01'
-    sequence_path = os.path.join(ROOT_TEST_DATA_DIR, 'PhC-C2DL-PSC/01/')
-    filename_format = 't*.tif'
-    data_reader = DataHandeling.CTCInferenceReader
-    data_format = 'NCHW'
-    FOV = 0
-    min_cell_size = 10
-    max_cell_size = 100
-    edge_dist = 2
-    pre_sequence_frames = 4
-    dry_run = True
-    save_intermediate = False
-    save_intermediate_path = output_path
-    precision = 'bf16'
-
     def __init__(self, params_dict: dict = None):
         if params_dict is not None:
             self._override_params_(params_dict)
