@@ -61,6 +61,9 @@ CASES = [
     ('cells_200x200', 200, 200, 'cells', 10, {'max_cell_size': 300}),
     ('cells_1x17', 1, 17, 'noise', 11, {'min_cell_size': 1}),
     ('cells_9x2', 9, 2, 'noise', 12, {'min_cell_size': 1}),
+    # larger frames, soft-max stored as float16 (the reference is fed the float16-rounded values)
+    ('cells_256x256_f16', 256, 256, 'cells', 13, {'max_cell_size': 200}),
+    ('noise_128x160_f16', 128, 160, 'noise', 14, {'min_cell_size': 2, 'edge_dist': 3, 'FOV': 5}),
 ]
 
 
@@ -70,9 +73,11 @@ def main():
     names = []
     for name, H, W, kind, seed, kw in CASES:
         sm = synthetic_softmax(H, W, seed, kind)
+        if name.endswith('_f16'):
+            sm = sm.astype(np.float16).astype(np.float32)
         labels, num = reference_postprocess(sm, **kw)
         names.append(name)
-        out[name + '/softmax'] = sm
+        out[name + '/softmax'] = sm.astype(np.float16) if name.endswith('_f16') else sm
         out[name + '/labels'] = labels.astype(np.uint16)
         out[name + '/num_cells'] = np.int64(num)
         out[name + '/params'] = np.array([kw.get('edge_dist', 2), kw.get('min_cell_size', 10),

@@ -18,7 +18,7 @@ def golden_cases():
         name = str(name)
         e, mn, mx, fov = g[name + '/params']
         kw = dict(edge_dist=float(e) if e != int(e) else int(e), min_cell_size=int(mn), max_cell_size=int(mx), FOV=int(fov))
-        yield name, g[name + '/softmax'], g[name + '/labels'], int(g[name + '/num_cells']), kw
+        yield name, g[name + '/softmax'].astype(np.float32), g[name + '/labels'], int(g[name + '/num_cells']), kw
 
 
 @pytest.mark.parametrize('case', list(golden_cases()), ids=lambda c: c[0])
