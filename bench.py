@@ -177,7 +177,8 @@ def run_ours(args):
     training = args.mode == 'train'
     model = ULSTMnet2D(CTC_NET, 'NCHW', pad_image=not training, precision=args.precision, a_mode=args.a_mode,
                        seed=0 if training else rank, train=training,
-                       cuda_graph={'auto': 'auto', 'on': True, 'off': False}[args.cuda_graph])
+                       cuda_graph={'auto': 'auto', 'on': True, 'off': False}[args.cuda_graph],
+                       sync_bn=bool(training and args.sync_bn))
     rng = np.random.default_rng(1234 + rank)
     x_host = rng.standard_normal((B, T, 1, H, W)).astype(np.float32)
     x_dev = torch.from_numpy(x_host).cuda()
@@ -556,6 +557,8 @@ def main():
     ap.add_argument('--unroll', type=int, default=8)
     ap.add_argument('--size', type=int, default=512)
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--sync-bn', dest='sync_bn', action='store_true',
+                    help='train mode, N>1: BatchNorm statistics over the batch of all ranks (one small fp64 all-reduce per BN layer)')
     ap.add_argument('--allreduce', default='overlapped', choices=['overlapped', 'single'],
                     help='train mode, N>1: gradient exchange started per block from inside the backward, or one collective after it')
     ap.add_argument('--post', action='store_true', help='e2e leg: label every step on the device (postprocess.PostProcessor) and read back the uint16 labels instead of the soft-max (Inference2D.py:59-124)')

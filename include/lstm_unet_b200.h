@@ -117,6 +117,15 @@ int lu_loss_backward(lu_handle h, const float* dev_labels, const float* class_we
  * point) while the rest of the backward runs.  NULL switches it off. */
 typedef void (*lu_grad_bucket_fn)(int64_t offset, int64_t count, void* user);
 int lu_set_grad_bucket_callback(lu_handle h, lu_grad_bucket_fn fn, void* user);
+/* Synchronised BatchNorm for data-parallel training (SURVEY 8e option ii; the survey's `lu_bn_stats_{export,import}`):
+ * the reference normalises with the statistics of the whole batch on one device; with the batch sharded over ranks
+ * each BN layer's local moments are exported to `fn(dev_vec, count, user)` in the middle of lu_forward(training=1) /
+ * lu_loss_backward -- the callee sums the fp64 vector over the ranks IN PLACE on the compute stream (one all-reduce of
+ * 3 x channels doubles per layer forward, 2 x channels backward) -- and imported back as the global mean / variance
+ * (forward) and the global means of g and g * xhat (backward).  Every rank must hold the same number of frames.
+ * fn == NULL (default): local statistics, no collective in the forward. */
+typedef void (*lu_bn_sync_fn)(double* dev_vec, int64_t count, void* user);
+int lu_set_bn_sync_callback(lu_handle h, lu_bn_sync_fn fn, void* user, int32_t world_size);
 /* optimizer.apply_gradients with Keras Adam (train2D.py:61,93): step is 1-based; m,v are flat fp32 buffers */
 int lu_adam_step(lu_handle h, const float* dev_grads, float* dev_m, float* dev_v, float lr, float beta1,
                  float beta2, float eps, int64_t step, void* stream);

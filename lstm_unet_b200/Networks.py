@@ -200,7 +200,7 @@ class Adam:
 class ULSTMnet2D:
     def __init__(self, net_params=DEFAULT_NET_DOWN_PARAMS, data_format='NCHW', pad_image=True, *, precision='bf16',
                  engine='tcgen05', gate='hard_sigmoid', a_mode='halo', train=False, seed=0, device=None,
-                 cuda_graph='auto'):
+                 cuda_graph='auto', sync_bn=False):
         # Networks.py:188-193: same ValueErrors, raised before anything touches the device
         _lib.make_config(net_params, data_format, pad_image)
         self.net_params = net_params
@@ -213,6 +213,8 @@ class ULSTMnet2D:
         # CUDA graph; True / False force it where the library allows it (B*T <= 8, not a training model)
         self.cuda_graph = cuda_graph
         self.graph_active = False
+        # data-parallel training: BatchNorm statistics over the batch of ALL ranks (parallel.enable_sync_batchnorm)
+        self.sync_bn = sync_bn
         self.seed, self._device = seed, device
         n = len(net_params['down_conv_kernels'])
         self.DownLayers = [DownBlock2D(c, l, 2 if i < n - 1 else 1, data_format, self, i)
@@ -252,6 +254,9 @@ class ULSTMnet2D:
         sess = LuSession(self._lib, be, cfg)
         want_graph = (B * T <= 2) if self.cuda_graph == 'auto' else bool(self.cuda_graph)
         self.graph_active = sess.set_graph_mode(want_graph and not self.train_capable)
+        if self.sync_bn:
+            from .parallel import enable_sync_batchnorm
+            enable_sync_batchnorm(sess)
         if old is not None:                       # longer unroll than before: carry weights and states over
             sess.params.copy_(old.params)
             sess.params_changed()

@@ -40,6 +40,7 @@ class lu_aug_params(ctypes.Structure):
 
 
 GRAD_BUCKET_FN = ctypes.CFUNCTYPE(None, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p)
+BN_SYNC_FN = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p)
 
 LIB_NAME = 'liblstm_unet_b200.so'
 
@@ -72,6 +73,7 @@ def bind(lib):
         'lu_set_state': [vp, i32, i32, i32, vp, vp],
         'lu_loss_backward': [vp, vp, P(f32), vp, vp, vp],
         'lu_set_grad_bucket_callback': [vp, vp, vp],
+        'lu_set_bn_sync_callback': [vp, vp, vp, i32],
         'lu_adam_step': [vp, vp, vp, vp, f32, f32, f32, f32, i64, vp],
         'lu_debug_buffer': [vp, ctypes.c_char_p, i32, vp, P(i64), vp],
         'lu_launch_count': [vp, P(i64), i32],
@@ -97,7 +99,7 @@ def bind(lib):
 EXPORTED_SYMBOLS = ['lu_last_error', 'lu_version', 'lu_is_cuda_build', 'lu_create', 'lu_destroy', 'lu_workspace_bytes',
                     'lu_bind_workspace', 'lu_param_count', 'lu_param_info', 'lu_bind_params', 'lu_params_changed',
                     'lu_forward', 'lu_set_graph_mode', 'lu_reset_states', 'lu_state_shape', 'lu_get_state', 'lu_set_state',
-                    'lu_loss_backward', 'lu_set_grad_bucket_callback', 'lu_adam_step', 'lu_debug_buffer', 'lu_launch_count', 'lu_forward_flops', 'lu_lstm_flops',
+                    'lu_loss_backward', 'lu_set_grad_bucket_callback', 'lu_set_bn_sync_callback', 'lu_adam_step', 'lu_debug_buffer', 'lu_launch_count', 'lu_forward_flops', 'lu_lstm_flops',
                     'lu_lstm_kernel_time', 'lu_post_workspace_bytes', 'lu_postprocess', 'lu_post_launch_count',
                     'lu_seg_workspace_bytes', 'lu_seg_measure', 'lu_aug_workspace_bytes', 'lu_augment_sequence',
                     'lu_elastic_coords']

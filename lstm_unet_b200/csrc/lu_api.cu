@@ -85,7 +85,7 @@ struct ConvPlan {
   LuSrcView views[LU_MAX_SRC];
   int view_buf[LU_MAX_SRC];    // ActBuf index (or -1 patches) behind each view
   size_t off_astages = 0, off_taps = 0, off_packs = 0, off_w = 0, off_bias = 0, off_scale = 0, off_shift = 0;
-  size_t off_bscale = 0, off_bshift = 0, off_sums = 0, off_save_mean = 0, off_save_invstd = 0;
+  size_t off_bscale = 0, off_bshift = 0, off_sums = 0, off_mom = 0, off_save_mean = 0, off_save_invstd = 0;
   int ktot = 0;
   int nA = 2, nB = 4, a_bytes = 0, b_bytes = 0, smem = 0, b_group = 1;
   bool b_resident = false;              // the whole weight panel of the (single) N tile stays in shared memory
@@ -163,6 +163,10 @@ struct lu_handle_s {
   // parameters (one Up / Down block = one contiguous range of the flat gradient buffer) have been enqueued
   lu_grad_bucket_fn bucket_fn = nullptr;
   void* bucket_user = nullptr;
+  // synchronised BatchNorm: in-place sum over the ranks of a small fp64 device vector, enqueued on the compute stream
+  lu_bn_sync_fn bn_sync_fn = nullptr;
+  void* bn_sync_user = nullptr;
+  int bn_sync_world = 1;
   // optional CUDA-event timing of every ConvLSTM launch (bench.py roofline)
   bool time_lstm = false;
   size_t ev_used = 0;
@@ -612,6 +616,7 @@ static void layout_workspace(lu_handle_s* h) {
       cv.off_bscale = take((size_t)cv.npad * 4);
       cv.off_bshift = take((size_t)cv.npad * 4);
       cv.off_sums = take((size_t)cv.npad * 2 * 8);
+      cv.off_mom = take((size_t)cv.npad * 3 * 8);
       cv.off_save_mean = take((size_t)cv.npad * 4);
       cv.off_save_invstd = take((size_t)cv.npad * 4);
       if (!cv.has_bn) cv.off_raw = take(rb);                     // logits
@@ -1008,7 +1013,22 @@ static int run_conv_layer(lu_handle_s* h, ConvPlan& cv, int T, int training, voi
     fin.save_mean = reinterpret_cast<float*>(h->ws + cv.off_save_mean);
     fin.save_invstd = reinterpret_cast<float*>(h->ws + cv.off_save_invstd);
     fin.npix = npix; fin.cpad = cv.raw_cpad; fin.c_real = cv.cout; fin.eps = 1e-3f; fin.momentum = 0.99f;
-    pf(h, cv.raw_cpad, stream, fin);
+    if (h->bn_sync_fn) {
+      // statistics over the GLOBAL batch (the reference's single-device semantics): local moments ->
+      // in-place sum over the ranks by the caller (one small fp64 vector per BN layer) -> combined mean / variance
+      LuBnMoments mo;
+      mo.sums = st.sums; mo.shift_src = raw; mo.mom = reinterpret_cast<double*>(h->ws + cv.off_mom);
+      mo.npix = npix; mo.cpad = cv.raw_cpad; mo.c_real = cv.cout;
+      pf(h, cv.raw_cpad, stream, mo);
+      h->bn_sync_fn(mo.mom, (int64_t)3 * cv.raw_cpad, h->bn_sync_user);
+      LuBnFinalizeSync fs;
+      fs.mom = mo.mom; fs.gamma = fin.gamma; fs.beta = fin.beta; fs.mov_mean = fin.mov_mean; fs.mov_var = fin.mov_var;
+      fs.scale = fin.scale; fs.shift = fin.shift; fs.save_mean = fin.save_mean; fs.save_invstd = fin.save_invstd;
+      fs.npix = npix; fs.cpad = cv.raw_cpad; fs.c_real = cv.cout; fs.world = h->bn_sync_world; fs.eps = fin.eps; fs.momentum = fin.momentum;
+      pf(h, cv.raw_cpad, stream, fs);
+    } else {
+      pf(h, cv.raw_cpad, stream, fin);
+    }
     LuBnApply ap;
     ap.raw = raw; ap.scale = fin.scale; ap.shift = fin.shift;
     ap.out = reinterpret_cast<uint16_t*>(h->ws + ob.off); ap.raw_cpad = cv.raw_cpad; ap.out_cpad = ob.cpad; ap.planes = ob.planes;
@@ -1290,6 +1310,13 @@ int lu_debug_buffer(lu_handle h, const char* name, int32_t kind, float* out, int
     return 0;
   }
   LU_FAIL("no conv named %s", name);
+}
+
+int lu_set_bn_sync_callback(lu_handle h, lu_bn_sync_fn fn, void* user, int32_t world_size) {
+  LU_REQUIRE(h, "null handle");
+  LU_REQUIRE(fn == nullptr || world_size >= 1, "world size must be >= 1");
+  h->bn_sync_fn = fn; h->bn_sync_user = user; h->bn_sync_world = fn ? world_size : 1;
+  return 0;
 }
 
 int lu_set_grad_bucket_callback(lu_handle h, lu_grad_bucket_fn fn, void* user) {

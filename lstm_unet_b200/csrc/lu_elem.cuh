@@ -186,6 +186,44 @@ struct LuBnFinalize {
     sums[c] = 0; sums[cpad + c] = 0;
   }
 };
+// ---- synchronised batch statistics (data-parallel training, SURVEY 8e option ii) -----------------------------------
+// local moments of this rank's frames in a form that adds up across ranks: mom = [mean | mean^2 | M2] per channel
+// (every rank holds the same number of pixels); item = channel
+struct LuBnMoments {
+  double* sums; const float* shift_src; double* mom; int64_t npix; int cpad, c_real;
+  LU_HD void operator()(int64_t c) const {
+    double mean = 0, m2 = 0;
+    if (c < c_real) {
+      const double n = (double)npix;
+      const double m0 = sums[c] / n;
+      double var = sums[cpad + c] / n - m0 * m0; if (var < 0) var = 0;
+      mean = m0 + (double)shift_src[c]; m2 = var * n;
+    }
+    mom[c] = mean; mom[cpad + c] = mean * mean; mom[2 * cpad + c] = m2;
+    sums[c] = 0; sums[cpad + c] = 0;
+  }
+};
+// scale / shift / moving statistics from the moments summed over `world` ranks (Chan's pairwise combination for equal
+// counts: M2 = sum M2_r + n * (sum mean_r^2 - world * mean^2)); item = channel
+struct LuBnFinalizeSync {
+  const double* mom; const float* gamma; const float* beta; float* mov_mean; float* mov_var;
+  float* scale; float* shift; float* save_mean; float* save_invstd;
+  int64_t npix; int cpad, c_real, world; float eps, momentum;
+  LU_HD void operator()(int64_t c) const {
+    if (c >= c_real) { scale[c] = 0.f; shift[c] = 0.f; return; }
+    const double n = (double)npix, R = (double)world, N = n * R;
+    const double mean = mom[c] / R;
+    double m2 = mom[2 * cpad + c] + n * (mom[cpad + c] - R * mean * mean); if (m2 < 0) m2 = 0;
+    const double var = m2 / N;
+    const double inv = 1.0 / sqrt(var + (double)eps);
+    scale[c] = (float)(gamma[c] * inv);
+    shift[c] = (float)(beta[c] - mean * gamma[c] * inv);
+    if (save_mean) { save_mean[c] = (float)mean; save_invstd[c] = (float)inv; }
+    const double unb = var * (N / (N > 1 ? N - 1 : 1));
+    mov_mean[c] = momentum * mov_mean[c] + (1.f - momentum) * (float)mean;
+    mov_var[c] = momentum * mov_var[c] + (1.f - momentum) * (float)unb;
+  }
+};
 // pass 3: y = lrelu(raw*scale + shift) -> bf16 planes; item = (pixel, channel)
 struct LuBnApply {
   const float* raw; const float* scale; const float* shift; uint16_t* out;

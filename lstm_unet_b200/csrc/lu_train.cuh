@@ -186,10 +186,13 @@ struct LuBnBwdApply {    // item = (pixel, group of 8 channels); means = [mean g
 };
 struct LuBnBwdParams {   // dgamma = sum g*xhat, dbeta = sum g, per-channel means for the apply pass; item = channel
   const double* sums; float* dgamma; float* dbeta; float* means; int64_t npix; int raw_cpad, c_real;
+  int write_grads;         // 0: only the means (second call of the synchronised-BN path, on the sums of all ranks)
   LU_HD void operator()(int64_t c) const {
     if (c >= c_real) { means[c] = 0.f; means[raw_cpad + c] = 0.f; return; }
-    dbeta[c] = (float)sums[c];
-    dgamma[c] = (float)sums[raw_cpad + c];
+    if (write_grads) {
+      dbeta[c] = (float)sums[c];
+      dgamma[c] = (float)sums[raw_cpad + c];
+    }
     means[c] = (float)(sums[c] / (double)npix);
     means[raw_cpad + c] = (float)(sums[raw_cpad + c] / (double)npix);
   }

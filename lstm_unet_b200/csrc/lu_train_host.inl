@@ -422,9 +422,16 @@ static int bwd_conv_layer(lu_handle_s* h, ConvPlan& f, int T, float* grads, std:
     pf(h, ((npix + r.chunk - 1) / r.chunk) * f.raw_cpad, stream, r);
     LuBnBwdParams bp;
     bp.sums = sums; bp.dgamma = grads + h->params[f.gamma].offset; bp.dbeta = grads + h->params[f.beta].offset;
-    bp.raw_cpad = f.raw_cpad; bp.c_real = f.cout; bp.npix = npix;
+    bp.raw_cpad = f.raw_cpad; bp.c_real = f.cout; bp.npix = npix; bp.write_grads = 1;
     bp.means = reinterpret_cast<float*>(h->ws + f.off_bwd_means);
     pf(h, f.raw_cpad, stream, bp);
+    if (h->bn_sync_fn) {
+      // synchronised BN: gamma / beta gradients stay local (the gradient all-reduce averages them); the input gradient
+      // needs the means of g and g * xhat over the GLOBAL batch
+      h->bn_sync_fn(sums, (int64_t)2 * f.raw_cpad, h->bn_sync_user);
+      bp.write_grads = 0; bp.npix = npix * h->bn_sync_world;
+      pf(h, f.raw_cpad, stream, bp);
+    }
     LuBnBwdApply a;
     a.dA = act_ptr(h, gbuf); a.raw = r.raw; a.scale = r.scale; a.shift = r.shift; a.mean = r.mean; a.invstd = r.invstd;
     a.means = bp.means; a.npix = npix; a.cpad = gb.cpad; a.planes = gb.planes; a.raw_cpad = f.raw_cpad; a.c_real = f.cout; a.alpha = 0.3f;

@@ -82,3 +82,21 @@ class OverlappedAllReduce:
         if flat.is_cuda and self.side is not None:
             torch.cuda.current_stream(flat.device).wait_stream(self.side)
         return flat
+
+
+def enable_sync_batchnorm(session):
+    """Synchronised BatchNorm (SURVEY 8e option ii): every BN layer of `session` normalises with the statistics of the
+    batch of ALL ranks, like the reference does on one device.  Adds one small float64 sum all-reduce per BN layer to the
+    training forward and one to the backward (enqueued on the compute stream by the callback).  Every rank must hold the
+    same number of frames.  No-op without an initialised process group of more than one rank."""
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        session.set_bn_sync_callback(None)
+        return False
+
+    def sum_over_ranks(ptr, count):
+        v = session.workspace_view(ptr, count, __import__('numpy').float64)
+        t = torch.from_numpy(v) if not isinstance(v, torch.Tensor) else v
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+
+    session.set_bn_sync_callback(sum_over_ranks, dist.get_world_size())
+    return True

@@ -143,6 +143,26 @@ class LuSession:
         cb = ctypes.cast(self._bucket_cb, ctypes.c_void_p) if self._bucket_cb is not None else None
         self._check(self.lib.lu_set_grad_bucket_callback(self.h, cb, None))
 
+    def set_bn_sync_callback(self, fn, world_size=1):
+        """fn(device_pointer, count): sum the `count` float64 values at `device_pointer` over the ranks, in place, on the
+        compute stream; None switches synchronised BatchNorm off.  See lu_set_bn_sync_callback."""
+        self._bn_cb = _lib.BN_SYNC_FN(lambda ptr, cnt, user: fn(int(ptr), int(cnt))) if fn is not None else None
+        cb = ctypes.cast(self._bn_cb, ctypes.c_void_p) if self._bn_cb is not None else None
+        self._check(self.lib.lu_set_bn_sync_callback(self.h, cb, None, int(world_size)))
+
+    def workspace_view(self, ptr, count, dtype):
+        """A tensor / array aliasing `count` elements of `dtype` at device pointer `ptr` inside the workspace."""
+        nbytes = int(count) * np.dtype(dtype).itemsize
+        base = self.be.ptr(self._ws_raw)
+        off = int(ptr) - base
+        if off < 0 or off + nbytes > self.ws_bytes + 1024:
+            raise LuError('pointer outside the workspace')
+        raw = self._ws_raw[off:off + nbytes]
+        if isinstance(raw, np.ndarray):
+            return raw.view(dtype)
+        td = {np.float64: self.be.torch.float64, np.float32: self.be.torch.float32}[dtype]
+        return raw.view(td)
+
     def adam_step(self, grads_ptr, m_ptr, v_ptr, lr, step, b1=0.9, b2=0.999, eps=1e-7):
         self._check(self.lib.lu_adam_step(self.h, grads_ptr, m_ptr, v_ptr, lr, b1, b2, eps, int(step), self.be.stream()))
 
