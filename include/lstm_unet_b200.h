@@ -123,7 +123,9 @@ int lu_set_grad_bucket_callback(lu_handle h, lu_grad_bucket_fn fn, void* user);
  * lu_loss_backward -- the callee sums the fp64 vector over the ranks IN PLACE on the compute stream (one all-reduce of
  * 3 x channels doubles per layer forward, 2 x channels backward) -- and imported back as the global mean / variance
  * (forward) and the global means of g and g * xhat (backward).  Every rank must hold the same number of frames.
- * fn == NULL (default): local statistics, no collective in the forward. */
+ * With the callback set the loss normaliser is global too (losses.py:26 divides by the valid pixels of the whole batch):
+ * the valid-pixel count is summed over the ranks and loss / gradients are scaled by world_size, so that their MEAN over
+ * the ranks equals the single-device value.  fn == NULL (default): local statistics, no collective in the forward. */
 typedef void (*lu_bn_sync_fn)(double* dev_vec, int64_t count, void* user);
 int lu_set_bn_sync_callback(lu_handle h, lu_bn_sync_fn fn, void* user, int32_t world_size);
 /* optimizer.apply_gradients with Keras Adam (train2D.py:61,93): step is 1-based; m,v are flat fp32 buffers */

@@ -51,9 +51,11 @@ struct LuCeReduce {      // item = chunk of pixels of the un-padded frames
 struct LuCeGrad {        // item = pixel of the PADDED frame
   const float* raw; const float* labels; const double* acc; float* loss_out; uint16_t* g;
   int H, W, Hp, Wp, py0, px0, raw_cpad, cpad, planes; float w0, w1, w2;
+  float rank_scale;        // 1, or the number of ranks when acc[1] holds the valid-pixel count of ALL ranks (the mean
+                           // over the ranks of loss and gradients is then the single-device value)
   LU_HD void operator()(int64_t p) const {
     const int xx = (int)(p % Wp); int64_t q = p / Wp; const int yy = (int)(q % Hp); const int64_t f = q / Hp;
-    if (p == 0) loss_out[0] = (float)(acc[0] / (acc[1] + 0.00001));
+    if (p == 0) loss_out[0] = (float)(acc[0] * (double)rank_scale / (acc[1] + 0.00001));
     float d[3] = {0.f, 0.f, 0.f};
     const int y = yy - py0, x = xx - px0;
     if (y >= 0 && y < H && x >= 0 && x < W) {
@@ -64,7 +66,7 @@ struct LuCeGrad {        // item = pixel of the PADDED frame
         const float mx = fmaxf(r[0], fmaxf(r[1], r[2]));
         const float e0 = expf(r[0] - mx), e1 = expf(r[1] - mx), e2 = expf(r[2] - mx);
         const float inv = 1.f / (e0 + e1 + e2);
-        const float w = (li == 0 ? w0 : (li == 1 ? w1 : w2)) / (float)(acc[1] + 0.00001);
+        const float w = (li == 0 ? w0 : (li == 1 ? w1 : w2)) * rank_scale / (float)(acc[1] + 0.00001);
         d[0] = w * (e0 * inv - (li == 0 ? 1.f : 0.f));
         d[1] = w * (e1 * inv - (li == 1 ? 1.f : 0.f));
         d[2] = w * (e2 * inv - (li == 2 ? 1.f : 0.f));
@@ -80,8 +82,8 @@ struct LuCeGrad {        // item = pixel of the PADDED frame
 };
 
 struct LuCeLossOnly {
-  const double* acc; float* loss_out;
-  LU_HD void operator()(int64_t) const { loss_out[0] = (float)(acc[0] / (acc[1] + 0.00001)); }
+  const double* acc; float* loss_out; float rank_scale;
+  LU_HD void operator()(int64_t) const { loss_out[0] = (float)(acc[0] * (double)rank_scale / (acc[1] + 0.00001)); }
 };
 
 LU_HDI float lu_ldplanes(const uint16_t* p, int cpad, int planes) {

@@ -487,16 +487,21 @@ static int train_loss_only(lu_handle_s* h, const float* labels, const float* cw,
   r.npix = (int64_t)N * c.height * c.width; r.H = c.height; r.W = c.width; r.Hp = h->Hp; r.Wp = h->Wp;
   r.py0 = h->pad_y0; r.px0 = h->pad_x0; r.raw_cpad = lc.raw_cpad; r.chunk = 256; r.w0 = cw[0]; r.w1 = cw[1]; r.w2 = cw[2];
   pf(h, (r.npix + r.chunk - 1) / r.chunk, stream, r);
+  // single-device semantics across ranks (losses.py:26 divides by the valid pixels of the WHOLE batch): with the rank-sum
+  // callback set, the valid count is summed over the ranks and loss / gradients are scaled so that their mean over the
+  // ranks is the single-device value
+  float rank_scale = 1.f;
+  if (h->bn_sync_fn) { h->bn_sync_fn(acc + 1, 1, h->bn_sync_user); rank_scale = (float)h->bn_sync_world; }
   LuCeGrad g;
   g.raw = r.raw; g.labels = labels; g.acc = acc; g.loss_out = loss_out; g.g = gout;
   g.H = c.height; g.W = c.width; g.Hp = h->Hp; g.Wp = h->Wp; g.py0 = h->pad_y0; g.px0 = h->pad_x0; g.raw_cpad = lc.raw_cpad;
-  g.w0 = cw[0]; g.w1 = cw[1]; g.w2 = cw[2]; g.cpad = 0; g.planes = 1;
+  g.w0 = cw[0]; g.w1 = cw[1]; g.w2 = cw[2]; g.cpad = 0; g.planes = 1; g.rank_scale = rank_scale;
   if (gout != nullptr) {
     const ActBuf& gb = h->acts[h->g_logits_buf];
     g.cpad = gb.cpad; g.planes = gb.planes;
     pf(h, (int64_t)N * h->Hp * h->Wp, stream, g);
   } else {
-    LuCeLossOnly lo; lo.acc = acc; lo.loss_out = loss_out;
+    LuCeLossOnly lo; lo.acc = acc; lo.loss_out = loss_out; lo.rank_scale = rank_scale;
     pf(h, 1, stream, lo);
   }
   return 0;

@@ -98,7 +98,8 @@ def _sync_bn_worker(rank, world, port, out_dir):
     params = O.init_params(NET_BN, seed=5, randomize_bn=True)
     rng = np.random.default_rng(1)
     x = rng.standard_normal((GB, T, 1, H, W)).astype(np.float32)
-    lab = rng.integers(0, 3, size=(GB, T, 1, H, W)).astype(np.float32)       # every pixel valid: equal loss normalisers
+    lab = rng.integers(-1, 3, size=(GB, T, 1, H, W)).astype(np.float32)
+    lab[0] = -1                                  # very unequal valid-pixel counts between the ranks
     lo, hi = shard_range(GB, rank, world)
     sess = emu_session(NET_BN, data_format='NCHW', pad_image=False, batch=hi - lo, max_t=T, height=H, width=W,
                        precision='bf16x3', train=True)
@@ -119,7 +120,8 @@ def _sync_bn_worker(rank, world, port, out_dir):
 
 def test_two_rank_sync_batchnorm_equals_single_device(tmp_path):
     """SURVEY 8e option ii: with the BN statistics summed over the ranks, two ranks holding half the batch each produce
-    the logits, moving statistics and (after the mean all-reduce) the gradients of ONE device holding the whole batch"""
+    the logits, moving statistics, loss (mean over the ranks, normalised by the valid pixels of the whole batch) and --
+    after the mean all-reduce -- the gradients of ONE device holding the whole batch"""
     world = 2
     mp.spawn(_sync_bn_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     r = [np.load(tmp_path / ('sync%d.npz' % i)) for i in range(world)]
@@ -128,7 +130,8 @@ def test_two_rank_sync_batchnorm_equals_single_device(tmp_path):
     params = O.init_params(NET_BN, seed=5, randomize_bn=True)
     rng = np.random.default_rng(1)
     x = rng.standard_normal((4, 2, 1, 8, 8)).astype(np.float32)
-    lab = rng.integers(0, 3, size=(4, 2, 1, 8, 8)).astype(np.float32)
+    lab = rng.integers(-1, 3, size=(4, 2, 1, 8, 8)).astype(np.float32)
+    lab[0] = -1
     sess = emu_session(NET_BN, data_format='NCHW', pad_image=False, batch=4, max_t=2, height=8, width=8, precision='bf16x3',
                        train=True)
     sess.set_params({k: v.numpy().copy() for k, v in params.items()})
