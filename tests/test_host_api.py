@@ -107,3 +107,43 @@ def test_inference_reader_mirror(tmp_path):
         assert f.dtype == np.float32 and np.allclose(f, want, rtol=1e-6, atol=1e-6)
     with pytest.raises(ValueError):
         CTCInferenceReader(str(tmp_path), 'nothing*.tif')
+
+
+def test_training_reader_loads_ctc_folder(tmp_path):
+    """data.CTCRAMReaderSequence2D._read_sequence_to_ram_ (DataHandeling.py:60-133) on a folder in the layout
+    create_sequence_metadata.py writes: filelist rows (raw, seg or None, tra, fully-annotated flag), per-frame z-score,
+    partially annotated frames get background = -1, frames without a segmentation file are all -1"""
+    import pickle
+    import cv2
+    from lstm_unet_b200.data import CTCRAMReaderSequence2D
+    rng = np.random.default_rng(0)
+    os.makedirs(tmp_path / '01')
+    os.makedirs(tmp_path / '01_GT' / 'SEG')
+    rows, raws, segs = [], [], []
+    for t in range(4):
+        raw = rng.integers(0, 4000, size=(20, 24)).astype(np.uint16)
+        cv2.imwrite(str(tmp_path / '01' / ('t%03d.tif' % t)), raw)
+        raws.append(raw)
+        if t == 3:
+            rows.append((os.path.join('01', 't%03d.tif' % t), None, None, None))
+            segs.append(None)
+            continue
+        seg = np.zeros((20, 24), np.uint16)
+        seg[3:8, 4:9] = 1
+        seg[12:17, 10:20] = 2
+        cv2.imwrite(str(tmp_path / '01_GT' / 'SEG' / ('man_seg%03d.tif' % t)), seg)
+        rows.append((os.path.join('01', 't%03d.tif' % t), os.path.join('01_GT', 'SEG', 'man_seg%03d.tif' % t), None, t != 1))
+        segs.append(seg)
+    with open(tmp_path / 'metadata_01.pickle', 'wb') as f:
+        pickle.dump({'filelist': rows, 'max': 4000, 'min': 0, 'shape': (20, 24)}, f)
+    rd = CTCRAMReaderSequence2D(sequence_folder_list=[(str(tmp_path), '01')], image_crop_size=(16, 16), unroll_len=2, batch_size=1,
+                                seed=0)
+    rd._read_sequence_to_ram_()
+    seq = rd.sequence_data[(str(tmp_path), '01')]
+    assert seq['images'].shape == (4, 20, 24) and list(seq['full_seg']) == [1, 0, 1, 0]
+    for t in range(4):
+        a = raws[t].astype(np.float32)
+        assert np.allclose(seq['images'][t], (a - a.mean()) / a.std(), rtol=1e-5, atol=1e-5)
+    assert np.array_equal(seq['segs'][0], segs[0])                       # fully annotated: labels as stored
+    assert np.array_equal(seq['segs'][1], np.where(segs[1] == 0, -1.0, segs[1].astype(np.float64)))   # partially annotated: background unknown
+    assert np.all(seq['segs'][3] == -1)                                  # no segmentation file
