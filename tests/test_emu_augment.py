@@ -115,3 +115,49 @@ def test_emu_randomized_sweep_against_oracle():
             ri, rs = A.augment_frame(imgs[t], segs[t], contrast[t], brightness[t], affine, coords, flip, rot)
             assert np.array_equal(seg[t], rs), (trial, t)
             np.testing.assert_allclose(img[t], ri, rtol=2e-6, atol=2e-4)
+
+
+REF_META = '/root/reference/metadata_files.tar.gz'
+
+
+@pytest.mark.skipif(not __import__('os').path.exists(REF_META), reason='the reference archive is only present in the build container')
+def test_reader_on_a_real_ctc_metadata_file(tmp_path):
+    """The reference ships the metadata pickles of seven CTC datasets (metadata_files.tar.gz).  One of them, with frames
+    synthesised at the paths it lists, goes through the reader mirror: folder loading (partial / missing annotations as in
+    the real file list), the reference-order draws, device augmentation (host build here) and batching."""
+    import os
+    import pickle
+    import tarfile
+    import cv2
+    from lstm_unet_b200.data import CTCRAMReaderSequence2D
+    with tarfile.open(REF_META) as tf:
+        member = next(m for m in tf.getmembers() if m.name.endswith('DIC-C2DH-HeLa/metadata_01.pickle'))
+        meta = pickle.load(tf.extractfile(member))
+    root = tmp_path / 'DIC-C2DH-HeLa'
+    H, W = meta['shape']
+    rng = np.random.default_rng(0)
+    yy, xx = np.mgrid[0:H, 0:W]
+    for t, (raw_name, seg_name, _, _flag) in enumerate(meta['filelist']):
+        os.makedirs(os.path.dirname(root / raw_name), exist_ok=True)
+        img = (rng.integers(0, 60, size=(H, W)) + 100 * (((yy - 200 - t) ** 2 + (xx - 250) ** 2) < 900)).astype(np.uint8)
+        cv2.imwrite(str(root / raw_name), img)
+        if seg_name is not None:
+            os.makedirs(os.path.dirname(root / seg_name), exist_ok=True)
+            seg = np.zeros((H, W), np.uint16)
+            seg[((yy - 200 - t) ** 2 + (xx - 250) ** 2) < 900] = 1
+            seg[((yy - 400) ** 2 + (xx - 100 - t) ** 2) < 400] = 2
+            cv2.imwrite(str(root / seg_name), seg)
+    with open(root / 'metadata_01.pickle', 'wb') as f:
+        pickle.dump(meta, f)
+    rd = CTCRAMReaderSequence2D(sequence_folder_list=[(str(root), '01')], image_crop_size=(64, 64), unroll_len=4, batch_size=2,
+                                seed=1, elastic_seed=2, _augmenter=emu_augmenter())
+    rd.start_queues()
+    seq = rd.sequence_data[(str(root), '01')]
+    n_seg = sum(r[1] is not None for r in meta['filelist'])
+    assert seq['images'].shape == (len(meta['filelist']), H, W)
+    assert int((seq['segs'].reshape(len(meta['filelist']), -1).max(1) > 0).sum()) == n_seg
+    assert int(seq['full_seg'].sum()) == sum(bool(r[3]) for r in meta['filelist'])
+    for _ in range(3):
+        image, seg, full, is_last = rd.get_batch()
+        assert image.shape == (2, 4, 1, 64, 64) and seg.shape == (2, 4, 1, 64, 64) and full.shape == (2, 4) and is_last.shape == (2,)
+        assert np.isfinite(image).all() and set(np.unique(seg)) <= {-1.0, 0.0, 1.0, 2.0}
