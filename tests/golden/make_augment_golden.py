@@ -27,6 +27,12 @@ class _Anything(types.ModuleType):
     def __call__(self, *a, **k):
         return _Anything('call')
 
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
 
 def reference_reader():
     for m in ('tensorflow', 'utils'):

@@ -161,3 +161,75 @@ def test_reader_on_a_real_ctc_metadata_file(tmp_path):
         image, seg, full, is_last = rd.get_batch()
         assert image.shape == (2, 4, 1, 64, 64) and seg.shape == (2, 4, 1, 64, 64) and full.shape == (2, 4) and is_last.shape == (2,)
         assert np.isfinite(image).all() and set(np.unique(seg)) <= {-1.0, 0.0, 1.0, 2.0}
+    # the reference's own loader (DataHandeling.py:60-133, imported with stand-in tensorflow / utils modules) on the same
+    # folder gives the same arrays
+    from tests.golden.make_augment_golden import reference_reader
+    R = reference_reader()
+    ref = R(sequence_folder_list=[(str(root), '01')], image_crop_size=(64, 64), unroll_len=4, batch_size=2, num_threads=1)
+    ref._read_sequence_to_ram_()
+    ref_seq = ref.sequence_data[(str(root), '01')]
+    assert np.array_equal(ref_seq['images'], seq['images'])
+    assert np.array_equal(ref_seq['segs'], seq['segs'])
+    assert np.array_equal(ref_seq['full_seg'], seq['full_seg'])
+
+
+@pytest.mark.skipif(not __import__('os').path.exists('/root/reference/DataHandeling.py'),
+                    reason='the reference is only present in the build container')
+def test_reader_sequence_equals_the_references_own_loop(tmp_path):
+    """One whole pass of the reference's ``_load_and_enqueue`` (DataHandeling.py:262-428: sequence choice, sub-sampling,
+    reversal, crop, flips, rotation, per-frame contrast / brightness draws, segmentation relabelling, queue payload) --
+    executed from /root/reference with stand-in tensorflow queues and seeded ``random`` / ``np.random`` -- against the
+    reader mirror seeded the same way.  Elastic augmentation is off here: the reference seeds that RandomState from OS
+    entropy (:159), its arithmetic is pinned separately (tests/golden/augment.npz)."""
+    import os
+    import pickle
+    import random
+    import types
+    import cv2
+    from lstm_unet_b200.data import CTCRAMReaderSequence2D
+    from tests.golden.make_augment_golden import reference_reader
+    rng = np.random.default_rng(3)
+    root = tmp_path / 'seq'
+    os.makedirs(root / '01')
+    os.makedirs(root / '01_GT' / 'SEG')
+    rows = []
+    yy, xx = np.mgrid[0:40, 0:48]
+    for t in range(11):
+        raw = (rng.integers(0, 50, size=(40, 48)) + 150 * (((yy - 12 - t) ** 2 + (xx - 20) ** 2) < 40)).astype(np.uint8)
+        cv2.imwrite(str(root / '01' / ('t%03d.tif' % t)), raw)
+        seg_name = None
+        if t % 4 != 3:
+            seg = np.zeros((40, 48), np.uint16)
+            seg[((yy - 12 - t) ** 2 + (xx - 20) ** 2) < 40] = 1
+            seg[((yy - 30) ** 2 + (xx - 35 + t) ** 2) < 30] = 2
+            seg_name = os.path.join('01_GT', 'SEG', 'man_seg%03d.tif' % t)
+            cv2.imwrite(str(root / seg_name), seg)
+        rows.append((os.path.join('01', 't%03d.tif' % t), seg_name, None, (t % 2 == 0) if seg_name else None))
+    with open(root / 'metadata_01.pickle', 'wb') as f:
+        pickle.dump({'filelist': rows, 'shape': (40, 48), 'max': 255, 'min': 0}, f)
+    folders = [(str(root), '01')]
+    kw = dict(image_crop_size=(16, 16), unroll_len=3, deal_with_end=0, batch_size=1, data_format='NCHW', randomize=True,
+              elastic_augmentation=False)
+    for seed in (0, 1, 2, 5):
+        # ---- the reference's loop, one sequence ----
+        R = reference_reader()
+        ref = R(sequence_folder_list=folders, num_threads=3, **kw)
+        random.seed(seed); np.random.seed(seed)
+        ref._read_sequence_to_ram_()
+        got = []
+        ref.coord = types.SimpleNamespace(should_stop=lambda: len(got) > 0)      # stop once one sequence is enqueued
+        q = types.SimpleNamespace(enqueue_many=lambda payload: got.append(payload))
+        q_stat = lambda: types.SimpleNamespace(numpy=lambda: 0.0)
+        ref._load_and_enqueue(q, q_stat)
+        assert len(got) == 1
+        r_img, r_seg, r_full, r_last, _names = got[0]
+        # ---- the mirror, same seeds, same call order ----
+        random.seed(seed); np.random.seed(seed)
+        rd = CTCRAMReaderSequence2D(sequence_folder_list=folders, _augmenter=emu_augmenter(), **kw)
+        rd.start_queues()
+        rd._produce(0)
+        m_img, m_seg, m_full, m_last, _ = rd._fifo[0][0]
+        assert len(r_img) == m_img.shape[0] and len(r_img) % 3 == 0
+        assert np.array_equal(np.stack(r_seg), m_seg), seed
+        np.testing.assert_allclose(m_img, np.stack(r_img), rtol=2e-6, atol=2e-6)
+        assert np.array_equal(np.asarray(r_full, np.float32), m_full) and np.array_equal(np.asarray(r_last, np.float32), m_last)
