@@ -4,13 +4,20 @@ Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / `
 leg may import this module.  The product path (``lstm_unet_b200``) never imports it and fails loudly
 if its CUDA library is missing.
 
-PARITY UNPINNED: the reference (arbellea/LSTM-UNet) delegates all arithmetic to TensorFlow 2 /
-Keras-2 (``requirements.txt:1`` ``tensorflow_gpu>=2.0.0a0``, un-vendored, unpinned) and ships no golden
-vectors or numeric tests.  TensorFlow is not installable in this image, so this
-restatement cannot be checked against outputs of the reference itself.  It is instead cross-checked
-against an independent loop-level numpy restatement of the published operator semantics
-(``oracle/np_semantics.py``, tests/test_oracle.py) and against the only behaviour the reference's own
-``unit_test`` methods pin: output shapes (``Networks.py:100-119,155-175,256-277``).
+PARITY UNPINNED (operator semantics): the reference (arbellea/LSTM-UNet) delegates all arithmetic to
+TensorFlow 2 / Keras-2 (``requirements.txt:1`` ``tensorflow_gpu>=2.0.0a0``, un-vendored, unpinned) and ships
+no golden vectors or numeric tests.  TensorFlow is not installable in this image,
+so the Keras-2 OPERATORS restated here (ConvLSTM2D, Conv2D SAME, BatchNormalization, LeakyReLU, bilinear
+resize) cannot be checked against outputs of TensorFlow itself.  They are cross-checked against an independent
+loop-level numpy restatement of the published semantics (``oracle/np_semantics.py``, tests/test_oracle.py).
+
+PINNED (wiring): everything around those operators IS checked against the reference's own code --
+tests/test_reference_wiring.py imports /root/reference/Networks.py and losses.py unmodified on a torch-backed
+stand-in for the handful of tf / Keras names they use (tests/keras_standin.py, whose layer arithmetic is this
+module's) and compares ``ULSTMnet2D.call`` (reflect-pad / crop arithmetic, block and skip order, reshapes,
+return_logits, the soft-max axis incl. the channels-last quirk, stateful carry), the state methods and
+``WeightedCELoss`` with OracleNet / weighted_ce_loss on real numbers; tests/test_host_api.py pins the layer
+hyper-parameters the reference's constructors pass to Keras and the Params defaults the same way.
 
 What is restated (reference file:line -> function here):
   Networks.py:35-75    DownBlock2D.__init__/call          -> OracleNet._down_block
