@@ -167,3 +167,17 @@ def test_train_step_decreases_loss_and_adam_formula():
     exp = p0 - 1e-3 * np.sqrt(1 - 0.999) / (1 - 0.9) * (0.1 * g) / (torch.sqrt(0.001 * g * g) + 1e-7)
     np.testing.assert_allclose(net.params[names[0]].numpy(), exp.numpy(), rtol=1e-9, atol=1e-12)
     assert float(loss) > 0
+
+
+def test_bilinear_x2_agrees_with_opencv():
+    """a third, independent implementation of the half-pixel-centre bilinear resize (tf.image.resize's TF2 default,
+    SURVEY App. A.5): OpenCV's INTER_LINEAR uses the same sampling convention for float images"""
+    cv2 = pytest.importorskip('cv2')
+    import torch
+    from oracle import lstm_unet_oracle as O
+    rng = np.random.default_rng(0)
+    for h, w in ((7, 9), (1, 5), (16, 3)):
+        x = rng.standard_normal((1, 1, h, w)).astype(np.float32)
+        mine = O.resize_bilinear(torch.from_numpy(x), 2)[0, 0].numpy()
+        ref = cv2.resize(x[0, 0], (2 * w, 2 * h), interpolation=cv2.INTER_LINEAR)
+        assert np.abs(mine - ref).max() < 1e-6
