@@ -201,7 +201,11 @@ class CTCRAMReaderSequence2D:
         if self._aug is None:
             self.start_queues()
         parts = [self._dequeue_many(b) for b in range(self.batch_size)]
-        stack = np.stack if isinstance(parts[0][0], np.ndarray) else __import__('torch').stack
+        if isinstance(parts[0][0], np.ndarray):
+            stack = np.stack
+        else:
+            import torch
+            stack = torch.stack
         image = stack([p[0] for p in parts])
         seg = stack([p[1] for p in parts])
         axis = 4 if self.data_format == 'NHWC' else 2

@@ -3,6 +3,7 @@
 Every sample's frames and its stateful h/c at all levels live on exactly one rank, so the forward needs no data-path
 collective.  The training step has one exchange: a sum all-reduce of the flat gradient buffer (NCCL over NVLink on the
 GPU box; the same code runs over gloo in the CPU tests).  Timing is the max over ranks."""
+import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -94,7 +95,7 @@ def enable_sync_batchnorm(session):
         return False
 
     def sum_over_ranks(ptr, count):
-        v = session.workspace_view(ptr, count, __import__('numpy').float64)
+        v = session.workspace_view(ptr, count, np.float64)
         t = torch.from_numpy(v) if not isinstance(v, torch.Tensor) else v
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
 
