@@ -114,3 +114,16 @@ def test_emu_randomized_sweep_against_oracle():
         flagged += int(pp.info()[0, 2])
         assert np.array_equal(got, P.postprocess_frame(sm, **kw)), (trial, H, W, kind, kw)
     assert flagged > 0
+
+
+def test_emu_nan_and_inf_soft_max_follow_numpy():
+    """np.argmax treats the first NaN as the maximum and `NaN >= 0.2` is False; +inf wins like any large value"""
+    rng = np.random.default_rng(9)
+    sm = P.synthetic_softmax(24, 28, 77, 'noise')
+    for c in range(3):
+        m = rng.random((24, 28)) < 0.05
+        sm[c][m] = np.nan
+    sm[1][rng.random((24, 28)) < 0.03] = np.inf
+    sm[2][rng.random((24, 28)) < 0.03] = -np.inf
+    kw = dict(edge_dist=2, min_cell_size=1, max_cell_size=10 ** 6)
+    assert np.array_equal(emu_post(**kw)(sm), P.postprocess_frame(sm, **kw))
