@@ -186,9 +186,27 @@ class Adam:
         self.iterations = 0
         self._m = self._v = None
 
+    def get_slots(self):
+        """(iterations, m, v) with the moment vectors as flat host arrays (None before the first step)."""
+        if self._m is None:
+            return self.iterations, None, None
+        return self.iterations, self._m.detach().cpu().numpy().copy(), self._v.detach().cpu().numpy().copy()
+
+    def set_slots(self, iterations, m, v, device=None):
+        import torch
+        self.iterations = int(iterations)
+        if m is None:
+            self._m = self._v = None
+            return
+        dev = device if device is not None else (self._m.device if self._m is not None else 'cpu')
+        self._m = torch.as_tensor(np.asarray(m, dtype=np.float32)).to(dev)
+        self._v = torch.as_tensor(np.asarray(v, dtype=np.float32)).to(dev)
+
     def _apply(self, model, grads):
         import torch
         sess = model._need_session()
+        if self._m is not None and self._m.device != grads.device:      # restored from a checkpoint on the host
+            self._m, self._v = self._m.to(grads.device), self._v.to(grads.device)
         if self._m is None:
             self._m = torch.zeros(sess.n_trainable, dtype=torch.float32, device=grads.device)
             self._v = torch.zeros_like(self._m)
@@ -423,9 +441,10 @@ class ULSTMnet2D:
         with open(path if str(path).endswith('.npz') else str(path) + '.npz', 'wb') as f:
             np.savez(f, **{k.replace('/', '|'): v for k, v in w.items()})
 
-    def _variable_names(self):
+    def _variable_layout(self):
+        """[{name, shape, offset, count, trainable}] of the flat parameter buffer (host logic only: works without a GPU)."""
         if self._sess is not None:
-            return [e['name'] for e in self._sess.layout]
+            return [dict(e) for e in self._sess.layout]
         cfg = _lib.make_config(self.net_params, self.data_format, self.pad_image, batch=1, max_t=1, height=64, width=64)
         import ctypes
         h = ctypes.c_void_p()
@@ -433,12 +452,18 @@ class ULSTMnet2D:
             raise LuError(self._lib.lu_last_error().decode())
         nt = ctypes.c_int32()
         self._lib.lu_param_count(h, ctypes.byref(nt), None, None)
-        buf, names = ctypes.create_string_buffer(256), []
+        buf, out = ctypes.create_string_buffer(256), []
         for i in range(nt.value):
-            self._lib.lu_param_info(h, i, buf, 256, None, None, None, None)
-            names.append(buf.value.decode())
+            shp, rank, off, tr = (ctypes.c_int64 * 4)(), ctypes.c_int32(), ctypes.c_int64(), ctypes.c_int32()
+            self._lib.lu_param_info(h, i, buf, 256, shp, ctypes.byref(rank), ctypes.byref(off), ctypes.byref(tr))
+            shape = tuple(int(shp[j]) for j in range(rank.value))
+            out.append({'name': buf.value.decode(), 'shape': shape, 'offset': off.value, 'count': int(np.prod(shape)),
+                        'trainable': bool(tr.value)})
         self._lib.lu_destroy(h)
-        return names
+        return out
+
+    def _variable_names(self):
+        return [e['name'] for e in self._variable_layout()]
 
     def load_weights(self, path):
         """Accepts a TF2 checkpoint prefix (``model.ckpt`` -> ``model.ckpt.index``; Inference2D.py:34) or an ``.npz``."""

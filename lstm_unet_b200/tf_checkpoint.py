@@ -283,16 +283,18 @@ def read_bundle(prefix, verify=True):
 
 
 def write_bundle(prefix, tensors):
-    """tensors: {key: float32 array}.  One shard.  Name-based readers (tf.train.load_checkpoint(prefix).get_tensor(key))
+    """tensors: {key: array} (float32, or int64 for integer arrays).  One shard.  Name-based readers (tf.train.load_checkpoint(prefix).get_tensor(key))
     can read the result; Keras' object-based ``load_weights`` additionally needs the serialized object graph, which is
     not written."""
     data, items, offset = bytearray(), [], 0
     header = b'\x08\x01' + b'\x1a\x02\x08\x01'        # num_shards = 1, version { producer: 1 }
     items.append((b'', header))
     for key in sorted(tensors):
-        a = np.ascontiguousarray(tensors[key], dtype=np.float32)
+        a = np.asarray(tensors[key])
+        dt = DT_INT64 if a.dtype.kind in 'iu' else DT_FLOAT          # step counters are int64 in TF checkpoints
+        a = np.ascontiguousarray(a, dtype=_NP_OF_DT[dt])
         raw = a.tobytes()
-        items.append((key.encode(), _encode_entry(DT_FLOAT, a.shape, 0, offset, len(raw), mask_crc(crc32c(raw)))))
+        items.append((key.encode(), _encode_entry(dt, a.shape, 0, offset, len(raw), mask_crc(crc32c(raw)))))
         data += raw
         offset += len(raw)
     os.makedirs(os.path.dirname(os.path.abspath(prefix)), exist_ok=True)

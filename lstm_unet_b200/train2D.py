@@ -2,8 +2,9 @@
 order -- providers, model construction with pad_image=False, Adam, train_step, reset_states_per_batch, validation
 with swapped recurrent states, and the per-step SEG measure / accuracy metrics (train2D.py:97-102,111-116) computed on the
 device, and the final export for inference (train2D.py:232-240: ``model.ckpt`` as a TF2 tensor bundle +
-``model_params.pickle``, what ``Inference2D.inference`` loads).  TensorBoard, the periodic checkpoint manager and AWS
-polling are out of scope.  Usage, as in the reference: set the module global ``params`` and call ``train()``."""
+``model_params.pickle``, what ``Inference2D.inference`` loads), and the training checkpoints (train2D.py:62-85,222-226:
+restore on ``load_checkpoint``, a checkpoint every ``save_checkpoint_iteration`` steps; checkpoint.py).  TensorBoard and
+AWS polling are out of scope.  Usage, as in the reference: set the module global ``params`` and call ``train()``."""
 import os
 import pickle
 
@@ -30,7 +31,20 @@ def train(num_iterations=None, allreduce=None, log=log_print):
     optimizer = Nets.Adam(lr=params.learning_rate)
     seg_measure = losses.seg_measure(params.channel_axis + 1, three_d=False)     # train2D.py:51
     metrics = {'train': {'SEG': [], 'accuracy': []}, 'val': {'SEG': [], 'accuracy': []}}
-    step = 0
+    # train2D.py:62-85: tf.train.Checkpoint(step, optimizer, net=model) + CheckpointManager, restore on request
+    from . import checkpoint as ck
+    ckpt = ck.Checkpoint(model, optimizer)
+    if getattr(params, 'load_checkpoint', False):
+        path = os.path.expanduser(params.load_checkpoint_path)
+        latest = ck.latest_checkpoint(path) if os.path.isdir(path) else path
+        if latest:
+            ckpt.restore(latest)
+            log('Restored from {}'.format(latest))
+        else:
+            log('Initializing from scratch.')
+    manager = ck.CheckpointManager(ckpt, os.path.join(os.path.expanduser(params.experiment_save_dir), 'tf_ckpts'),
+                                   max_to_keep=getattr(params, 'save_checkpoint_max_to_keep', 5))
+    step = ckpt.step
 
     def train_step(image, label):
         softmax, predictions, loss = model.train_step(image, label, params.class_weights, optimizer, allreduce)
@@ -56,6 +70,9 @@ def train(num_iterations=None, allreduce=None, log=log_print):
         losses_seen.append(float(train_loss_value))
         if not step % params.print_to_console_interval:
             log('Training: Step {}, Loss: {}'.format(step, losses_seen[-1]))
+        if not getattr(params, 'dry_run', True) and not step % getattr(params, 'save_checkpoint_iteration', 5000):
+            ckpt.step = step                                 # train2D.py:222-226
+            log('Saved checkpoint for step {}: {}'.format(step, manager.save(step)))
         if not step % params.validation_interval:
             train_states = model.get_states()
             model.set_states(val_states)

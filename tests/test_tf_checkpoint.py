@@ -109,3 +109,51 @@ def test_model_save_load_tf_format(tmp_path):
     m2.load_weights(str(tmp_path / 'model.ckpt'))
     for k in params:
         np.testing.assert_array_equal(m2._pending_weights[k], params[k])
+
+
+def test_training_checkpoint_manager_round_trip(tmp_path):
+    """checkpoint.Checkpoint / CheckpointManager / latest_checkpoint (train2D.py:62-85,222-226) on the host: model
+    variables under net/, Adam moments as optimizer slots, int64 counters, max_to_keep, the `checkpoint` state file"""
+    import torch
+    from lstm_unet_b200 import checkpoint as ck
+    from lstm_unet_b200 import tf_checkpoint as tfc
+    from lstm_unet_b200.Networks import ULSTMnet2D, Adam
+    from oracle import lstm_unet_oracle as O
+    net = {'down_conv_kernels': [[(3, 6)], [(3, 8)]], 'lstm_kernels': [[(3, 5)], [(5, 7)]], 'up_conv_kernels': [[(3, 6)], [(3, 5), (1, 3)]]}
+    params = {k: v.numpy() for k, v in O.init_params(net, seed=2, randomize_bn=True).items()}
+    model = ULSTMnet2D(net, 'NCHW', False, train=True)
+    model.set_weights_dict(params)
+    layout = model._variable_layout()
+    n_train = sum(e['count'] for e in layout if e['trainable'])
+    rng = np.random.default_rng(0)
+    opt = Adam(lr=3e-4)
+    opt.set_slots(17, rng.standard_normal(n_train).astype(np.float32), rng.random(n_train).astype(np.float32))
+    c = ck.Checkpoint(model, opt, step=17)
+    mgr = ck.CheckpointManager(c, str(tmp_path / 'tf_ckpts'), max_to_keep=2)
+    assert ck.latest_checkpoint(str(tmp_path / 'tf_ckpts')) is None
+    paths = []
+    for step in (17, 18, 19):
+        c.step = step
+        paths.append(mgr.save(step))
+    assert [os.path.basename(p) for p in mgr.checkpoints] == ['ckpt-18', 'ckpt-19']
+    assert not os.path.exists(paths[0] + '.index') and os.path.exists(paths[2] + '.data-00000-of-00001')
+    assert ck.latest_checkpoint(str(tmp_path / 'tf_ckpts')) == paths[2]
+    bundle = tfc.read_bundle(paths[2])
+    assert bundle['step/.ATTRIBUTES/VARIABLE_VALUE'].dtype == np.int64 and int(bundle['step/.ATTRIBUTES/VARIABLE_VALUE']) == 19
+    assert 'net/DownLayers/0/ConvLSTM/0/cell/kernel/.OPTIMIZER_SLOT/optimizer/m/.ATTRIBUTES/VARIABLE_VALUE' in bundle
+    # restore into a fresh model / optimizer
+    model2, opt2 = ULSTMnet2D(net, 'NCHW', False, train=True), Adam(lr=1.0)
+    c2 = ck.Checkpoint(model2, opt2).restore(ck.latest_checkpoint(str(tmp_path / 'tf_ckpts')))
+    assert c2.step == 19 and opt2.iterations == 17
+    for k, v in params.items():
+        assert np.array_equal(model2._pending_weights[k], v), k
+    it, m, v = opt.get_slots()
+    it2, m2, v2 = opt2.get_slots()
+    assert np.array_equal(m, m2) and np.array_equal(v, v2)
+    # a manager opened on an existing directory continues the list; a plain save_weights file restores weights only
+    mgr2 = ck.CheckpointManager(c2, str(tmp_path / 'tf_ckpts'), max_to_keep=2)
+    assert mgr2.latest_checkpoint == paths[2]
+    model.save_weights(str(tmp_path / 'model.ckpt'), save_format='tf')
+    opt3 = Adam()
+    c3 = ck.Checkpoint(ULSTMnet2D(net, 'NCHW', False), opt3).restore(str(tmp_path / 'model.ckpt'))
+    assert c3.step == 0 and opt3.iterations == 0 and opt3.get_slots()[1] is None
