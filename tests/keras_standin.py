@@ -48,6 +48,13 @@ class Model:
     def __call__(self, *args, **kwargs):
         return self.call(*args, **kwargs)
 
+    def load_weights(self, prefix):
+        """keras.Model.load_weights on a TF2 checkpoint prefix: through the repository's tensor-bundle reader"""
+        from lstm_unet_b200 import tf_checkpoint
+        names = [n for n, _, _ in O.build_param_specs(self._standin_net_params)]
+        named = tf_checkpoint.load_model_weights(str(prefix), names)
+        load_weights(self, {k: torch.from_numpy(np.array(v, dtype=np.float32)) for k, v in named.items()})
+
 
 class ConvLSTM2D:
     def __init__(self, filters, kernel_size, strides, padding, data_format, return_sequences, stateful):
@@ -136,14 +143,46 @@ def _pad(x, paddings, mode):
     return x
 
 
+class _Anything:
+    """whatever else the reference touches at import time (default arguments such as tf.train.Coordinator())"""
+
+    def __getattr__(self, k):
+        if k.startswith('__'):
+            raise AttributeError(k)
+        return _Anything()
+
+    def __call__(self, *a, **k):
+        return _Anything()
+
+
+class _PermissiveModule(types.ModuleType):
+    def __getattr__(self, k):
+        if k.startswith('__'):
+            raise AttributeError(k)
+        return _Anything()
+
+
 def install():
     """Registers the stand-in as ``tensorflow`` / ``tensorflow.python.keras``; returns a function that removes it."""
-    tf = types.ModuleType('tensorflow')
+    tf = _PermissiveModule('tensorflow')
     tf.__version__ = '2.0.standin'
     tf.pad = _pad
-    tf.reshape = lambda x, shape: x.reshape([int(s) for s in shape])
+    tf.reshape = lambda x, shape: torch.as_tensor(x).reshape([int(s) for s in shape])
     tf.concat = lambda xs, axis: torch.cat(list(xs), dim=axis)
     tf.math = types.SimpleNamespace(mod=lambda a, b: int(a) % int(b))
+
+    class _Device:                            # `with tf.device('/cpu:0'):`
+        def __init__(self, name):
+            pass
+
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *a):
+            return False
+    tf.device = _Device
+    # tf.data.Dataset.from_generator(gen, dtype): the generator itself (Inference2D.py iterates it)
+    tf.data = types.SimpleNamespace(Dataset=types.SimpleNamespace(from_generator=lambda gen, dtype: gen()))
     # the tensor ops losses.WeightedCELoss uses (losses.py:13-27)
     tf.float32, tf.int32 = torch.float32, torch.int32
     tf.squeeze = lambda x, axis: torch.squeeze(torch.as_tensor(x), dim=axis)

@@ -114,3 +114,72 @@ def test_reference_weighted_ce_loss_equals_oracle(ref_networks, channel_axis, sh
         sys.modules.pop('losses', None)
         if saved is not None:
             sys.modules['losses'] = saved
+
+
+def test_reference_inference_script_equals_oracle_pipeline(ref_networks, tmp_path):
+    """The reference's whole ``Inference2D.inference()`` (Inference2D.py:25-136, imported unmodified) on the stand-in:
+    model_params.pickle + model.ckpt loading, the CTCInferenceReader sequence with its reversed warm-up prefix, the
+    per-frame B=1 / T=1 stateful call, the post-processing and the mask TIFFs it writes -- against the oracle pipeline
+    (OracleNet streaming + postprocess_frame) on the same TIFF frames.  Pins the orchestration of SURVEY row a12."""
+    import pickle
+    import types
+    import cv2
+    from oracle import postprocess_oracle as P
+    from lstm_unet_b200 import tf_checkpoint
+    RN, standin = ref_networks
+    net = NET_B
+    params = O.init_params(net, seed=21, randomize_bn=True)
+    # a model directory as train2D.py leaves it (train2D.py:232-240)
+    model_dir, seq_dir, out_dir = tmp_path / 'model', tmp_path / 'seq', tmp_path / 'out'
+    os.makedirs(model_dir); os.makedirs(seq_dir)
+    tf_checkpoint.save_model_weights(str(model_dir / 'model.ckpt'), {k: v.numpy() for k, v in params.items()})
+    with open(model_dir / 'model_params.pickle', 'wb') as f:
+        pickle.dump({'name': 'ULSTMnet2D', 'params': (net,)}, f)
+    rng = np.random.default_rng(5)
+    yy, xx = np.mgrid[0:24, 0:28]
+    raws = []
+    for t in range(4):
+        a = (rng.integers(0, 80, size=(24, 28)) + 900 * (((yy - 8 - t) ** 2 + (xx - 10) ** 2) < 16)).astype(np.uint16)
+        cv2.imwrite(str(seq_dir / ('t%03d.tif' % t)), a)
+        raws.append(a)
+    # the modules Inference2D.py imports next to Networks
+    saved = {n: sys.modules.pop(n, None) for n in ('Inference2D', 'Params', 'DataHandeling', 'utils', 'distutils', 'distutils.util')}
+    du = types.ModuleType('distutils.util'); du.strtobool = lambda v: int(str(v).lower() in ('1', 'true', 'y', 'yes'))
+    sys.modules['distutils'] = types.ModuleType('distutils'); sys.modules['distutils.util'] = du
+    # keras_standin's Model.load_weights needs the architecture: the reference passes it to the constructor
+    orig_init = RN.ULSTMnet2D.__init__
+
+    def init_and_remember(self, net_params=RN.DEFAULT_NET_DOWN_PARAMS, *a, **k):
+        orig_init(self, net_params, *a, **k)
+        self._standin_net_params = net_params
+    RN.ULSTMnet2D.__init__ = init_and_remember
+    try:
+        ref_inf = importlib.import_module('Inference2D')
+        assert ref_inf.__file__.startswith('/root/reference')
+        pre = 2
+        ref_inf.params = types.SimpleNamespace(
+            model_path=str(model_dir), gpu_id=-1, data_format='NCHW', dry_run=False, save_intermediate=False,
+            save_intermediate_path=None, output_path=str(out_dir), data_reader=ref_inf.DataHandeling.CTCInferenceReader,
+            sequence_path=str(seq_dir), filename_format='t*.tif', pre_sequence_frames=pre, edge_dist=2, FOV=0,
+            min_cell_size=1, max_cell_size=10000)
+        os.makedirs(out_dir)
+        ref_inf.inference()
+    finally:
+        RN.ULSTMnet2D.__init__ = orig_init
+        for n, m in saved.items():
+            sys.modules.pop(n, None)
+            if m is not None:
+                sys.modules[n] = m
+    # the oracle pipeline on the same frames
+    ora = O.OracleNet(net, 'NCHW', True, params={k: v.clone() for k, v in params.items()})
+    frames = [(a.astype(np.float32) - a.astype(np.float32).mean()) / a.astype(np.float32).std() for a in raws]
+    sequence = frames[:pre][::-1] + frames
+    for T, img in enumerate(sequence):
+        _, sm = ora(torch.from_numpy(img).reshape(1, 1, 1, 24, 28), False)
+        t = T - pre
+        if t < 0:
+            continue
+        want = P.postprocess_frame(sm[0, 0].numpy(), edge_dist=2, min_cell_size=1, max_cell_size=10000)
+        got = cv2.imread(str(out_dir / ('mask%03d.tif' % t)), -1)
+        assert got is not None and got.dtype == np.uint16 and np.array_equal(got, want), t
+    assert sorted(os.listdir(out_dir)) == ['mask%03d.tif' % t for t in range(4)]
