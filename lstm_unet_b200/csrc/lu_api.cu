@@ -729,7 +729,7 @@ static int launch_conv(lu_handle_s* h, ConvPlan& cv, int frames, const int* mul,
 #ifdef LU_HOST_EMU
   LU_FAIL("the tcgen05 engine does not exist in the host test build");
 #else
-  static bool attr_set[9] = {false, false, false, false, false, false, false, false, false};
+  static bool attr_set[12] = {false, false, false, false, false, false, false, false, false, false, false, false};
   LuTcParams tp;
   memset(&tp, 0, sizeof tp);
   for (int i = 0; i < cv.n_views; ++i) tp.tmA[i] = cv.tmA[i];
@@ -749,6 +749,22 @@ static int launch_conv(lu_handle_s* h, ConvPlan& cv, int frames, const int* mul,
   if (wide_env < 0) { const char* ce = getenv("LU_CLUSTER_WIDE"); wide_env = ce ? atoi(ce) : 1; }
   const bool wide = wide_env == 1 && epi.kind != LU_EPI_LSTM && cv.ktot >= 2048 && cv.BN >= 128 && m_tiles >= 2 * h->num_sms;
   const bool cl2 = cluster_env == 2 && (epi.kind == LU_EPI_LSTM || wide) && cv.ptab_ok && (h->num_sms % 2 == 0);
+  // LU_PAIR=1: the cluster launches run one M = 256 MMA per CTA pair (tcgen05.mma.cta_group::2, kernel cluster mode 3)
+  // instead of two M = 128 MMAs fed by a multicast weight stage.  Each CTA then stages only half of every weight K block,
+  // so the weight stages shrink to half and the shared memory they free goes to deeper activation prefetch.
+  // Off by default: compiled and inspected (SASS), not yet run on hardware.
+  static int pair_env = -1;
+  if (pair_env < 0) { const char* ce = getenv("LU_PAIR"); pair_env = ce ? atoi(ce) : 0; }
+  const bool pair = cl2 && pair_env == 1 && cv.BN >= 32;
+  int smem_bytes = cv.smem;
+  if (pair) {
+    const int budget = 232448 - 1024 - 512 - 6144;               // as in the stage sizing of the plan
+    tp.b_stage_bytes = cv.b_bytes / 2;
+    int na = (budget - cv.nB * tp.b_stage_bytes) / cv.a_bytes;
+    if (na > 8) na = 8;
+    if (na > cv.nA) tp.n_a_stages = na;
+    smem_bytes = tp.n_a_stages * cv.a_bytes + tp.n_b_stages * tp.b_stage_bytes + 1024 + 512 + 6144;
+  }
   tp.num_mt = (int)m_tiles;
   tp.total_tiles = cl2 ? (int)(((m_tiles + 1) / 2) * cv.n_tiles_n) : (int)(m_tiles * cv.n_tiles_n);
   tp.tmBh = cv.tmBh;
@@ -761,13 +777,15 @@ static int launch_conv(lu_handle_s* h, ConvPlan& cv, int frames, const int* mul,
     memcpy(tp.tap_tab, cv.ptaps.data(), cv.ptaps.size() * sizeof(uint16_t));
   }
   int grid = tp.total_tiles * (cl2 ? 2 : 1) < h->num_sms ? tp.total_tiles * (cl2 ? 2 : 1) : h->num_sms;
-  const int ei = cl2 ? (epi.kind == LU_EPI_LSTM ? 6 : (epi.kind == LU_EPI_GRAD ? 7 : 8)) : epi.kind * 2 + (cv.ptab_ok ? 1 : 0);
+  const int ei = cl2 ? (epi.kind == LU_EPI_LSTM ? 6 : (epi.kind == LU_EPI_GRAD ? 7 : 8)) + (pair ? 3 : 0) : epi.kind * 2 + (cv.ptab_ok ? 1 : 0);
   typedef void (*KernelFn)(const LuTcParams);
-  static const KernelFn kfn[9] = {lu_conv_tc_kernel<LU_EPI_CONV, false, 1>, lu_conv_tc_kernel<LU_EPI_CONV, true, 1>,
+  static const KernelFn kfn[12] = {lu_conv_tc_kernel<LU_EPI_CONV, false, 1>, lu_conv_tc_kernel<LU_EPI_CONV, true, 1>,
                                   lu_conv_tc_kernel<LU_EPI_LSTM, false, 1>, lu_conv_tc_kernel<LU_EPI_LSTM, true, 1>,
                                   lu_conv_tc_kernel<LU_EPI_GRAD, false, 1>, lu_conv_tc_kernel<LU_EPI_GRAD, true, 1>,
                                   lu_conv_tc_kernel<LU_EPI_LSTM, true, 2>, lu_conv_tc_kernel<LU_EPI_GRAD, true, 2>,
-                                  lu_conv_tc_kernel<LU_EPI_CONV, true, 2>};
+                                  lu_conv_tc_kernel<LU_EPI_CONV, true, 2>,
+                                  lu_conv_tc_kernel<LU_EPI_LSTM, true, 3>, lu_conv_tc_kernel<LU_EPI_GRAD, true, 3>,
+                                  lu_conv_tc_kernel<LU_EPI_CONV, true, 3>};
   if (!attr_set[ei]) {
     cudaError_t e = cudaFuncSetAttribute(kfn[ei], cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     LU_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
@@ -777,7 +795,7 @@ static int launch_conv(lu_handle_s* h, ConvPlan& cv, int frames, const int* mul,
   if (cl2) {
     cudaLaunchConfig_t lc;
     memset(&lc, 0, sizeof lc);
-    lc.gridDim = dim3((unsigned)grid); lc.blockDim = dim3(lutc::kThreads); lc.dynamicSmemBytes = cv.smem;
+    lc.gridDim = dim3((unsigned)grid); lc.blockDim = dim3(lutc::kThreads); lc.dynamicSmemBytes = smem_bytes;
     lc.stream = (cudaStream_t)stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;

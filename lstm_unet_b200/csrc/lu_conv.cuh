@@ -307,6 +307,46 @@ __device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
                : "memory");
 }
+// ---- cta_group::2 forms (cluster mode 3): operands of one M = 256 MMA are spread over the CTA pair ---------------
+// address of the same shared-memory offset in CTA `rank` of the cluster (shared::cluster window)
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+// TMA loads whose completion bytes are counted on an mbarrier that may live in the PEER CTA (the pair leader's)
+__device__ __forceinline__ void tma_load_5d_pair(uint32_t dst, const CUtensorMap* tm, uint32_t bar_cluster, int c0, int c1,
+                                                 int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* tm, uint32_t bar_cluster, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar_cluster), "r"(c0), "r"(c1)
+      : "memory");
+}
+// the leader's commit: one arrive on the barrier at this offset in every CTA of the mask, once the pair's MMAs retire
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+}
+__device__ __forceinline__ void mma_bf16_pair(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                              uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc)
+      : "memory");
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -373,12 +413,20 @@ constexpr int kTmemCols = 512;
 
 }  // namespace lutc
 
-// CL = thread-block cluster size.  CL == 2: the two CTAs of a cluster work on two M tiles of the SAME N tile and each
-// multicasts one half of every weight K block into both CTAs' shared memory (half the L2->SM weight traffic); the MMA
-// and the accumulators stay per-CTA (cta_group::1).
+// CL = cluster mode.  1: no cluster.  2 and 3: the two CTAs of a 2-CTA cluster work on two M tiles of the SAME N tile.
+//   CL == 2: each CTA multicasts one half of every weight K block into both CTAs' shared memory (half the L2->SM weight
+//            traffic); the MMA and the accumulators stay per-CTA (cta_group::1).
+//   CL == 3: the pair runs ONE M = 256 MMA per K step (tcgen05.mma.cta_group::2, issued by the even CTA): every CTA
+//            stages its own 128-pixel window and only ITS half of the weight K block (rows [rank*BN/2, +BN/2), no
+//            multicast), the tensor core reads the two halves from the two shared memories.  Per SM and K step the
+//            operand read drops from (128 + BN) to (128 + BN/2) rows of 32 bytes.  All "full" barriers that the issuer
+//            waits on live in the leader CTA: both producers' TMA bytes complete there, the peer's epilogue threads
+//            arrive there; every "empty" / "accumulator ready" barrier is released in both CTAs by the leader's
+//            multicast commit.  (Compiled, not yet run on hardware: LU_PAIR=1 selects it.)
 template <int EPI, bool PTAB, int CL>
 __global__ void __launch_bounds__(lutc::kThreads, 1) lu_conv_tc_kernel(const __grid_constant__ LuTcParams P) {
   using namespace lutc;
+  constexpr bool PAIR = CL == 3;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t pad = ((raw_addr + 1023u) & ~1023u) - raw_addr;   // SWIZZLE_128B needs 1024-byte aligned stages
@@ -404,14 +452,20 @@ __global__ void __launch_bounds__(lutc::kThreads, 1) lu_conv_tc_kernel(const __g
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < nA; ++i) { mbar_init(full_a + 8u * i, 1); mbar_init(empty_a + 8u * i, 1); }
-    for (int i = 0; i < nB; ++i) { mbar_init(full_b + 8u * i, 1); mbar_init(empty_b + 8u * i, CL); }
-    for (int i = 0; i < 2; ++i) { mbar_init(tmem_full + 8u * i, 1); mbar_init(tmem_empty + 8u * i, kEpiThreads); }
+    for (int i = 0; i < nB; ++i) { mbar_init(full_b + 8u * i, 1); mbar_init(empty_b + 8u * i, CL == 2 ? 2 : 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tmem_full + 8u * i, 1); mbar_init(tmem_empty + 8u * i, PAIR ? 2 * kEpiThreads : kEpiThreads); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTmemCols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {            // the same warp of BOTH CTAs: the columns are allocated in the two tensor memories together
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTmemCols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTmemCols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   if (CL == 1) __syncthreads(); else cluster_sync_all();       // barrier inits visible cluster-wide before any remote arrive
@@ -421,11 +475,13 @@ __global__ void __launch_bounds__(lutc::kThreads, 1) lu_conv_tc_kernel(const __g
   const int tiles_per_frame = cp.tiles_x * cp.tiles_y;
   // work decomposition: item -> (N tile, M tile).  cluster 1: item = tile, N fastest.  cluster 2: item = pair of
   // consecutive M tiles of one N tile; an odd tail pair re-does the last M tile in the second CTA with stores masked.
-  const int crank = (CL == 2) ? (int)cluster_ctarank() : 0;
-  const int item0 = (CL == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-  const int item_step = (CL == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int crank = (CL >= 2) ? (int)cluster_ctarank() : 0;
+  const int item0 = (CL >= 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int item_step = (CL >= 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  // pair mode: the leader's copy of a barrier, as seen from this CTA
+  auto leader = [&](uint32_t bar) { return PAIR ? map_to_rank(bar, 0u) : bar; };
   auto decode = [&](int item, int& nt, int& mt, bool& dummy) {
-    if (CL == 2) {
+    if (CL >= 2) {
       nt = item % cp.n_tiles_n; mt = 2 * (item / cp.n_tiles_n) + crank;      // N fastest: concurrent clusters share the activation tiles (L2)
       dummy = mt >= P.num_mt;
       if (dummy) mt = P.num_mt - 1;
@@ -448,9 +504,15 @@ __global__ void __launch_bounds__(lutc::kThreads, 1) lu_conv_tc_kernel(const __g
         const LuSrcView& v = cp.src[st.src];
         mbar_wait(empty_a + 8u * sa, ph ^ 1u);
         if (elect_one()) {
-          mbar_expect_tx(full_a + 8u * sa, (uint32_t)(v.rows * v.pitch) * 128u);
-          tma_load_5d(sA + (uint32_t)sa * P.a_stage_bytes, &P.tmA[st.src], full_a + 8u * sa, st.c, x0 + st.dx, st.plane,
-                      y0 + st.dy, frame * v.frame_mul + v.frame_add);
+          if (PAIR) {          // both windows of the pair are counted on the leader's barrier
+            if (crank == 0) mbar_expect_tx(full_a + 8u * sa, 2u * (uint32_t)(v.rows * v.pitch) * 128u);
+            tma_load_5d_pair(sA + (uint32_t)sa * P.a_stage_bytes, &P.tmA[st.src], leader(full_a + 8u * sa), st.c, x0 + st.dx,
+                             st.plane, y0 + st.dy, frame * v.frame_mul + v.frame_add);
+          } else {
+            mbar_expect_tx(full_a + 8u * sa, (uint32_t)(v.rows * v.pitch) * 128u);
+            tma_load_5d(sA + (uint32_t)sa * P.a_stage_bytes, &P.tmA[st.src], full_a + 8u * sa, st.c, x0 + st.dx, st.plane,
+                        y0 + st.dy, frame * v.frame_mul + v.frame_add);
+          }
         }
         __syncwarp();
         if (++sa == nA) { sa = 0; ph ^= 1u; }
@@ -468,10 +530,12 @@ __global__ void __launch_bounds__(lutc::kThreads, 1) lu_conv_tc_kernel(const __g
         const int g = (nkb - kb) < G ? (nkb - kb) : G;
         mbar_wait(empty_b + 8u * sb, ph ^ 1u);               // cluster 2: released by BOTH CTAs' MMA issuers
         if (elect_one()) {
-          mbar_expect_tx(full_b + 8u * sb, (uint32_t)(g * BN) * 128u);
+          if (!PAIR || crank == 0) mbar_expect_tx(full_b + 8u * sb, (uint32_t)(g * BN) * 128u);   // pair: both halves, on the leader
           for (int j = 0; j < g; ++j) {
-            const uint32_t dst = sB + (uint32_t)sb * P.b_stage_bytes + (uint32_t)(j * BN) * 128u;
-            if (CL == 2)
+            const uint32_t dst = sB + (uint32_t)sb * P.b_stage_bytes + (uint32_t)(j * (PAIR ? (BN >> 1) : BN)) * 128u;
+            if (PAIR)            // this CTA's half of the K block only, at the same offset in both shared memories
+              tma_load_2d_pair(dst, &P.tmBh, leader(full_b + 8u * sb), (kb + j) * LU_KBLK, nt * BN + crank * (BN >> 1));
+            else if (CL == 2)
               tma_load_2d_mc(dst + (uint32_t)(crank * (BN >> 1)) * 128u, &P.tmBh, full_b + 8u * sb, (kb + j) * LU_KBLK,
                              nt * BN + crank * (BN >> 1), (uint16_t)3);
             else
@@ -487,12 +551,13 @@ __global__ void __launch_bounds__(lutc::kThreads, 1) lu_conv_tc_kernel(const __g
     // One lane is elected ONCE and runs the whole loop nest (waits included); inside, everything it touches is
     // warp-uniform by construction, so ptxas keeps descriptors in uniform registers and the per-tap cost is a
     // handful of instructions.
-    if (elect_one()) {
+    if ((!PAIR || crank == 0) && elect_one()) {                 // pair mode: the even CTA issues for both
       int sa = 0, sb = 0, acc = 0; uint32_t pha = 0, phb = 0, phacc = 0;
       const int G = P.b_group;
       const uint32_t b_hi = desc_hi(1024u);
-      const uint32_t bn_bytes16 = (uint32_t)BN * 8u;            // one K block of weights, in 16-byte units
-      const uint32_t idesc = P.idesc;
+      const uint32_t bn_bytes16 = (uint32_t)(PAIR ? (BN >> 1) : BN) * 8u;   // one K block of weights in this CTA, in 16-byte units
+      // pair mode: M = 256 (bits [24,29) hold M >> 4)
+      const uint32_t idesc = PAIR ? ((P.idesc & ~(0x1Fu << 24)) | ((uint32_t)(256 >> 4) << 24)) : P.idesc;
       const bool resident = P.b_resident != 0;
       bool first_tile = true;
       for (int tile = item0; tile < P.total_tiles; tile += item_step) {
@@ -521,27 +586,33 @@ __global__ void __launch_bounds__(lutc::kThreads, 1) lu_conv_tc_kernel(const __g
               b_lo = desc_lo(sB + (uint32_t)sb * P.b_stage_bytes);
             }
 #pragma unroll
-            for (int k = 0; k < LU_KBLK / 16; ++k)
-              mma_bf16(d_tmem, a_lo + off8 + 2u * k, a_hi, b_lo + 2u * k, b_hi, idesc, accum | (uint32_t)k);
+            for (int k = 0; k < LU_KBLK / 16; ++k) {
+              if (PAIR) mma_bf16_pair(d_tmem, a_lo + off8 + 2u * k, a_hi, b_lo + 2u * k, b_hi, idesc, accum | (uint32_t)k);
+              else mma_bf16(d_tmem, a_lo + off8 + 2u * k, a_hi, b_lo + 2u * k, b_hi, idesc, accum | (uint32_t)k);
+            }
             accum = 1;
             b_lo += bn_bytes16;
             if (++gi == G) {
-              if (CL == 2) tc_commit_mc(empty_b + 8u * sb, (uint16_t)3);   // weight stage is shared by the cluster
+              if (PAIR) tc_commit_pair(empty_b + 8u * sb, (uint16_t)3);    // both CTAs' halves of the stage
+              else if (CL == 2) tc_commit_mc(empty_b + 8u * sb, (uint16_t)3);   // weight stage is shared by the cluster
               else if (!resident) tc_commit(empty_b + 8u * sb);  // frees the weight stage once its MMAs retire
               gi = 0;
               if (++sb == nB) { sb = 0; phb ^= 1u; }
             }
           }
-          tc_commit(empty_a + 8u * sa);                         // frees the activation window
+          if (PAIR) tc_commit_pair(empty_a + 8u * sa, (uint16_t)3);   // frees both CTAs' windows
+          else tc_commit(empty_a + 8u * sa);                    // frees the activation window
           if (++sa == nA) { sa = 0; pha ^= 1u; }
         }
         if (gi != 0) {                                          // partial last weight group of the tile
-          if (CL == 2) tc_commit_mc(empty_b + 8u * sb, (uint16_t)3);
+          if (PAIR) tc_commit_pair(empty_b + 8u * sb, (uint16_t)3);
+          else if (CL == 2) tc_commit_mc(empty_b + 8u * sb, (uint16_t)3);
           else if (!resident) tc_commit(empty_b + 8u * sb);
           if (++sb == nB) { sb = 0; phb ^= 1u; }
         }
         first_tile = false;
-        tc_commit(tmem_full + 8u * acc);                        // accumulator complete -> epilogue
+        if (PAIR) tc_commit_pair(tmem_full + 8u * acc, (uint16_t)3);   // both halves of the M = 256 accumulator
+        else tc_commit(tmem_full + 8u * acc);                   // accumulator complete -> epilogue
         if (++acc == 2) { acc = 0; phacc ^= 1u; }
       }
     }
@@ -607,7 +678,8 @@ __global__ void __launch_bounds__(lutc::kThreads, 1) lu_conv_tc_kernel(const __g
         }
       }
       tc_fence_before();
-      mbar_arrive(tmem_empty + 8u * acc);
+      if (PAIR && crank != 0) mbar_arrive_cluster(leader(tmem_empty + 8u * acc));   // the issuer waits for both epilogues
+      else mbar_arrive(tmem_empty + 8u * acc);
       if (++acc == 2) { acc = 0; phacc ^= 1u; }
     }
   }
@@ -616,7 +688,8 @@ __global__ void __launch_bounds__(lutc::kThreads, 1) lu_conv_tc_kernel(const __g
   if (CL == 1) __syncthreads(); else cluster_sync_all();       // no CTA may exit while its peer can still multicast into it
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
   }
 }
 #endif  // !LU_HOST_EMU
