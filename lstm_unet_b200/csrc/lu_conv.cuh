@@ -694,15 +694,8 @@ __global__ void __launch_bounds__(lutc::kThreads, 1) lu_conv_tc_kernel(const __g
 }
 #endif  // !LU_HOST_EMU
 
-#ifndef LU_HOST_EMU
-// =============================================================================================================
-// Weight gradient on tcgen05: dWp[n][k] += sum over pixels  A_k[pixel] * dY[pixel][n]      (packed space)
-//
-// Both operands are NHWC, i.e. MN-major for a reduction over pixels: the MMA "K" rows are pixels (128-byte rows of
-// 64 channels), exactly what the forward's halo windows already are.  One task = (up to 2 activation stages = 128
-// rows of channels, up to 4 taps, one 64/128-column slab of output channels, a range of pixel tiles); the 4 taps'
-// accumulators (128 x N fp32 each) stay in TMEM for the whole pixel range and are flushed with fp32 atomics.
-// =============================================================================================================
+// one task of the tcgen05 weight-gradient kernel below (plain data: the task lists are built on the host, and the host
+// test build replays them with scalar loops)
 struct LuWgTask {
   int16_t stage0, stage1;        // forward A stages giving rows [0,64) / [64,128); stage1 < 0: rows 64.. unused
   int16_t ntaps, a_is_lo;        // a_is_lo: bf16x3 lo plane of the activation (pairs with the hi plane of dY only)
@@ -713,6 +706,15 @@ struct LuWgTask {
   int32_t ychan[2];              // channel coordinate in dY of each 64-column chunk
 };
 
+#ifndef LU_HOST_EMU
+// =============================================================================================================
+// Weight gradient on tcgen05: dWp[n][k] += sum over pixels  A_k[pixel] * dY[pixel][n]      (packed space)
+//
+// Both operands are NHWC, i.e. MN-major for a reduction over pixels: the MMA "K" rows are pixels (128-byte rows of
+// 64 channels), exactly what the forward's halo windows already are.  One task = (up to 2 activation stages = 128
+// rows of channels, up to 4 taps, one 64/128-column slab of output channels, a range of pixel tiles); the 4 taps'
+// accumulators (128 x N fp32 each) stay in TMEM for the whole pixel range and are flushed with fp32 atomics.
+// =============================================================================================================
 struct LuWgParams {
   CUtensorMap tmA[LU_MAX_SRC];
   CUtensorMap tmY;
@@ -735,10 +737,18 @@ __device__ __forceinline__ uint32_t desc_lo_mn(uint32_t addr, uint32_t lbo_bytes
 // pixel range).  Every operand box of a stage is fetched from L2 by ONE of them and multicast into both CTAs' shared
 // memory (half the L2->SM traffic per MMA); a stage is released by both MMA issuers (multicast tcgen05.commit).  A task
 // with ntaps == 0 is a partner that only takes part in the staging.
+// CL == 3: the pair runs ONE M = 256 MMA per K step (tcgen05.mma.cta_group::2 issued by the even CTA).  Both tasks have
+// the same channel rows, pixel range and 128-column slab; the peer's taps are the leader's displaced by a constant
+// (off[i] of the odd task = off[i] of the even task + d, d >= 0), which the peer realises by displacing its window by d,
+// so that the leader's descriptors read the right pixels in both shared memories.  Each
+// CTA stages its own windows and ONE 64-column half of the dY tile (N = 128 split over the pair): per SM and K step the
+// operand read drops from 8 KB to 6 KB.  bf16 mode with two-chunk slabs only; the host falls back to CL == 1 otherwise.
+// (Compiled, not yet run on hardware: LU_WGRAD_CLUSTER=3 selects it.)
 template <int CL>
 __global__ void __launch_bounds__(256, 1) lu_wgrad_tc_kernel(const __grid_constant__ LuWgParams P) {
   using namespace lutc;
-  const int crank = (CL == 2) ? (int)cluster_ctarank() : 0;
+  constexpr bool PAIR = CL == 3;
+  const int crank = (CL >= 2) ? (int)cluster_ctarank() : 0;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t pad = ((raw_addr + 1023u) & ~1023u) - raw_addr;
@@ -758,16 +768,27 @@ __global__ void __launch_bounds__(256, 1) lu_wgrad_tc_kernel(const __grid_consta
   const int nyp = (P.dy_planes == 2 && !tk.a_is_lo) ? 2 : 1;
   const uint32_t b_off = 2u * (uint32_t)P.a_win_bytes;            // B region inside a stage
   const int tiles_per_frame = P.tiles_x * P.tiles_y;
+  int shift_y = 0, shift_x = 0;                                    // pair mode, odd CTA: displacement of its windows in pixels
+  if (PAIR && crank == 1 && tk.ntaps > 0) {
+    const int d = tk.off[0] - P.tasks[blockIdx.x ^ 1].off[0];      // rows of the window (pitch pixels per image row)
+    shift_y = (d + (v.pitch >> 1)) / v.pitch;
+    shift_x = d - shift_y * v.pitch;
+  }
 
   if (warp == 0 && lane == 0) { prefetch_tmap(&P.tmA[st0.src]); prefetch_tmap(&P.tmY); }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < nS; ++i) { mbar_init(full + 8u * i, 1); mbar_init(empty + 8u * i, CL); }
+    for (int i = 0; i < nS; ++i) { mbar_init(full + 8u * i, 1); mbar_init(empty + 8u * i, CL == 2 ? 2 : 1); }
     mbar_init(done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   if (CL == 1) __syncthreads(); else cluster_sync_all();
@@ -783,7 +804,21 @@ __global__ void __launch_bounds__(256, 1) lu_wgrad_tc_kernel(const __grid_consta
       if (st0.src == P.skip_t0_src && (frame % P.T) == 0) continue;
       const int y0 = (rem / P.tiles_x) * LU_TILE_H, x0 = (rem % P.tiles_x) * LU_TILE_W;
       mbar_wait(empty + 8u * s, ph ^ 1u);
-      if (elect_one()) {
+      if (PAIR) {
+        // own windows (displaced by the task's shift) + own 64-column half of the dY tile; every byte of the pair is
+        // counted on the leader's barrier
+        if (elect_one()) {
+          const uint32_t base = s0 + (uint32_t)s * P.stage_bytes;
+          const uint32_t lfull = map_to_rank(full + 8u * s, 0u);
+          if (crank == 0) mbar_expect_tx(full + 8u * s, 2u * ((uint32_t)(v.rows * v.pitch) * 128u * (tk.stage1 >= 0 ? 2u : 1u) + 16384u));
+          const int fa = frame * v.frame_mul + v.frame_add;
+          const int xs = x0 + shift_x, ys = y0 + shift_y;
+          tma_load_5d_pair(base, &P.tmA[st0.src], lfull, st0.c, xs + st0.dx, st0.plane, ys + st0.dy, fa);
+          if (tk.stage1 >= 0)
+            tma_load_5d_pair(base + (uint32_t)P.a_win_bytes, &P.tmA[st1.src], lfull, st1.c, xs + st1.dx, st1.plane, ys + st1.dy, fa);
+          tma_load_5d_pair(base + b_off, &P.tmY, lfull, tk.ychan[crank], x0, 0, y0, frame * P.dy_frame_mul + P.dy_frame_add);
+        }
+      } else if (elect_one()) {
         const uint32_t base = s0 + (uint32_t)s * P.stage_bytes;
         mbar_expect_tx(full + 8u * s, bytes);
         const int fa = frame * v.frame_mul + v.frame_add;
@@ -811,7 +846,8 @@ __global__ void __launch_bounds__(256, 1) lu_wgrad_tc_kernel(const __grid_consta
   } else if (warp == 1) {
     // ---------------------------------------------------------------- MMA issuer (MN-major A and B)
     int s = 0; uint32_t ph = 0;
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) |
+                           ((uint32_t)((PAIR ? 256 : 128) >> 4) << 24);
     const uint32_t a_hi = desc_hi_mn((uint32_t)v.pitch * 128u), b_hi = desc_hi_mn(1024u);
     const uint32_t a_lbo = tk.stage1 >= 0 ? (uint32_t)P.a_win_bytes : 0u;
     const uint32_t row2 = (uint32_t)v.pitch * 128u * 2u;           // two image rows = 16 pixels = one MMA K step
@@ -819,6 +855,7 @@ __global__ void __launch_bounds__(256, 1) lu_wgrad_tc_kernel(const __grid_consta
     for (int tile = tk.tile0; tile < tk.tile1; ++tile) {
       const int frame = tile / tiles_per_frame;
       if (st0.src == P.skip_t0_src && (frame % P.T) == 0) continue;
+      if (PAIR && crank != 0) continue;                          // the even CTA issues for the pair
       mbar_wait(full + 8u * s, ph);
       tc_fence_after();
       const uint32_t base = s0 + (uint32_t)s * P.stage_bytes;
@@ -829,19 +866,24 @@ __global__ void __launch_bounds__(256, 1) lu_wgrad_tc_kernel(const __grid_consta
           for (int dp = 0; dp < nyp; ++dp) {
             const uint32_t b0 = base + b_off + (uint32_t)(dp * tk.nch) * 16384u;
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              mma_bf16(d_tmem, desc_lo_mn(a0 + (uint32_t)j * row2, a_lbo), a_hi, desc_lo_mn(b0 + (uint32_t)j * 2048u, 16384u), b_hi,
-                       idesc, (first && dp == 0 && j == 0) ? 0u : 1u);
+            for (int j = 0; j < 8; ++j) {
+              if (PAIR) mma_bf16_pair(d_tmem, desc_lo_mn(a0 + (uint32_t)j * row2, a_lbo), a_hi, desc_lo_mn(b0 + (uint32_t)j * 2048u, 16384u), b_hi,
+                                      idesc, (first && dp == 0 && j == 0) ? 0u : 1u);
+              else mma_bf16(d_tmem, desc_lo_mn(a0 + (uint32_t)j * row2, a_lbo), a_hi, desc_lo_mn(b0 + (uint32_t)j * 2048u, 16384u), b_hi,
+                            idesc, (first && dp == 0 && j == 0) ? 0u : 1u);
+            }
           }
         }
-        if (CL == 2) tc_commit_mc(empty + 8u * s, (uint16_t)3);      // the stage is shared by the cluster
+        if (PAIR) tc_commit_pair(empty + 8u * s, (uint16_t)3);     // both CTAs' halves of the stage
+        else if (CL == 2) tc_commit_mc(empty + 8u * s, (uint16_t)3);      // the stage is shared by the cluster
         else tc_commit(empty + 8u * s);
       }
       __syncwarp();
       first = 0;
       if (++s == nS) { s = 0; ph ^= 1u; }
     }
-    if (elect_one()) tc_commit(done);
+    if (PAIR) { if (crank == 0 && elect_one()) tc_commit_pair(done, (uint16_t)3); }   // both epilogues
+    else if (elect_one()) tc_commit(done);
     __syncwarp();
   } else if (warp >= 4) {
     // ---------------------------------------------------------------- epilogue: TMEM -> fp32 atomics into dWp
@@ -875,7 +917,8 @@ __global__ void __launch_bounds__(256, 1) lu_wgrad_tc_kernel(const __grid_consta
   if (CL == 1) __syncthreads(); else cluster_sync_all();       // no CTA may exit while its peer can still multicast into it
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
 }
 #endif  // !LU_HOST_EMU

@@ -190,7 +190,6 @@ static void run_colsum(lu_handle_s* h, int gbuf, int frames_used, float* dst, in
   pf(h, ((cs.npix + cs.chunk - 1) / cs.chunk) * g.cpad, stream, cs);
 }
 
-#ifndef LU_HOST_EMU
 // ---- tcgen05 weight gradient: task list for one forward conv (see lu_wgrad_tc_kernel) --------------------------------
 static void build_wg_tasks(lu_handle_s* h, const ConvPlan& f, int frames, int only_src, int pair, std::vector<LuWgTask>& out) {
   const bool x3 = h->planes == 2;
@@ -246,8 +245,43 @@ static void build_wg_tasks(lu_handle_s* h, const ConvPlan& f, int frames, int on
     if (pair && (n & 1)) ++n;
     return n;
   };
+  // pair == 3 (one M = 256 MMA per CTA pair): a task pair = (leader taps L, peer taps L + d) with ONE displacement d per
+  // pair, realised by the peer displacing its window (the kernel derives d from the two tasks' first offsets).  Taps are matched greedily with their right
+  // neighbour (d = one column), the rest with the tap below (d = one row); what is left runs with an idle partner.
+  struct PairTpl { std::vector<int> lead, peer; int sy, sx; };      // positions in Base::taps
+  auto pair_templates = [&](const Base& b) {
+    const int pitch = f.views[f.astages[b.s0].src].pitch;
+    const uint32_t tb = f.astages[b.s0].tap_begin;
+    const int n = (int)b.taps.size();
+    std::vector<int> rr(n), ss(n);
+    for (int i = 0; i < n; ++i) { const int off = f.taps[tb + b.taps[i]]; rr[i] = off / pitch; ss[i] = off % pitch; }
+    std::vector<char> done(n, 0);
+    auto find = [&](int r, int c) { for (int i = 0; i < n; ++i) if (!done[i] && rr[i] == r && ss[i] == c) return i; return -1; };
+    std::vector<PairTpl> tpl;
+    for (int pass = 0; pass < 3; ++pass) {
+      const int sy = pass == 1 ? 1 : 0, sx = pass == 0 ? 1 : 0;
+      std::vector<std::pair<int, int>> m;
+      for (int i = 0; i < n; ++i) {
+        if (done[i]) continue;
+        if (pass == 2) { done[i] = 1; m.push_back({i, -1}); continue; }
+        done[i] = 1;
+        const int j = find(rr[i] + sy, ss[i] + sx);
+        if (j < 0) { done[i] = 0; continue; }
+        done[j] = 1; m.push_back({i, j});
+      }
+      const int nt = ((int)m.size() + 3) / 4;
+      size_t at = 0;
+      for (int k = 0; k < nt; ++k) {
+        const int cnt = (int)m.size() / nt + (k < (int)m.size() % nt ? 1 : 0);
+        PairTpl t; t.sy = pass == 2 ? 0 : sy; t.sx = pass == 2 ? 0 : sx;
+        for (int q = 0; q < cnt; ++q, ++at) { t.lead.push_back(m[at].first); if (m[at].second >= 0) t.peer.push_back(m[at].second); }
+        tpl.push_back(t);
+      }
+    }
+    return tpl;
+  };
   int base_tasks = 0;
-  for (auto& b : bases) base_tasks += n_tasks_of(b.taps.size()) * (int)slabs.size();
+  for (auto& b : bases) base_tasks += (pair == 3 ? 2 * (int)pair_templates(b).size() : n_tasks_of(b.taps.size())) * (int)slabs.size();
   // enough tasks to fill the machine, and pixel ranges small enough (~256 tiles = 32k pixels) that the range's
   // activations + gradients stay L2-resident while the wave of tasks sharing it runs
   int split = (4 * h->num_sms + base_tasks - 1) / (base_tasks > 0 ? base_tasks : 1);
@@ -260,6 +294,32 @@ static void build_wg_tasks(lu_handle_s* h, const ConvPlan& f, int frames, int on
   // once per task (measured before the reorder: 84 GB of DRAM reads for a 6 GB working set).
   for (int sp = 0; sp < split; ++sp)
     for (auto& b : bases) {
+      if (pair == 3) {
+        const std::vector<PairTpl> tpl = pair_templates(b);
+        const uint32_t tb = f.astages[b.s0].tap_begin;
+        for (auto& sl : slabs)
+          for (auto& t : tpl)
+            for (int who = 0; who < 2; ++who) {
+              LuWgTask tk; memset(&tk, 0, sizeof tk);
+              tk.stage0 = (int16_t)b.s0; tk.stage1 = (int16_t)b.s1; tk.a_is_lo = (int16_t)b.a_is_lo;
+              const std::vector<int>& mine = who == 0 ? t.lead : t.peer;
+              tk.ntaps = (int16_t)mine.size();
+              for (size_t i = 0; i < mine.size(); ++i) {
+                const int ti = b.taps[mine[i]];
+                tk.off[i] = f.taps[tb + ti];                    // own taps: the odd task's are the even task's + one constant
+                tk.kb0[i] = kb_begin[b.s0] + ti;
+                tk.kb1[i] = b.s1 >= 0 ? kb_begin[b.s1] + ti : -1;
+              }
+              tk.n0 = sl.first * 64; tk.nch = sl.second;
+              for (int c = 0; c < sl.second; ++c) {
+                const int ci = sl.first + c;
+                tk.ychan[c] = f.kind == LU_EPI_LSTM ? (ci % 4) * f.fpad + (ci / 4) * 64 : ci * 64;
+              }
+              tk.tile0 = (int)((int64_t)tiles * sp / split); tk.tile1 = (int)((int64_t)tiles * (sp + 1) / split);
+              if (tk.tile1 > tk.tile0) out.push_back(tk);
+            }
+        continue;
+      }
       const int nt = n_tasks_of(b.taps.size());
       const int per = (int)b.taps.size() / nt, extra = (int)b.taps.size() % nt;
       for (auto& sl : slabs) {
@@ -286,6 +346,88 @@ static void build_wg_tasks(lu_handle_s* h, const ConvPlan& f, int frames, int on
       }
     }
 }
+
+#ifdef LU_HOST_EMU
+// TEST-ONLY (host build): replays a task list with scalar loops, statement by statement what lu_wgrad_tc_kernel does
+// with it -- windows staged as flat [rows * pitch] arrays with the tensor map's zero fill, taps as row offsets into
+// them, 128-pixel tiles, dY boxes per column chunk / plane, accumulators per tap, flush into the packed gradient --
+// including the CTA-pair semantics of cluster mode 3 (the odd task's window displaced, the even task's offsets read in
+// both).  Lets the CPU suite check the task builder against the scalar mirror (tests/test_emu_wgrad_tasks.py).
+static void emulate_wg_tasks(const LuWgradMirror& w, const std::vector<LuWgTask>& tasks, int mode, int tiles_x, int tiles_y) {
+  const LuConvParams& cp = w.p;
+  const int tiles_per_frame = tiles_x * tiles_y;
+  std::vector<float> win[2], D;
+  auto stage_window = [&](const LuAStage& st, const LuSrcView& v, int frame, int y0, int x0, std::vector<float>& dst) {
+    dst.assign((size_t)v.rows * v.pitch * 64, 0.f);
+    const int64_t n = (int64_t)frame * v.frame_mul + v.frame_add;
+    if (n < 0 || n >= v.dimN) return;
+    for (int wy = 0; wy < v.rows; ++wy)
+      for (int wx = 0; wx < v.pitch; ++wx) {
+        const int yy = y0 + wy, xx = x0 + wx;
+        if (yy < 0 || yy >= v.dimH || xx < 0 || xx >= v.dimW) continue;
+        const uint16_t* a = v.ptr + n * v.sn + (int64_t)yy * v.sh + (int64_t)st.plane * v.sp + (int64_t)xx * v.sw + st.c;
+        for (int kk = 0; kk < 64 && st.c + kk < v.dimC; ++kk) dst[((size_t)wy * v.pitch + wx) * 64 + kk] = lu_bf2f(a[kk]);
+      }
+  };
+  const size_t step = mode == 3 ? 2 : 1;
+  for (size_t i = 0; i + step <= tasks.size(); i += step) {
+    const LuWgTask& lead = tasks[i];
+    for (size_t who = 0; who < step; ++who) {
+      const LuWgTask& tk = tasks[i + who];
+      if (tk.ntaps == 0) continue;                                   // idle partner
+      const LuAStage st0 = cp.astages[tk.stage0];
+      const LuAStage st1 = cp.astages[tk.stage1 >= 0 ? tk.stage1 : tk.stage0];
+      const LuSrcView& v = cp.src[st0.src];
+      int shift_y = 0, shift_x = 0;
+      if (mode == 3 && who == 1) {
+        const int d = tk.off[0] - lead.off[0];
+        shift_y = (d + (v.pitch >> 1)) / v.pitch; shift_x = d - shift_y * v.pitch;
+      }
+      const int N = tk.nch * 64;
+      const int nyp = (w.dy_planes == 2 && !tk.a_is_lo) ? 2 : 1;
+      D.assign((size_t)tk.ntaps * 128 * N, 0.f);
+      bool any = false;
+      for (int tile = tk.tile0; tile < tk.tile1; ++tile) {
+        const int frame = tile / tiles_per_frame, rem = tile % tiles_per_frame;
+        if (st0.src == w.skip_t0_src && (frame % w.T) == 0) continue;
+        any = true;
+        const int y0 = (rem / tiles_x) * LU_TILE_H, x0 = (rem % tiles_x) * LU_TILE_W;
+        stage_window(st0, v, frame, y0 + st0.dy + shift_y, x0 + st0.dx + shift_x, win[0]);
+        if (tk.stage1 >= 0) stage_window(st1, cp.src[st1.src], frame, y0 + st1.dy + shift_y, x0 + st1.dx + shift_x, win[1]);
+        const int64_t fy = (int64_t)frame * w.dy_frame_mul + w.dy_frame_add;
+        for (int ti = 0; ti < tk.ntaps; ++ti) {
+          const int off = (mode == 3 ? lead : tk).off[ti];           // the issuing CTA's descriptors address both windows
+          for (int m = 0; m < 128; ++m) {
+            const int ty = m / LU_TILE_W, tx = m % LU_TILE_W;
+            const int y = y0 + ty, x = x0 + tx;
+            if (y >= w.H || x >= w.W) continue;                      // dY box: zero fill outside the frame
+            const size_t wi = (size_t)off + (size_t)ty * v.pitch + tx;
+            const uint16_t* gy = w.dY + ((fy * w.H + y) * w.W + x) * (int64_t)(w.dy_cpad * w.dy_planes);
+            for (int row = 0; row < 128; ++row) {
+              if (row >= 64 && tk.stage1 < 0) break;
+              const float a = win[row >> 6][wi * 64 + (row & 63)];
+              if (a == 0.f) continue;
+              float* d = &D[((size_t)ti * 128 + row) * N];
+              for (int dp = 0; dp < nyp; ++dp)
+                for (int c = 0; c < tk.nch; ++c) {
+                  const uint16_t* g = gy + tk.ychan[c] + dp * w.dy_cpad;
+                  for (int j = 0; j < 64; ++j) d[c * 64 + j] += a * lu_bf2f(g[j]);
+                }
+            }
+          }
+        }
+      }
+      if (!any) continue;
+      for (int ti = 0; ti < tk.ntaps; ++ti)
+        for (int row = 0; row < 128; ++row) {
+          const int kb = row >= 64 ? (tk.stage1 >= 0 ? tk.kb1[ti] : -1) : tk.kb0[ti];
+          if (kb < 0) continue;
+          for (int col = 0; col < N; ++col)
+            w.dWp[(int64_t)(tk.n0 + col) * cp.ktot + (int64_t)kb * LU_KBLK + (row & 63)] += D[((size_t)ti * 128 + row) * N + col];
+        }
+    }
+  }
+}
 #endif
 
 // weight gradient of forward conv f from the upstream gradient buffer gbuf, in packed space:
@@ -306,7 +448,11 @@ static int run_wgrad(lu_handle_s* h, ConvPlan& f, int gbuf, int T, float* grads,
   // the default stays independent CTAs.  The way past that bound is cta_group::2 (each SM then supplies half of B).
   static int wg_cluster_env = -1;
   if (wg_cluster_env < 0) { const char* ce = getenv("LU_WGRAD_CLUSTER"); wg_cluster_env = ce ? atoi(ce) : 1; }
-  const int wg_pair = wg_cluster_env == 2 ? 1 : 0;
+  // LU_WGRAD_CLUSTER=3: that variant -- one M = 256 MMA per CTA pair, the partners' taps differing by a constant
+  // displacement (lu_wgrad_tc_kernel<3>; bf16 mode and an even number of 64-column chunks, else independent CTAs).
+  // Compiled and inspected, not yet run on hardware.
+  const bool mma_pair_ok = h->planes == 1 && ((f.kind == LU_EPI_LSTM ? f.npad / 64 : ceil_to(f.cout, 64) / 64) % 2) == 0;
+  const int wg_pair = wg_cluster_env == 2 ? 1 : (wg_cluster_env == 3 && mma_pair_ok ? 3 : 0);
   for (int pass = 0; pass < n_launch; ++pass) {
     LuWgradMirror w; memset(&w, 0, sizeof w);
     for (int i = 0; i < f.n_views; ++i) {
@@ -371,6 +517,8 @@ static int run_wgrad(lu_handle_s* h, ConvPlan& f, int gbuf, int T, float* grads,
         LU_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         e = cudaFuncSetAttribute(lu_wgrad_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
         LU_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        e = cudaFuncSetAttribute(lu_wgrad_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+        LU_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         attr = true;
       }
       h->launches++;
@@ -385,7 +533,7 @@ static int run_wgrad(lu_handle_s* h, ConvPlan& f, int gbuf, int T, float* grads,
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         lc.attrs = at; lc.numAttrs = 1;
-        e = cudaLaunchKernelEx(&lc, lu_wgrad_tc_kernel<2>, wp);
+        e = wg_pair == 3 ? cudaLaunchKernelEx(&lc, lu_wgrad_tc_kernel<3>, wp) : cudaLaunchKernelEx(&lc, lu_wgrad_tc_kernel<2>, wp);
         LU_REQUIRE(e == cudaSuccess, "wgrad cluster launch (%s) failed: %s", f.name.c_str(), cudaGetErrorString(e));
       } else {
         lu_wgrad_tc_kernel<1><<<(unsigned)n_tasks, 256, wg_smem, (cudaStream_t)stream>>>(wp);
@@ -393,6 +541,19 @@ static int run_wgrad(lu_handle_s* h, ConvPlan& f, int gbuf, int T, float* grads,
       e = cudaGetLastError();
       LU_REQUIRE(e == cudaSuccess, "wgrad launch (%s) failed: %s", f.name.c_str(), cudaGetErrorString(e));
       continue;
+    }
+#endif
+#ifdef LU_HOST_EMU
+    // TEST-ONLY: LU_WGRAD_EMU_TASKS=1|2|3 replays the task list the tcgen05 kernel would get in that cluster mode
+    if (const char* te = getenv("LU_WGRAD_EMU_TASKS")) {
+      int mode = atoi(te);
+      if (mode == 3 && !mma_pair_ok) mode = 1;
+      if (mode >= 1 && mode <= 3 && h->cfg.a_mode == LU_AMODE_HALO) {
+        std::vector<LuWgTask> tasks;
+        build_wg_tasks(h, f, w.frames, w.only_src, mode == 1 ? 0 : (mode == 2 ? 1 : 3), tasks);
+        emulate_wg_tasks(w, tasks, mode, (f.Wout + LU_TILE_W - 1) / LU_TILE_W, (f.Hout + LU_TILE_H - 1) / LU_TILE_H);
+        continue;
+      }
     }
 #endif
     const int64_t npix = (int64_t)w.frames * w.H * w.W;
