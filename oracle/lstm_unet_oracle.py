@@ -10,6 +10,10 @@ no golden vectors or numeric tests.  TensorFlow is no
 so the Keras-2 OPERATORS restated here (ConvLSTM2D, Conv2D SAME, BatchNormalization, LeakyReLU, bilinear
 resize) cannot be checked against outputs of TensorFlow itself.  They are cross-checked against an independent
 loop-level numpy restatement of the published semantics (``oracle/np_semantics.py``, tests/test_oracle.py).
+and against a THIRD-PARTY implementation of the TensorFlow operators: tests/tf_graphdef.py writes the network's
+forward as the GraphDef of TF ops Keras-2 lowers it to and OpenCV's TensorFlow importer executes it
+(tests/test_tf_graph_opencv.py: operators, ConvLSTM steps and whole networks agree to 3e-6 relative).  That
+is still not an output of the reference itself, hence the heading.
 
 PINNED (wiring): everything around those operators IS checked against the reference's own code --
 tests/test_reference_wiring.py imports /root/reference/Networks.py and losses.py unmodified on a torch-backed

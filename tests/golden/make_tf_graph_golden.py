@@ -1,0 +1,52 @@
+"""Generates tests/golden/tf_graph_opencv.npz: outputs of the reference network's TensorFlow-op graph EXECUTED BY OPENCV.
+
+TensorFlow itself is not installable, so neither the oracle nor the CUDA path can be compared with the
+reference's own outputs.  This is the nearest thing available offline: `tests/tf_graphdef.py` writes ULSTMnet2D's forward
+as the GraphDef of TensorFlow ops Keras-2 lowers it to, and OpenCV's TensorFlow importer (an implementation of those ops
+that shares no code with torch or with this repository) runs it.  The vectors it produces are committed so that the GPU
+tests compare the tcgen05 path with them directly.  Cases:
+  * 'pad'  -- the inputs and weights of forward_pad.npz (3 levels, 21x26, pad_image, two stateful calls of T = 2 == one
+              unrolled sequence of 4 frames), so the same case is covered by the fp64 oracle AND by OpenCV;
+  * 'odd'  -- 4 levels, the reference unit_test's 35x35 pad_image shape (Networks.py:256-277), B = 2, T = 3.
+python tests/golden/make_tf_graph_golden.py      (needs cv2; no TensorFlow, no /root/reference)"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import lstm_unet_oracle as O            # noqa: E402   (only for the seeded weight initialiser)
+from tests import tf_graphdef as G                  # noqa: E402
+from tests.golden.make_golden import NET            # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+NET_ODD = {
+    'down_conv_kernels': [[(3, 8), (3, 8)], [(3, 12), (3, 12)], [(3, 12), (3, 12)], [(3, 16), (3, 16)]],
+    'lstm_kernels': [[(5, 8)], [(5, 12)], [(5, 12)], [(5, 16)]],
+    'up_conv_kernels': [[(3, 12), (3, 12)], [(3, 8), (3, 8)], [(3, 8), (3, 8)], [(3, 4), (3, 4), (1, 3)]],
+}
+
+
+def main():
+    out = {}
+    z = np.load(os.path.join(HERE, 'forward_pad.npz'))
+    params = {k[2:]: z[k] for k in z.files if k.startswith('p:')}
+    x = z['x']                                                       # (call, B, T, 1, H, W)
+    seq = np.concatenate([x[0], x[1]], axis=1)                       # two stateful calls == one sequence of 4 frames
+    logits, soft, states = G.ulstm_forward_opencv(NET, params, seq.transpose(0, 1, 3, 4, 2), True)
+    out.update({'pad:logits': logits, 'pad:softmax': soft, 'pad:h_lvl0': states[0][0], 'pad:c_lvl2': states[2][1]})
+
+    p = {k: v.numpy() for k, v in O.init_params(NET_ODD, seed=11, randomize_bn=True).items()}
+    xo = np.random.default_rng(5).standard_normal((2, 3, 1, 35, 35)).astype(np.float32)
+    logits, soft, states = G.ulstm_forward_opencv(NET_ODD, p, xo.transpose(0, 1, 3, 4, 2), True)
+    out.update({'odd:x': xo, 'odd:logits': logits, 'odd:softmax': soft})
+    for i, (h, c) in enumerate(states):
+        out['odd:h%d' % i], out['odd:c%d' % i] = h, c
+    out.update({'odd:p:' + k: v for k, v in p.items()})
+    np.savez_compressed(os.path.join(HERE, 'tf_graph_opencv.npz'), **out)
+    print('wrote tf_graph_opencv.npz:', {k: v.shape for k, v in out.items() if ':p:' not in k})
+
+
+if __name__ == '__main__':
+    main()

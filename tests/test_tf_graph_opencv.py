@@ -1,0 +1,185 @@
+"""A third implementation beside the oracle and the CUDA path: the reference network written as the graph of TensorFlow
+ops Keras-2 lowers it to (tests/tf_graphdef.py, serialised by hand) and EXECUTED BY OPENCV's TensorFlow importer.
+
+TensorFlow cannot be installed, so this is as close to "the reference's arithmetic run here" as the image
+allows: OpenCV's implementation of Conv2D / SAME, FusedBatchNormV3, LeakyRelu, ResizeBilinear (half-pixel), MirrorPad,
+ConcatV2, Softmax and the element-wise ops of the ConvLSTM cell shares no code with torch (the oracle) or with this
+repository.  Per operator, per ConvLSTM step and for whole networks the oracle must agree with it to float32 rounding; the
+committed vectors it produced (tests/golden/tf_graph_opencv.npz) are then the target of the host build here and of the
+tcgen05 path on the GPU (north_star tolerance: 1e-3 relative in the bf16x3 parity mode)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import lstm_unet_oracle as O
+from oracle import np_semantics as S
+from tests import tf_graphdef as G
+from tests.golden.make_golden import NET
+from tests.golden.make_tf_graph_golden import NET_ODD
+
+cv2 = pytest.importorskip('cv2')
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+NET_TWO = {
+    'down_conv_kernels': [[(3, 6)], [(3, 10), (3, 10)]],
+    'lstm_kernels': [[(3, 5), (3, 7)], [(5, 9)]],
+    'up_conv_kernels': [[(3, 6)], [(3, 5), (1, 3)]],
+}
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def nchw(a):
+    return np.ascontiguousarray(np.asarray(a).transpose(0, 3, 1, 2))
+
+
+def run1(graph, x_nhwc, out):
+    return G.run_with_opencv(graph, x_nhwc, [out])[0]
+
+
+# ---- operator by operator -------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("H,W,k,s,cin,cout", [
+    (10, 12, 3, 2, 3, 5),      # even sizes, stride 2: SAME pads 0 before / 1 after
+    (11, 13, 3, 2, 2, 4),      # odd sizes, stride 2: SAME pads 1 / 1
+    (8, 7, 3, 2, 1, 2),        # mixed
+    (9, 9, 5, 1, 2, 3), (7, 10, 3, 1, 4, 4), (6, 5, 1, 1, 3, 2), (12, 12, 5, 2, 2, 2),
+])
+def test_conv2d_same_as_opencv_runs_it(H, W, k, s, cin, cout):
+    rng = np.random.default_rng(H * 100 + W)
+    x = rng.standard_normal((2, H, W, cin)).astype(np.float32)
+    w = rng.standard_normal((k, k, cin, cout)).astype(np.float32)
+    b = rng.standard_normal(cout).astype(np.float32)
+    g = G.placeholder('x', [2, H, W, cin]) + G.conv2d('y', 'x', w, s, b)
+    got = run1(g, x, 'y/Conv2D')
+    ora = O.conv2d_same(torch.from_numpy(nchw(x)), torch.from_numpy(w), torch.from_numpy(b), s).numpy()
+    assert got.shape == ora.shape == (2, cout, -(-H // s), -(-W // s))
+    assert rel(got, ora) < 1e-5
+    assert rel(got, nchw(S.conv2d_same_nhwc(x, w, b, s))) < 1e-5
+
+
+def test_batchnorm_leakyrelu_resize_mirrorpad_softmax_as_opencv_runs_them():
+    rng = np.random.default_rng(3)
+    H, W, C = 6, 7, 4
+    x = rng.standard_normal((1, H, W, C)).astype(np.float32)
+    xt = torch.from_numpy(nchw(x))
+    gam, bet, mean = [rng.standard_normal(C).astype(np.float32) for _ in range(3)]
+    var = rng.uniform(1e-4, 2, C).astype(np.float32)               # small variances: where epsilon = 1e-3 enters matters
+    ph = G.placeholder('x', [1, H, W, C])
+    got = run1(ph + G.batchnorm('bn', 'x', gam, bet, mean, var), x, 'bn')
+    ora = O.batchnorm(xt, *[torch.from_numpy(a) for a in (gam, bet, mean, var)], False)
+    ora = ora[0] if isinstance(ora, tuple) else ora
+    assert rel(got, ora.numpy()) < 1e-5
+    assert np.array_equal(run1(ph + G.leaky_relu('a', 'x'), x, 'a'), O.leaky_relu(xt).numpy())      # alpha = 0.3
+    got = run1(ph + G.resize_bilinear('up', 'x', 2 * H, 2 * W), x, 'up')
+    assert rel(got, O.resize_bilinear(xt, 2).numpy()) < 1e-6 and rel(got, nchw(S.bilinear_up_nhwc(x, 2))) < 1e-6
+    assert rel(run1(ph + G.resize_bilinear('same', 'x', H, W), x, 'same'), nchw(x)) < 1e-7          # the factor-1 UpBlock
+    got = run1(ph + G.mirror_pad('p', 'x', 2, 3, 1, 4), x, 'p')
+    assert np.array_equal(got, S.reflect_pad_hw(nchw(x), 2, 3, 1, 4))
+    assert rel(run1(ph + G.softmax('s', 'x'), x, 's'), torch.softmax(xt, 1).numpy()) < 1e-6
+
+
+@pytest.mark.parametrize("k,scale", [(5, 0.2), (3, 1.5)])          # scale 1.5 saturates the hard-sigmoid on both sides
+def test_convlstm_cell_as_opencv_runs_it(k, scale):
+    rng = np.random.default_rng(k)
+    H, W, Cin, F_ = 6, 7, 3, 4
+    x = rng.standard_normal((1, H, W, Cin)).astype(np.float32)
+    h0 = (rng.standard_normal((1, H, W, F_)) * 0.5).astype(np.float32)
+    c0 = (rng.standard_normal((1, H, W, F_)) * 0.5).astype(np.float32)
+    wk = (rng.standard_normal((k, k, Cin, 4 * F_)) * scale).astype(np.float32)
+    wr = (rng.standard_normal((k, k, F_, 4 * F_)) * scale).astype(np.float32)
+    b = rng.standard_normal(4 * F_).astype(np.float32)
+    inp = np.concatenate([x, h0, c0], axis=3)
+    ct = inp.shape[3]
+    g = G.placeholder('inp', [1, H, W, ct]) + G.select_channels('x', 'inp', ct, 0, Cin)
+    g += G.select_channels('h0', 'inp', ct, Cin, F_) + G.select_channels('c0', 'inp', ct, Cin + F_, F_)
+    gg, hn, cn = G.convlstm_cell('cell', 'x', 'h0', 'c0', wk, wr, b)
+    h1, c1 = G.run_with_opencv(g + gg, inp, [hn, cn])
+    rh, rc = S.convlstm_step_nhwc(x, h0, c0, wk, wr, b)
+    z = S.conv2d_same_nhwc(x, wk, b, 1) + S.conv2d_same_nhwc(h0, wr, None, 1)
+    if scale > 1:
+        lin = 0.2 * z[..., :F_] + 0.5
+        assert (lin < 0).any() and (lin > 1).any()                  # both clip branches are exercised
+    assert rel(h1, nchw(rh)) < 2e-5 and rel(c1, nchw(rc)) < 2e-5
+
+
+# ---- whole networks ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("net,B,T,H,W,pad", [
+    (NET_TWO, 1, 2, 18, 22, False),        # two ConvLSTM layers in one level
+    (NET_TWO, 2, 2, 17, 21, True),         # odd sizes + pad_image
+    (NET_ODD, 1, 2, 35, 35, True),         # the reference unit_test's shape (Networks.py:256-277)
+    (NET_ODD, 2, 3, 40, 48, True),
+    (NET, 2, 3, 24, 32, False),
+])
+def test_oracle_matches_the_tf_graph_run_by_opencv(net, B, T, H, W, pad):
+    params = O.init_params(net, seed=3, randomize_bn=True)
+    x = np.random.default_rng(0).standard_normal((B, T, 1, H, W)).astype(np.float32)
+    ora = O.OracleNet(net, 'NCHW', pad, params=params)
+    ref_l, ref_s = ora(torch.from_numpy(x), False)
+    logits, soft, states = G.ulstm_forward_opencv(net, {k: v.numpy() for k, v in params.items()},
+                                                  x.transpose(0, 1, 3, 4, 2), pad)
+    assert logits.shape == tuple(ref_l.shape) == (B, T, 3, H, W)
+    assert rel(logits, ref_l.numpy()) < 2e-5 and rel(soft, ref_s.numpy()) < 2e-5
+    flat = [hc for lvl in ora.get_states() for hc in lvl]
+    assert len(flat) == len(states)
+    for (h, c), (rh, rc) in zip(states, flat):
+        assert rel(h, rh) < 2e-5 and rel(c, rc) < 2e-5
+
+
+def load_gold():
+    return np.load(os.path.join(GOLD, 'tf_graph_opencv.npz'))
+
+
+def test_committed_vectors_are_what_opencv_produces_and_agree_with_the_fp64_oracle_vectors():
+    z = load_gold()
+    f = np.load(os.path.join(GOLD, 'forward_pad.npz'))
+    # the fp64-oracle vectors of the same case: two stateful calls of 2 frames == frames 0-1 / 2-3 of the unrolled graph
+    assert rel(z['pad:logits'][:, 0:2], f['logits0']) < 2e-5 and rel(z['pad:logits'][:, 2:4], f['logits1']) < 2e-5
+    assert rel(z['pad:softmax'][:, 2:4], f['softmax1']) < 2e-5
+    assert rel(z['pad:h_lvl0'], f['h_lvl0']) < 2e-5 and rel(z['pad:c_lvl2'], f['c_lvl2']) < 2e-5
+    # regenerate the second case: the file is OpenCV's output, not an edited copy
+    p = {k[len('odd:p:'):]: z[k] for k in z.files if k.startswith('odd:p:')}
+    logits, soft, states = G.ulstm_forward_opencv(NET_ODD, p, z['odd:x'].transpose(0, 1, 3, 4, 2), True)
+    assert rel(logits, z['odd:logits']) < 1e-6 and rel(soft, z['odd:softmax']) < 1e-6
+    assert rel(states[3][1], z['odd:c3']) < 1e-6
+
+
+def test_host_build_matches_the_opencv_vectors():
+    from tests.emu_backend import emu_session, emu_forward
+    z = load_gold()
+    p = {k[len('odd:p:'):]: z[k] for k in z.files if k.startswith('odd:p:')}
+    sess = emu_session(NET_ODD, data_format='NCHW', pad_image=True, batch=2, max_t=3, height=35, width=35, precision='bf16x3')
+    sess.set_params(p)
+    logits, softmax = emu_forward(sess, z['odd:x'], False)
+    assert rel(logits, z['odd:logits']) < 1e-3 and rel(softmax, z['odd:softmax']) < 1e-3
+    for lvl in range(4):
+        out = np.zeros(sess.state_shape(lvl, 0), np.float32)
+        sess.get_state(lvl, 0, 1, out.ctypes.data)
+        assert rel(out, z['odd:c%d' % lvl]) < 1e-3, lvl
+    sess.close()
+
+
+@pytest.mark.gpu
+def test_tcgen05_matches_the_tf_graph_run_by_opencv():
+    """The CUDA path against vectors that neither the oracle nor this repository produced."""
+    from lstm_unet_b200.Networks import ULSTMnet2D
+    z = load_gold()
+    p = {k[len('odd:p:'):]: z[k] for k in z.files if k.startswith('odd:p:')}
+    m = ULSTMnet2D(NET_ODD, 'NCHW', True, precision='bf16x3')
+    m.set_weights_dict(p)
+    logits, softmax = m(z['odd:x'], False)
+    assert rel(logits.numpy(), z['odd:logits']) < 1e-3 and rel(softmax.numpy(), z['odd:softmax']) < 1e-3
+    st = m.get_states()
+    for lvl in range(4):
+        assert rel(st[lvl][0][0], z['odd:h%d' % lvl]) < 1e-3 and rel(st[lvl][0][1], z['odd:c%d' % lvl]) < 1e-3, lvl
+    f = np.load(os.path.join(GOLD, 'forward_pad.npz'))
+    m = ULSTMnet2D(NET, 'NCHW', True, precision='bf16x3')
+    m.set_weights_dict({k[2:]: f[k] for k in f.files if k.startswith('p:')})
+    for call in range(2):                                             # stateful carry == frames 2-3 of the unrolled graph
+        logits, _ = m(f['x'][call], False)
+        assert rel(logits.numpy(), z['pad:logits'][:, 2 * call:2 * call + 2]) < 1e-3, call
+    assert m.launch_count() > 0
