@@ -130,6 +130,31 @@ def test_oracle_matches_the_tf_graph_run_by_opencv(net, B, T, H, W, pad):
         assert rel(h, rh) < 2e-5 and rel(c, rc) < 2e-5
 
 
+@pytest.mark.skipif(not os.path.exists('/root/reference/Networks.py'), reason='the reference is only present in the build container')
+@pytest.mark.parametrize("net,B,T,H,W,pad,calls", [
+    (NET_TWO, 1, 2, 18, 22, False, 2), (NET_TWO, 2, 1, 17, 21, True, 3), (NET_ODD, 1, 2, 35, 35, True, 1),
+])
+def test_graph_emitted_by_the_references_own_networks_py(net, B, T, H, W, pad, calls):
+    """The reference's unmodified ULSTMnet2D.call run on the graph-emitting stand-in (tests/keras_graph_standin.py): its
+    graph, executed by OpenCV, gives bit for bit what the reference-free builder's graph gives (so the committed vectors are
+    'the reference's wiring + OpenCV's arithmetic'), and the oracle agrees with both, stateful calls included."""
+    from tests.golden.make_tf_graph_golden import reference_driven
+    params = O.init_params(net, seed=21, randomize_bn=True)
+    pn = {k: v.numpy() for k, v in params.items()}
+    rng = np.random.default_rng(1)
+    xs = [rng.standard_normal((B, T, 1, H, W)).astype(np.float32) for _ in range(calls)]
+    per_call, states = reference_driven(net, pn, xs, pad)
+    seq = np.concatenate(xs, axis=1)
+    logits, soft, st = G.ulstm_forward_opencv(net, pn, seq.transpose(0, 1, 3, 4, 2), pad)
+    ora = O.OracleNet(net, 'NCHW', pad, params=params)
+    for c, (rl, rs) in enumerate(per_call):
+        assert np.array_equal(rl, logits[:, c * T:(c + 1) * T]) and np.array_equal(rs, soft[:, c * T:(c + 1) * T])
+        ol, os_ = ora(torch.from_numpy(xs[c]), False)
+        assert rel(rl, ol.numpy()) < 2e-5 and rel(rs, os_.numpy()) < 2e-5
+    for (h, c_), (h2, c2) in zip(states, st):
+        assert np.array_equal(h, h2) and np.array_equal(c_, c2)
+
+
 def load_gold():
     return np.load(os.path.join(GOLD, 'tf_graph_opencv.npz'))
 
