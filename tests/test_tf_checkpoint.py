@@ -157,3 +157,16 @@ def test_training_checkpoint_manager_round_trip(tmp_path):
     opt3 = Adam()
     c3 = ck.Checkpoint(ULSTMnet2D(net, 'NCHW', False), opt3).restore(str(tmp_path / 'model.ckpt'))
     assert c3.step == 0 and opt3.iterations == 0 and opt3.get_slots()[1] is None
+
+
+def test_crc32c_and_masking_against_tensorboards_implementation():
+    """TensorBoard carries its own CRC-32C + TensorFlow masking (for TFRecord event files): a third-party implementation of
+    the checksum every table block and every tensor of a bundle is guarded with."""
+    pw = pytest.importorskip('tensorboard.compat.tensorflow_stub.pywrap_tensorflow')
+    rng = np.random.default_rng(0)
+    for n in (0, 1, 3, 4, 5, 63, 64, 65, 1000, 4099):
+        buf = rng.integers(0, 256, size=n, dtype=np.uint8).tobytes()
+        assert T.crc32c(buf) == pw.crc32c(buf), n
+        assert T.mask_crc(T.crc32c(buf)) == pw.masked_crc32c(buf), n
+    a, b = os.urandom(100), os.urandom(77)
+    assert T.crc32c(b, T.crc32c(a)) == pw.crc32c(a + b)          # incremental form used for the multi-part tensors

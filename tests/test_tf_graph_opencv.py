@@ -208,3 +208,51 @@ def test_tcgen05_matches_the_tf_graph_run_by_opencv():
         logits, _ = m(f['x'][call], False)
         assert rel(logits.numpy(), z['pad:logits'][:, 2 * call:2 * call + 2]) < 1e-3, call
     assert m.launch_count() > 0
+
+
+def test_hand_written_graphdef_parses_with_tensorflows_own_proto_schema():
+    """TensorBoard ships TensorFlow's compiled .proto definitions: the bytes tf_graphdef.py writes must decode with them into
+    the nodes, attributes and tensors that were meant (field numbers, wire types, packed lists, tensor_content)."""
+    graph_pb2 = pytest.importorskip('tensorboard.compat.proto.graph_pb2')
+    rng = np.random.default_rng(0)
+    w = rng.standard_normal((3, 3, 2, 4)).astype(np.float32)
+    b = rng.standard_normal(4).astype(np.float32)
+    raw = G.placeholder('x', [1, 8, 9, 2]) + G.conv2d('c', 'x', w, 2, b) + G.batchnorm('bn', 'c', b, b, b, np.abs(b)) + \
+        G.leaky_relu('a', 'bn') + G.resize_bilinear('up', 'a', 8, 10) + G.concat('cat', ['up', 'up']) + \
+        G.mirror_pad('pad', 'cat', 1, 2, 3, 4) + G.softmax('sm', 'pad')
+    gd = graph_pb2.GraphDef.FromString(raw)
+    nodes = {n.name: n for n in gd.node}
+    assert [n.op for n in gd.node if n.op != 'Const'] == ['Placeholder', 'Conv2D', 'BiasAdd', 'FusedBatchNormV3', 'LeakyRelu',
+                                                          'ResizeBilinear', 'ConcatV2', 'MirrorPad', 'Softmax']
+    ph = nodes['x']
+    assert ph.attr['dtype'].type == 1 and [d.size for d in ph.attr['shape'].shape.dim] == [1, 8, 9, 2]
+    conv = nodes['c/Conv2D']
+    assert list(conv.input) == ['x', 'c/kernel'] and conv.attr['padding'].s == b'SAME' and conv.attr['data_format'].s == b'NHWC'
+    assert list(conv.attr['strides'].list.i) == [1, 2, 2, 1] and conv.attr['T'].type == 1
+    k = nodes['c/kernel'].attr['value'].tensor
+    assert k.dtype == 1 and [d.size for d in k.tensor_shape.dim] == [3, 3, 2, 4]
+    assert np.array_equal(np.frombuffer(k.tensor_content, np.float32).reshape(3, 3, 2, 4), w)
+    assert list(nodes['c'].input) == ['c/Conv2D', 'c/bias']
+    bn = nodes['bn']
+    assert abs(bn.attr['epsilon'].f - 1e-3) < 1e-9 and bn.attr['is_training'].b is False and len(bn.input) == 5
+    assert abs(nodes['a'].attr['alpha'].f - 0.3) < 1e-7
+    up = nodes['up']
+    assert up.attr['half_pixel_centers'].b is True and up.attr['align_corners'].b is False
+    size = nodes['up/size'].attr['value'].tensor
+    assert size.dtype == 3 and list(np.frombuffer(size.tensor_content, np.int32)) == [8, 10]
+    axis = nodes['cat/axis'].attr['value'].tensor
+    assert axis.dtype == 3 and list(axis.int_val) == [3] and len(axis.tensor_shape.dim) == 0 and nodes['cat'].attr['N'].i == 2
+    pads = nodes['pad/paddings'].attr['value'].tensor
+    assert np.frombuffer(pads.tensor_content, np.int32).reshape(4, 2).tolist() == [[0, 0], [1, 2], [3, 4], [0, 0]]
+    assert nodes['pad'].attr['mode'].s == b'REFLECT'
+    # and a whole network: every input of every node names a node of the graph, no name is used twice
+    params = {k_: v.numpy() for k_, v in O.init_params(NET_TWO, seed=1, randomize_bn=True).items()}
+    g, names = G.build_ulstm_graph(NET_TWO, params, 1, 2, 1, 10, 12, True)
+    gd = graph_pb2.GraphDef.FromString(g)
+    seen = set()
+    for n in gd.node:
+        assert n.name not in seen, n.name
+        assert all(i in seen for i in n.input), (n.name, list(n.input))       # topological order, as TensorFlow writes it
+        seen.add(n.name)
+    assert all(x in seen for x in names['softmax']) and all(h in seen and c in seen for h, c in names['states'])
+    assert sum(n.op == 'Conv2D' for n in gd.node) > 50
