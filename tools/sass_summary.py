@@ -10,7 +10,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, 'lstm_unet_b200', 'liblstm_unet_b200.so')
-PAT = re.compile(r'\s(UTC[A-Z0-9]+(?:\.[A-Z0-9_]+)*|UTMALDG(?:\.[A-Z0-9_]+)*|SYNCS(?:\.[A-Z0-9_]+)*|UCGABAR_[A-Z]+|LDTM(?:\.[A-Z0-9_]+)*)\s')
+PAT = re.compile(r'\s(UTC[A-Z0-9]+(?:\.[A-Z0-9_]+)*|UTMALDG(?:\.[A-Z0-9_]+)*|SYNCS(?:\.[A-Z0-9_]+)*|UCGABAR_[A-Z]+|LDTM(?:\.[A-Za-z0-9_]+)*)\s')
 
 
 def main():
