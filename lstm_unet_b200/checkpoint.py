@@ -51,7 +51,7 @@ class Checkpoint:
         layout = self.net._variable_layout()
         self.net.set_weights_dict(tfc.load_model_weights(prefix, [e['name'] for e in layout]))
         if 'step' + tfc.VAR_SUFFIX in tensors:
-            self.step = int(tensors['step' + tfc.VAR_SUFFIX])
+            self.step = int(np.asarray(tensors['step' + tfc.VAR_SUFFIX]).reshape(-1)[0])
         if self.optimizer is not None and 'optimizer/iter' + tfc.VAR_SUFFIX in tensors:
             n = sum(e['count'] for e in layout if e['trainable'])
             m, v, have = np.zeros(n, np.float32), np.zeros(n, np.float32), False
@@ -62,7 +62,7 @@ class Checkpoint:
                     m[sl] = tensors[km].reshape(-1)
                     v[sl] = tensors[_var_path(e['name']) + _SLOT % 'v'].reshape(-1)
                     have = True
-            self.optimizer.set_slots(int(tensors['optimizer/iter' + tfc.VAR_SUFFIX]), m if have else None, v if have else None)
+            self.optimizer.set_slots(int(np.asarray(tensors['optimizer/iter' + tfc.VAR_SUFFIX]).reshape(-1)[0]), m if have else None, v if have else None)
         return self
 
 

@@ -1,8 +1,6 @@
 """CPU tests of the post-processing host logic and kernels' arithmetic: the TEST-ONLY host build of the library
 (tests/_emu, -DLU_HOST_EMU: every kernel body runs as plain loops, one "thread" per CTA) through the same C-ABI and the
 same PostProcessor driver the product uses, against the reference-pinned oracle and the golden vectors."""
-import os
-
 import numpy as np
 import pytest
 

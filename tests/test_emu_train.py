@@ -1,7 +1,6 @@
 """Host-logic parity of the training step (loss, backward, Adam) through the C-ABI, TEST-ONLY host build, vs autograd
 through the oracle.  Same plan / tables drive the GPU path (tests -m gpu)."""
 import numpy as np
-import pytest
 import torch
 
 from oracle import lstm_unet_oracle as O

@@ -114,7 +114,6 @@ def test_model_save_load_tf_format(tmp_path):
 def test_training_checkpoint_manager_round_trip(tmp_path):
     """checkpoint.Checkpoint / CheckpointManager / latest_checkpoint (train2D.py:62-85,222-226) on the host: model
     variables under net/, Adam moments as optimizer slots, int64 counters, max_to_keep, the `checkpoint` state file"""
-    import torch
     from lstm_unet_b200 import checkpoint as ck
     from lstm_unet_b200 import tf_checkpoint as tfc
     from lstm_unet_b200.Networks import ULSTMnet2D, Adam
@@ -139,7 +138,7 @@ def test_training_checkpoint_manager_round_trip(tmp_path):
     assert not os.path.exists(paths[0] + '.index') and os.path.exists(paths[2] + '.data-00000-of-00001')
     assert ck.latest_checkpoint(str(tmp_path / 'tf_ckpts')) == paths[2]
     bundle = tfc.read_bundle(paths[2])
-    assert bundle['step/.ATTRIBUTES/VARIABLE_VALUE'].dtype == np.int64 and int(bundle['step/.ATTRIBUTES/VARIABLE_VALUE']) == 19
+    assert bundle['step/.ATTRIBUTES/VARIABLE_VALUE'].dtype == np.int64 and int(bundle['step/.ATTRIBUTES/VARIABLE_VALUE'].reshape(-1)[0]) == 19
     assert 'net/DownLayers/0/ConvLSTM/0/cell/kernel/.OPTIMIZER_SLOT/optimizer/m/.ATTRIBUTES/VARIABLE_VALUE' in bundle
     # restore into a fresh model / optimizer
     model2, opt2 = ULSTMnet2D(net, 'NCHW', False, train=True), Adam(lr=1.0)
