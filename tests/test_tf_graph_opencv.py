@@ -186,6 +186,12 @@ def test_host_build_matches_the_opencv_vectors():
         sess.get_state(lvl, 0, 1, out.ctypes.data)
         assert rel(out, z['odd:c%d' % lvl]) < 1e-3, lvl
     sess.close()
+    # the throughput mode (bf16 operands, 8 significant bits; measured here: 6e-3 / 2e-3)
+    sess = emu_session(NET_ODD, data_format='NCHW', pad_image=True, batch=2, max_t=3, height=35, width=35, precision='bf16')
+    sess.set_params(p)
+    logits, softmax = emu_forward(sess, z['odd:x'], False)
+    assert rel(logits, z['odd:logits']) < 2e-2 and rel(softmax, z['odd:softmax']) < 2e-2
+    sess.close()
 
 
 @pytest.mark.gpu
@@ -201,6 +207,10 @@ def test_tcgen05_matches_the_tf_graph_run_by_opencv():
     st = m.get_states()
     for lvl in range(4):
         assert rel(st[lvl][0][0], z['odd:h%d' % lvl]) < 1e-3 and rel(st[lvl][0][1], z['odd:c%d' % lvl]) < 1e-3, lvl
+    m = ULSTMnet2D(NET_ODD, 'NCHW', True, precision='bf16')            # the bench's precision: 5e-2 as in test_gpu_forward
+    m.set_weights_dict(p)
+    logits, softmax = m(z['odd:x'], False)
+    assert rel(logits.numpy(), z['odd:logits']) < 5e-2 and rel(softmax.numpy(), z['odd:softmax']) < 5e-2
     f = np.load(os.path.join(GOLD, 'forward_pad.npz'))
     m = ULSTMnet2D(NET, 'NCHW', True, precision='bf16x3')
     m.set_weights_dict({k[2:]: f[k] for k in f.files if k.startswith('p:')})
