@@ -22,6 +22,11 @@ from tests.golden.make_tf_graph_golden import NET_ODD
 cv2 = pytest.importorskip('cv2')
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 
+NET_WIDE = {   # CTC channel structure at 1/4 width (every buffer a multiple of 64 except the 32 / 16-wide tail)
+    'down_conv_kernels': [[(3, 64), (3, 64)], [(3, 128), (3, 128)], [(3, 128), (3, 128)], [(3, 192), (3, 192)]],
+    'lstm_kernels': [[(5, 64)], [(5, 128)], [(5, 128)], [(5, 192)]],
+    'up_conv_kernels': [[(3, 128), (3, 128)], [(3, 64), (3, 64)], [(3, 32), (3, 32)], [(3, 16), (3, 16), (1, 3)]],
+}
 NET_TWO = {
     'down_conv_kernels': [[(3, 6)], [(3, 10), (3, 10)]],
     'lstm_kernels': [[(3, 5), (3, 7)], [(5, 9)]],
@@ -114,6 +119,7 @@ def test_convlstm_cell_as_opencv_runs_it(k, scale):
     (NET_ODD, 1, 2, 35, 35, True),         # the reference unit_test's shape (Networks.py:256-277)
     (NET_ODD, 2, 3, 40, 48, True),
     (NET, 2, 3, 24, 32, False),
+    (NET_WIDE, 1, 2, 64, 48, False),       # the wide case of test_gpu_forward's parity list
 ])
 def test_oracle_matches_the_tf_graph_run_by_opencv(net, B, T, H, W, pad):
     params = O.init_params(net, seed=3, randomize_bn=True)
@@ -266,3 +272,21 @@ def test_hand_written_graphdef_parses_with_tensorflows_own_proto_schema():
         seen.add(n.name)
     assert all(x in seen for x in names['softmax']) and all(h in seen and c in seen for h, c in names['states'])
     assert sum(n.op == 'Conv2D' for n in gd.node) > 50
+
+
+@pytest.mark.gpu
+def test_tcgen05_wide_network_matches_the_tf_graph_run_by_opencv_live():
+    """Multiple-of-64 channel counts (full tensor-core tiles, two-source decoder convs) against OpenCV run on the spot: the
+    weights are too large to commit as vectors, and the reference-free graph builder is bit-identical to the reference-driven
+    one (test_graph_emitted_by_the_references_own_networks_py)."""
+    from lstm_unet_b200.Networks import ULSTMnet2D
+    params = {k: v.numpy() for k, v in O.init_params(NET_WIDE, seed=7, randomize_bn=True).items()}
+    x = np.random.default_rng(2).standard_normal((1, 2, 1, 64, 48)).astype(np.float32)
+    ref_l, ref_s, ref_st = G.ulstm_forward_opencv(NET_WIDE, params, x.transpose(0, 1, 3, 4, 2), False)
+    m = ULSTMnet2D(NET_WIDE, 'NCHW', False, precision='bf16x3')
+    m.set_weights_dict({k: v.copy() for k, v in params.items()})
+    logits, softmax = m(x, False)
+    assert rel(logits.numpy(), ref_l) < 1e-3 and rel(softmax.numpy(), ref_s) < 1e-3
+    st = m.get_states()
+    for lvl in range(4):
+        assert rel(st[lvl][0][0], ref_st[lvl][0]) < 1e-3 and rel(st[lvl][0][1], ref_st[lvl][1]) < 1e-3, lvl
