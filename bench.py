@@ -286,7 +286,10 @@ def run_ours(args):
                    'global_batch': B * world, 'parallelism': ('data parallel x%d: batch-sharded, NCCL mean all-reduce of the 74.6M fp32 gradients per step (started per block from inside the backward)'
                                    if training else 'batch-sharded replicas x%d (no data-path collective)') % world,
                    'l2_policy': 'inputs+activations per step (>6 GB) exceed the 126 MB L2; no flush needed',
-                   'a_mode': args.a_mode, 'step_tflop': flops_step / 1e12, 'cuda_graph': bool(model.graph_active)},
+                   'a_mode': args.a_mode, 'step_tflop': flops_step / 1e12, 'cuda_graph': bool(model.graph_active),
+                   # experiment switches of the library that were set for this run (none = the default kernels)
+                   'switches': {k: os.environ[k] for k in ('LU_PAIR', 'LU_WGRAD_CLUSTER', 'LU_CLUSTER', 'LU_CLUSTER_WIDE',
+                                                           'LU_B_RESIDENT', 'LU_WGRAD_ENGINE') if k in os.environ}},
         'e2e': {'value': e2e_value, 'unit': 'frames/s',
                 'h2d_bytes_per_step': int(x_host.nbytes) * (2 if training else 1),
                 'd2h_bytes_per_step': int(sm.nbytes), 'steps': e2e_steps, 'ms_per_step': e2e_wall_ms / e2e_steps,
