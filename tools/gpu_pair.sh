@@ -33,3 +33,10 @@ for c in 1 3; do
   cut -c1-200 gpurun_out/bench_train_wg$c.json
 done
 echo "ALL STEPS PASSED"
+# ncu --set full of the same launches round 1 profiled with the default kernels (tools/gpu_final2.sh: level-1 ConvLSTM launch,
+# level-1 weight-gradient launch), now in pair mode -- compare tensor-pipe activity and the tensor memory pipe with
+# profiles/r1_ncu_prof_lstm_l1.txt / r1_ncu_prof_wgrad_l1.txt
+NCU="ncu --set full --clock-control none --import-source on"
+LU_PAIR=1 LU_WGRAD_CLUSTER=1 timeout -k 10 1500 $NCU -k regex:lu_conv_tc_kernel -s 110 -c 1 -o gpurun_out/prof_lstm_l1_pair python bench.py --steps 1 --warmup 3 --no-cpu > /dev/null 2>&1; echo "ncu lstm pair rc=$?"
+LU_PAIR=0 LU_WGRAD_CLUSTER=3 timeout -k 10 1500 $NCU -k regex:lu_wgrad_tc_kernel -s 69 -c 1 -o gpurun_out/prof_wgrad_l1_pair python bench.py --mode train --steps 1 --warmup 3 --no-cpu > /dev/null 2>&1; echo "ncu wgrad pair rc=$?"
+ls -la gpurun_out/*.ncu-rep
