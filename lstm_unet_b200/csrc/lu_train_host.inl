@@ -507,6 +507,7 @@ static int run_wgrad(lu_handle_s* h, ConvPlan& f, int gbuf, int T, float* grads,
       wp.dy_frame_mul = (int)w.dy_frame_mul; wp.dy_frame_add = (int)w.dy_frame_add; wp.dy_planes = g.planes; wp.dy_cpad = g.cpad;
       // stage = two activation windows + two 16 KB dY boxes (bf16: 2 column chunks; bf16x3: hi and lo plane of one chunk)
       wp.a_win_bytes = f.a_bytes; wp.stage_bytes = 2 * f.a_bytes + 2 * 16384;
+      if (wg_pair == 3) wp.stage_bytes = 2 * f.a_bytes + 16384;    // pair mode stages ONE 64-column half of dY per CTA: deeper ring
       const int budget = 232448 - 1024 - 256;
       wp.n_stages = budget / wp.stage_bytes;
       if (wp.n_stages > 4) wp.n_stages = 4;
