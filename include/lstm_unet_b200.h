@@ -28,7 +28,9 @@ extern "C" {
 #define LU_MAX_LEVELS 4
 #define LU_MAX_PER_LEVEL 4
 
-enum { LU_PREC_BF16 = 0, LU_PREC_BF16X3 = 1 };       /* tensor-core operand precision */
+/* tensor-core operand precision: bf16 = throughput / training mode; bf16x3 = split-bf16, fp32-equivalent
+ * (3x the MMA work); fp16 = 11-bit mantissa operands at the bf16 rate, inference handles only */
+enum { LU_PREC_BF16 = 0, LU_PREC_BF16X3 = 1, LU_PREC_FP16 = 2 };
 enum { LU_ENGINE_TCGEN05 = 0, LU_ENGINE_SIMT = 1 };   /* SIMT = on-GPU scalar mirror used to debug the TC path */
 enum { LU_GATE_HARD_SIGMOID = 0, LU_GATE_SIGMOID = 1 };
 enum { LU_AMODE_HALO = 0, LU_AMODE_DIRECT = 1 };      /* how activation tiles are staged in shared memory */
@@ -100,6 +102,8 @@ int lu_set_graph_mode(lu_handle h, int32_t enable, int32_t* effective);
 
 /* reset_states_per_batch (Networks.py:77-84,279-281): h,c *= mask[b]; mask is (B,) fp32 on the device */
 int lu_reset_states(lu_handle h, const float* dev_mask, void* stream);
+/* DownBlock2D.reset_states_per_batch (Networks.py:77-84) called on one block alone: the ConvLSTM layers of `level` only */
+int lu_reset_level_states(lu_handle h, int32_t level, const float* dev_mask, void* stream);
 /* get_states / set_states (Networks.py:86-98,283-291): one (B,F,H,W)/(B,H,W,F) fp32 tensor per call;
  * which: 0 = h, 1 = c.  dev_in == NULL zeroes the state (Keras reset_states(None)). */
 int lu_state_shape(lu_handle h, int32_t level, int32_t layer, int64_t* shape4);
@@ -146,6 +150,12 @@ int lu_lstm_flops(lu_handle h, int32_t T, double* flops);
  * CUDA-event pairs recorded around every ConvLSTM launch since the last call (synchronises on the last event),
  * then enables / disables the recording for the following forwards */
 int lu_lstm_kernel_time(lu_handle h, int32_t enable, float* ms_total, int32_t* launches);
+/* the same for every tensor-core kernel class (bench.py's `train` block names the dominant kernel of the training step):
+ * ms4 / launches4 are indexed by LU_KC_*; lu_class_flops gives the algorithmic FLOPs (2*MAC) of each class for one
+ * training step over T frames per sample at the bound batch size */
+enum { LU_KC_LSTM_FWD = 0, LU_KC_CONV_FWD = 1, LU_KC_DGRAD = 2, LU_KC_WGRAD = 3, LU_KC_COUNT = 4 };
+int lu_kernel_times(lu_handle h, int32_t enable, float* ms4, int32_t* launches4);
+int lu_class_flops(lu_handle h, int32_t T, double* flops4);
 
 /* ---- instance labelling of the soft-max maps (Inference2D.py:64-123): replaces the reference's numpy / SciPy / OpenCV
  * post-processing that follows the model call; results are bit-identical to it.  Stateless: everything

@@ -50,21 +50,30 @@ DEFAULT_NET_DOWN_PARAMS = {
 }
 
 
-_PINNED_RING = {}
+_PINNED_POOL = {}
+_POOL_KEEP = 4          # idle pinned buffers kept per (shape, dtype); more than that are released to the driver
 
 
-def _pinned_like(t):
-    """Ring of three pinned host buffers per (shape, dtype): device->host copies run at DMA speed.  The array returned
-    by ``.numpy()`` therefore stays valid until three later ``.numpy()`` calls on same-shaped outputs (the reference's
-    inference loop consumes it within the iteration, Inference2D.py:60-131)."""
+def _pinned_for(t):
+    """A pinned host buffer for the device -> host copy of `t` (DMA speed), owned by the caller through the array
+    ``.numpy()`` returns: the buffer goes back to the pool only when that array (and every view of it) has been garbage
+    collected, so results collected in a list are never overwritten -- like the fresh array tf.Tensor.numpy() returns
+    (Inference2D.py:60) -- while a loop that drops each result reuses the same one or two buffers."""
     import torch
+    import weakref
     key = (tuple(t.shape), t.dtype)
-    ring = _PINNED_RING.setdefault(key, {'bufs': [], 'next': 0})
-    if len(ring['bufs']) < 3:
-        ring['bufs'].append(torch.empty(t.shape, dtype=t.dtype, pin_memory=True))
-        return ring['bufs'][-1]
-    ring['next'] = (ring['next'] + 1) % 3
-    return ring['bufs'][ring['next']]
+    pool = _PINNED_POOL.setdefault(key, [])
+    free = [e for e in pool if e[1] is None or e[1]() is None]
+    if free:
+        entry = free[0]
+        for extra in free[_POOL_KEEP:]:
+            pool.remove(extra)
+    else:
+        entry = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True), None]
+        pool.append(entry)
+    arr = entry[0].numpy()
+    entry[1] = weakref.ref(arr)
+    return entry[0], arr
 
 
 def _device_array_type():
@@ -75,10 +84,10 @@ def _device_array_type():
 
         def numpy(self):
             t = self.as_subclass(torch.Tensor).detach()
-            host = _pinned_like(t)
+            host, arr = _pinned_for(t)
             host.copy_(t, non_blocking=True)
             torch.cuda.current_stream(t.device).synchronize()
-            return host.numpy()
+            return arr
 
     return DeviceArray
 
@@ -96,9 +105,10 @@ def _wrap(t):
 class Variable:
     """A named view into the flat parameter buffer (stands in for a tf.Variable of model.trainable_variables)."""
 
-    def __init__(self, name, view, trainable):
+    def __init__(self, name, view, trainable, session=None):
         self.name, self.value, self.trainable = name, view, trainable
         self.shape = tuple(view.shape)
+        self._session = session
 
     def numpy(self):
         return self.value.detach().cpu().numpy()
@@ -106,6 +116,8 @@ class Variable:
     def assign(self, arr):
         import torch
         self.value.copy_(torch.as_tensor(np.asarray(arr, dtype=np.float32)).reshape(self.value.shape))
+        if self._session is not None:             # the library runs on packed bf16 copies / folded BN constants
+            self._session.params_changed()
 
 
 class DownBlock2D:
@@ -324,9 +336,13 @@ class ULSTMnet2D:
             if self._x_pin is None or self._x_pin.numel() < n:
                 self._x_pin = torch.empty(n, dtype=torch.float32, pin_memory=True)
                 self._x_dev = torch.empty(n, dtype=torch.float32, device=dev)
+                self._x_event = torch.cuda.Event()
+            else:
+                self._x_event.synchronize()       # the previous call's H2D may still be queued behind its forward
             self._x_pin[:n].copy_(x.reshape(-1).to(torch.float32))
             xd = self._x_dev[:n]
             xd.copy_(self._x_pin[:n], non_blocking=True)
+            self._x_event.record(torch.cuda.current_stream(dev))
         else:
             xd = x.to(device=dev, dtype=torch.float32).contiguous().reshape(-1)
         shape = (B, T, self.last_depth, H, W) if self.channel_axis == 1 else (B, T, H, W, self.last_depth)
@@ -343,19 +359,28 @@ class ULSTMnet2D:
     def _n_lstm(self, level):
         return len(self.net_params['lstm_kernels'][level])
 
-    def _reset_level(self, level, is_last_batch):
-        # the library masks all levels at once; per-level fan-out keeps the reference's call structure
-        if level == 0:
-            self.reset_states_per_batch(is_last_batch)
-
-    def reset_states_per_batch(self, is_last_batch):
+    def _mask_dev(self, is_last_batch):
         import torch
-        if self._sess is None:
-            return
         m = torch.as_tensor(np.asarray(is_last_batch, dtype=np.float32)).reshape(-1)
         if m.numel() != self._shape[0]:
             raise ValueError('mask has %d entries for batch size %d' % (m.numel(), self._shape[0]))
-        md = m.to(self._be.device)
+        return m.to(self._be.device)
+
+    def _reset_level(self, level, is_last_batch):
+        """DownBlock2D.reset_states_per_batch (Networks.py:77-84): the ConvLSTM layers of that block only."""
+        import torch
+        if self._sess is None:
+            return
+        md = self._mask_dev(is_last_batch)
+        self._sess.reset_level_states(level, md.data_ptr())
+        torch.cuda.current_stream(self._be.device).synchronize()      # md must outlive the kernel
+
+    def reset_states_per_batch(self, is_last_batch):
+        """ULSTMnet2D.reset_states_per_batch (Networks.py:279-281): every block."""
+        import torch
+        if self._sess is None:
+            return
+        md = self._mask_dev(is_last_batch)
         self._sess.reset_states(md.data_ptr())
         torch.cuda.current_stream(self._be.device).synchronize()      # md must outlive the kernel
 
@@ -411,7 +436,7 @@ class ULSTMnet2D:
     @property
     def variables(self):
         s = self._need_session()
-        return [Variable(e['name'], s.params[e['offset']:e['offset'] + e['count']].view(e['shape']), e['trainable'])
+        return [Variable(e['name'], s.params[e['offset']:e['offset'] + e['count']].view(e['shape']), e['trainable'], s)
                 for e in s.layout]
 
     @property

@@ -7,9 +7,10 @@ import os
 
 LU_MAX_LEVELS = 4
 LU_MAX_PER_LEVEL = 4
-PRECISIONS = {'bf16': 0, 'bf16x3': 1}
+PRECISIONS = {'bf16': 0, 'bf16x3': 1, 'fp16': 2}
 ENGINES = {'tcgen05': 0, 'simt': 1}
 GATES = {'hard_sigmoid': 0, 'sigmoid': 1}
+KERNEL_CLASSES = ('lstm_fwd', 'conv_fwd', 'dgrad', 'wgrad')     # LU_KC_* of include/lstm_unet_b200.h
 A_MODES = {'halo': 0, 'direct': 1}
 
 _I32 = ctypes.c_int32
@@ -68,6 +69,7 @@ def bind(lib):
         'lu_forward': [vp, vp, i32, i32, vp, vp, vp],
         'lu_set_graph_mode': [vp, i32, P(i32)],
         'lu_reset_states': [vp, vp, vp],
+        'lu_reset_level_states': [vp, i32, vp, vp],
         'lu_state_shape': [vp, i32, i32, P(i64)],
         'lu_get_state': [vp, i32, i32, i32, vp, vp],
         'lu_set_state': [vp, i32, i32, i32, vp, vp],
@@ -80,6 +82,8 @@ def bind(lib):
         'lu_forward_flops': [vp, i32, P(ctypes.c_double)],
         'lu_lstm_flops': [vp, i32, P(ctypes.c_double)],
         'lu_lstm_kernel_time': [vp, i32, P(f32), P(i32)],
+        'lu_kernel_times': [vp, i32, P(f32), P(i32)],
+        'lu_class_flops': [vp, i32, P(ctypes.c_double)],
         'lu_post_workspace_bytes': [i32, i32, i32, P(ctypes.c_size_t)],
         'lu_postprocess': [vp, i32, i32, i32, P(lu_post_params), vp, vp, vp, ctypes.c_size_t, vp],
         'lu_post_launch_count': [P(i64), i32],
@@ -98,9 +102,9 @@ def bind(lib):
 
 EXPORTED_SYMBOLS = ['lu_last_error', 'lu_version', 'lu_is_cuda_build', 'lu_create', 'lu_destroy', 'lu_workspace_bytes',
                     'lu_bind_workspace', 'lu_param_count', 'lu_param_info', 'lu_bind_params', 'lu_params_changed',
-                    'lu_forward', 'lu_set_graph_mode', 'lu_reset_states', 'lu_state_shape', 'lu_get_state', 'lu_set_state',
+                    'lu_forward', 'lu_set_graph_mode', 'lu_reset_states', 'lu_reset_level_states', 'lu_state_shape', 'lu_get_state', 'lu_set_state',
                     'lu_loss_backward', 'lu_set_grad_bucket_callback', 'lu_set_bn_sync_callback', 'lu_adam_step', 'lu_debug_buffer', 'lu_launch_count', 'lu_forward_flops', 'lu_lstm_flops',
-                    'lu_lstm_kernel_time', 'lu_post_workspace_bytes', 'lu_postprocess', 'lu_post_launch_count',
+                    'lu_lstm_kernel_time', 'lu_kernel_times', 'lu_class_flops', 'lu_post_workspace_bytes', 'lu_postprocess', 'lu_post_launch_count',
                     'lu_seg_workspace_bytes', 'lu_seg_measure', 'lu_aug_workspace_bytes', 'lu_augment_sequence',
                     'lu_elastic_coords']
 

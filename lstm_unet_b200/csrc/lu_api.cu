@@ -119,6 +119,7 @@ struct UpStage {
 struct lu_handle_s {
   lu_config cfg;
   int L = 0, pw = 0, planes = 1;
+  int fmt = 0;                    // 16-bit operand format: 0 bf16, 1 fp16 (LU_PREC_FP16, inference handles only)
   int Hp = 0, Wp = 0, pad_y0 = 0, pad_x0 = 0;
   int lvlH[LU_MAX_LEVELS + 1], lvlW[LU_MAX_LEVELS + 1];
   std::vector<ParamT> params;
@@ -167,13 +168,32 @@ struct lu_handle_s {
   lu_bn_sync_fn bn_sync_fn = nullptr;
   void* bn_sync_user = nullptr;
   int bn_sync_world = 1;
-  // optional CUDA-event timing of every ConvLSTM launch (bench.py roofline)
-  bool time_lstm = false;
+  // optional CUDA-event timing of every tensor-core launch, by kernel class (bench.py rooflines)
+  bool time_on = false;
   size_t ev_used = 0;
+  std::vector<int> ev_class;      // class of event pair i (events[2i], events[2i+1])
 #ifndef LU_HOST_EMU
   std::vector<cudaEvent_t> events;
 #endif
+  // cudaFuncSetAttribute is per device and a handle is bound to one device: remembered per handle, not per process
+  bool attr_set[12] = {false, false, false, false, false, false, false, false, false, false, false, false};
+  bool wg_attr_set = false;
 };
+
+#ifndef LU_HOST_EMU
+static void time_begin(lu_handle_s* h, int cls, void* stream) {
+  if (!h->time_on) return;
+  while (h->events.size() < h->ev_used + 2) { cudaEvent_t ev; cudaEventCreate(&ev); h->events.push_back(ev); }
+  if (h->ev_class.size() < h->ev_used / 2 + 1) h->ev_class.resize(h->ev_used / 2 + 1);
+  h->ev_class[h->ev_used / 2] = cls;
+  cudaEventRecord(h->events[h->ev_used], (cudaStream_t)stream);
+}
+static void time_end(lu_handle_s* h, void* stream) {
+  if (!h->time_on) return;
+  cudaEventRecord(h->events[h->ev_used + 1], (cudaStream_t)stream);
+  h->ev_used += 2;
+}
+#endif
 
 static void train_layout(lu_handle_s* h, size_t& off);
 static int build_train_plan(lu_handle_s* h);
@@ -666,12 +686,12 @@ static int get_encode() {
   return 0;
 }
 
-static int encode_view(CUtensorMap* tm, const LuSrcView& v, const void* ptr) {
+static int encode_view(CUtensorMap* tm, const LuSrcView& v, const void* ptr, int fmt = 0) {
   cuuint64_t dims[5] = {(cuuint64_t)v.dimC, (cuuint64_t)v.dimW, (cuuint64_t)v.dimP, (cuuint64_t)v.dimH, (cuuint64_t)v.dimN};
   cuuint64_t strides[4] = {(cuuint64_t)v.sw * 2, (cuuint64_t)v.sp * 2, (cuuint64_t)v.sh * 2, (cuuint64_t)v.sn * 2};
   cuuint32_t box[5] = {64, (cuuint32_t)v.pitch, 1, (cuuint32_t)v.rows, 1};
   cuuint32_t es[5] = {1, 1, 1, 1, 1};
-  CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, es,
+  CUresult r = g_encode(tm, fmt ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, es,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   LU_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(A) failed: %d (dims %d %d %d %d %d)", (int)r, v.dimC, v.dimW, v.dimP,
@@ -679,12 +699,12 @@ static int encode_view(CUtensorMap* tm, const LuSrcView& v, const void* ptr) {
   return 0;
 }
 
-static int encode_weights(CUtensorMap* tm, const void* ptr, int npad, int ktot, int BN) {
+static int encode_weights(CUtensorMap* tm, const void* ptr, int npad, int ktot, int BN, int fmt = 0) {
   cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)npad};
   cuuint64_t strides[1] = {(cuuint64_t)ktot * 2};
   cuuint32_t box[2] = {64, (cuuint32_t)BN};
   cuuint32_t es[2] = {1, 1};
-  CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, es,
+  CUresult r = g_encode(tm, fmt ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, es,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   LU_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(B) failed: %d", (int)r);
@@ -729,7 +749,7 @@ static int launch_conv(lu_handle_s* h, ConvPlan& cv, int frames, const int* mul,
 #ifdef LU_HOST_EMU
   LU_FAIL("the tcgen05 engine does not exist in the host test build");
 #else
-  static bool attr_set[12] = {false, false, false, false, false, false, false, false, false, false, false, false};
+  bool* attr_set = h->attr_set;
   LuTcParams tp;
   memset(&tp, 0, sizeof tp);
   for (int i = 0; i < cv.n_views; ++i) tp.tmA[i] = cv.tmA[i];
@@ -738,7 +758,9 @@ static int launch_conv(lu_handle_s* h, ConvPlan& cv, int frames, const int* mul,
   tp.cp = p;
   tp.n_a_stages = cv.nA; tp.n_b_stages = cv.nB; tp.a_stage_bytes = cv.a_bytes; tp.b_stage_bytes = cv.b_bytes;
   tp.b_group = cv.b_group;
-  tp.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(cv.BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  // instruction descriptor: D = fp32 (bit 4), A / B format at bits [7,10) / [10,13): 1 = bf16, 0 = fp16; N >> 3, M >> 4
+  const uint32_t ab_fmt = h->fmt ? 0u : ((1u << 7) | (1u << 10));
+  tp.idesc = (1u << 4) | ab_fmt | ((uint32_t)(cv.BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   // thread-block clusters of 2 (weight multicast) for the ConvLSTM launches; LU_CLUSTER=1 disables
   static int cluster_env = -1;
   if (cluster_env < 0) { const char* ce = getenv("LU_CLUSTER"); cluster_env = ce ? atoi(ce) : 2; }
@@ -792,6 +814,7 @@ static int launch_conv(lu_handle_s* h, ConvPlan& cv, int frames, const int* mul,
     attr_set[ei] = true;
   }
   h->launches++;
+  time_begin(h, epi.kind == LU_EPI_LSTM ? LU_KC_LSTM_FWD : (epi.kind == LU_EPI_GRAD ? LU_KC_DGRAD : LU_KC_CONV_FWD), stream);
   if (cl2) {
     cudaLaunchConfig_t lc;
     memset(&lc, 0, sizeof lc);
@@ -806,6 +829,7 @@ static int launch_conv(lu_handle_s* h, ConvPlan& cv, int frames, const int* mul,
   } else {
     kfn[ei]<<<grid, lutc::kThreads, cv.smem, (cudaStream_t)stream>>>(tp);
   }
+  time_end(h, stream);
   cudaError_t e = cudaGetLastError();
   LU_REQUIRE(e == cudaSuccess, "conv launch (%s) failed: %s", cv.name.c_str(), cudaGetErrorString(e));
   return 0;
@@ -844,7 +868,11 @@ int lu_create(const lu_config* cfg, lu_handle* out) {
   lu_handle_s* h = new lu_handle_s();
   h->cfg = *cfg;
   h->L = cfg->n_levels;
+  LU_REQUIRE(cfg->precision == LU_PREC_BF16 || cfg->precision == LU_PREC_BF16X3 || cfg->precision == LU_PREC_FP16, "unknown precision %d", cfg->precision);
+  LU_REQUIRE(!(cfg->precision == LU_PREC_FP16 && cfg->train),
+             "fp16 operands are an inference mode (gradients of ~1e-7 underflow fp16); train with bf16 or bf16x3");
   h->planes = cfg->precision == LU_PREC_BF16X3 ? 2 : 1;
+  h->fmt = cfg->precision == LU_PREC_FP16 ? 1 : 0;
   build_params(h);
   if (build_plan(h)) { delete h; return 1; }
   layout_workspace(h);
@@ -910,15 +938,15 @@ int lu_bind_workspace(lu_handle h, void* dev_ws, size_t bytes, void* stream) {
     if (get_encode()) return 1;
     for (auto& cv : h->convs) {
       for (int i = 0; i < cv.n_views; ++i)
-        if (encode_view(&cv.tmA[i], cv.views[i], view_ptr(h, cv.view_buf[i]))) return 1;
+        if (encode_view(&cv.tmA[i], cv.views[i], view_ptr(h, cv.view_buf[i]), h->fmt)) return 1;
       if (cv.kind == LU_EPI_LSTM)
         for (int s = 0; s < 2; ++s) {
           LuSrcView v = cv.views[1];
           v.dimN = h->cfg.batch;
-          if (encode_view(&cv.tmHstate[s], v, h->ws + cv.off_hstate[s])) return 1;
+          if (encode_view(&cv.tmHstate[s], v, h->ws + cv.off_hstate[s], h->fmt)) return 1;
         }
-      if (encode_weights(&cv.tmB, h->ws + cv.off_w, cv.npad, cv.ktot, cv.BN)) return 1;
-      if (encode_weights(&cv.tmBh, h->ws + cv.off_w, cv.npad, cv.ktot, cv.BN / 2)) return 1;
+      if (encode_weights(&cv.tmB, h->ws + cv.off_w, cv.npad, cv.ktot, cv.BN, h->fmt)) return 1;
+      if (encode_weights(&cv.tmBh, h->ws + cv.off_w, cv.npad, cv.ktot, cv.BN / 2, h->fmt)) return 1;
     }
     if (h->cfg.train) {
       h->acts_tm.resize(h->acts.size());
@@ -973,7 +1001,7 @@ int lu_params_changed(lu_handle h, void* stream) {
   for (auto& cv : h->convs) {
     LuPackWeights pw;
     pw.params = h->dparams; pw.descs = reinterpret_cast<const LuPackDesc*>(h->ws + cv.off_packs);
-    pw.out = reinterpret_cast<uint16_t*>(h->ws + cv.off_w); pw.cm = cv.cm; pw.ktot = cv.ktot;
+    pw.out = reinterpret_cast<uint16_t*>(h->ws + cv.off_w); pw.cm = cv.cm; pw.ktot = cv.ktot; pw.fmt = h->fmt;
     pf(h, (int64_t)cv.npad * cv.ktot, stream, pw);
     if (cv.kind == LU_EPI_GRAD) continue;
     LuPackVec pb;
@@ -998,7 +1026,7 @@ static int run_conv_layer(lu_handle_s* h, ConvPlan& cv, int T, int training, voi
   int mul[LU_MAX_SRC] = {1, 1, 1, 1}, add[LU_MAX_SRC] = {0, 0, 0, 0};
   LuEpi e;
   memset(&e, 0, sizeof e);
-  e.kind = LU_EPI_CONV; e.H = cv.Hout; e.W = cv.Wout;
+  e.kind = LU_EPI_CONV; e.H = cv.Hout; e.W = cv.Wout; e.fmt = h->fmt;
   e.oy_mul = 1; e.ox_mul = 1; e.OH = cv.Hout; e.OW = cv.Wout;
   e.bias = reinterpret_cast<const float*>(h->ws + cv.off_bias);
   e.out_frame_mul = 1; e.out_frame_add = 0; e.alpha = 0.3f;
@@ -1050,7 +1078,7 @@ static int run_conv_layer(lu_handle_s* h, ConvPlan& cv, int T, int training, voi
     LuBnApply ap;
     ap.raw = raw; ap.scale = fin.scale; ap.shift = fin.shift;
     ap.out = reinterpret_cast<uint16_t*>(h->ws + ob.off); ap.raw_cpad = cv.raw_cpad; ap.out_cpad = ob.cpad; ap.planes = ob.planes;
-    ap.alpha = 0.3f;
+    ap.alpha = 0.3f; ap.fmt = h->fmt;
     pf(h, npix * (ob.cpad / 8), stream, ap);
   }
   return 0;
@@ -1066,7 +1094,7 @@ static int run_lstm_layer(lu_handle_s* h, ConvPlan& cv, int T, int training, voi
     if (t == 0) { sel = h->hcur; mul[1] = 1; add[1] = 0; }
     LuEpi e;
     memset(&e, 0, sizeof e);
-    e.kind = LU_EPI_LSTM; e.H = cv.Hout; e.W = cv.Wout;
+    e.kind = LU_EPI_LSTM; e.H = cv.Hout; e.W = cv.Wout; e.fmt = h->fmt;
     e.oy_mul = 1; e.ox_mul = 1; e.OH = cv.Hout; e.OW = cv.Wout;
     e.bias = reinterpret_cast<const float*>(h->ws + cv.off_bias);
     e.out_frame_mul = T; e.out_frame_add = t;
@@ -1078,16 +1106,7 @@ static int run_lstm_layer(lu_handle_s* h, ConvPlan& cv, int T, int training, voi
       e.save_gates = reinterpret_cast<uint16_t*>(h->ws + cv.off_save_gates);
       e.save_c = reinterpret_cast<float*>(h->ws + cv.off_save_c);
     }
-#ifndef LU_HOST_EMU
-    if (h->time_lstm) {
-      while (h->events.size() < h->ev_used + 2) { cudaEvent_t ev; cudaEventCreate(&ev); h->events.push_back(ev); }
-      cudaEventRecord(h->events[h->ev_used], (cudaStream_t)stream);
-    }
-#endif
     if (launch_conv(h, cv, h->cfg.batch, mul, add, sel, e, stream)) return 1;
-#ifndef LU_HOST_EMU
-    if (h->time_lstm) { cudaEventRecord(h->events[h->ev_used + 1], (cudaStream_t)stream); h->ev_used += 2; }
-#endif
   }
   return 0;
 }
@@ -1112,7 +1131,7 @@ int lu_forward(lu_handle h, const float* dev_x, int32_t T, int32_t training, flo
   LU_REQUIRE(T >= 1 && T <= h->cfg.max_t, "T=%d outside [1,%d]", T, h->cfg.max_t);
   if (!h->packed && lu_params_changed(h, stream)) return 1;
 #ifndef LU_HOST_EMU
-  if (h->graph_mode && !training && !h->time_lstm) {
+  if (h->graph_mode && !training && !h->time_on) {
     // replay path: stage the input, launch the instantiated graph of this (T, state parity), copy the outputs out
     const lu_config& c = h->cfg;
     float* gx = reinterpret_cast<float*>(h->ws + h->off_gx);
@@ -1168,7 +1187,7 @@ static int forward_body(lu_handle h, const float* dev_x, int32_t T, int32_t trai
     LuPrepPatches pp;
     pp.x = dev_x; pp.out = reinterpret_cast<uint16_t*>(h->ws + h->off_patches);
     pp.H = c.height; pp.W = c.width; pp.Hp = h->Hp; pp.Wp = h->Wp; pp.pad_y0 = h->pad_y0; pp.pad_x0 = h->pad_x0;
-    pp.pw = h->pw; pp.x3 = h->planes == 2;
+    pp.pw = h->pw; pp.x3 = h->planes == 2; pp.fmt = h->fmt;
     pf(h, (int64_t)N * h->Hp * h->Wp, stream, pp);
   }
   for (int l = 0; l < h->L; ++l) {
@@ -1183,7 +1202,7 @@ static int forward_body(lu_handle h, const float* dev_x, int32_t T, int32_t trai
       const ActBuf& d = h->acts[h->ups[u].dst_buf];
       LuUpsample2x up;
       up.in = reinterpret_cast<const uint16_t*>(h->ws + s.off); up.out = reinterpret_cast<uint16_t*>(h->ws + d.off);
-      up.h = s.H; up.w = s.W; up.cpad = s.cpad; up.planes = s.planes;
+      up.h = s.H; up.w = s.W; up.cpad = s.cpad; up.planes = s.planes; up.fmt = h->fmt;
       pf(h, (int64_t)N * s.H * s.W * (s.cpad / 8), stream, up);     // one item per INPUT pixel and 8 channels
     }
     for (int ci : h->conv_of_up[u])
@@ -1214,20 +1233,30 @@ static ConvPlan* find_lstm(lu_handle_s* h, int level, int layer) {
   return &h->convs[h->lstm_of_level[level][layer]];
 }
 
+static void reset_level(lu_handle_s* h, int l, const float* dev_mask, void* stream) {
+  for (int ci : h->lstm_of_level[l]) {
+    ConvPlan& cv = h->convs[ci];
+    const int64_t px = (int64_t)cv.Hout * cv.Wout;
+    LuStateMask mh;
+    mh.h = reinterpret_cast<uint16_t*>(h->ws + cv.off_hstate[h->hcur]); mh.c = nullptr; mh.mask = dev_mask;
+    mh.per_sample_h = px * cv.fpad * h->planes; mh.per_sample_c = 0; mh.fmt = h->fmt;
+    pf(h, (int64_t)h->cfg.batch * mh.per_sample_h, stream, mh);
+    LuStateMaskC mc;
+    mc.c = reinterpret_cast<float*>(h->ws + cv.off_cstate); mc.mask = dev_mask; mc.per_sample = px * cv.fpad;
+    pf(h, (int64_t)h->cfg.batch * mc.per_sample, stream, mc);
+  }
+}
+
 int lu_reset_states(lu_handle h, const float* dev_mask, void* stream) {
   LU_REQUIRE(h && h->bound && dev_mask, "null argument / unbound handle");
-  for (int l = 0; l < h->L; ++l)
-    for (int ci : h->lstm_of_level[l]) {
-      ConvPlan& cv = h->convs[ci];
-      const int64_t px = (int64_t)cv.Hout * cv.Wout;
-      LuStateMask mh;
-      mh.h = reinterpret_cast<uint16_t*>(h->ws + cv.off_hstate[h->hcur]); mh.c = nullptr; mh.mask = dev_mask;
-      mh.per_sample_h = px * cv.fpad * h->planes; mh.per_sample_c = 0;
-      pf(h, (int64_t)h->cfg.batch * mh.per_sample_h, stream, mh);
-      LuStateMaskC mc;
-      mc.c = reinterpret_cast<float*>(h->ws + cv.off_cstate); mc.mask = dev_mask; mc.per_sample = px * cv.fpad;
-      pf(h, (int64_t)h->cfg.batch * mc.per_sample, stream, mc);
-    }
+  for (int l = 0; l < h->L; ++l) reset_level(h, l, dev_mask, stream);
+  return 0;
+}
+
+int lu_reset_level_states(lu_handle h, int32_t level, const float* dev_mask, void* stream) {
+  LU_REQUIRE(h && h->bound && dev_mask, "null argument / unbound handle");
+  LU_REQUIRE(level >= 0 && level < h->L, "no level %d", level);
+  reset_level(h, level, dev_mask, stream);
   return 0;
 }
 
@@ -1247,7 +1276,7 @@ int lu_get_state(lu_handle h, int32_t level, int32_t layer, int32_t which, float
   LuStateGet g;
   g.h = reinterpret_cast<const uint16_t*>(h->ws + cv->off_hstate[h->hcur]); g.c = reinterpret_cast<const float*>(h->ws + cv->off_cstate);
   g.out = dev_out; g.which = which; g.H = cv->Hout; g.W = cv->Wout; g.F = cv->F; g.fpad = cv->fpad; g.planes = h->planes;
-  g.channels_first = h->cfg.channels_first;
+  g.channels_first = h->cfg.channels_first; g.fmt = h->fmt;
   pf(h, (int64_t)h->cfg.batch * cv->F * cv->Hout * cv->Wout, stream, g);
   return 0;
 }
@@ -1259,7 +1288,7 @@ int lu_set_state(lu_handle h, int32_t level, int32_t layer, int32_t which, const
   LuStateSet s;
   s.h = reinterpret_cast<uint16_t*>(h->ws + cv->off_hstate[h->hcur]); s.c = reinterpret_cast<float*>(h->ws + cv->off_cstate);
   s.in = dev_in; s.which = which; s.H = cv->Hout; s.W = cv->Wout; s.F = cv->F; s.fpad = cv->fpad; s.planes = h->planes;
-  s.channels_first = h->cfg.channels_first;
+  s.channels_first = h->cfg.channels_first; s.fmt = h->fmt;
   pf(h, (int64_t)h->cfg.batch * cv->F * cv->Hout * cv->Wout, stream, s);
   return 0;
 }
@@ -1287,9 +1316,9 @@ int lu_lstm_flops(lu_handle h, int32_t T, double* flops) {
   return 0;
 }
 
-int lu_lstm_kernel_time(lu_handle h, int32_t enable, float* ms_total, int32_t* launches) {
+int lu_kernel_times(lu_handle h, int32_t enable, float* ms4, int32_t* launches4) {
   LU_REQUIRE(h, "null handle");
-  float total = 0.f; int n = 0;
+  float total[LU_KC_COUNT] = {0.f, 0.f, 0.f, 0.f}; int n[LU_KC_COUNT] = {0, 0, 0, 0};
 #ifndef LU_HOST_EMU
   if (h->ev_used) {
     cudaError_t e = cudaEventSynchronize(h->events[h->ev_used - 1]);
@@ -1297,14 +1326,43 @@ int lu_lstm_kernel_time(lu_handle h, int32_t enable, float* ms_total, int32_t* l
     for (size_t i = 0; i + 1 < h->ev_used; i += 2) {
       float ms = 0.f;
       cudaEventElapsedTime(&ms, h->events[i], h->events[i + 1]);
-      total += ms; ++n;
+      const int c = h->ev_class[i / 2];
+      total[c] += ms; ++n[c];
     }
   }
 #endif
   h->ev_used = 0;
-  h->time_lstm = enable != 0;
-  if (ms_total) *ms_total = total;
-  if (launches) *launches = n;
+  h->time_on = enable != 0;
+  for (int c = 0; c < LU_KC_COUNT; ++c) { if (ms4) ms4[c] = total[c]; if (launches4) launches4[c] = n[c]; }
+  return 0;
+}
+
+int lu_lstm_kernel_time(lu_handle h, int32_t enable, float* ms_total, int32_t* launches) {
+  float ms[LU_KC_COUNT]; int32_t n[LU_KC_COUNT];
+  if (lu_kernel_times(h, enable, ms, n)) return 1;
+  if (ms_total) *ms_total = ms[LU_KC_LSTM_FWD];
+  if (launches) *launches = n[LU_KC_LSTM_FWD];
+  return 0;
+}
+
+// algorithmic FLOPs (2 * MAC) per kernel class of one training step (forward over T frames per sample x batch, and its
+// backward): ConvLSTM forward, other forward convolutions, data gradients (no gradient flows to the image; the
+// recurrent term exists for t > 0 only), weight gradients (every forward MAC once)
+int lu_class_flops(lu_handle h, int32_t T, double* flops4) {
+  LU_REQUIRE(h && flops4, "null argument");
+  double lstm = 0, conv = 0, dgrad = 0;
+  for (auto& cv : h->convs) {
+    if (cv.kind == LU_EPI_GRAD) continue;
+    (cv.kind == LU_EPI_LSTM ? lstm : conv) += cv.macs_per_frame;
+    for (int i = 0; i < cv.n_in; ++i) {
+      if (cv.in[i].buf < 0) continue;
+      const double m = (double)cv.k * cv.k * cv.in[i].creal * cv.cout * cv.Hout * cv.Wout;
+      dgrad += (cv.kind == LU_EPI_LSTM && i == 1) ? m * (T - 1) / (double)T : m;
+    }
+  }
+  const double f = 2.0 * T * h->cfg.batch;
+  flops4[LU_KC_LSTM_FWD] = f * lstm; flops4[LU_KC_CONV_FWD] = f * conv; flops4[LU_KC_DGRAD] = f * dgrad;
+  flops4[LU_KC_WGRAD] = f * (lstm + conv);
   return 0;
 }
 
@@ -1322,7 +1380,7 @@ int lu_debug_buffer(lu_handle h, const char* name, int32_t kind, float* out, int
     shape4[0] = a.frames; shape4[1] = a.H; shape4[2] = a.W; shape4[3] = a.creal;
     if (out) {
       LuDebugRead r;
-      r.src = reinterpret_cast<const uint16_t*>(h->ws + a.off); r.out = out; r.creal = a.creal; r.cpad = a.cpad; r.planes = a.planes;
+      r.src = reinterpret_cast<const uint16_t*>(h->ws + a.off); r.out = out; r.creal = a.creal; r.cpad = a.cpad; r.planes = a.planes; r.fmt = h->fmt;
       pf(h, (int64_t)a.frames * a.H * a.W * a.creal, stream, r);
     }
     return 0;

@@ -60,9 +60,19 @@ LU_HDI void lu_store16_bf16(uint16_t* dst, const uint16_t* h) {
 }
 
 // ---- bf16 packing of 16 values (hi plane, optional lo plane) ---------------------------------------------------
-LU_HDI void lu_store16_split(uint16_t* dst, int lo_off, bool want_lo, const float* a) {
+LU_HDI void lu_store16_split(uint16_t* dst, int lo_off, bool want_lo, const float* a, int fmt = 0) {
 #ifdef __CUDA_ARCH__
   uint32_t h[8], l[8];
+  if (fmt) {                                  // fp16 operands: one plane
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const __half2 hv = __floats2half2_rn(a[2 * j], a[2 * j + 1]);
+      h[j] = *reinterpret_cast<const uint32_t*>(&hv);
+    }
+    reinterpret_cast<uint4*>(dst)[0] = make_uint4(h[0], h[1], h[2], h[3]);
+    reinterpret_cast<uint4*>(dst)[1] = make_uint4(h[4], h[5], h[6], h[7]);
+    return;
+  }
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const __nv_bfloat162 hv = __floats2bfloat162_rn(a[2 * j], a[2 * j + 1]);
@@ -81,6 +91,7 @@ LU_HDI void lu_store16_split(uint16_t* dst, int lo_off, bool want_lo, const floa
   }
 #else
   for (int j = 0; j < 16; ++j) {
+    if (fmt) { dst[j] = lu_f2half(a[j]); continue; }
     uint16_t hi, lo; lu_split(a[j], hi, lo);
     dst[j] = hi;
     if (want_lo) dst[lo_off + j] = lo;
@@ -102,7 +113,7 @@ LU_HDI void lu_epi_conv_chunk(const LuEpi& e, int64_t pix, int n, float* v, cons
       const float a = v[j] * scale[j] + shift[j];
       v[j] = a > 0.f ? a : e.alpha * a;
     }
-    lu_store16_split(e.out_act + pix * (int64_t)(e.out_cpad * e.out_planes) + n, e.out_cpad, e.out_planes == 2, v);
+    lu_store16_split(e.out_act + pix * (int64_t)(e.out_cpad * e.out_planes) + n, e.out_cpad, e.out_planes == 2, v, e.fmt);
   }
 }
 
@@ -141,8 +152,8 @@ LU_HDI void lu_epi_lstm_chunk(const LuEpi& e, int64_t pix_state, int64_t pix_out
   lu_store16_f32(cp, c);
   const int64_t ctot = (int64_t)e.f_pad * e.out_planes;
   const bool lo = e.out_planes == 2;
-  lu_store16_split(e.out_act + pix_out * ctot + ch0, e.f_pad, lo, hh);
-  if (e.h_state_out != nullptr) lu_store16_split(e.h_state_out + pix_state * ctot + ch0, e.f_pad, lo, hh);
+  lu_store16_split(e.out_act + pix_out * ctot + ch0, e.f_pad, lo, hh, e.fmt);
+  if (e.h_state_out != nullptr) lu_store16_split(e.h_state_out + pix_state * ctot + ch0, e.f_pad, lo, hh, e.fmt);
   if (e.save_c != nullptr) lu_store16_f32(e.save_c + pix_out * e.f_pad + ch0, c);
   if (e.save_gates != nullptr) {
     uint16_t* g = e.save_gates + pix_out * (int64_t)(4 * e.f_pad * e.out_planes) + ch0;
@@ -173,9 +184,9 @@ LU_HDI void lu_mirror_acc16(const LuConvParams& p, int frame, int y0, int x0, in
       int cmax = v.dimC - st.c;
       if (cmax > LU_KBLK) cmax = LU_KBLK;
       for (int kk = 0; kk < cmax; ++kk) {
-        const float av = lu_bf2f(a[kk]);
+        const float av = lu_h162f(a[kk], p.epi.fmt);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) acc[j] += av * lu_bf2f(w[(int64_t)j * p.ktot + kk]);
+        for (int j = 0; j < 16; ++j) acc[j] += av * lu_h162f(w[(int64_t)j * p.ktot + kk], p.epi.fmt);
       }
     }
   }

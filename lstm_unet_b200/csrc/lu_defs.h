@@ -17,6 +17,7 @@
 #else
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #define LU_HD __host__ __device__
 #define LU_HDI __host__ __device__ __forceinline__
 #endif
@@ -58,6 +59,48 @@ LU_HDI void lu_split(float v, uint16_t& hi, uint16_t& lo) {
   lo = lu_f2bf(v - lu_bf2f(hi));
 }
 
+// ---- fp16 <-> fp32 (round to nearest even, subnormals kept), portable; and the handle's 16-bit operand format ------
+// fmt 0 = bf16 (8-bit mantissa, fp32 range; the training / throughput format), fmt 1 = fp16 (11-bit mantissa, inference:
+// same tensor-core rate, 8x smaller operand rounding error -- the 1e-3 mode at full speed)
+LU_HDI uint16_t lu_f2half(float f) {
+#ifdef __CUDA_ARCH__
+  return __half_as_ushort(__float2half_rn(f));
+#else
+  uint32_t x = lu_f2u(f);
+  const uint32_t sign = (x >> 16) & 0x8000u;
+  x &= 0x7fffffffu;
+  if (x > 0x7f800000u) return (uint16_t)(sign | 0x7e00u);                    // NaN
+  if (x >= 0x47800000u) return (uint16_t)(sign | 0x7c00u);                   // >= 65536 (and inf)
+  const int e = (int)(x >> 23) - 127 + 15;
+  uint32_t mant = x & 0x7fffffu, half;
+  if (e >= 1) {
+    half = ((uint32_t)e << 10) | (mant >> 13);
+    const uint32_t rem = mant & 0x1fffu;
+    if (rem > 0x1000u || (rem == 0x1000u && (half & 1u))) ++half;            // a carry into the exponent is correct (up to inf)
+  } else {
+    if (e < -10) return (uint16_t)sign;                                      // below half the smallest subnormal
+    mant |= 0x800000u;
+    const int shift = 14 - e;
+    half = mant >> shift;
+    const uint32_t rem = mant & ((1u << shift) - 1u), halfway = 1u << (shift - 1);
+    if (rem > halfway || (rem == halfway && (half & 1u))) ++half;
+  }
+  return (uint16_t)(sign | half);
+#endif
+}
+LU_HDI float lu_half2f(uint16_t h) {
+#ifdef __CUDA_ARCH__
+  return __half2float(__ushort_as_half(h));
+#else
+  const uint32_t sign = ((uint32_t)h & 0x8000u) << 16, e = (h >> 10) & 0x1fu, mant = h & 0x3ffu;
+  if (e == 0) { const float v = (float)mant * 5.9604644775390625e-8f; return sign ? -v : v; }   // mant * 2^-24
+  if (e == 31) return lu_u2f(sign | 0x7f800000u | (mant << 13));
+  return lu_u2f(sign | ((e + 112u) << 23) | (mant << 13));
+#endif
+}
+LU_HDI uint16_t lu_f2h16(float f, int fmt) { return fmt ? lu_f2half(f) : lu_f2bf(f); }
+LU_HDI float lu_h162f(uint16_t h, int fmt) { return fmt ? lu_half2f(h) : lu_bf2f(h); }
+
 // ---- activation-tile staging tables ----------------------------------------------------------------------
 // One "A stage" = one TMA box of activations (a [rows x pitch] pixel window x 64 channels) that is reused by
 // `ntaps` consecutive K blocks; tap i of the stage reads the 128 output pixels' operand rows starting at row
@@ -92,6 +135,7 @@ struct LuEpi {
   // classes of a stride-2 convolution's data gradient)
   int32_t oy_mul, oy_add, ox_mul, ox_add, OH, OW;
   int32_t accumulate;         // LU_EPI_GRAD: add to the existing contents of out_act
+  int32_t fmt;                // 16-bit format of the activation buffers (0 bf16, 1 fp16)
   const float* bias;          // [Npad], packed column order
   int32_t out_frame_mul, out_frame_add;
   // conv

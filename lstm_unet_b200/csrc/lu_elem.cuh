@@ -48,6 +48,20 @@ LU_HDI void lu_load8_bf16(const uint16_t* src, float* v) {
   for (int j = 0; j < 8; ++j) v[j] = lu_bf2f(src[j]);
 #endif
 }
+LU_HDI void lu_load8_h16(const uint16_t* src, float* v, int fmt) {
+  if (!fmt) { lu_load8_bf16(src, v); return; }
+#ifdef __CUDA_ARCH__
+  const uint4 q = *reinterpret_cast<const uint4*>(src);
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
+    v[2 * j] = f.x; v[2 * j + 1] = f.y;
+  }
+#else
+  for (int j = 0; j < 8; ++j) v[j] = lu_half2f(src[j]);
+#endif
+}
 LU_HDI void lu_store8_bf16(uint16_t* dst, const uint16_t* h) {
 #ifdef __CUDA_ARCH__
   uint4 a;
@@ -71,7 +85,7 @@ LU_HDI int lu_reflect(int i, int n) {     // tf.pad REFLECT index (no edge repea
 // channels [32, 32+pw*pw) hold the lo parts.
 struct LuPrepPatches {
   const float* x; uint16_t* out;
-  int H, W, Hp, Wp, pad_y0, pad_x0, pw, x3;
+  int H, W, Hp, Wp, pad_y0, pad_x0, pw, x3, fmt;
   LU_HD void operator()(int64_t p) const {        // item = one pixel of the padded frame: 64 channels = 128 bytes
     const int xx = (int)(p % Wp); int64_t q = p / Wp;
     const int yy = (int)(q % Hp); const int64_t n = q / Hp;
@@ -90,7 +104,7 @@ struct LuPrepPatches {
         const float v = row[lu_reflect(px - pad_x0, W)];
         const int t = dy * pw + dx;
         if (x3) { uint16_t h, l; lu_split(v, h, l); r[t] = h; r[32 + t] = l; }
-        else r[t] = lu_f2bf(v);
+        else r[t] = lu_f2h16(v, fmt);
       }
     }
     uint16_t* o = out + p * 64;
@@ -103,10 +117,10 @@ struct LuPrepPatches {
 // in (N,h,w,planes*cpad) -> out (N,2h,2w,planes*cpad); value = hi + lo, re-split on store.
 struct LuUpsample2x {
   const uint16_t* in; uint16_t* out;
-  int h, w, cpad, planes;
+  int h, w, cpad, planes, fmt;
   LU_HD void load(const uint16_t* b, int y, int x, float* v) const {
     const int ct = cpad * planes;
-    lu_load8_bf16(b + ((int64_t)y * w + x) * ct, v);
+    lu_load8_h16(b + ((int64_t)y * w + x) * ct, v, fmt);
     if (planes == 2) {
       float t[8];
       lu_load8_bf16(b + ((int64_t)y * w + x) * ct + cpad, t);
@@ -139,7 +153,7 @@ struct LuUpsample2x {
         for (int j = 0; j < 8; ++j) {
           const float top = 0.75f * v[1][1][j] + 0.25f * v[1][fx][j], bot = 0.75f * v[fy][1][j] + 0.25f * v[fy][fx][j];
           if (planes == 2) lu_split(0.75f * top + 0.25f * bot, hi[j], lo[j]);
-          else hi[j] = lu_f2bf(0.75f * top + 0.25f * bot);
+          else hi[j] = lu_f2h16(0.75f * top + 0.25f * bot, fmt);
         }
         uint16_t* o = out + (((n * 2 * h + 2 * iy + qy) * 2 * w) + 2 * ix + qx) * (int64_t)ct + c;
         lu_store8_bf16(o, hi);
@@ -227,7 +241,7 @@ struct LuBnFinalizeSync {
 // pass 3: y = lrelu(raw*scale + shift) -> bf16 planes; item = (pixel, channel)
 struct LuBnApply {
   const float* raw; const float* scale; const float* shift; uint16_t* out;
-  int raw_cpad, out_cpad, planes; float alpha;
+  int raw_cpad, out_cpad, planes, fmt; float alpha;
   LU_HD void operator()(int64_t i) const {        // item = (pixel, group of 8 channels)
     const int cg = out_cpad / 8;
     const int c = (int)(i % cg) * 8; const int64_t p = i / cg;
@@ -237,7 +251,7 @@ struct LuBnApply {
       float a = 0.f;
       if (c + j < raw_cpad) { a = raw[p * raw_cpad + c + j] * scale[c + j] + shift[c + j]; a = a > 0.f ? a : alpha * a; }
       if (planes == 2) lu_split(a, hi[j], lo[j]);
-      else hi[j] = lu_f2bf(a);
+      else hi[j] = lu_f2h16(a, fmt);
     }
     uint16_t* o = out + p * (int64_t)(out_cpad * planes) + c;
     lu_store8_bf16(o, hi);
@@ -298,7 +312,7 @@ struct LuSoftmaxCrop {
 
 // ---- weight packing: Keras HWIO fp32 -> K-major bf16 [Npad][ktot] in table order ----------------------------------
 struct LuPackWeights {
-  const float* params; const LuPackDesc* descs; uint16_t* out; LuColMap cm; int ktot;
+  const float* params; const LuPackDesc* descs; uint16_t* out; LuColMap cm; int ktot, fmt;
   LU_HD void operator()(int64_t i) const {
     const int k = (int)(i % ktot); const int n = (int)(i / ktot);
     const int kb = k / LU_KBLK, kk = k % LU_KBLK;
@@ -322,7 +336,10 @@ struct LuPackWeights {
           }
         }
       }
-      if (ok) { uint16_t hi, lo; lu_split(w, hi, lo); r = d.wpart ? lo : hi; }
+      if (ok) {
+        if (fmt) r = lu_f2half(w);
+        else { uint16_t hi, lo; lu_split(w, hi, lo); r = d.wpart ? lo : hi; }
+      }
     }
     out[i] = r;
   }
@@ -334,8 +351,8 @@ struct LuPackVec {       // per-column vectors (bias, gamma...) into packed colu
 
 // ---- recurrent state maintenance (Networks.py:77-98) ---------------------------------------------------------------
 struct LuStateMask {     // h *= mask[b] (bf16 planes; mask is 0/1 in the reference's use, so hi/lo scale exactly)
-  uint16_t* h; float* c; const float* mask; int64_t per_sample_h, per_sample_c;
-  LU_HD void operator()(int64_t i) const { h[i] = lu_f2bf(lu_bf2f(h[i]) * mask[i / per_sample_h]); }
+  uint16_t* h; float* c; const float* mask; int64_t per_sample_h, per_sample_c; int fmt;
+  LU_HD void operator()(int64_t i) const { h[i] = lu_f2h16(lu_h162f(h[i], fmt) * mask[i / per_sample_h], fmt); }
 };
 struct LuStateMaskC {
   float* c; const float* mask; int64_t per_sample;
@@ -343,7 +360,7 @@ struct LuStateMaskC {
 };
 // internal (B,H,W,planes*fpad) bf16 / (B,H,W,fpad) fp32  <->  API (B,F,H,W) or (B,H,W,F) fp32
 struct LuStateGet {
-  const uint16_t* h; const float* c; float* out; int which, H, W, F, fpad, planes, channels_first;
+  const uint16_t* h; const float* c; float* out; int which, H, W, F, fpad, planes, channels_first, fmt;
   LU_HD void operator()(int64_t i) const {
     int f, y, x; int64_t b;
     if (channels_first) { x = (int)(i % W); int64_t p = i / W; y = (int)(p % H); p /= H; f = (int)(p % F); b = p / F; }
@@ -351,14 +368,14 @@ struct LuStateGet {
     const int64_t pix = (b * H + y) * W + x;
     if (which == 1) out[i] = c[pix * fpad + f];
     else {
-      float v = lu_bf2f(h[pix * (int64_t)(fpad * planes) + f]);
+      float v = lu_h162f(h[pix * (int64_t)(fpad * planes) + f], fmt);
       if (planes == 2) v += lu_bf2f(h[pix * (int64_t)(fpad * planes) + fpad + f]);
       out[i] = v;
     }
   }
 };
 struct LuStateSet {
-  uint16_t* h; float* c; const float* in; int which, H, W, F, fpad, planes, channels_first;
+  uint16_t* h; float* c; const float* in; int which, H, W, F, fpad, planes, channels_first, fmt;
   LU_HD void operator()(int64_t i) const {
     int f, y, x; int64_t b;
     if (channels_first) { x = (int)(i % W); int64_t p = i / W; y = (int)(p % H); p /= H; f = (int)(p % F); b = p / F; }
@@ -368,6 +385,7 @@ struct LuStateSet {
     if (which == 1) c[pix * fpad + f] = v;
     else {
       uint16_t hi, lo; lu_split(v, hi, lo);
+      if (fmt) hi = lu_f2half(v);
       h[pix * (int64_t)(fpad * planes) + f] = hi;
       if (planes == 2) h[pix * (int64_t)(fpad * planes) + fpad + f] = lo;
     }
@@ -375,10 +393,10 @@ struct LuStateSet {
 };
 
 struct LuDebugRead {     // bf16 planes NHWC (padded channels) -> fp32 NHWC (real channels)
-  const uint16_t* src; float* out; int creal, cpad, planes;
+  const uint16_t* src; float* out; int creal, cpad, planes, fmt;
   LU_HD void operator()(int64_t i) const {
     const int c = (int)(i % creal); const int64_t p = i / creal;
-    float v = lu_bf2f(src[p * (int64_t)(cpad * planes) + c]);
+    float v = lu_h162f(src[p * (int64_t)(cpad * planes) + c], fmt);
     if (planes == 2) v += lu_bf2f(src[p * (int64_t)(cpad * planes) + cpad + c]);
     out[i] = v;
   }

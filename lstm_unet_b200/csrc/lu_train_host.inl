@@ -512,7 +512,7 @@ static int run_wgrad(lu_handle_s* h, ConvPlan& f, int gbuf, int T, float* grads,
       wp.n_stages = budget / wp.stage_bytes;
       if (wp.n_stages > 4) wp.n_stages = 4;
       LU_REQUIRE(wp.n_stages >= 1, "weight-gradient stage does not fit shared memory");
-      static bool attr = false;
+      bool& attr = h->wg_attr_set;
       if (!attr) {
         e = cudaFuncSetAttribute(lu_wgrad_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
         LU_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
@@ -523,6 +523,7 @@ static int run_wgrad(lu_handle_s* h, ConvPlan& f, int gbuf, int T, float* grads,
         attr = true;
       }
       h->launches++;
+      time_begin(h, LU_KC_WGRAD, stream);
       const size_t wg_smem = (size_t)wp.n_stages * wp.stage_bytes + 1024 + 256;
       if (wg_pair) {
         LU_REQUIRE((n_tasks & 1) == 0, "paired weight-gradient task list has odd length %d", n_tasks);
@@ -539,6 +540,7 @@ static int run_wgrad(lu_handle_s* h, ConvPlan& f, int gbuf, int T, float* grads,
       } else {
         lu_wgrad_tc_kernel<1><<<(unsigned)n_tasks, 256, wg_smem, (cudaStream_t)stream>>>(wp);
       }
+      time_end(h, stream);
       e = cudaGetLastError();
       LU_REQUIRE(e == cudaSuccess, "wgrad launch (%s) failed: %s", f.name.c_str(), cudaGetErrorString(e));
       continue;

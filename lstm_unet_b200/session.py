@@ -121,6 +121,9 @@ class LuSession:
     def reset_states(self, mask_ptr):
         self._check(self.lib.lu_reset_states(self.h, mask_ptr, self.be.stream()))
 
+    def reset_level_states(self, level, mask_ptr):
+        self._check(self.lib.lu_reset_level_states(self.h, int(level), mask_ptr, self.be.stream()))
+
     def state_shape(self, level, layer):
         s = (ctypes.c_int64 * 4)()
         self._check(self.lib.lu_state_shape(self.h, level, layer, s))
@@ -187,6 +190,21 @@ class LuSession:
         ms, n = ctypes.c_float(), ctypes.c_int32()
         self._check(self.lib.lu_lstm_kernel_time(self.h, 1 if enable else 0, ctypes.byref(ms), ctypes.byref(n)))
         return ms.value, n.value
+
+    def kernel_times(self, enable):
+        """-> {class: (milliseconds, launches)} of the tensor-core kernel classes (_lib.KERNEL_CLASSES) accumulated
+        since the last call; then switches the event recording."""
+        n = len(_lib.KERNEL_CLASSES)
+        ms, cnt = (ctypes.c_float * n)(), (ctypes.c_int32 * n)()
+        self._check(self.lib.lu_kernel_times(self.h, 1 if enable else 0, ms, cnt))
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(_lib.KERNEL_CLASSES)}
+
+    def class_flops(self, T):
+        """-> {class: algorithmic FLOPs of one training step over T frames per sample at the bound batch}."""
+        n = len(_lib.KERNEL_CLASSES)
+        f = (ctypes.c_double * n)()
+        self._check(self.lib.lu_class_flops(self.h, int(T), f))
+        return {k: float(f[i]) for i, k in enumerate(_lib.KERNEL_CLASSES)}
 
     def debug_buffer(self, name, kind=0):
         """Test hook: an internal NHWC buffer of layer `name` as a host fp32 array (frames, H, W, C)."""

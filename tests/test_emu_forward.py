@@ -192,3 +192,53 @@ def test_channels_last_training_step():
     g = grads[e['offset']:e['offset'] + e['count']].reshape(e['shape'])
     assert rel_err(g, ref_grads[e['name']].numpy()) < 5e-3
     sess.close()
+
+
+def test_forward_fp16_mode_is_8x_closer_than_bf16_and_inference_only():
+    """precision='fp16' (LU_PREC_FP16): fp16 operands through the same tables / epilogues.  Against the fp32 oracle the
+    error must sit well below the bf16 mode's (11 vs 8 mantissa bits) and below the north_star's 1e-3 on this small
+    network; creating a training handle in this mode is rejected."""
+    from lstm_unet_b200.session import LuError
+    net, B, T, H, W = NET_A, 2, 2, 19, 21
+    p_t, p_np = oracle_params_np(net, 7)
+    x = np.random.default_rng(2).standard_normal((B, T, 1, H, W)).astype(np.float32)
+    errs = {}
+    for prec in ('fp16', 'bf16'):
+        ora = O.OracleNet(net, 'NCHW', True, params={k: v.clone() for k, v in p_t.items()})
+        sess = emu_session(net, data_format='NCHW', pad_image=True, batch=B, max_t=T, height=H, width=W, precision=prec)
+        sess.set_params(p_np)
+        e = 0.0
+        for call in range(2):
+            ref_l, ref_s = ora(torch.from_numpy(x), False)
+            got_l, got_s = emu_forward(sess, x, False)
+            e = max(e, rel_err(got_l, ref_l.numpy()), rel_err(got_s, ref_s.numpy()))
+        errs[prec] = e
+        sess.close()
+    assert errs['fp16'] < 1e-3, errs
+    assert errs['fp16'] < errs['bf16'] / 3, errs
+    with pytest.raises(LuError):
+        emu_session(net, data_format='NCHW', pad_image=False, batch=1, max_t=1, height=16, width=16, precision='fp16', train=True)
+
+
+def test_fp16_conversions_match_numpy_float16():
+    """The portable fp32 <-> fp16 conversions of the host build (lu_f2half / lu_half2f: round to nearest even,
+    subnormals, overflow) against numpy's float16, through set_state / get_state of an fp16 handle (h is stored in
+    the operand format)."""
+    net = {'down_conv_kernels': [[(3, 4)]], 'lstm_kernels': [[(3, 64)]], 'up_conv_kernels': [[(3, 4), (1, 3)]]}
+    B, H, W, F = 1, 16, 16, 64
+    sess = emu_session(net, data_format='NCHW', pad_image=False, batch=B, max_t=1, height=H, width=W, precision='fp16')
+    rng = np.random.default_rng(0)
+    v = rng.standard_normal(B * F * H * W).astype(np.float32)
+    v[:4000] *= 10.0 ** rng.uniform(-9, 5, 4000).astype(np.float32)           # subnormals ... overflow
+    special = np.array([0.0, -0.0, 65504.0, 65519.9, 65520.0, 1e6, -1e6, 5.9604645e-8, 2.9802322e-8, 2.98023224e-8 * 1.0001,
+                        6.1035156e-5, 6.0975552e-5, 1.0 + 2.0 ** -11, 1.0 + 2.0 ** -11 + 2.0 ** -20, 1.0 + 3 * 2.0 ** -11,
+                        2047.5, 2048.5, 0.33325195], dtype=np.float32)
+    v[4000:4000 + special.size] = special
+    x = v.reshape(B, F, H, W)
+    sess.set_state(0, 0, 0, x.ctypes.data)
+    out = np.zeros_like(x)
+    sess.get_state(0, 0, 0, out.ctypes.data)
+    with np.errstate(over='ignore'):
+        want = x.astype(np.float16).astype(np.float32)
+    np.testing.assert_array_equal(out, want)
+    sess.close()

@@ -1,0 +1,166 @@
+"""Parity of the sm_100a path on the BENCHMARKED network: CTCParams.net_kernel_params (/root/reference/Params.py:49-69;
+74.6 M parameters, ConvLSTM filters 128/256/256/512, K up to 19 200, 8 N tiles at level 3, the 65-channel decoder conv)
+through the public Networks.ULSTMnet2D API against the CPU oracle on the same seeded inputs.
+
+  * C1 shape of BASELINE.json (B=2, T=4, 128x128), both pad_image modes, two stateful calls: logits, soft-max and the
+    final h / c of every ConvLSTM level.
+  * one 512x512 sequence with pad_image: the network then sees 528x528, i.e. the 66 / 132 / 264-pixel levels whose
+    last tile row / column is partial with the 16x8 pixel tiles (the C2 bench shape's geometry).
+  * a full train step (loss + every gradient tensor) at B=1, T=2, 64x64.
+
+Tolerances (max-abs error over max-abs reference, per tensor):
+  bf16x3  1e-3  the north_star's tolerance (fp32-equivalent split-bf16 operands; measured ~1e-5)
+  fp16    1e-3  fp16 operands, fp32 accumulation: same tensor-core rate as bf16, 11-bit mantissa (inference only)
+  bf16    2e-2  the throughput mode; 8-bit mantissa operands through 4 stacked recurrent levels.  The bound is what operand
+                rounding alone produces (torch-CPU simulation of bf16-rounded conv operands on this network:
+                5.9e-3 on the logits, 1.4e-3 on the soft-max) with 3x head-room; the measured value is printed.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import lstm_unet_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+CTC = O.CTC_NET_PARAMS
+CW = [0.15, 0.25, 0.6]
+TOL = {'bf16x3': 1e-3, 'fp16': 1e-3, 'bf16': 2e-2}
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def precisions():
+    from lstm_unet_b200 import _lib
+    return [p for p in ('bf16x3', 'fp16', 'bf16') if p in _lib.PRECISIONS]
+
+
+@pytest.fixture(scope='module')
+def ctc_weights():
+    params = O.init_params(CTC, seed=0, randomize_bn=True)
+    return params, {k: v.numpy().copy() for k, v in params.items()}
+
+
+def run_oracle(params, pad, xs):
+    ora = O.OracleNet(CTC, 'NCHW', pad, params={k: v.clone() for k, v in params.items()})
+    outs = []
+    with torch.no_grad():
+        for x in xs:
+            l, s = ora(torch.from_numpy(x), False)
+            outs.append((l.numpy(), s.numpy()))
+    return outs, ora.get_states()
+
+
+def run_model(weights, pad, xs, precision):
+    from lstm_unet_b200.Networks import ULSTMnet2D
+    model = ULSTMnet2D(CTC, 'NCHW', pad, precision=precision)
+    model.set_weights_dict(weights)
+    outs = []
+    for x in xs:
+        l, s = model(x, training=False)
+        outs.append((l.numpy().copy(), s.numpy().copy()))
+    states = model.get_states()
+    model.close()
+    return outs, states
+
+
+def compare(tag, precision, ref, ref_states, got, got_states):
+    tol = TOL[precision]
+    worst = 0.0
+    for call, ((rl, rs), (gl, gs)) in enumerate(zip(ref, got)):
+        assert gl.shape == rl.shape and gs.shape == rs.shape
+        el, es = rel_err(gl, rl), rel_err(gs, rs)
+        worst = max(worst, el, es)
+        print('%s [%s] call %d: logits %.3e soft-max %.3e (tol %.0e)' % (tag, precision, call, el, es, tol))
+        assert el < tol and es < tol, (tag, precision, call, el, es)
+    for lvl, (rl_, gl_) in enumerate(zip(ref_states, got_states)):
+        for lay, (rp, gp) in enumerate(zip(rl_, gl_)):
+            for which, nm in ((0, 'h'), (1, 'c')):
+                assert gp[which].shape == rp[which].shape
+                e = rel_err(gp[which], rp[which])
+                print('%s [%s] level %d %s: %.3e' % (tag, precision, lvl, nm, e))
+                assert e < tol, (tag, precision, lvl, nm, e)
+    return worst
+
+
+@pytest.mark.parametrize("pad", [True, False])
+def test_ctc_network_c1_shape_forward_parity(ctc_weights, pad):
+    """BASELINE.json configs[0] shape (B=2, T=4, 128x128) on the CTC network, two stateful calls."""
+    params, weights = ctc_weights
+    rng = np.random.default_rng(100 + int(pad))
+    xs = [rng.standard_normal((2, 4, 1, 128, 128)).astype(np.float32) for _ in range(2)]
+    ref, ref_states = run_oracle(params, pad, xs)
+    for precision in precisions():
+        got, got_states = run_model(weights, pad, xs, precision)
+        compare('C1 pad_image=%s' % pad, precision, ref, ref_states, got, got_states)
+
+
+def test_ctc_network_528_internal_size_partial_tiles(ctc_weights):
+    """One 512x512 sequence (B=1, T=2) with pad_image: internal size 528 -> level sizes 528 / 264 / 132 / 66, the partial
+    16x8 tiles of the C2 bench shape."""
+    params, weights = ctc_weights
+    rng = np.random.default_rng(7)
+    xs = [rng.standard_normal((1, 2, 1, 512, 512)).astype(np.float32)]
+    ref, ref_states = run_oracle(params, True, xs)
+    for precision in precisions():
+        got, got_states = run_model(weights, True, xs, precision)
+        compare('512x512 pad_image', precision, ref, ref_states, got, got_states)
+
+
+def test_ctc_network_train_step_parity(ctc_weights):
+    """train2D.py:87-93 on the CTC network (B=1, T=2, 64x64, pad_image=False as in training): loss and every gradient
+    tensor vs autograd through the oracle, two steps (the second from non-zero recurrent states, after one Adam update).
+    At this size pre-activations within rounding distance of a LeakyReLU / hard_sigmoid kink are certain to exist
+    (~1e7 pre-activations); each flips one element's sub-gradient, which is invisible at the per-tensor max-norm
+    tolerance, so every step is compared (the small-network tests skip such steps instead)."""
+    from lstm_unet_b200.Networks import ULSTMnet2D, Adam
+    params, weights = ctc_weights
+    params = {k: v.clone() for k, v in params.items()}
+    ora = O.OracleNet(CTC, 'NCHW', False, params=params)
+    model = ULSTMnet2D(CTC, 'NCHW', False, precision='bf16x3', train=True)
+    model.set_weights_dict(weights)
+    opt = Adam(lr=1e-5)
+    names = ora.trainable_names()
+    m = {n: torch.zeros_like(ora.params[n]) for n in names}
+    v = {n: torch.zeros_like(ora.params[n]) for n in names}
+    rng = np.random.default_rng(5)
+    B, T, H, W = 1, 2, 64, 64
+    worst = ('', 0.0)
+    for step in (1, 2):
+        x = rng.standard_normal((B, T, 1, H, W)).astype(np.float32)
+        lab = rng.integers(-1, 3, size=(B, T, 1, H, W)).astype(np.float32)
+        ref_loss, ref_logits, _, ref_grads = O.train_step(ora, torch.from_numpy(x), torch.from_numpy(lab), CW, m, v, step, 1e-5)
+        logits, _ = model(x, True)
+        assert rel_err(logits.numpy(), ref_logits.numpy()) < 1e-3
+        loss, grads = model.backward(lab, CW)
+        g = grads.cpu().numpy()
+        assert abs(float(loss) - float(ref_loss)) < 1e-4 * max(1.0, abs(float(ref_loss)))
+        n_checked = 0
+        for e in model._sess.layout:
+            if not e['trainable']:
+                continue
+            r = ref_grads[e['name']].numpy()
+            mine = g[e['offset']:e['offset'] + e['count']].reshape(e['shape'])
+            if np.abs(r).max() < 1e-7:              # conv bias in front of a training-mode BatchNorm: analytically zero
+                assert np.abs(mine).max() < 1e-5, e['name']
+                continue
+            err = rel_err(mine, r)
+            if err > worst[1]:
+                worst = (e['name'], err)
+            assert err < 5e-3, (step, e['name'], err)
+            n_checked += 1
+        assert n_checked >= 60                       # 78 trainable tensors, 16 of them BN-shadowed conv biases
+        model.apply_gradients(grads, opt)
+    print('CTC train step: worst gradient tensor %s %.3e' % worst)
+    # the Adam update itself: parameters after two steps.  Adam normalises every element's update to ~lr, so an element
+    # whose tiny gradient changes sign between two correct implementations moves by up to 2 * lr per step: the bound on
+    # single elements is a few lr, the bound on the mean is far below lr
+    got = model.get_weights_dict()
+    for n in names:
+        r = ora.params[n].detach().numpy()
+        d = np.abs(got[n] - r)
+        assert d.max() <= 4.5e-5 and d.mean() <= 2e-6, (n, d.max(), d.mean())
+    model.close()
