@@ -114,13 +114,32 @@ class ClockSampler:
                 'reasons': sorted(reasons), 'samples': len(sm)}
 
 
-def cpu_reference_run(steps, warmup, B=1, T=4, H=256, W=256):
-    """CPU restatement of the reference forward (Inference2D call: pad_image=True, training=False) on a bounded
-    sample of the workload (smaller frames / batch, same network, same T-unrolled stateful call)."""
+def workload_config(args, world, training=False):
+    """`config` of the JSON line: names the workload only, identical for `--impl ours` and `--impl reference`."""
+    B, T, S = args.batch, args.unroll, args.size
+    if args.mode == 'train' or training:
+        wl = ('C3/C4: ConvLSTM-UNet (CTCParams net, 74.6M params) full train step (fwd + WeightedCELoss + bwd + gradient '
+              'all-reduce + Adam), %dx%d, T=%d, batch %d per GPU, pad_image=False, stateful' % (S, S, T, B))
+    else:
+        wl = ('C2: ConvLSTM-UNet (CTCParams net, 74.6M params) inference forward, %dx%d, T=%d, batch %d per GPU, '
+              'pad_image=True, stateful' % (S, S, T, B))
+    return {'workload': wl, 'global_batch': B * world,
+            'l2_policy': 'inputs+activations per step (>6 GB) exceed the 126 MB L2; no flush needed'}
+
+
+def _oracle():
     import torch
     from oracle import lstm_unet_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    return torch, O, cores
+
+
+def cpu_infer_run(steps, warmup, B=1, T=2, H=512, W=512):
+    """CPU restatement of the reference forward (Inference2D call: pad_image=True, training=False, stateful) on a
+    bounded sample of the C2 workload: the same network and the same 512x512 frames (528x528 after pad_image), fewer
+    of them per step (B=1, T=2 instead of B=4, T=8).  frames/s needs no rescaling."""
+    torch, O, cores = _oracle()
     net = O.OracleNet(O.CTC_NET_PARAMS, 'NCHW', True, seed=0)
     x = torch.randn(B, T, 1, H, W)
     with torch.no_grad():
@@ -130,29 +149,145 @@ def cpu_reference_run(steps, warmup, B=1, T=4, H=256, W=256):
         for _ in range(steps):
             net(x, False)
         dt = time.perf_counter() - t0
-    fps = B * T * steps / dt
-    # frames differ in size from the workload's: scale by pixels so the number is frames/s of 512x512 frames
-    scale = (H * W) / (512.0 * 512.0)
-    return {'value': fps * scale, 'unit': 'frames/s', 'cores': cores, 'kind': 'port',
-            'sample': 'oracle (torch-CPU restatement; TF not installable) forward, CTC net, B=%d T=%d %dx%d pad_image, '
-                      '%d steps; %.3f frames/s at %dx%d scaled by pixel count to 512x512' % (B, T, H, W, steps, fps, H, W),
+    return {'value': B * T * steps / dt, 'unit': 'frames/s', 'cores': cores, 'kind': 'port',
+            'sample': 'oracle (torch-CPU fp32 restatement of the reference; TensorFlow is not installable) inference forward, '
+                      'CTC net, %dx%d frames, pad_image, stateful, B=%d T=%d per step (C2 has B=4 T=8), %d steps after %d '
+                      'warm-up; no rescaling' % (H, W, B, T, steps, warmup),
             'ms_per_step': dt / steps * 1e3}
 
 
+def cpu_full_c2_step(B=4, T=8, H=512, W=512):
+    """ONE inference step at the true C2 shape on the host cores (about a minute): shows the bounded sample's frames/s
+    is the full shape's."""
+    torch, O, cores = _oracle()
+    net = O.OracleNet(O.CTC_NET_PARAMS, 'NCHW', True, seed=0)
+    x = torch.randn(B, T, 1, H, W)
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        net(x, False)
+        dt = time.perf_counter() - t0
+    return {'value': B * T / dt, 'unit': 'frames/s', 'ms_per_step': dt * 1e3, 'cores': cores,
+            'shape': 'B=%d T=%d %dx%d pad_image (true C2 shape), 1 step, no warm-up' % (B, T, H, W)}
+
+
+def cpu_train_run(steps=1, warmup=1, B=2, T=4, H=128, W=128):
+    """BASELINE.json configs[0] on the host cores: train2D.py's train step (forward(training=True) + WeightedCELoss +
+    backward + Keras Adam, train2D.py:87-93) at 128x128, T=4, batch 2, through the oracle."""
+    torch, O, cores = _oracle()
+    net = O.OracleNet(O.CTC_NET_PARAMS, 'NCHW', False, seed=0)
+    names = net.trainable_names()
+    m = {n: torch.zeros_like(net.params[n]) for n in names}
+    v = {n: torch.zeros_like(net.params[n]) for n in names}
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(B, T, 1, H, W, generator=g)
+    lab = torch.randint(-1, 3, (B, T, 1, H, W), generator=g).to(torch.float32)
+    for i in range(warmup):
+        O.train_step(net, x, lab, [0.15, 0.25, 0.6], m, v, i + 1, 1e-5)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        O.train_step(net, x, lab, [0.15, 0.25, 0.6], m, v, warmup + i + 1, 1e-5)
+    dt = time.perf_counter() - t0
+    return {'value': B * T * steps / dt, 'unit': 'frames/s', 'ms_per_step': dt / steps * 1e3, 'cores': cores, 'kind': 'port',
+            'sample': 'C1 (BASELINE.json configs[0]): oracle train step fwd+loss+bwd+Adam, CTC net, %dx%d, T=%d, batch %d, '
+                      '%d step(s) after %d warm-up' % (H, W, T, B, steps, warmup)}
+
+
 def run_reference(args):
+    """The reference arm: the CPU restatement of the reference (oracle/; the reference itself needs TensorFlow) with all
+    host threads, exactly --steps timed steps after --warmup untimed ones, each step a bounded sample of the workload
+    (same network, same frame size, fewer frames); plus ONE step at the true C2 shape and the C1 train step."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 5))
-    cb = cpu_reference_run(steps, max(1, min(args.warmup, 1)))
+    training = args.mode == 'train'
+    if training:
+        cb = cpu_train_run(max(1, args.steps), max(0, args.warmup), B=1, T=2, H=args.size, W=args.size)
+        cb['sample'] = ('oracle train step fwd+loss+bwd+Adam, CTC net, %dx%d frames, B=1 T=2 per step (C3 has B=4 T=8), %d steps '
+                        'after %d warm-up' % (args.size, args.size, args.steps, args.warmup))
+    else:
+        cb = cpu_infer_run(max(1, args.steps), max(0, args.warmup), H=args.size, W=args.size)
     line = {'impl': 'reference', 'metric': METRIC, 'value': cb['value'], 'unit': 'frames/s', 'n_gpus': args.gpus,
-            'steps': steps, 'warmup': 1, 'ms_per_step': cb['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak',
-            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': 'C2 inference forward 512x512 T=8 B=4 (bounded sample, see cpu_baseline.sample)'},
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': cb['ms_per_step'], 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': workload_config(args, max(1, args.gpus)),
             'cpu_baseline': {k: cb[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')},
             'e2e': {'value': cb['value'], 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
+    if not training and not args.no_full:
+        line['full_shape'] = cpu_full_c2_step(args.batch, args.unroll, args.size, args.size)
+        tr = cpu_train_run()
+        line['train'] = {k: tr[k] for k in ('value', 'unit', 'ms_per_step', 'cores', 'kind', 'sample')}
     emit(line)
+
+
+CW = [0.15, 0.25, 0.6]          # Params.py:72 class_weights
+
+
+def parity_spot_check(rank):
+    """Pre-timing check of the timed path against the oracle with the SAME weights the timed model uses (Keras default
+    initialisation, seed 0): CTC network, one stateful sequence B=1, T=4 at 128x128 with pad_image, every operand
+    precision; and one train step (loss + all gradients) at B=1, T=2, 64x64.  max-abs error over max-abs reference."""
+    if rank != 0:
+        return None
+    import torch
+    from oracle import lstm_unet_oracle as O
+    from lstm_unet_b200.Networks import ULSTMnet2D, keras_default_init
+    from lstm_unet_b200 import _lib
+    torch.set_num_threads(os.cpu_count() or 1)
+
+    def rel(a, b):
+        return float(np.abs(np.asarray(a, np.float64) - np.asarray(b, np.float64)).max() / max(np.abs(b).max(), 1e-30))
+    out = {'network': 'CTCParams.net_kernel_params, Keras default init seed 0 (the timed models\' weights)',
+           'metric': 'max|ours - oracle| / max|oracle|', 'north_star_tolerance': 1e-3}
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal((1, 4, 1, 128, 128)).astype(np.float32)
+    weights = None
+    ref = None
+    inf = {}
+    for prec in [p for p in ('bf16', 'fp16', 'bf16x3') if p in _lib.PRECISIONS]:
+        m = ULSTMnet2D(CTC_NET, 'NCHW', True, precision=prec, seed=0, cuda_graph=False)
+        lg, sm = m(x, False)
+        if weights is None:
+            weights = m.get_weights_dict()
+            ora = O.OracleNet(O.CTC_NET_PARAMS, 'NCHW', True, params={k: torch.from_numpy(v.copy()) for k, v in weights.items()})
+            with torch.no_grad():
+                ref = [t.numpy() for t in ora(torch.from_numpy(x), False)]
+        inf[prec] = {'logits': rel(lg.numpy(), ref[0]), 'softmax': rel(sm.numpy(), ref[1])}
+        m.close()
+    out['inference'] = {'shape': 'B=1 T=4 128x128 pad_image', **inf}
+    # train step
+    xt = rng.standard_normal((1, 2, 1, 64, 64)).astype(np.float32)
+    lab = rng.integers(-1, 3, size=(1, 2, 1, 64, 64)).astype(np.float32)
+    ora = O.OracleNet(O.CTC_NET_PARAMS, 'NCHW', False, params={k: torch.from_numpy(v.copy()) for k, v in weights.items()})
+    names = ora.trainable_names()
+    mm = {n: torch.zeros_like(ora.params[n]) for n in names}
+    vv = {n: torch.zeros_like(ora.params[n]) for n in names}
+    ref_loss, _, _, ref_grads = O.train_step(ora, torch.from_numpy(xt), torch.from_numpy(lab), CW, mm, vv, 1, 1e-5)
+    tr = {}
+    for prec in ('bf16', 'bf16x3'):
+        m = ULSTMnet2D(CTC_NET, 'NCHW', False, precision=prec, seed=0, train=True)
+        m.set_weights_dict(weights)
+        m(xt, True)
+        loss, grads = m.backward(lab, CW)
+        g = grads.cpu().numpy()
+        worst, worst_name, num, den = 0.0, '', 0.0, 0.0
+        for e in m._sess.layout:
+            if not e['trainable']:
+                continue
+            r = ref_grads[e['name']].numpy().reshape(-1)
+            if np.abs(r).max() < 1e-7:
+                continue
+            mine = g[e['offset']:e['offset'] + e['count']]
+            err = rel(mine, r)
+            num += float(((mine - r) ** 2).sum()); den += float((r ** 2).sum())
+            if err > worst:
+                worst, worst_name = err, e['name']
+        tr[prec] = {'loss': abs(float(loss) - float(ref_loss)) / abs(float(ref_loss)), 'worst_gradient_tensor': worst,
+                    'worst_gradient_name': worst_name, 'all_gradients_l2': (num / den) ** 0.5}
+        m.close()
+    out['train_step'] = {'shape': 'B=1 T=2 64x64', **tr}
+    torch.cuda.empty_cache()
+    return out
 
 
 def run_ours(args):
@@ -173,139 +308,275 @@ def run_ours(args):
     ge.build()
     from lstm_unet_b200.Networks import ULSTMnet2D
 
-    B, T, H, W = args.batch, args.unroll, args.size, args.size
-    training = args.mode == 'train'
-    model = ULSTMnet2D(CTC_NET, 'NCHW', pad_image=not training, precision=args.precision, a_mode=args.a_mode,
-                       seed=0 if training else rank, train=training,
-                       cuda_graph={'auto': 'auto', 'on': True, 'off': False}[args.cuda_graph],
-                       sync_bn=bool(training and args.sync_bn))
-    rng = np.random.default_rng(1234 + rank)
-    x_host = rng.standard_normal((B, T, 1, H, W)).astype(np.float32)
-    x_dev = torch.from_numpy(x_host).cuda()
-    if training:
-        # config 3/4: full train step = forward(training=True) + weighted CE + backward + (N>1: one NCCL all-reduce of
-        # the flat gradients) + Keras Adam; same initial weights on every rank (seed 0), batch-sharded data
-        from lstm_unet_b200.Networks import Adam
-        from lstm_unet_b200.parallel import all_reduce_mean_, OverlappedAllReduce
-        reducer = None
-        if world > 1:
-            reducer = OverlappedAllReduce() if args.allreduce == 'overlapped' else all_reduce_mean_
-        lab_host = rng.integers(-1, 3, size=(B, T, 1, H, W)).astype(np.float32)
-        lab_dev = torch.from_numpy(lab_host).cuda()
-        opt = Adam(lr=1e-5)
-        cw = [0.15, 0.25, 0.6]
-        fwd = model
-
-        class _Step:
-            def __call__(self, x, tr):
-                lab = lab_dev if x.__class__ is not np.ndarray else lab_host
-                sm, lg, loss = fwd.train_step(x, lab, cw, opt, reducer)
-                return loss, sm
-        step_fn = _Step()
-    else:
-        step_fn = None
-    run = (lambda x, tr: step_fn(x, tr)) if training else (lambda x, tr: model(x, tr))
-    # shard by batch: every rank owns its B samples and their recurrent states (weak scaling, no data-path collective)
-    run(x_dev, training)
-    torch.cuda.synchronize()
-    sess = model._sess
-    flops_step = sess.forward_flops(T) * B * (3 if training else 1)     # train step = 3 x forward
-    lstm_flops_step = sess.lstm_flops(T) * B
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        run(x_dev, training)
+    def max_ranks(vals):
+        if world == 1:
+            return [float(v) for v in vals]
+        t = torch.tensor(list(vals), device='cuda', dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t.tolist()]
+
+    B, T, H, W = args.batch, args.unroll, args.size, args.size
+    sustained, burst, which = peaks()
+    rng = np.random.default_rng(1234 + rank)
+    x_host = rng.standard_normal((B, T, 1, H, W)).astype(np.float32)
+    x_dev = torch.from_numpy(x_host).cuda()
+    parity = parity_spot_check(rank) if not args.no_parity else None
     barrier()
-    sess.launch_count(reset=True)
-    sess.lstm_kernel_time(True)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for _ in range(args.steps):
-        run(x_dev, training)          # states carry over between iterations, like the train / inference loops
-    ev1.record()
-    barrier()
-    ms = ev0.elapsed_time(ev1)
-    launches = sess.launch_count()
-    lstm_ms, lstm_n = sess.lstm_kernel_time(False)
+
+    # ------------------------------------------------------------------ C2: inference forward (Inference2D call)
+    def time_infer(precision, with_e2e):
+        model = ULSTMnet2D(CTC_NET, 'NCHW', pad_image=True, precision=precision, a_mode=args.a_mode, seed=0,
+                           cuda_graph={'auto': 'auto', 'on': True, 'off': False}[args.cuda_graph])
+        model(x_dev, False)
+        torch.cuda.synchronize()
+        sess = model._sess
+        for _ in range(args.warmup):
+            model(x_dev, False)
+        barrier()
+        sess.launch_count(reset=True)
+        sess.kernel_times(True)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(args.steps):
+            model(x_dev, False)          # states carry over between iterations, like the inference loop
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        launches = sess.launch_count()
+        kt = sess.kernel_times(False)
+        res = {'ms': ms, 'launches': launches, 'kt': kt, 'flops_step': sess.forward_flops(T) * B,
+               'lstm_flops_step': sess.lstm_flops(T) * B, 'graph': bool(model.graph_active)}
+        if with_e2e:
+            # end to end through the public API with HOST buffers: every step's frames go host -> device from pinned
+            # memory and its soft-max comes back device -> host (Inference2D.py:59-60), both inside the timed region.
+            # (a) the reference's own per-call form: model(x_host) then .numpy()
+            post = None
+            if args.post:
+                from lstm_unet_b200.postprocess import PostProcessor
+                post = PostProcessor()
+
+            def once():
+                o = model(x_host, False)
+                return post(o[1]).numpy() if post is not None else o[1].numpy()
+            for _ in range(3):
+                sm = once()
+            barrier()
+            n_e2e = max(2, min(args.steps, 10))
+            t0 = time.perf_counter()
+            for _ in range(n_e2e):
+                sm = once()
+            barrier()
+            serial_ms = (time.perf_counter() - t0) * 1e3
+            # (b) the pipelined form of the same public API: copies of batch i+1 / i-1 overlap the compute of batch i
+            for _ in model.predict_batches(x_host for _ in range(3)):
+                pass
+            barrier()
+            t0 = time.perf_counter()
+            for sm2 in model.predict_batches(x_host for _ in range(n_e2e)):
+                pass
+            barrier()
+            pipe_ms = (time.perf_counter() - t0) * 1e3
+            res.update({'e2e_serial_ms': serial_ms, 'e2e_pipe_ms': pipe_ms, 'e2e_steps': n_e2e, 'd2h': int(sm.nbytes),
+                        'labelled': post is not None})
+        model.close()
+        del model
+        torch.cuda.empty_cache()
+        return res
+
+    # ------------------------------------------------------------------ C3 / C4: full train step
+    def time_train():
+        from lstm_unet_b200.Networks import Adam
+        from lstm_unet_b200.parallel import all_reduce_mean_, OverlappedAllReduce
+        model = ULSTMnet2D(CTC_NET, 'NCHW', pad_image=False, precision='bf16', a_mode=args.a_mode, seed=0, train=True,
+                           sync_bn=bool(args.sync_bn))
+        lab_host = rng.integers(-1, 3, size=(B, T, 1, H, W)).astype(np.float32)
+        lab_dev = torch.from_numpy(lab_host).cuda()
+        opt = Adam(lr=1e-5)
+        reducers = {'none': None}
+        if world > 1:
+            reducers = {'overlapped': OverlappedAllReduce(), 'single': all_reduce_mean_, 'none': None}
+        main = args.allreduce if world > 1 else 'none'
+
+        def step(red, x=x_dev, lab=lab_dev):
+            return model.train_step(x, lab, CW, opt, reducers[red])
+        step(main)
+        torch.cuda.synchronize()
+        sess = model._sess
+        for _ in range(args.warmup):
+            step(main)
+        barrier()
+        sess.launch_count(reset=True)
+        sess.kernel_times(True)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(args.steps):
+            step(main)
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        launches = sess.launch_count()
+        kt = sess.kernel_times(False)
+        # exposed cost of the gradient exchange: the same step with no exchange / one collective after the backward
+        variants = {}
+        if world > 1:
+            n_var = max(2, min(args.steps, 5))
+            for name in ('none', 'single', 'overlapped'):
+                step(name)
+                barrier()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(n_var):
+                    step(name)
+                b.record()
+                barrier()
+                variants[name] = a.elapsed_time(b) / n_var
+        # e2e: frames and labels from pinned host memory every step, loss read back (train2D.py:103 feeds the metrics)
+        for _ in range(2):
+            float(step(main, x_host, lab_host)[2])
+        barrier()
+        n_e2e = max(2, min(args.steps, 5))
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            loss = float(step(main, x_host, lab_host)[2])
+        barrier()
+        e2e_ms = (time.perf_counter() - t0) * 1e3
+        res = {'ms': ms, 'launches': launches, 'kt': kt, 'class_flops': sess.class_flops(T), 'variants': variants,
+               'e2e_ms': e2e_ms, 'e2e_steps': n_e2e, 'loss': loss, 'grad_bytes': int(sess.n_trainable) * 4,
+               'flops_step': sess.forward_flops(T) * B * 3, 'main': main}
+        model.close()
+        del model
+        torch.cuda.empty_cache()
+        return res
+
+    def roofline_of(cls_name, kernel, kt, flops_step, steps, ms_total, extra=None):
+        k_ms, k_n = kt[cls_name]
+        tf = flops_step * steps / (k_ms * 1e-3) / 1e12 if k_ms > 0 else None
+        r = {'bound': 'tensor', 'achieved': tf, 'peak': sustained, 'unit': 'TFLOP/s', 'frac': (tf / sustained) if tf else None,
+             'traffic': None, 'kernel': '%s (%d launches)' % (kernel, k_n), 'kernel_ms_per_step': k_ms / steps,
+             'kernel_share_of_step': k_ms / ms_total if ms_total else None,
+             'peak_source': which + ' bf16_tflops_sustained (kernel timed inside a long step); burst %.1f' % burst}
+        if extra:
+            r.update(extra)
+        return r
+
+    do_infer = args.mode in ('all', 'infer', 'stream')
+    do_train = args.mode in ('all', 'train')
+    inf = time_infer(args.precision, True) if do_infer else None
+    variants = {}
+    if do_infer and args.mode == 'all' and not args.no_variants:
+        for prec in ('fp16', 'bf16x3'):
+            if prec != args.precision:
+                variants[prec] = time_infer(prec, False)
+    trn = time_train() if do_train else None
     clocks = sampler.stop() if rank == 0 else None
 
-    # end to end through the public API with host buffers: pinned H2D of the frames + D2H of the soft-max
-    post = None
-    if args.post and not training:
-        from lstm_unet_b200.postprocess import PostProcessor
-        post = PostProcessor()
-
-    def e2e_once():
-        out = run(x_host, training)
-        if post is not None:
-            return post(out[1]).numpy()
-        # inference: D2H of the soft-max (Inference2D.py:60); training: D2H of the loss (train2D.py:103 -> metrics)
-        return out[1].numpy() if not training else np.asarray(float(out[0]), dtype=np.float32)
-    for _ in range(4):          # >= 3: the .numpy() read-back cycles through a ring of three pinned host buffers, each
-        e2e_once()              # allocated (cudaHostAlloc, tens of ms for 100 MB) the first time it is used
-    barrier()
-    t0 = time.perf_counter()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    e2e_steps = max(2, min(args.steps, 5))
-    for _ in range(e2e_steps):
-        sm = e2e_once()
-    e1.record()
-    barrier()
-    e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3 * 0.0)
-    e2e_wall_ms = (time.perf_counter() - t0) * 1e3
-
-    if world > 1:
-        t = torch.tensor([ms, e2e_ms, e2e_wall_ms], device='cuda', dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_ms, e2e_wall_ms = [float(v) for v in t.tolist()]
+    vals = []
+    if inf:
+        vals += [inf['ms'], inf['e2e_serial_ms'], inf['e2e_pipe_ms']] + [variants[k]['ms'] for k in sorted(variants)]
+    if trn:
+        vals += [trn['ms'], trn['e2e_ms']] + [trn['variants'][k] for k in sorted(trn['variants'])]
+    red = max_ranks(vals)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    frames = B * T * args.steps * world
-    value = frames / (ms * 1e-3)
-    e2e_value = B * T * e2e_steps * world / (e2e_wall_ms * 1e-3)
-    sustained, burst, which = peaks()
-    lstm_tflops = (lstm_flops_step * args.steps / (lstm_ms * 1e-3)) / 1e12 if lstm_ms > 0 else None
-    cb = cpu_reference_run(4, 1) if (world == 1 and not args.no_cpu) else None      # ~10 s of host work on 16 cores
-    line = {
-        'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
-        'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'bf16' if args.precision == 'bf16' else 'bf16x3(split-bf16, fp32-equivalent)', 'data': 'synthetic',
-        'config': {'workload': '%s: ConvLSTM-UNet (CTCParams net, 74.6M params) %s, %dx%d, T=%d, batch %d per GPU, '
-                               'pad_image=%s, stateful' % ('C3' if training else 'C2', 'full train step (fwd+loss+bwd+Adam)' if training
-                                                           else 'inference forward', H, W, T, B, not training),
-                   'global_batch': B * world, 'parallelism': ('data parallel x%d: batch-sharded, NCCL mean all-reduce of the 74.6M fp32 gradients per step (started per block from inside the backward)'
-                                   if training else 'batch-sharded replicas x%d (no data-path collective)') % world,
-                   'l2_policy': 'inputs+activations per step (>6 GB) exceed the 126 MB L2; no flush needed',
-                   'a_mode': args.a_mode, 'step_tflop': flops_step / 1e12, 'cuda_graph': bool(model.graph_active),
-                   # experiment switches of the library that were set for this run (none = the default kernels)
-                   'switches': {k: os.environ[k] for k in ('LU_PAIR', 'LU_WGRAD_CLUSTER', 'LU_CLUSTER', 'LU_CLUSTER_WIDE',
-                                                           'LU_B_RESIDENT', 'LU_WGRAD_ENGINE') if k in os.environ}},
-        'e2e': {'value': e2e_value, 'unit': 'frames/s',
-                'h2d_bytes_per_step': int(x_host.nbytes) * (2 if training else 1),
-                'd2h_bytes_per_step': int(sm.nbytes), 'steps': e2e_steps, 'ms_per_step': e2e_wall_ms / e2e_steps,
-                'labelled_on_device': post is not None},
-        'gpu_launches': int(launches),
-        'clocks': clocks,
-        'roofline': {'bound': 'tensor', 'achieved': lstm_tflops, 'peak': sustained, 'unit': 'TFLOP/s',
-                     'frac': (lstm_tflops / sustained) if lstm_tflops else None, 'traffic': lstm_traffic_bytes(),
-                     'traffic_note': 'DRAM bytes of one level-1 ConvLSTM launch (ncu --set full, profiles/r1_ncu_prof_lstm_l1.txt)',
-                     'kernel': 'lu_conv_tc_kernel<LSTM> forward launches (all 4 ConvLSTM levels, %d launches)' % lstm_n,
-                     'kernel_ms_per_step': lstm_ms / args.steps, 'kernel_share_of_step': lstm_ms / ms if ms else None,
-                     'peak_source': which + ' bf16_tflops_sustained (kernel timed inside a long step); burst %.1f' % burst,
-                     'whole_step_tflops': flops_step * args.steps / (ms * 1e-3) / 1e12},
-    }
-    if cb is not None:
-        line['cpu_baseline'] = {k: cb[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
+    it = iter(red)
+    line = {}
+    if inf:
+        ms, serial_ms, pipe_ms = next(it), next(it), next(it)
+        var_ms = {k: next(it) for k in sorted(variants)}
+        frames = B * T * world
+        tf = roofline_of('lstm_fwd', 'lu_conv_tc_kernel<LSTM> forward launches, all 4 ConvLSTM levels', inf['kt'],
+                         inf['lstm_flops_step'], args.steps, ms,
+                         {'traffic': lstm_traffic_bytes(),
+                          'traffic_note': 'DRAM bytes of one level-1 ConvLSTM launch (ncu --set full, profiles/r1_ncu_prof_lstm_l1.txt)',
+                          'whole_step_tflops': inf['flops_step'] * args.steps / (ms * 1e-3) / 1e12})
+        cfg = workload_config(args, world)
+        cfg.update({'parallelism': 'batch-sharded replicas x%d (no data-path collective)' % world, 'a_mode': args.a_mode,
+                    'step_tflop': inf['flops_step'] / 1e12, 'cuda_graph': inf['graph'],
+                    'switches': {k: os.environ[k] for k in ('LU_PAIR', 'LU_WGRAD_CLUSTER', 'LU_CLUSTER', 'LU_CLUSTER_WIDE',
+                                                            'LU_B_RESIDENT', 'LU_WGRAD_ENGINE') if k in os.environ}})
+        dt = {'bf16': 'bf16', 'fp16': 'fp16', 'bf16x3': 'bf16x3(split-bf16, fp32-equivalent)'}
+        line = {
+            'metric': METRIC, 'value': frames * args.steps / (ms * 1e-3), 'unit': 'frames/s', 'n_gpus': world,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': dt[args.precision], 'data': 'synthetic', 'config': cfg,
+            'e2e': {'value': frames * inf['e2e_steps'] / (pipe_ms * 1e-3), 'unit': 'frames/s',
+                    'h2d_bytes_per_step': int(x_host.nbytes), 'd2h_bytes_per_step': inf['d2h'], 'steps': inf['e2e_steps'],
+                    'ms_per_step': pipe_ms / inf['e2e_steps'],
+                    'api': 'ULSTMnet2D.predict_batches(host batches) -> host soft-max per batch (copies of batch i+1 / i-1 '
+                           'overlap the compute of batch i; every byte still crosses PCIe inside the timed region)',
+                    'per_call_form': {'value': frames * inf['e2e_steps'] / (serial_ms * 1e-3), 'unit': 'frames/s',
+                                      'ms_per_step': serial_ms / inf['e2e_steps'],
+                                      'api': 'model(x_host, training=False)[1].numpy() per step (Inference2D.py:59-60), copies serial with the compute'},
+                    'labelled_on_device': inf['labelled']},
+            'gpu_launches': int(inf['launches']), 'clocks': clocks, 'roofline': tf,
+        }
+        if variants:
+            line['dtype_variants'] = {k: {'value': frames * args.steps / (var_ms[k] * 1e-3), 'unit': 'frames/s',
+                                          'ms_per_step': var_ms[k] / args.steps, 'dtype': dt[k]} for k in variants}
+            line['dtype_variants'][args.precision] = {'value': line['value'], 'unit': 'frames/s',
+                                                      'ms_per_step': line['ms_per_step'], 'dtype': dt[args.precision]}
+    if trn:
+        ms, e2e_ms = next(it), next(it)
+        var_ms = {k: next(it) for k in sorted(trn['variants'])}
+        frames = B * T * world
+        cf = trn['class_flops']
+        blk = {
+            'workload': workload_config(args, world, training=True)['workload'],
+            'value': frames * args.steps / (ms * 1e-3), 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'dtype': 'bf16', 'step_tflop': trn['flops_step'] / 1e12,
+            'whole_step_tflops': trn['flops_step'] * args.steps / (ms * 1e-3) / 1e12,
+            'whole_step_frac_of_sustained': trn['flops_step'] * args.steps / (ms * 1e-3) / 1e12 / sustained,
+            'sync_bn': bool(args.sync_bn), 'final_loss': trn['loss'], 'gpu_launches': int(trn['launches']),
+            'parallelism': ('data parallel x%d: batch-sharded, NCCL mean all-reduce of the %.0f MB fp32 gradient buffer per step (%s)'
+                            % (world, trn['grad_bytes'] / 1e6, trn['main'])) if world > 1 else 'single GPU (no exchange)',
+            'allreduce': {'bytes_per_step': trn['grad_bytes'] if world > 1 else 0, 'mode': trn['main'],
+                          'ms_per_step_by_mode': var_ms,
+                          'allreduce_exposed_ms': {k: var_ms[k] - var_ms['none'] for k in var_ms if k != 'none'} if var_ms else None},
+            'e2e': {'value': frames * trn['e2e_steps'] / (e2e_ms * 1e-3), 'unit': 'frames/s',
+                    'h2d_bytes_per_step': int(x_host.nbytes) * 2, 'd2h_bytes_per_step': 4, 'steps': trn['e2e_steps'],
+                    'ms_per_step': e2e_ms / trn['e2e_steps'],
+                    'api': 'ULSTMnet2D.train_step(host frames, host labels, ...) + float(loss) (train2D.py:87-103)'},
+            'roofline': roofline_of('wgrad', 'lu_wgrad_tc_kernel (dominant kernel of the train step)', trn['kt'], cf['wgrad'], args.steps, ms),
+            'rooflines': {
+                'wgrad': roofline_of('wgrad', 'lu_wgrad_tc_kernel', trn['kt'], cf['wgrad'], args.steps, ms),
+                'dgrad': roofline_of('dgrad', 'lu_conv_tc_kernel<GRAD>', trn['kt'], cf['dgrad'], args.steps, ms),
+                'lstm_fwd': roofline_of('lstm_fwd', 'lu_conv_tc_kernel<LSTM>', trn['kt'], cf['lstm_fwd'], args.steps, ms),
+                'conv_fwd': roofline_of('conv_fwd', 'lu_conv_tc_kernel<CONV>', trn['kt'], cf['conv_fwd'], args.steps, ms),
+            },
+        }
+        tc_ms = sum(trn['kt'][k][0] for k in trn['kt']) / args.steps
+        blk['elementwise_and_other_ms_per_step'] = ms / args.steps - tc_ms
+        if inf:
+            line['train'] = blk
+        else:
+            cfg = workload_config(args, world, training=True)
+            cfg.update({'parallelism': blk['parallelism'], 'a_mode': args.a_mode, 'step_tflop': blk['step_tflop'],
+                        'switches': {k: os.environ[k] for k in ('LU_PAIR', 'LU_WGRAD_CLUSTER', 'LU_CLUSTER', 'LU_CLUSTER_WIDE',
+                                                                'LU_B_RESIDENT', 'LU_WGRAD_ENGINE') if k in os.environ}})
+            line = {'metric': METRIC, 'value': blk['value'], 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps,
+                    'warmup': args.warmup, 'ms_per_step': blk['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak',
+                    'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic', 'config': cfg, 'e2e': blk['e2e'],
+                    'gpu_launches': blk['gpu_launches'], 'clocks': clocks, 'roofline': blk['roofline'], 'train': blk}
+    if parity is not None:
+        line['parity_err'] = parity
+    if world == 1 and not args.no_cpu:
+        cb = cpu_infer_run(2, 1, H=H, W=W) if inf else None       # ~15 s of host work
+        ct = cpu_train_run()                                        # ~20 s
+        if cb is not None:
+            line['cpu_baseline'] = {k: cb[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
+            line['cpu_baseline']['train'] = {k: ct[k] for k in ('value', 'unit', 'ms_per_step', 'sample')}
+        else:
+            line['cpu_baseline'] = {k: ct[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
     emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -552,9 +823,13 @@ def main():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--mode', default='infer', choices=['infer', 'train', 'stream', 'postprocess', 'augment'],
-                    help="infer = C2 (default, headline); train = C3/C4 full train step; stream = Inference2D's real per-frame call (B=1, T=1)")
-    ap.add_argument('--precision', default='bf16', choices=['bf16', 'bf16x3'])
+    ap.add_argument('--mode', default='all', choices=['all', 'infer', 'train', 'stream', 'postprocess', 'augment'],
+                    help="all (default) = C2 inference headline + a `train` block with the C3/C4 train step; infer / train = one of "
+                         "them; stream = Inference2D's real per-frame call (B=1, T=1)")
+    ap.add_argument('--precision', default='bf16', choices=['bf16', 'bf16x3', 'fp16'])
+    ap.add_argument('--no-parity', dest='no_parity', action='store_true', help='skip the pre-timing spot check against the oracle')
+    ap.add_argument('--no-variants', dest='no_variants', action='store_true', help='skip the fp16 / bf16x3 timings of the C2 forward')
+    ap.add_argument('--no-full', dest='no_full', action='store_true', help='--impl reference: skip the one step at the true C2 shape and the C1 train step')
     ap.add_argument('--a-mode', dest='a_mode', default='halo', choices=['halo', 'direct'])
     ap.add_argument('--batch', type=int, default=4)
     ap.add_argument('--unroll', type=int, default=8)

@@ -314,6 +314,10 @@ class ULSTMnet2D:
             return self._build(B, T, H, W)
         return self._sess
 
+    def _check_channels(self, C):
+        if C != 1:
+            raise ValueError('only single-channel images are supported on this backend (got %d channels)' % C)
+
     # ---- call (Networks.py:208-254) ------------------------------------------------------------------
     def __call__(self, inputs, training=None, mask=None):
         import torch
@@ -326,8 +330,7 @@ class ULSTMnet2D:
             B, T, C, H, W = x.shape
         else:
             B, T, H, W, C = x.shape
-        if C != 1:
-            raise ValueError('only single-channel images are supported on this backend (got %d channels)' % C)
+        self._check_channels(C)
         sess = self._ensure(B, T, H, W)
         dev = self._be.device
         if x.device.type != 'cuda':
@@ -354,6 +357,72 @@ class ULSTMnet2D:
         return lg, sm
 
     call = __call__
+
+    def predict_batches(self, batches, training=False):
+        """Pipelined inference over an iterable of HOST batches (numpy, 5-D, same shape): yields the soft-max of every
+        batch, in order, as a host array the caller owns (Inference2D.py:59-60: ``model(image, training=False)`` followed
+        by ``image_softmax.numpy()``).  Two slots: while batch i is computed, batch i+1 is copied host -> device and the
+        soft-max of batch i-1 device -> host, each on its own stream, so the copies cost no step time.  Recurrent states
+        carry from batch to batch exactly as with successive calls."""
+        import collections
+        import torch
+        pending = collections.deque()
+        slots, streams = [], None
+        for i, x in enumerate(batches):
+            x = np.ascontiguousarray(np.asarray(x, dtype=np.float32))
+            if x.ndim != 5:
+                raise ValueError('expected a 5-D input, got shape %s' % (x.shape,))
+            if self.channel_axis == 1:
+                B, T, C, H, W = x.shape
+            else:
+                B, T, H, W, C = x.shape
+            self._check_channels(C)
+            sess = self._ensure(B, T, H, W)
+            dev = self._be.device
+            comp = torch.cuda.current_stream(dev)
+            if streams is None:
+                streams = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+            h2d, d2h = streams
+            shape = (B, T, self.last_depth, H, W) if self.channel_axis == 1 else (B, T, H, W, self.last_depth)
+            if len(slots) < 2:
+                slots.append({'x_pin': torch.empty(x.size, dtype=torch.float32, pin_memory=True),
+                              'x_dev': torch.empty(x.size, dtype=torch.float32, device=dev),
+                              'lg': torch.empty(shape, dtype=torch.float32, device=dev),
+                              'sm': torch.empty(shape, dtype=torch.float32, device=dev),
+                              'h2d_done': None, 'x_free': None, 'd2h_done': None})
+            s = slots[i % 2]
+            if s['x_pin'].numel() != x.size or tuple(s['sm'].shape) != shape:
+                raise ValueError('every batch of a pipelined run must have the same shape')
+            if s['h2d_done'] is not None:
+                s['h2d_done'].synchronize()                       # the pinned staging buffer of batch i-2 has been read
+            s['x_pin'].copy_(torch.from_numpy(x.reshape(-1)))
+            with torch.cuda.stream(h2d):
+                if s['x_free'] is not None:
+                    h2d.wait_event(s['x_free'])                   # forward i-2 has consumed this slot's device input
+                s['x_dev'].copy_(s['x_pin'], non_blocking=True)
+                s['h2d_done'] = torch.cuda.Event()
+                s['h2d_done'].record(h2d)
+            comp.wait_event(s['h2d_done'])
+            if s['d2h_done'] is not None:
+                comp.wait_event(s['d2h_done'])                    # the soft-max of batch i-2 has left this slot
+            sess.forward(s['x_dev'].data_ptr(), T, bool(training), s['lg'].data_ptr(), s['sm'].data_ptr())
+            s['x_free'] = torch.cuda.Event()
+            s['x_free'].record(comp)
+            with torch.cuda.stream(d2h):
+                d2h.wait_event(s['x_free'])
+                host, arr = _pinned_for(s['sm'])
+                host.copy_(s['sm'], non_blocking=True)
+                s['d2h_done'] = torch.cuda.Event()
+                s['d2h_done'].record(d2h)
+            pending.append((s['d2h_done'], arr))
+            if len(pending) == 2:
+                ev, out = pending.popleft()
+                ev.synchronize()
+                yield out
+        while pending:
+            ev, out = pending.popleft()
+            ev.synchronize()
+            yield out
 
     # ---- recurrent state API (Networks.py:77-98, 279-291) ---------------------------------------------
     def _n_lstm(self, level):

@@ -200,3 +200,69 @@ def test_cuda_graph_replay_is_bitwise_the_plain_forward(precision):
     big = ULSTMnet2D(NET_WIDE, 'NCHW', True, precision=precision)
     big(np.zeros((2, 2, 1, 40, 56), np.float32), False)
     assert not big.graph_active
+
+
+def test_fp16_operand_mode_meets_the_north_star_tolerance():
+    """precision='fp16': fp16 operands at the bf16 tensor-core rate; 11-bit mantissa -> 1e-3 without the 3x split."""
+    ora, model = make_pair(NET_WIDE, 'NCHW', True, 5, precision='fp16')
+    rng = np.random.default_rng(1)
+    for call in range(2):
+        x = rng.standard_normal((2, 2, 1, 40, 56)).astype(np.float32)
+        ref_l, ref_s = ora(torch.from_numpy(x), False)
+        logits, softmax = model(x, training=False)
+        assert rel_err(logits.numpy(), ref_l.numpy()) < 1e-3 and rel_err(softmax.numpy(), ref_s.numpy()) < 1e-3
+    # h comes back through get_states in fp16
+    rs, gs = ora.get_states(), model.get_states()
+    assert rel_err(gs[1][0][0], rs[1][0][0]) < 1e-3 and rel_err(gs[1][0][1], rs[1][0][1]) < 1e-3
+    from lstm_unet_b200.Networks import ULSTMnet2D
+    m = ULSTMnet2D(NET_TWO, 'NCHW', False, precision='fp16', train=True)
+    with pytest.raises(ValueError):
+        m(np.zeros((1, 1, 1, 16, 16), np.float32), True)
+
+
+def test_predict_batches_is_bitwise_the_successive_calls_and_results_are_caller_owned():
+    """ULSTMnet2D.predict_batches (copies overlapped with compute on side streams) == model(x)[1].numpy() per batch,
+    state carry included; arrays handed out by .numpy() are never overwritten by later read-backs."""
+    from lstm_unet_b200.Networks import ULSTMnet2D
+    params = O.init_params(NET_WIDE, seed=5, randomize_bn=True)
+    w = {k: v.numpy().copy() for k, v in params.items()}
+    rng = np.random.default_rng(3)
+    batches = [rng.standard_normal((2, 2, 1, 40, 56)).astype(np.float32) for _ in range(6)]
+    a = ULSTMnet2D(NET_WIDE, 'NCHW', True)
+    a.set_weights_dict(w)
+    seq = [a(x, False)[1].numpy() for x in batches]                 # kept in a list: must stay intact
+    copies = [s.copy() for s in seq]
+    b = ULSTMnet2D(NET_WIDE, 'NCHW', True)
+    b.set_weights_dict(w)
+    piped = list(b.predict_batches(iter(batches)))
+    assert len(piped) == len(batches)
+    for s, c, p in zip(seq, copies, piped):
+        assert np.array_equal(s, c)
+        assert np.array_equal(p, c)
+    assert len({s.ctypes.data for s in seq}) == len(seq)
+    with pytest.raises(ValueError):
+        list(b.predict_batches([batches[0], batches[0][:, :1]]))
+
+
+def test_variable_assign_and_per_block_state_reset():
+    """tf.Variable.assign on a kernel changes the next forward (the packed operand copies are rebuilt);
+    DownBlock2D.reset_states_per_batch (Networks.py:77-84) touches its own block only."""
+    ora, model = make_pair(NET_TWO, 'NCHW', False, 9, precision='bf16x3')
+    x = np.random.default_rng(3).standard_normal((2, 2, 1, 16, 16)).astype(np.float32)
+    before = model(x, False)[0].numpy().copy()
+    before_states = model.get_states()
+    model.DownLayers[1].reset_states_per_batch(np.array([0.0, 1.0], np.float32))
+    after = model.get_states()
+    for lay in range(len(after[0])):
+        for which in (0, 1):
+            assert np.array_equal(after[0][lay][which], before_states[0][lay][which])       # level 0 untouched
+    assert np.all(after[1][0][0][0] == 0) and np.all(after[1][0][1][0] == 0)
+    assert np.array_equal(after[1][0][1][1], before_states[1][0][1][1])
+    model.reset_states_per_batch(np.zeros(2, np.float32))
+    v = [t for t in model.trainable_variables if t.name == 'UpLayers/1/Conv/1/kernel'][0]
+    v.assign(v.numpy() * 2.0)
+    ora.params['UpLayers/1/Conv/1/kernel'] *= 2.0
+    ora.reset_states_per_batch(np.zeros(2, np.float32)) if ora.states[0][0] is not None else None
+    ref = ora(torch.from_numpy(x), False)[0].numpy()
+    got = model(x, False)[0].numpy()
+    assert rel_err(got, ref) < 1e-3 and rel_err(got, before) > 1e-2

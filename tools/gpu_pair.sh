@@ -22,14 +22,14 @@ step 180 "diag odd  pair"  python tools/diag_tc.py odd tcgen05 halo bf16x3 2 64 
 step 900 "forward suite pair" python -m pytest tests/test_gpu_forward.py -m gpu -x -q
 step 900 "train suite pair (data-gradient launches)" python -m pytest tests/test_gpu_train.py -m gpu -x -q
 for p in 0 1; do
-  LU_PAIR=$p step 600 "bench infer LU_PAIR=$p" bash -c "python bench.py --steps 10 --warmup 3 --no-cpu > gpurun_out/bench_infer_pair$p.json"
+  LU_PAIR=$p step 600 "bench infer LU_PAIR=$p" bash -c "python bench.py --mode infer --no-parity --no-variants --steps 10 --warmup 3 --no-cpu > gpurun_out/bench_infer_pair$p.json"
   cut -c1-200 gpurun_out/bench_infer_pair$p.json
 done
 export LU_PAIR=0
 export LU_WGRAD_CLUSTER=3
 step 900 "wgrad pair vs scalar wgrad" python -m pytest tests/test_gpu_train.py -m gpu -x -q -k "wgrad or train_step"
 for c in 1 3; do
-  LU_WGRAD_CLUSTER=$c step 900 "bench train LU_WGRAD_CLUSTER=$c" bash -c "python bench.py --mode train --steps 5 --warmup 3 --no-cpu > gpurun_out/bench_train_wg$c.json"
+  LU_WGRAD_CLUSTER=$c step 900 "bench train LU_WGRAD_CLUSTER=$c" bash -c "python bench.py --mode train --no-parity --steps 5 --warmup 3 --no-cpu > gpurun_out/bench_train_wg$c.json"
   cut -c1-200 gpurun_out/bench_train_wg$c.json
 done
 echo "ALL STEPS PASSED"
@@ -37,6 +37,6 @@ echo "ALL STEPS PASSED"
 # level-1 weight-gradient launch), now in pair mode -- compare tensor-pipe activity and the tensor memory pipe with
 # profiles/r1_ncu_prof_lstm_l1.txt / r1_ncu_prof_wgrad_l1.txt
 NCU="ncu --set full --clock-control none --import-source on"
-LU_PAIR=1 LU_WGRAD_CLUSTER=1 timeout -k 10 1500 $NCU -k regex:lu_conv_tc_kernel -s 110 -c 1 -o gpurun_out/prof_lstm_l1_pair python bench.py --steps 1 --warmup 3 --no-cpu > /dev/null 2>&1; echo "ncu lstm pair rc=$?"
-LU_PAIR=0 LU_WGRAD_CLUSTER=3 timeout -k 10 1500 $NCU -k regex:lu_wgrad_tc_kernel -s 69 -c 1 -o gpurun_out/prof_wgrad_l1_pair python bench.py --mode train --steps 1 --warmup 3 --no-cpu > /dev/null 2>&1; echo "ncu wgrad pair rc=$?"
+LU_PAIR=1 LU_WGRAD_CLUSTER=1 timeout -k 10 1500 $NCU -k regex:lu_conv_tc_kernel -s 117 -c 1 -o gpurun_out/prof_lstm_l1_pair python bench.py --mode infer --no-parity --no-variants --steps 1 --warmup 3 --no-cpu > /dev/null 2>&1; echo "ncu lstm pair rc=$?"
+LU_PAIR=0 LU_WGRAD_CLUSTER=3 timeout -k 10 1500 $NCU -k regex:lu_wgrad_tc_kernel -s 69 -c 1 -o gpurun_out/prof_wgrad_l1_pair python bench.py --mode train --no-parity --steps 1 --warmup 3 --no-cpu > /dev/null 2>&1; echo "ncu wgrad pair rc=$?"
 ls -la gpurun_out/*.ncu-rep
