@@ -75,31 +75,39 @@ class ClockSampler:
         self.rows, self.proc, self.gpu = [], None, gpu_index
 
     def start(self):
+        """(Re)start sampling: called around every timed region, so that the reported median is the clock UNDER LOAD."""
         q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
              'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
              'clocks_event_reasons.sw_power_cap')
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + q,
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                          '--format=csv,noheader,nounits', '-lms', '50'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread = threading.Thread(target=self._read, args=(self.proc,), daemon=True)
             self.thread.start()
         except Exception:
             self.proc = None
 
-    def _read(self):
-        for line in self.proc.stdout:
+    def pause(self):
+        if self.proc is not None:
+            time.sleep(0.06)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                pass
+            self.thread.join(timeout=2)
+            self.proc = None
+            self.seen = True
+
+    def _read(self, proc):
+        for line in proc.stdout:
             self.rows.append([c.strip() for c in line.split(',')])
 
     def stop(self):
-        if self.proc is None:
+        self.pause()
+        if not getattr(self, 'seen', False):
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            pass
         sm, mx, reasons = [], [], set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
         for r in self.rows:
@@ -255,17 +263,25 @@ def parity_spot_check(rank):
         inf[prec] = {'logits': rel(lg.numpy(), ref[0]), 'softmax': rel(sm.numpy(), ref[1])}
         m.close()
     out['inference'] = {'shape': 'B=1 T=4 128x128 pad_image', **inf}
-    # train step
+    # train step: reference configuration (bf16 = the timed dtype, bf16x3), and the smooth variant of the network
+    # (sigmoid gates, LeakyReLU slope 1) where no sub-gradient can flip for a 1e-5 forward difference
     xt = rng.standard_normal((1, 2, 1, 64, 64)).astype(np.float32)
     lab = rng.integers(-1, 3, size=(1, 2, 1, 64, 64)).astype(np.float32)
-    ora = O.OracleNet(O.CTC_NET_PARAMS, 'NCHW', False, params={k: torch.from_numpy(v.copy()) for k, v in weights.items()})
-    names = ora.trainable_names()
-    mm = {n: torch.zeros_like(ora.params[n]) for n in names}
-    vv = {n: torch.zeros_like(ora.params[n]) for n in names}
-    ref_loss, _, _, ref_grads = O.train_step(ora, torch.from_numpy(xt), torch.from_numpy(lab), CW, mm, vv, 1, 1e-5)
     tr = {}
-    for prec in ('bf16', 'bf16x3'):
-        m = ULSTMnet2D(CTC_NET, 'NCHW', False, precision=prec, seed=0, train=True)
+    for tag, prec, smooth in (('bf16', 'bf16', False), ('bf16x3', 'bf16x3', False), ('bf16x3_smooth_network', 'bf16x3', True)):
+        gate = 'sigmoid' if smooth else 'hard_sigmoid'
+        ora = O.OracleNet(O.CTC_NET_PARAMS, 'NCHW', False, gate=gate,
+                          params={k: torch.from_numpy(v.copy()) for k, v in weights.items()})
+        names = ora.trainable_names()
+        mm = {n: torch.zeros_like(ora.params[n]) for n in names}
+        vv = {n: torch.zeros_like(ora.params[n]) for n in names}
+        saved = O.LRELU_ALPHA
+        O.LRELU_ALPHA = 1.0 if smooth else saved
+        try:
+            ref_loss, _, _, ref_grads = O.train_step(ora, torch.from_numpy(xt), torch.from_numpy(lab), CW, mm, vv, 1, 1e-5)
+        finally:
+            O.LRELU_ALPHA = saved
+        m = ULSTMnet2D(CTC_NET, 'NCHW', False, precision=prec, seed=0, train=True, gate=gate, lrelu_alpha=1.0 if smooth else 0.3)
         m.set_weights_dict(weights)
         m(xt, True)
         loss, grads = m.backward(lab, CW)
@@ -274,17 +290,20 @@ def parity_spot_check(rank):
         for e in m._sess.layout:
             if not e['trainable']:
                 continue
+            if '/Conv/' in e['name'] and e['name'].endswith('bias') and not e['name'].startswith('UpLayers/3/Conv/2'):
+                continue                     # conv bias in front of a training-mode BatchNorm: analytically zero
             r = ref_grads[e['name']].numpy().reshape(-1)
-            if np.abs(r).max() < 1e-7:
-                continue
             mine = g[e['offset']:e['offset'] + e['count']]
             err = rel(mine, r)
             num += float(((mine - r) ** 2).sum()); den += float((r ** 2).sum())
             if err > worst:
                 worst, worst_name = err, e['name']
-        tr[prec] = {'loss': abs(float(loss) - float(ref_loss)) / abs(float(ref_loss)), 'worst_gradient_tensor': worst,
-                    'worst_gradient_name': worst_name, 'all_gradients_l2': (num / den) ** 0.5}
+        tr[tag] = {'loss': abs(float(loss) - float(ref_loss)) / abs(float(ref_loss)), 'worst_gradient_tensor': worst,
+                   'worst_gradient_name': worst_name, 'all_gradients_l2': (num / den) ** 0.5}
         m.close()
+    tr['note'] = ('reference configuration: gradients of two correct implementations whose forwards differ by 1e-5 differ by '
+                  '~1e-2 (LeakyReLU / hard_sigmoid sub-gradients flip; tools/grad_sensitivity_probe.py), so the tight check '
+                  'is the smooth variant')
     out['train_step'] = {'shape': 'B=1 T=2 64x64', **tr}
     torch.cuda.empty_cache()
     return out
@@ -327,9 +346,7 @@ def run_ours(args):
     x_dev = torch.from_numpy(x_host).cuda()
     parity = parity_spot_check(rank) if not args.no_parity else None
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    sampler = ClockSampler(local)        # rank 0 samples nvidia-smi during the timed regions only
 
     # ------------------------------------------------------------------ C2: inference forward (Inference2D call)
     def time_infer(precision, with_e2e):
@@ -338,6 +355,8 @@ def run_ours(args):
         model(x_dev, False)
         torch.cuda.synchronize()
         sess = model._sess
+        if rank == 0 and with_e2e:
+            sampler.start()              # from the warm-up on (the same load): nvidia-smi needs a moment to start
         for _ in range(args.warmup):
             model(x_dev, False)
         barrier()
@@ -349,6 +368,8 @@ def run_ours(args):
             model(x_dev, False)          # states carry over between iterations, like the inference loop
         ev1.record()
         barrier()
+        if rank == 0 and with_e2e:
+            sampler.pause()
         ms = ev0.elapsed_time(ev1)
         launches = sess.launch_count()
         kt = sess.kernel_times(False)
@@ -410,6 +431,8 @@ def run_ours(args):
         step(main)
         torch.cuda.synchronize()
         sess = model._sess
+        if rank == 0:
+            sampler.start()
         for _ in range(args.warmup):
             step(main)
         barrier()
@@ -421,6 +444,8 @@ def run_ours(args):
             step(main)
         ev1.record()
         barrier()
+        if rank == 0:
+            sampler.pause()
         ms = ev0.elapsed_time(ev1)
         launches = sess.launch_count()
         kt = sess.kernel_times(False)

@@ -58,6 +58,8 @@ typedef struct lu_config {
   int32_t gate;            /* LU_GATE_* */
   int32_t a_mode;          /* LU_AMODE_* */
   int32_t train;           /* 1: allocate what forward(training=True)+backward need */
+  float lrelu_alpha;       /* slope of the LeakyReLU after every BatchNorm; 0.3 = Keras-2 LeakyReLU() as the reference
+                              constructs it (Networks.py:58,139) -- the caller must set it */
 } lu_config;
 
 typedef struct lu_handle_s* lu_handle;

@@ -230,7 +230,7 @@ class Adam:
 class ULSTMnet2D:
     def __init__(self, net_params=DEFAULT_NET_DOWN_PARAMS, data_format='NCHW', pad_image=True, *, precision='bf16',
                  engine='tcgen05', gate='hard_sigmoid', a_mode='halo', train=False, seed=0, device=None,
-                 cuda_graph='auto', sync_bn=False):
+                 cuda_graph='auto', sync_bn=False, lrelu_alpha=0.3):
         # Networks.py:188-193: same ValueErrors, raised before anything touches the device
         _lib.make_config(net_params, data_format, pad_image)
         self.net_params = net_params
@@ -245,6 +245,7 @@ class ULSTMnet2D:
         self.graph_active = False
         # data-parallel training: BatchNorm statistics over the batch of ALL ranks (parallel.enable_sync_batchnorm)
         self.sync_bn = sync_bn
+        self.lrelu_alpha = lrelu_alpha            # Keras LeakyReLU() default; another value only for smooth-network tests
         self.seed, self._device = seed, device
         n = len(net_params['down_conv_kernels'])
         self.DownLayers = [DownBlock2D(c, l, 2 if i < n - 1 else 1, data_format, self, i)
@@ -280,7 +281,7 @@ class ULSTMnet2D:
         self._be = be
         cfg = _lib.make_config(self.net_params, self.data_format, self.pad_image, batch=B, max_t=T, height=H, width=W,
                                precision=self.precision, engine=self.engine, gate=self.gate, a_mode=self.a_mode,
-                               train=self.train_capable)
+                               train=self.train_capable, lrelu_alpha=self.lrelu_alpha)
         sess = LuSession(self._lib, be, cfg)
         want_graph = (B * T <= 2) if self.cuda_graph == 'auto' else bool(self.cuda_graph)
         self.graph_active = sess.set_graph_mode(want_graph and not self.train_capable)
@@ -390,9 +391,9 @@ class ULSTMnet2D:
                               'lg': torch.empty(shape, dtype=torch.float32, device=dev),
                               'sm': torch.empty(shape, dtype=torch.float32, device=dev),
                               'h2d_done': None, 'x_free': None, 'd2h_done': None})
-            s = slots[i % 2]
-            if s['x_pin'].numel() != x.size or tuple(s['sm'].shape) != shape:
+            if tuple(slots[0]['sm'].shape) != shape or slots[0]['x_pin'].numel() != x.size:
                 raise ValueError('every batch of a pipelined run must have the same shape')
+            s = slots[i % 2]
             if s['h2d_done'] is not None:
                 s['h2d_done'].synchronize()                       # the pinned staging buffer of batch i-2 has been read
             s['x_pin'].copy_(torch.from_numpy(x.reshape(-1)))

@@ -27,6 +27,7 @@ class lu_config(ctypes.Structure):
         ('in_channels', _I32), ('channels_first', _I32), ('pad_image', _I32),
         ('batch', _I32), ('max_t', _I32), ('height', _I32), ('width', _I32),
         ('precision', _I32), ('engine', _I32), ('gate', _I32), ('a_mode', _I32), ('train', _I32),
+        ('lrelu_alpha', ctypes.c_float),
     ]
 
 
@@ -129,7 +130,8 @@ def load_library(path=None):
 
 
 def make_config(net_params, data_format='NCHW', pad_image=True, batch=1, max_t=1, height=0, width=0,
-                precision='bf16', engine='tcgen05', gate='hard_sigmoid', a_mode='halo', train=False, in_channels=1):
+                precision='bf16', engine='tcgen05', gate='hard_sigmoid', a_mode='halo', train=False, in_channels=1,
+                lrelu_alpha=0.3):
     """Flatten the reference's `net_kernel_params` dict (Params.py:49-69) + call shapes into the C struct.
     Raises ValueError on the level-count mismatches ULSTMnet2D.__init__ rejects (Networks.py:188-193)."""
     down, lstm, up = net_params['down_conv_kernels'], net_params['lstm_kernels'], net_params['up_conv_kernels']
@@ -161,4 +163,5 @@ def make_config(net_params, data_format='NCHW', pad_image=True, batch=1, max_t=1
     c.gate = GATES[gate]
     c.a_mode = A_MODES[a_mode]
     c.train = 1 if train else 0
+    c.lrelu_alpha = float(lrelu_alpha)      # Keras-2 LeakyReLU() default (Networks.py:58,139)
     return c

@@ -857,6 +857,7 @@ int lu_create(const lu_config* cfg, lu_handle* out) {
   LU_REQUIRE(cfg && out, "null argument");
   LU_REQUIRE(cfg->n_levels >= 1 && cfg->n_levels <= LU_MAX_LEVELS, "n_levels must be in [1,%d]", LU_MAX_LEVELS);
   LU_REQUIRE(cfg->batch >= 1 && cfg->max_t >= 1 && cfg->height >= 1 && cfg->width >= 1, "bad shape");
+  LU_REQUIRE(cfg->lrelu_alpha >= 0.f && cfg->lrelu_alpha <= 1.f, "lrelu_alpha must be in [0, 1] (Keras LeakyReLU default: 0.3), got %g", (double)cfg->lrelu_alpha);
   for (int l = 0; l < cfg->n_levels; ++l) {
     LU_REQUIRE(cfg->n_lstm[l] >= (l == 0 ? 1 : 0) && cfg->n_lstm[l] <= LU_MAX_PER_LEVEL, "bad ConvLSTM count at level %d", l);
     LU_REQUIRE(cfg->n_down[l] >= 1 && cfg->n_down[l] <= LU_MAX_PER_LEVEL, "bad conv count at level %d", l);
@@ -1029,7 +1030,7 @@ static int run_conv_layer(lu_handle_s* h, ConvPlan& cv, int T, int training, voi
   e.kind = LU_EPI_CONV; e.H = cv.Hout; e.W = cv.Wout; e.fmt = h->fmt;
   e.oy_mul = 1; e.ox_mul = 1; e.OH = cv.Hout; e.OW = cv.Wout;
   e.bias = reinterpret_cast<const float*>(h->ws + cv.off_bias);
-  e.out_frame_mul = 1; e.out_frame_add = 0; e.alpha = 0.3f;
+  e.out_frame_mul = 1; e.out_frame_add = 0; e.alpha = h->cfg.lrelu_alpha;
   e.raw_cpad = cv.raw_cpad;
   float* raw = reinterpret_cast<float*>(h->ws + cv.off_raw);
   const bool bn_batch = cv.has_bn && training;
@@ -1078,7 +1079,7 @@ static int run_conv_layer(lu_handle_s* h, ConvPlan& cv, int T, int training, voi
     LuBnApply ap;
     ap.raw = raw; ap.scale = fin.scale; ap.shift = fin.shift;
     ap.out = reinterpret_cast<uint16_t*>(h->ws + ob.off); ap.raw_cpad = cv.raw_cpad; ap.out_cpad = ob.cpad; ap.planes = ob.planes;
-    ap.alpha = 0.3f; ap.fmt = h->fmt;
+    ap.alpha = h->cfg.lrelu_alpha; ap.fmt = h->fmt;
     pf(h, npix * (ob.cpad / 8), stream, ap);
   }
   return 0;

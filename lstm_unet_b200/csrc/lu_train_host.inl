@@ -582,7 +582,7 @@ static int bwd_conv_layer(lu_handle_s* h, ConvPlan& f, int T, float* grads, std:
     r.scale = reinterpret_cast<const float*>(h->ws + f.off_bscale); r.shift = reinterpret_cast<const float*>(h->ws + f.off_bshift);
     r.mean = reinterpret_cast<const float*>(h->ws + f.off_save_mean); r.invstd = reinterpret_cast<const float*>(h->ws + f.off_save_invstd);
     r.sums = sums; r.npix = npix; r.cpad = gb.cpad; r.planes = gb.planes; r.raw_cpad = f.raw_cpad; r.c_real = f.cout;
-    r.chunk = 256; r.alpha = 0.3f;
+    r.chunk = 256; r.alpha = h->cfg.lrelu_alpha;
     pf(h, ((npix + r.chunk - 1) / r.chunk) * f.raw_cpad, stream, r);
     LuBnBwdParams bp;
     bp.sums = sums; bp.dgamma = grads + h->params[f.gamma].offset; bp.dbeta = grads + h->params[f.beta].offset;
@@ -598,7 +598,7 @@ static int bwd_conv_layer(lu_handle_s* h, ConvPlan& f, int T, float* grads, std:
     }
     LuBnBwdApply a;
     a.dA = act_ptr(h, gbuf); a.raw = r.raw; a.scale = r.scale; a.shift = r.shift; a.mean = r.mean; a.invstd = r.invstd;
-    a.means = bp.means; a.npix = npix; a.cpad = gb.cpad; a.planes = gb.planes; a.raw_cpad = f.raw_cpad; a.c_real = f.cout; a.alpha = 0.3f;
+    a.means = bp.means; a.npix = npix; a.cpad = gb.cpad; a.planes = gb.planes; a.raw_cpad = f.raw_cpad; a.c_real = f.cout; a.alpha = h->cfg.lrelu_alpha;
     pf(h, npix * (gb.cpad / 8), stream, a);
   }
   // a conv bias in front of a training-mode BatchNorm has an exactly zero gradient (BN removes the batch mean; the

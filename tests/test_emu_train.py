@@ -51,13 +51,15 @@ class TieWatch:
         return self.min_lrelu > tol and self.min_gate > tol
 
 
-def run_case(net, B, T, H, W, seed, steps=2):
+def run_case(net, B, T, H, W, seed, steps=2, smooth=False):
     params = O.init_params(net, seed=seed, randomize_bn=True)
     p_np = {k: v.numpy().copy() for k, v in params.items()}
-    ora = O.OracleNet(net, 'NCHW', False, params=params)
-    ora.gate = lambda x: O.hard_sigmoid(x)       # late-bound so TieWatch sees the calls
+    ora = O.OracleNet(net, 'NCHW', False, params=params, gate='sigmoid' if smooth else 'hard_sigmoid')
+    if not smooth:
+        ora.gate = lambda x: O.hard_sigmoid(x)       # late-bound so TieWatch sees the calls
     sess = emu_session(net, data_format='NCHW', pad_image=False, batch=B, max_t=T, height=H, width=W,
-                       precision='bf16x3', train=True)
+                       precision='bf16x3', train=True, gate='sigmoid' if smooth else 'hard_sigmoid',
+                       lrelu_alpha=1.0 if smooth else 0.3)
     sess.set_params(p_np)
     names = ora.trainable_names()
     m = {n: torch.zeros_like(ora.params[n]) for n in names}
@@ -80,7 +82,7 @@ def run_case(net, B, T, H, W, seed, steps=2):
         sess.loss_backward(lab.ctypes.data, CW, loss.ctypes.data, grads.ctypes.data)
         assert abs(float(loss[0]) - float(ref_loss)) < 1e-4 * max(1.0, abs(float(ref_loss)))
         worst = ('', 0.0)
-        compared = tw.clean()
+        compared = tw.clean() or smooth
         for e in sess.layout:
             if not compared:
                 break
@@ -117,6 +119,15 @@ def test_train_step_two_levels():
 def test_train_step_three_levels():
     worst, n = run_case(NET_C, 1, 2, 16, 16, 31)
     assert n == 2, 'choose a seed without near-ties'
+
+
+def test_train_step_smooth_variant_needs_no_tie_watch(monkeypatch):
+    """sigmoid gates + LeakyReLU slope 1 (lu_config.gate / lrelu_alpha): the gradient is continuous in the forward, every
+    step is compared -- the configuration tests/test_gpu_ctc_parity.py uses for the CTC-size backward.  Seed 21 has a
+    near-tie in the reference configuration (next test)."""
+    monkeypatch.setattr(O, 'LRELU_ALPHA', 1.0)
+    worst, n = run_case(NET_B, 2, 2, 8, 8, 21, smooth=True)
+    assert n == 2 and worst[1] < 1e-3
 
 
 def test_near_tie_step_is_detected():
