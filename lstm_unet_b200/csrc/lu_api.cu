@@ -668,6 +668,13 @@ static void pf(lu_handle_s* h, int64_t n, void* stream, F f) {
   h->launches++;
   lu_parallel_for_impl(n, stream, f);
 }
+// row-loop launch: `groups` groups of 8 channels x npix pixels (lu_elem.cuh)
+template <class F>
+static void rows(lu_handle_s* h, int64_t npix, int groups, void* stream, F f) {
+  if (npix <= 0 || groups <= 0) return;
+  h->launches++;
+  lu_rows_impl(npix, groups, stream, f);
+}
 
 #ifndef LU_HOST_EMU
 typedef CUresult (*PFN_tmEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -771,12 +778,13 @@ static int launch_conv(lu_handle_s* h, ConvPlan& cv, int frames, const int* mul,
   if (wide_env < 0) { const char* ce = getenv("LU_CLUSTER_WIDE"); wide_env = ce ? atoi(ce) : 1; }
   const bool wide = wide_env == 1 && epi.kind != LU_EPI_LSTM && cv.ktot >= 2048 && cv.BN >= 128 && m_tiles >= 2 * h->num_sms;
   const bool cl2 = cluster_env == 2 && (epi.kind == LU_EPI_LSTM || wide) && cv.ptab_ok && (h->num_sms % 2 == 0);
-  // LU_PAIR=1: the cluster launches run one M = 256 MMA per CTA pair (tcgen05.mma.cta_group::2, kernel cluster mode 3)
-  // instead of two M = 128 MMAs fed by a multicast weight stage.  Each CTA then stages only half of every weight K block,
-  // so the weight stages shrink to half and the shared memory they free goes to deeper activation prefetch.
-  // Off by default: compiled and inspected (SASS), not yet run on hardware.
+  // The cluster launches run ONE M = 256 MMA per CTA pair (tcgen05.mma.cta_group::2, kernel cluster mode 3) instead of two
+  // M = 128 MMAs fed by a multicast weight stage: each CTA stages only half of every weight K block, so the weight stages
+  // shrink to half, the shared memory they free goes to deeper activation prefetch, and every MMA reads a third less
+  // operand data per SM.  Measured on B200 (round 2, profiles/README.md): C2 inference 358.7 -> 376.9 frames/s, ConvLSTM
+  // launches 0.92 -> 0.975 of the sustained bf16 peak.  LU_PAIR=0 selects the multicast form (cluster mode 2) for A/B runs.
   static int pair_env = -1;
-  if (pair_env < 0) { const char* ce = getenv("LU_PAIR"); pair_env = ce ? atoi(ce) : 0; }
+  if (pair_env < 0) { const char* ce = getenv("LU_PAIR"); pair_env = ce ? atoi(ce) : 1; }
   const bool pair = cl2 && pair_env == 1 && cv.BN >= 32;
   int smem_bytes = cv.smem;
   if (pair) {
@@ -1050,8 +1058,8 @@ static int run_conv_layer(lu_handle_s* h, ConvPlan& cv, int T, int training, voi
     const int64_t npix = (int64_t)N * cv.Hout * cv.Wout;
     LuBnStats st;
     st.raw = raw; st.sums = reinterpret_cast<double*>(h->ws + cv.off_sums); st.shift_src = raw;
-    st.npix = npix; st.cpad = cv.raw_cpad; st.c_real = cv.cout; st.chunk = 256;
-    pf(h, ((npix + st.chunk - 1) / st.chunk) * cv.raw_cpad, stream, st);
+    st.cpad = cv.raw_cpad; st.c_real = cv.cout;
+    rows(h, npix, cv.raw_cpad / 8, stream, st);
     LuBnFinalize fin;
     fin.sums = st.sums; fin.shift_src = raw;
     fin.gamma = h->dparams + h->params[cv.gamma].offset; fin.beta = h->dparams + h->params[cv.beta].offset;
@@ -1080,7 +1088,7 @@ static int run_conv_layer(lu_handle_s* h, ConvPlan& cv, int T, int training, voi
     ap.raw = raw; ap.scale = fin.scale; ap.shift = fin.shift;
     ap.out = reinterpret_cast<uint16_t*>(h->ws + ob.off); ap.raw_cpad = cv.raw_cpad; ap.out_cpad = ob.cpad; ap.planes = ob.planes;
     ap.alpha = h->cfg.lrelu_alpha; ap.fmt = h->fmt;
-    pf(h, npix * (ob.cpad / 8), stream, ap);
+    rows(h, npix, ob.cpad / 8, stream, ap);
   }
   return 0;
 }

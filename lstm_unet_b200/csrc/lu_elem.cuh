@@ -73,6 +73,95 @@ LU_HDI void lu_store8_bf16(uint16_t* dst, const uint16_t* h) {
 #endif
 }
 
+LU_HDI void lu_ld8f(const float* p, float* v) {
+#ifdef __CUDA_ARCH__
+  const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+#else
+  for (int j = 0; j < 8; ++j) v[j] = p[j];
+#endif
+}
+LU_HDI void lu_st8f(float* p, const float* v) {
+#ifdef __CUDA_ARCH__
+  reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+#else
+  for (int j = 0; j < 8; ++j) p[j] = v[j];
+#endif
+}
+
+// ---- row-loop kernels ---------------------------------------------------------------------------------------------
+// For the passes over an NHWC tensor that need per-CHANNEL constants or per-channel sums (BatchNorm statistics / apply /
+// backward, bias gradients): a thread owns ONE group of 8 channels for its whole life and walks pixels, so the constants
+// are loaded once into registers, there is no index division per element, and channel sums are accumulated in registers,
+// combined across the block's pixel lanes in shared memory and flushed with one atomic per channel and block.
+//   struct F { struct State; static constexpr int NSUM;
+//              void begin(int group, State&) const; void pixel(int64_t p, int group, State&) const;
+//              void partials(const State&, float* part) const; void flush(int group, const float* part) const; }  (last two: NSUM > 0)
+// Threads of a block: (pixel lane, group) with the group fastest, so a warp reads consecutive 16 / 32-byte pieces of a pixel.
+#ifdef LU_HOST_EMU
+template <class F>
+static void lu_rows_impl(int64_t npix, int ngroups, void* /*stream*/, F f) {
+  for (int g = 0; g < ngroups; ++g) {
+    typename F::State st;
+    f.begin(g, st);
+    for (int64_t p = 0; p < npix; ++p) f.pixel(p, g, st);
+    if (F::NSUM > 0) {
+      float part[F::NSUM > 0 ? F::NSUM : 1];
+      f.partials(st, part);
+      f.flush(g, part);
+    }
+  }
+}
+#else
+template <class F>
+__global__ void __launch_bounds__(256) lu_rows_kernel(int64_t npix, int ngroups, F f) {
+  constexpr int NS = F::NSUM > 0 ? F::NSUM : 1;
+  __shared__ float red[F::NSUM > 0 ? F::NSUM * 256 : 1];
+  const int gpb = ngroups < 256 ? ngroups : 256, PL = 256 / gpb;
+  const int gl = (int)threadIdx.x % gpb, pl = (int)threadIdx.x / gpb;
+  const int g = (int)blockIdx.y * gpb + gl;
+  const bool active = pl < PL && g < ngroups;
+  typename F::State st;
+  if (active) {
+    f.begin(g, st);
+#pragma unroll 2
+    for (int64_t p = (int64_t)blockIdx.x * PL + pl; p < npix; p += (int64_t)gridDim.x * PL) f.pixel(p, g, st);
+  }
+  if (F::NSUM > 0) {
+    float part[NS];
+    if (active) f.partials(st, part);
+    else {
+#pragma unroll
+      for (int k = 0; k < NS; ++k) part[k] = 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < NS; ++k) red[k * 256 + threadIdx.x] = part[k];
+    __syncthreads();
+    if (pl == 0 && g < ngroups) {
+#pragma unroll
+      for (int k = 0; k < NS; ++k) {
+        float s = 0.f;
+        for (int q = 0; q < PL; ++q) s += red[k * 256 + q * gpb + gl];
+        part[k] = s;
+      }
+      f.flush(g, part);
+    }
+  }
+}
+template <class F>
+static void lu_rows_impl(int64_t npix, int ngroups, void* stream, F f) {
+  if (npix <= 0 || ngroups <= 0) return;
+  const int gpb = ngroups < 256 ? ngroups : 256, PL = 256 / gpb;
+  const int gy = (ngroups + gpb - 1) / gpb;
+  int64_t bx = (npix + PL - 1) / PL;
+  int64_t cap = (148 * 8 * 2) / gy;            // two waves of resident blocks: few flushes, still balanced
+  if (cap < 1) cap = 1;
+  if (bx > cap) bx = cap;
+  lu_rows_kernel<<<dim3((unsigned)bx, (unsigned)gy), 256, 0, (cudaStream_t)stream>>>(npix, ngroups, f);
+}
+#endif
+
 LU_HDI int lu_reflect(int i, int n) {     // tf.pad REFLECT index (no edge repeat); pad < n guaranteed
   if (i < 0) i = -i;
   if (i >= n) i = 2 * (n - 1) - i;
@@ -163,20 +252,35 @@ struct LuUpsample2x {
 };
 
 // ---- batch norm (keras BatchNormalization, eps 1e-3, momentum .99) ----------------------------
-// pass 1: per-channel sum / sum of squares of the fp32 conv output; item = (pixel chunk, channel)
+// pass 1 (row-loop): per-channel sum / sum of squares of the fp32 conv output about a per-channel shift
 struct LuBnStats {
   const float* raw; double* sums;      // sums[0:cpad] = sum, sums[cpad:2cpad] = sum sq (about a per-channel shift)
   const float* shift_src;              // per-channel shift (first pixel) to avoid cancellation
-  int64_t npix; int cpad, c_real, chunk;
-  LU_HD void operator()(int64_t i) const {
-    const int c = (int)(i % cpad); const int64_t pc = i / cpad;
-    if (c >= c_real) return;
-    const float sh = shift_src[c];
-    int64_t p0 = pc * chunk, p1 = p0 + chunk; if (p1 > npix) p1 = npix;
-    float s = 0.f, s2 = 0.f;
-    for (int64_t p = p0; p < p1; ++p) { const float v = raw[p * cpad + c] - sh; s += v; s2 += v * v; }
-    lu_atomic_add(&sums[c], (double)s);
-    lu_atomic_add(&sums[cpad + c], (double)s2);
+  int cpad, c_real;
+  struct State { float sh[8], s[8], s2[8]; };
+  static constexpr int NSUM = 16;
+  LU_HD void begin(int g, State& st) const {
+    lu_ld8f(shift_src + g * 8, st.sh);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { st.s[j] = 0.f; st.s2[j] = 0.f; }
+  }
+  LU_HD void pixel(int64_t p, int g, State& st) const {
+    float v[8];
+    lu_ld8f(raw + p * cpad + g * 8, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { const float d = v[j] - st.sh[j]; st.s[j] += d; st.s2[j] += d * d; }
+  }
+  LU_HD void partials(const State& st, float* part) const {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { part[j] = st.s[j]; part[8 + j] = st.s2[j]; }
+  }
+  LU_HD void flush(int g, const float* part) const {
+    for (int j = 0; j < 8; ++j) {
+      const int c = g * 8 + j;
+      if (c >= c_real) continue;
+      lu_atomic_add(&sums[c], (double)part[j]);
+      lu_atomic_add(&sums[cpad + c], (double)part[8 + j]);
+    }
   }
 };
 // pass 2: scale/shift from batch statistics + moving-statistics update; item = channel
@@ -238,18 +342,32 @@ struct LuBnFinalizeSync {
     mov_var[c] = momentum * mov_var[c] + (1.f - momentum) * (float)unb;
   }
 };
-// pass 3: y = lrelu(raw*scale + shift) -> bf16 planes; item = (pixel, channel)
+// pass 3 (row-loop): y = lrelu(raw*scale + shift) -> 16-bit planes; a thread keeps scale / shift of its 8 channels
 struct LuBnApply {
   const float* raw; const float* scale; const float* shift; uint16_t* out;
   int raw_cpad, out_cpad, planes, fmt; float alpha;
-  LU_HD void operator()(int64_t i) const {        // item = (pixel, group of 8 channels)
-    const int cg = out_cpad / 8;
-    const int c = (int)(i % cg) * 8; const int64_t p = i / cg;
+  struct State { float sc[8], sh[8]; };
+  static constexpr int NSUM = 0;
+  LU_HD void begin(int g, State& st) const {
+    if (g * 8 < raw_cpad) { lu_ld8f(scale + g * 8, st.sc); lu_ld8f(shift + g * 8, st.sh); }
+    else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { st.sc[j] = 0.f; st.sh[j] = 0.f; }
+    }
+  }
+  LU_HD void pixel(int64_t p, int g, State& st) const {
+    const int c = g * 8;
+    float r[8];
+    if (c < raw_cpad) lu_ld8f(raw + p * raw_cpad + c, r);
+    else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] = 0.f;
+    }
     uint16_t hi[8], lo[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float a = 0.f;
-      if (c + j < raw_cpad) { a = raw[p * raw_cpad + c + j] * scale[c + j] + shift[c + j]; a = a > 0.f ? a : alpha * a; }
+      float a = r[j] * st.sc[j] + st.sh[j];
+      a = a > 0.f ? a : alpha * a;
       if (planes == 2) lu_split(a, hi[j], lo[j]);
       else hi[j] = lu_f2h16(a, fmt);
     }
@@ -257,6 +375,8 @@ struct LuBnApply {
     lu_store8_bf16(o, hi);
     if (planes == 2) lu_store8_bf16(o + out_cpad, lo);
   }
+  LU_HD void partials(const State&, float*) const {}
+  LU_HD void flush(int, const float*) const {}
 };
 // inference: fold moving statistics into per-channel scale/shift (applied in the conv epilogue)
 struct LuBnFold {

@@ -114,77 +114,79 @@ LU_HDI void lu_st8planes(uint16_t* p, int cpad, int planes, const float* v) {
   lu_store8_bf16(p, hi);
   if (planes == 2) lu_store8_bf16(p + cpad, lo);
 }
-LU_HDI void lu_ld8f(const float* p, float* v) {
-#ifdef __CUDA_ARCH__
-  const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
-  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-#else
-  for (int j = 0; j < 8; ++j) v[j] = p[j];
-#endif
-}
-LU_HDI void lu_st8f(float* p, const float* v) {
-#ifdef __CUDA_ARCH__
-  reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
-  reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
-#else
-  for (int j = 0; j < 8; ++j) p[j] = v[j];
-#endif
-}
-
 // ---- BatchNorm (training) + LeakyReLU backward ------------------------------------------------------------------
-// g = dA * lrelu'(bn_out); sums: [0:cpad) = sum g, [cpad:2cpad) = sum g * xhat        item = (pixel chunk, channel)
+// (row-loop kernels, lu_elem.cuh: a thread keeps the per-channel constants of its 8 channels in registers)
+// g = dA * lrelu'(bn_out); sums: [0:cpad) = sum g, [cpad:2cpad) = sum g * xhat
 struct LuBnBwdReduce {
   const uint16_t* dA; const float* raw; const float* scale; const float* shift; const float* mean; const float* invstd;
-  double* sums; int64_t npix; int cpad, planes, raw_cpad, c_real, chunk; float alpha;
-  LU_HD void operator()(int64_t i) const {
-    const int c = (int)(i % raw_cpad); const int64_t pc = i / raw_cpad;
-    if (c >= c_real) return;
-    int64_t p0 = pc * chunk, p1 = p0 + chunk; if (p1 > npix) p1 = npix;
-    float s = 0.f, sx = 0.f;
-    for (int64_t p = p0; p < p1; ++p) {
-      const float r = raw[p * raw_cpad + c];
-      const float bn = r * scale[c] + shift[c];
-      const float g = lu_ldplanes(dA + p * (int64_t)(cpad * planes) + c, cpad, planes) * (bn > 0.f ? 1.f : alpha);
-      s += g; sx += g * (r - mean[c]) * invstd[c];
+  double* sums; int cpad, planes, raw_cpad, c_real; float alpha;
+  struct State { float sc[8], sh[8], mu[8], is[8], s[8], sx[8]; };
+  static constexpr int NSUM = 16;
+  LU_HD void begin(int g, State& st) const {
+    const int c = g * 8;
+    lu_ld8f(scale + c, st.sc); lu_ld8f(shift + c, st.sh); lu_ld8f(mean + c, st.mu); lu_ld8f(invstd + c, st.is);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { st.s[j] = 0.f; st.sx[j] = 0.f; }
+  }
+  LU_HD void pixel(int64_t p, int g, State& st) const {
+    const int c = g * 8;
+    float r[8], d[8];
+    lu_ld8f(raw + p * raw_cpad + c, r);
+    lu_ld8planes(dA + p * (int64_t)(cpad * planes) + c, cpad, planes, d);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float bn = r[j] * st.sc[j] + st.sh[j];
+      const float gg = d[j] * (bn > 0.f ? 1.f : alpha);
+      st.s[j] += gg; st.sx[j] += gg * (r[j] - st.mu[j]) * st.is[j];
     }
-    lu_atomic_add(&sums[c], (double)s);
-    lu_atomic_add(&sums[raw_cpad + c], (double)sx);
+  }
+  LU_HD void partials(const State& st, float* part) const {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { part[j] = st.s[j]; part[8 + j] = st.sx[j]; }
+  }
+  LU_HD void flush(int g, const float* part) const {
+    for (int j = 0; j < 8; ++j) {
+      const int c = g * 8 + j;
+      if (c >= c_real) continue;
+      lu_atomic_add(&sums[c], (double)part[j]);
+      lu_atomic_add(&sums[raw_cpad + c], (double)part[8 + j]);
+    }
   }
 };
-// dRaw = scale * (g - sum_g/n - xhat * sum_gx/n), written IN PLACE over dA; item = (pixel, channel)
-struct LuBnBwdApply {    // item = (pixel, group of 8 channels); means = [mean g | mean g*xhat] per channel (fp32)
+// dRaw = scale * (g - sum_g/n - xhat * sum_gx/n), written IN PLACE over dA; means = [mean g | mean g*xhat] per channel
+struct LuBnBwdApply {
   uint16_t* dA; const float* raw; const float* scale; const float* shift; const float* mean; const float* invstd;
-  const float* means; int64_t npix; int cpad, planes, raw_cpad, c_real; float alpha;
-  LU_HD void operator()(int64_t i) const {
-    const int cg = cpad / 8;
-    const int c = (int)(i % cg) * 8; const int64_t p = i / cg;
+  const float* means; int cpad, planes, raw_cpad, c_real; float alpha;
+  struct State { float sc[8], sh[8], mu[8], is[8], mg[8], mx[8]; };
+  static constexpr int NSUM = 0;
+  LU_HD void begin(int g, State& st) const {
+    const int c = g * 8;
+    if (c < raw_cpad) {
+      lu_ld8f(scale + c, st.sc); lu_ld8f(shift + c, st.sh); lu_ld8f(mean + c, st.mu); lu_ld8f(invstd + c, st.is);
+      lu_ld8f(means + c, st.mg); lu_ld8f(means + raw_cpad + c, st.mx);
+    }
+  }
+  LU_HD void pixel(int64_t p, int g, State& st) const {
+    const int c = g * 8;
     uint16_t* o = dA + p * (int64_t)(cpad * planes) + c;
-    float g[8], d[8];
-    lu_ld8planes(o, cpad, planes, g);
-    if (c + 8 <= c_real) {
-      float r[8], sc[8], sh[8], mu[8], is[8], mg[8], mx[8];
-      lu_ld8f(raw + p * raw_cpad + c, r); lu_ld8f(scale + c, sc); lu_ld8f(shift + c, sh); lu_ld8f(mean + c, mu);
-      lu_ld8f(invstd + c, is); lu_ld8f(means + c, mg); lu_ld8f(means + raw_cpad + c, mx);
+    float gv[8], d[8], r[8];
+    if (c < raw_cpad) {
+      lu_ld8planes(o, cpad, planes, gv);
+      lu_ld8f(raw + p * raw_cpad + c, r);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float bn = r[j] * sc[j] + sh[j];
-        const float gg = g[j] * (bn > 0.f ? 1.f : alpha);
-        d[j] = sc[j] * (gg - mg[j] - (r[j] - mu[j]) * is[j] * mx[j]);
+        const float bn = r[j] * st.sc[j] + st.sh[j];
+        const float gg = gv[j] * (bn > 0.f ? 1.f : alpha);
+        d[j] = (c + j < c_real) ? st.sc[j] * (gg - st.mg[j] - (r[j] - st.mu[j]) * st.is[j] * st.mx[j]) : 0.f;
       }
     } else {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        d[j] = 0.f;
-        if (c + j < c_real) {
-          const float r = raw[p * raw_cpad + c + j];
-          const float bn = r * scale[c + j] + shift[c + j];
-          const float gg = g[j] * (bn > 0.f ? 1.f : alpha);
-          d[j] = scale[c + j] * (gg - means[c + j] - (r - mean[c + j]) * invstd[c + j] * means[raw_cpad + c + j]);
-        }
-      }
+      for (int j = 0; j < 8; ++j) d[j] = 0.f;
     }
     lu_st8planes(o, cpad, planes, d);
   }
+  LU_HD void partials(const State&, float*) const {}
+  LU_HD void flush(int, const float*) const {}
 };
 struct LuBnBwdParams {   // dgamma = sum g*xhat, dbeta = sum g, per-channel means for the apply pass; item = channel
   const double* sums; float* dgamma; float* dbeta; float* means; int64_t npix; int raw_cpad, c_real;
@@ -243,14 +245,22 @@ struct LuUpsample2xBwd {   // item = (n, iy, ix, c)
 };
 
 // ---- ConvLSTM cell backward for one time step ----------------------------------------------------------------------
-// item = (sample pixel, channel < fpad).  gates: (frames,H,W,planes*4*fpad) [i|f|g|o]; dZ same layout (bf16 planes).
-struct LuLstmCellBwd {    // item = (sample pixel, group of 8 channels)
+// Row-loop kernel over the B*H*W sample pixels of one time step; a thread owns 8 channels (of each of the 4 gates).
+// gates: (frames,H,W,planes*4*fpad) [i|f|g|o]; dZ same layout (bf16 planes).  The bias gradient (sum of dZ over pixels and
+// steps) is accumulated on the way, from the un-rounded fp32 values: no separate pass over dZ.
+struct LuLstmCellBwd {
   const uint16_t* dH; const uint16_t* gates; const float* c_t; const float* c_prev; float* dC; uint16_t* dZ;
-  int64_t pix_per_sample; int T, t, fpad, planes, gate_kind, c_prev_is_init, first;
-  LU_HD void operator()(int64_t i) const {
-    const int cg = fpad / 8;
-    const int ch = (int)(i % cg) * 8; const int64_t sp = i / cg;            // sp = b*HW + pixel
-    const int64_t b = sp / pix_per_sample, px = sp % pix_per_sample;
+  float* dbias;              // (4*F) gradient of the ConvLSTM bias, gate-major like the Keras tensor; accumulated atomically
+  int64_t pix_per_sample; int T, t, fpad, F, planes, gate_kind, c_prev_is_init, first;
+  struct State { float bs[32]; };
+  static constexpr int NSUM = 32;
+  LU_HD void begin(int, State& st) const {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) st.bs[j] = 0.f;
+  }
+  LU_HD void pixel(int64_t sp, int g, State& st) const {                      // sp = b*HW + pixel
+    const int ch = g * 8;
+    const int64_t b = sp / pix_per_sample, px = sp - b * pix_per_sample;
     const int64_t fp = (b * T + t) * pix_per_sample + px;                   // pixel index in frame-major buffers
     const int g4 = 4 * fpad;
     const uint16_t* gp = gates + fp * (int64_t)(g4 * planes) + ch;
@@ -278,11 +288,23 @@ struct LuLstmCellBwd {    // item = (sample pixel, group of 8 channels)
         zi[j] = d_i * gi[j] * (1.f - gi[j]); zf[j] = d_f * gf[j] * (1.f - gf[j]); zo[j] = d_o * go[j] * (1.f - go[j]);
       }
       zg[j] = d_g * (1.f - gg[j] * gg[j]);
+      st.bs[j] += zi[j]; st.bs[8 + j] += zf[j]; st.bs[16 + j] += zg[j]; st.bs[24 + j] += zo[j];
     }
     lu_st8f(dC + sp * fpad + ch, dc);
     uint16_t* zp = dZ + fp * (int64_t)(g4 * planes) + ch;
     lu_st8planes(zp, g4, planes, zi); lu_st8planes(zp + fpad, g4, planes, zf);
     lu_st8planes(zp + 2 * fpad, g4, planes, zg); lu_st8planes(zp + 3 * fpad, g4, planes, zo);
+  }
+  LU_HD void partials(const State& st, float* part) const {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) part[j] = st.bs[j];
+  }
+  LU_HD void flush(int g, const float* part) const {
+    for (int gate = 0; gate < 4; ++gate)
+      for (int j = 0; j < 8; ++j) {
+        const int ch = g * 8 + j;
+        if (ch < F) lu_atomic_add(&dbias[gate * F + ch], part[gate * 8 + j]);
+      }
   }
 };
 

@@ -581,9 +581,9 @@ static int bwd_conv_layer(lu_handle_s* h, ConvPlan& f, int T, float* grads, std:
     r.dA = act_ptr(h, gbuf); r.raw = reinterpret_cast<const float*>(h->ws + f.off_raw);
     r.scale = reinterpret_cast<const float*>(h->ws + f.off_bscale); r.shift = reinterpret_cast<const float*>(h->ws + f.off_bshift);
     r.mean = reinterpret_cast<const float*>(h->ws + f.off_save_mean); r.invstd = reinterpret_cast<const float*>(h->ws + f.off_save_invstd);
-    r.sums = sums; r.npix = npix; r.cpad = gb.cpad; r.planes = gb.planes; r.raw_cpad = f.raw_cpad; r.c_real = f.cout;
-    r.chunk = 256; r.alpha = h->cfg.lrelu_alpha;
-    pf(h, ((npix + r.chunk - 1) / r.chunk) * f.raw_cpad, stream, r);
+    r.sums = sums; r.cpad = gb.cpad; r.planes = gb.planes; r.raw_cpad = f.raw_cpad; r.c_real = f.cout;
+    r.alpha = h->cfg.lrelu_alpha;
+    rows(h, npix, f.raw_cpad / 8, stream, r);
     LuBnBwdParams bp;
     bp.sums = sums; bp.dgamma = grads + h->params[f.gamma].offset; bp.dbeta = grads + h->params[f.beta].offset;
     bp.raw_cpad = f.raw_cpad; bp.c_real = f.cout; bp.npix = npix; bp.write_grads = 1;
@@ -598,8 +598,8 @@ static int bwd_conv_layer(lu_handle_s* h, ConvPlan& f, int T, float* grads, std:
     }
     LuBnBwdApply a;
     a.dA = act_ptr(h, gbuf); a.raw = r.raw; a.scale = r.scale; a.shift = r.shift; a.mean = r.mean; a.invstd = r.invstd;
-    a.means = bp.means; a.npix = npix; a.cpad = gb.cpad; a.planes = gb.planes; a.raw_cpad = f.raw_cpad; a.c_real = f.cout; a.alpha = h->cfg.lrelu_alpha;
-    pf(h, npix * (gb.cpad / 8), stream, a);
+    a.means = bp.means; a.cpad = gb.cpad; a.planes = gb.planes; a.raw_cpad = f.raw_cpad; a.c_real = f.cout; a.alpha = h->cfg.lrelu_alpha;
+    rows(h, npix, gb.cpad / 8, stream, a);
   }
   // a conv bias in front of a training-mode BatchNorm has an exactly zero gradient (BN removes the batch mean; the
   // gradient buffer was zero-filled): only the un-normalised logits conv needs the column sum
@@ -628,11 +628,11 @@ static int bwd_lstm_layer(lu_handle_s* h, ConvPlan& f, int T, float* grads, std:
     c.dC = reinterpret_cast<float*>(h->ws + f.off_dc); c.dZ = act_ptr(h, f.dz_buf);
     c.pix_per_sample = pps; c.T = T; c.t = t; c.fpad = f.fpad; c.planes = h->planes; c.gate_kind = h->cfg.gate;
     c.first = t == T - 1;
-    pf(h, (int64_t)B * pps * (f.fpad / 8), stream, c);
+    c.dbias = grads + h->params[f.bias_param].offset; c.F = f.F;      // bias gradient accumulated on the way (grads was zeroed)
+    rows(h, (int64_t)B * pps, f.fpad / 8, stream, c);
     if (t > 0)                              // dh_{t-1} += conv^T(dz_t, recurrent_kernel)
       if (run_dgrads(h, f, 1, B, T, t, T, t - 1, 1, gwritten, stream)) return 1;
   }
-  run_colsum(h, f.dz_buf, B * T, grads + h->params[f.bias_param].offset, 0, f.F, f.fpad, stream);
   if (run_wgrad(h, f, f.dz_buf, T, grads, stream)) return 1;
   if (run_dgrads(h, f, 0, B * T, 1, 0, 1, 0, -1, gwritten, stream)) return 1;   // dx_t for all frames at once
   return 0;

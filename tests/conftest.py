@@ -15,6 +15,10 @@ def pytest_configure(config):
 def pytest_collection_modifyitems(config, items):
     import torch
     if torch.cuda.is_available():
+        # GPU box: make sure the in-tree CUDA library matches the sources of this snapshot (rebuilt only when the
+        # content hash differs -- a stale .so would silently test old kernels)
+        import __graft_entry__ as ge
+        ge.build()
         return
     skip = pytest.mark.skip(reason="no CUDA device")
     for item in items:
