@@ -281,7 +281,8 @@ class ULSTMnet2D:
         self._be = be
         cfg = _lib.make_config(self.net_params, self.data_format, self.pad_image, batch=B, max_t=T, height=H, width=W,
                                precision=self.precision, engine=self.engine, gate=self.gate, a_mode=self.a_mode,
-                               train=self.train_capable, lrelu_alpha=self.lrelu_alpha)
+                               train=self.train_capable, lrelu_alpha=self.lrelu_alpha,
+                               in_channels=getattr(self, '_in_channels', 1))
         sess = LuSession(self._lib, be, cfg)
         want_graph = (B * T <= 2) if self.cuda_graph == 'auto' else bool(self.cuda_graph)
         self.graph_active = sess.set_graph_mode(want_graph and not self.train_capable)
@@ -296,6 +297,10 @@ class ULSTMnet2D:
             old.close()
         else:
             w = self._pending_weights or keras_default_init(sess.layout, self.seed)
+            if self._pending_weights is not None:
+                k0 = 'DownLayers/0/ConvLSTM/0/kernel'
+                if k0 in w and np.asarray(w[k0]).shape[2] != self._in_channels:
+                    raise ValueError('weights were made for %d image channels, input has %d' % (np.asarray(w[k0]).shape[2], self._in_channels))
             sess.set_params(w)
             self._pending_weights = None
             self._sess = sess
@@ -316,8 +321,10 @@ class ULSTMnet2D:
         return self._sess
 
     def _check_channels(self, C):
-        if C != 1:
-            raise ValueError('only single-channel images are supported on this backend (got %d channels)' % C)
+        """The number of image channels is frozen by the first call, like every Keras variable shape."""
+        if self._sess is not None and C != self._in_channels:
+            raise ValueError('the model was built for %d image channels, got %d' % (self._in_channels, C))
+        self._in_channels = int(C)
 
     # ---- call (Networks.py:208-254) ------------------------------------------------------------------
     def __call__(self, inputs, training=None, mask=None):
@@ -630,9 +637,9 @@ class ULSTMnet2D:
 
     @classmethod
     def unit_test(cls):
-        """Networks.py:256-277 (shape contract), channels-first single-channel variant for this backend."""
-        model = cls(DEFAULT_NET_DOWN_PARAMS, 'NCHW', True)
+        """Networks.py:256-277 (shape contract)."""
+        model = cls(DEFAULT_NET_DOWN_PARAMS, 'NHWC', True)
         for i in range(4):
-            x = np.random.randn(2, 2, 1, 35, 35).astype(np.float32)
+            x = np.random.randn(2, 2, 35, 35, 3).astype(np.float32)      # the reference's own case: 3 channels, channels-last
             out = model(x, True)
             print(i, tuple(out[0].shape))

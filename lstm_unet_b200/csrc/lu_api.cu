@@ -130,6 +130,7 @@ struct lu_handle_s {
   std::vector<std::vector<int>> lstm_of_level, conv_of_level, conv_of_up;
   std::vector<UpStage> ups;       // per up block (src_buf = -1: no resize)
   int logits_conv = -1;
+  int img_buf = -1;               // in_channels > 1: the reflect-padded image as an ordinary NHWC activation buffer
   size_t off_patches = 0, off_raw_scratch = 0, raw_scratch_bytes = 0, off_logits_raw = 0;
   size_t ws_bytes = 0;
   uint8_t* ws = nullptr;
@@ -486,16 +487,23 @@ static int build_plan(lu_handle_s* h) {
              "REFLECT padding needs pad < image size (H=%d W=%d pad=%d/%d)", c.height, c.width, pad_y1, pad_x1);
   h->Hp = c.height + minpad + pad_y1; h->Wp = c.width + minpad + pad_x1;
   for (int l = 0; l <= L; ++l) { h->lvlH[l] = h->Hp >> (l < L ? l : L - 1); h->lvlW[l] = h->Wp >> (l < L ? l : L - 1); }
-  LU_REQUIRE(c.in_channels == 1, "only single-channel images are supported (in_channels=%d)", c.in_channels);
-  // patch window = the largest kernel that reads the image directly
-  h->pw = c.lstm_k[0][0];
-  if (c.up_k[L - 1][0] > h->pw) h->pw = c.up_k[L - 1][0];
-  LU_REQUIRE(h->pw * h->pw <= (h->planes == 2 ? 32 : 64), "kernel size %d too large for the image patch path", h->pw);
+  LU_REQUIRE(c.in_channels >= 1 && c.in_channels <= 4096, "bad in_channels=%d", c.in_channels);
+  if (c.in_channels == 1) {
+    // the CTC path: the 1-channel image is expanded into pw x pw patches (64 "channels", one 1x1 tap);
+    // patch window = the largest kernel that reads the image directly
+    h->pw = c.lstm_k[0][0];
+    if (c.up_k[L - 1][0] > h->pw) h->pw = c.up_k[L - 1][0];
+    LU_REQUIRE(h->pw * h->pw <= (h->planes == 2 ? 32 : 64), "kernel size %d too large for the image patch path", h->pw);
+  }
 
   h->lstm_of_level.assign(L, {}); h->conv_of_level.assign(L, {}); h->conv_of_up.assign(L, {});
   h->ups.assign(L, UpStage());
   char nm[128];
-  int cur_buf = -1, cur_c = c.in_channels;      // -1 = image
+  int cur_buf = -1, cur_c = c.in_channels;      // -1 = image patches
+  if (c.in_channels > 1) {                      // multi-channel images (the reference unit_test feeds 3, Networks.py:266):
+    h->img_buf = new_act(h, N, h->Hp, h->Wp, c.in_channels);      // generic path, the image is just another NHWC source
+    cur_buf = h->img_buf;
+  }
   std::vector<int> skip_buf, skip_c;
   for (int l = 0; l < L; ++l) {
     const int H = h->lvlH[l], W = h->lvlW[l];
@@ -606,7 +614,7 @@ static void layout_workspace(lu_handle_s* h) {
   const int B = c.batch, N = c.batch * c.max_t;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return o; };
-  h->off_patches = take((size_t)N * h->Hp * h->Wp * 64 * 2);
+  h->off_patches = take(c.in_channels == 1 ? (size_t)N * h->Hp * h->Wp * 64 * 2 : 1024);
   for (auto& a : h->acts) a.off = take(a.bytes());
   h->raw_scratch_bytes = 0;
   for (auto& cv : h->convs) {
@@ -776,7 +784,11 @@ static int launch_conv(lu_handle_s* h, ConvPlan& cv, int frames, const int* mul,
   // data gradient: 70 % tensor-pipe activity at ~14 TB/s of L2->SM weight traffic).  LU_CLUSTER_WIDE=0 disables.
   static int wide_env = -1;
   if (wide_env < 0) { const char* ce = getenv("LU_CLUSTER_WIDE"); wide_env = ce ? atoi(ce) : 1; }
-  const bool wide = wide_env == 1 && epi.kind != LU_EPI_LSTM && cv.ktot >= 2048 && cv.BN >= 128 && m_tiles >= 2 * h->num_sms;
+  // thresholds of "large weight stream" (experiment switches LU_WIDE_MIN_K / LU_WIDE_MIN_BN)
+  static int wide_min_k = -1, wide_min_bn = -1;
+  if (wide_min_k < 0) { const char* ce = getenv("LU_WIDE_MIN_K"); wide_min_k = ce ? atoi(ce) : 2048; }
+  if (wide_min_bn < 0) { const char* ce = getenv("LU_WIDE_MIN_BN"); wide_min_bn = ce ? atoi(ce) : 128; }
+  const bool wide = wide_env == 1 && epi.kind != LU_EPI_LSTM && cv.ktot >= wide_min_k && cv.BN >= wide_min_bn && m_tiles >= 2 * h->num_sms;
   const bool cl2 = cluster_env == 2 && (epi.kind == LU_EPI_LSTM || wide) && cv.ptab_ok && (h->num_sms % 2 == 0);
   // The cluster launches run ONE M = 256 MMA per CTA pair (tcgen05.mma.cta_group::2, kernel cluster mode 3) instead of two
   // M = 128 MMAs fed by a multicast weight stage: each CTA stages only half of every weight K block, so the weight stages
@@ -1192,7 +1204,14 @@ static int forward_body(lu_handle h, const float* dev_x, int32_t T, int32_t trai
                         float* dev_softmax, void* stream) {
   const lu_config& c = h->cfg;
   const int N = c.batch * T;
-  {
+  if (h->img_buf >= 0) {
+    const ActBuf& ib = h->acts[h->img_buf];
+    LuPrepImage pi;
+    pi.x = dev_x; pi.out = reinterpret_cast<uint16_t*>(h->ws + ib.off);
+    pi.C = c.in_channels; pi.H = c.height; pi.W = c.width; pi.Hp = h->Hp; pi.Wp = h->Wp; pi.pad_y0 = h->pad_y0; pi.pad_x0 = h->pad_x0;
+    pi.cpad = ib.cpad; pi.planes = ib.planes; pi.fmt = h->fmt; pi.channels_first = c.channels_first;
+    pf(h, (int64_t)N * h->Hp * h->Wp * (ib.cpad / 8), stream, pi);
+  } else {
     LuPrepPatches pp;
     pp.x = dev_x; pp.out = reinterpret_cast<uint16_t*>(h->ws + h->off_patches);
     pp.H = c.height; pp.W = c.width; pp.Hp = h->Hp; pp.Wp = h->Wp; pp.pad_y0 = h->pad_y0; pp.pad_x0 = h->pad_x0;

@@ -155,7 +155,9 @@ static void lu_rows_impl(int64_t npix, int ngroups, void* stream, F f) {
   const int gpb = ngroups < 256 ? ngroups : 256, PL = 256 / gpb;
   const int gy = (ngroups + gpb - 1) / gpb;
   int64_t bx = (npix + PL - 1) / PL;
-  int64_t cap = (148 * 8 * 2) / gy;            // two waves of resident blocks: few flushes, still balanced
+  // streaming passes: two waves of resident blocks.  Reductions: every block ends with one atomic per channel on the SAME
+  // few hundred addresses (serialised in L2), so fewer, longer-lived blocks: 4 per SM, one wave
+  int64_t cap = (F::NSUM > 0 ? 148 * 4 : 148 * 8 * 2) / gy;
   if (cap < 1) cap = 1;
   if (bx > cap) bx = cap;
   lu_rows_kernel<<<dim3((unsigned)bx, (unsigned)gy), 256, 0, (cudaStream_t)stream>>>(npix, ngroups, f);
@@ -199,6 +201,31 @@ struct LuPrepPatches {
     uint16_t* o = out + p * 64;
 #pragma unroll
     for (int g = 0; g < 8; ++g) lu_store8_bf16(o + g * 8, r + g * 8);
+  }
+};
+
+// multi-channel images (in_channels > 1): reflect-pad + layout change into an ordinary NHWC 16-bit activation buffer
+// x: (N,C,H,W) [channels_first] or (N,H,W,C); out (N,Hp,Wp,planes*cpad); item = (padded pixel, group of 8 channels)
+struct LuPrepImage {
+  const float* x; uint16_t* out;
+  int C, H, W, Hp, Wp, pad_y0, pad_x0, cpad, planes, fmt, channels_first;
+  LU_HD void operator()(int64_t i) const {
+    const int cg = cpad / 8;
+    const int c0 = (int)(i % cg) * 8; const int64_t p = i / cg;
+    const int xx = (int)(p % Wp); const int64_t q = p / Wp;
+    const int yy = (int)(q % Hp); const int64_t n = q / Hp;
+    const int sy = lu_reflect(yy - pad_y0, H), sx = lu_reflect(xx - pad_x0, W);
+    uint16_t hi[8], lo[8];
+    for (int j = 0; j < 8; ++j) {
+      const int c = c0 + j;
+      float v = 0.f;
+      if (c < C) v = channels_first ? x[((n * C + c) * H + sy) * (int64_t)W + sx] : x[((n * H + sy) * (int64_t)W + sx) * C + c];
+      if (planes == 2) lu_split(v, hi[j], lo[j]);
+      else hi[j] = lu_f2h16(v, fmt);
+    }
+    uint16_t* o = out + p * (int64_t)(cpad * planes) + c0;
+    lu_store8_bf16(o, hi);
+    if (planes == 2) lu_store8_bf16(o + cpad, lo);
   }
 };
 

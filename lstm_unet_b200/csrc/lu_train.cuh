@@ -245,22 +245,16 @@ struct LuUpsample2xBwd {   // item = (n, iy, ix, c)
 };
 
 // ---- ConvLSTM cell backward for one time step ----------------------------------------------------------------------
-// Row-loop kernel over the B*H*W sample pixels of one time step; a thread owns 8 channels (of each of the 4 gates).
-// gates: (frames,H,W,planes*4*fpad) [i|f|g|o]; dZ same layout (bf16 planes).  The bias gradient (sum of dZ over pixels and
-// steps) is accumulated on the way, from the un-rounded fp32 values: no separate pass over dZ.
-struct LuLstmCellBwd {
+// (A row-loop variant that also accumulated the bias gradient in registers was measured in round 2: 160 registers, one
+// resident block per SM, 16.6 instead of 9.3 ms per step -- the bias gradient is a separate row-loop pass over dZ instead.)
+// item = (sample pixel, channel < fpad).  gates: (frames,H,W,planes*4*fpad) [i|f|g|o]; dZ same layout (bf16 planes).
+struct LuLstmCellBwd {    // item = (sample pixel, group of 8 channels)
   const uint16_t* dH; const uint16_t* gates; const float* c_t; const float* c_prev; float* dC; uint16_t* dZ;
-  float* dbias;              // (4*F) gradient of the ConvLSTM bias, gate-major like the Keras tensor; accumulated atomically
-  int64_t pix_per_sample; int T, t, fpad, F, planes, gate_kind, c_prev_is_init, first;
-  struct State { float bs[32]; };
-  static constexpr int NSUM = 32;
-  LU_HD void begin(int, State& st) const {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) st.bs[j] = 0.f;
-  }
-  LU_HD void pixel(int64_t sp, int g, State& st) const {                      // sp = b*HW + pixel
-    const int ch = g * 8;
-    const int64_t b = sp / pix_per_sample, px = sp - b * pix_per_sample;
+  int64_t pix_per_sample; int T, t, fpad, planes, gate_kind, c_prev_is_init, first;
+  LU_HD void operator()(int64_t i) const {
+    const int cg = fpad / 8;
+    const int ch = (int)(i % cg) * 8; const int64_t sp = i / cg;            // sp = b*HW + pixel
+    const int64_t b = sp / pix_per_sample, px = sp % pix_per_sample;
     const int64_t fp = (b * T + t) * pix_per_sample + px;                   // pixel index in frame-major buffers
     const int g4 = 4 * fpad;
     const uint16_t* gp = gates + fp * (int64_t)(g4 * planes) + ch;
@@ -288,40 +282,43 @@ struct LuLstmCellBwd {
         zi[j] = d_i * gi[j] * (1.f - gi[j]); zf[j] = d_f * gf[j] * (1.f - gf[j]); zo[j] = d_o * go[j] * (1.f - go[j]);
       }
       zg[j] = d_g * (1.f - gg[j] * gg[j]);
-      st.bs[j] += zi[j]; st.bs[8 + j] += zf[j]; st.bs[16 + j] += zg[j]; st.bs[24 + j] += zo[j];
     }
     lu_st8f(dC + sp * fpad + ch, dc);
     uint16_t* zp = dZ + fp * (int64_t)(g4 * planes) + ch;
     lu_st8planes(zp, g4, planes, zi); lu_st8planes(zp + fpad, g4, planes, zf);
     lu_st8planes(zp + 2 * fpad, g4, planes, zg); lu_st8planes(zp + 3 * fpad, g4, planes, zo);
   }
-  LU_HD void partials(const State& st, float* part) const {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) part[j] = st.bs[j];
-  }
-  LU_HD void flush(int g, const float* part) const {
-    for (int gate = 0; gate < 4; ++gate)
-      for (int j = 0; j < 8; ++j) {
-        const int ch = g * 8 + j;
-        if (ch < F) lu_atomic_add(&dbias[gate * F + ch], part[gate * 8 + j]);
-      }
-  }
 };
 
-// ---- bias gradient: column sums of a gradient buffer; item = (pixel chunk, channel) -----------------------------
+// ---- bias gradient: column sums of a gradient buffer (row-loop kernel: a thread owns 8 channels) ---------------------
 struct LuColSumGrad {
-  const uint16_t* g; float* dst; int64_t npix; int cpad, planes, chunk;
+  const uint16_t* g; float* dst; int cpad, planes;
   int c_real;        // identity layout: channel c < c_real -> dst[c]
   int gate_F, gate_fpad;   // gate layout (gate_F > 0): channel gate*fpad + ch -> dst[gate*F + ch]
-  LU_HD void operator()(int64_t i) const {
-    const int c = (int)(i % cpad); const int64_t pc = i / cpad;
-    int d;
-    if (gate_F > 0) { const int gt = c / gate_fpad, ch = c % gate_fpad; if (ch >= gate_F) return; d = gt * gate_F + ch; }
-    else { if (c >= c_real) return; d = c; }
-    int64_t p0 = pc * chunk, p1 = p0 + chunk; if (p1 > npix) p1 = npix;
-    float s = 0.f;
-    for (int64_t p = p0; p < p1; ++p) s += lu_ldplanes(g + p * (int64_t)(cpad * planes) + c, cpad, planes);
-    lu_atomic_add(&dst[d], s);
+  struct State { float s[8]; };
+  static constexpr int NSUM = 8;
+  LU_HD void begin(int, State& st) const {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) st.s[j] = 0.f;
+  }
+  LU_HD void pixel(int64_t p, int grp, State& st) const {
+    float v[8];
+    lu_ld8planes(g + p * (int64_t)(cpad * planes) + grp * 8, cpad, planes, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) st.s[j] += v[j];
+  }
+  LU_HD void partials(const State& st, float* part) const {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) part[j] = st.s[j];
+  }
+  LU_HD void flush(int grp, const float* part) const {
+    for (int j = 0; j < 8; ++j) {
+      const int c = grp * 8 + j;
+      int d;
+      if (gate_F > 0) { const int gt = c / gate_fpad, ch = c % gate_fpad; if (ch >= gate_F) continue; d = gt * gate_F + ch; }
+      else { if (c >= c_real) continue; d = c; }
+      lu_atomic_add(&dst[d], part[j]);
+    }
   }
 };
 

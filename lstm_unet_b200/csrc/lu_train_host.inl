@@ -102,7 +102,7 @@ static int build_train_plan(lu_handle_s* h) {
   for (int fi = 0; fi < n_fwd; ++fi) {
     const int n_in = h->convs[fi].n_in, s = h->convs[fi].stride;
     for (int i = 0; i < n_in; ++i) {
-      if (h->convs[fi].in[i].buf < 0) continue;                 // the image needs no gradient
+      if (h->convs[fi].in[i].buf < 0 || h->convs[fi].in[i].buf == h->img_buf) continue;   // the image needs no gradient
       for (int ry = 0; ry < s; ++ry)
         for (int rx = 0; rx < s; ++rx) {
           const int di = add_dgrad(h, fi, i, ry, rx);
@@ -185,9 +185,9 @@ static void run_colsum(lu_handle_s* h, int gbuf, int frames_used, float* dst, in
                        void* stream) {
   const ActBuf& g = h->acts[gbuf];
   LuColSumGrad cs;
-  cs.g = act_ptr(h, gbuf); cs.dst = dst; cs.npix = (int64_t)frames_used * g.H * g.W; cs.cpad = g.cpad; cs.planes = g.planes;
-  cs.chunk = 256; cs.c_real = c_real; cs.gate_F = gate_F; cs.gate_fpad = gate_fpad;
-  pf(h, ((cs.npix + cs.chunk - 1) / cs.chunk) * g.cpad, stream, cs);
+  cs.g = act_ptr(h, gbuf); cs.dst = dst; cs.cpad = g.cpad; cs.planes = g.planes;
+  cs.c_real = c_real; cs.gate_F = gate_F; cs.gate_fpad = gate_fpad;
+  rows(h, (int64_t)frames_used * g.H * g.W, g.cpad / 8, stream, cs);
 }
 
 // ---- tcgen05 weight gradient: task list for one forward conv (see lu_wgrad_tc_kernel) --------------------------------
@@ -628,11 +628,11 @@ static int bwd_lstm_layer(lu_handle_s* h, ConvPlan& f, int T, float* grads, std:
     c.dC = reinterpret_cast<float*>(h->ws + f.off_dc); c.dZ = act_ptr(h, f.dz_buf);
     c.pix_per_sample = pps; c.T = T; c.t = t; c.fpad = f.fpad; c.planes = h->planes; c.gate_kind = h->cfg.gate;
     c.first = t == T - 1;
-    c.dbias = grads + h->params[f.bias_param].offset; c.F = f.F;      // bias gradient accumulated on the way (grads was zeroed)
-    rows(h, (int64_t)B * pps, f.fpad / 8, stream, c);
+    pf(h, (int64_t)B * pps * (f.fpad / 8), stream, c);
     if (t > 0)                              // dh_{t-1} += conv^T(dz_t, recurrent_kernel)
       if (run_dgrads(h, f, 1, B, T, t, T, t - 1, 1, gwritten, stream)) return 1;
   }
+  run_colsum(h, f.dz_buf, B * T, grads + h->params[f.bias_param].offset, 0, f.F, f.fpad, stream);
   if (run_wgrad(h, f, f.dz_buf, T, grads, stream)) return 1;
   if (run_dgrads(h, f, 0, B * T, 1, 0, 1, 0, -1, gwritten, stream)) return 1;   // dx_t for all frames at once
   return 0;

@@ -242,3 +242,25 @@ def test_fp16_conversions_match_numpy_float16():
         want = x.astype(np.float16).astype(np.float32)
     np.testing.assert_array_equal(out, want)
     sess.close()
+
+
+@pytest.mark.parametrize("fmt,C,H,W,pad", [('NHWC', 3, 35, 35, True), ('NCHW', 2, 16, 24, False)])
+def test_multi_channel_images(fmt, C, H, W, pad):
+    """in_channels > 1 (the reference's unit_test feeds d=3 channels, channels-last, 35x35 with pad_image:
+    Networks.py:266-270): the image is an ordinary NHWC source of the level-0 ConvLSTM and of the last decoder block's
+    skip connection."""
+    net, B, T = NET_B, 2, 2
+    p_t = O.init_params(net, seed=11, randomize_bn=True, in_channels=C)
+    ora = O.OracleNet(net, fmt, pad, params=p_t, in_channels=C)
+    sess = emu_session(net, data_format=fmt, pad_image=pad, batch=B, max_t=T, height=H, width=W, precision='bf16x3',
+                       in_channels=C)
+    sess.set_params({k: v.numpy() for k, v in p_t.items()})
+    rng = np.random.default_rng(0)
+    shape = (B, T, C, H, W) if fmt == 'NCHW' else (B, T, H, W, C)
+    for call in range(2):
+        x = rng.standard_normal(shape).astype(np.float32)
+        ref_l, ref_s = ora(torch.from_numpy(x), False)
+        got_l, got_s = emu_forward(sess, x, False)
+        assert got_l.shape == tuple(ref_l.shape)
+        assert rel_err(got_l, ref_l.numpy()) < 1e-3 and rel_err(got_s, ref_s.numpy()) < 1e-3
+    sess.close()

@@ -51,15 +51,15 @@ class TieWatch:
         return self.min_lrelu > tol and self.min_gate > tol
 
 
-def run_case(net, B, T, H, W, seed, steps=2, smooth=False):
-    params = O.init_params(net, seed=seed, randomize_bn=True)
+def run_case(net, B, T, H, W, seed, steps=2, smooth=False, C=1):
+    params = O.init_params(net, seed=seed, randomize_bn=True, in_channels=C)
     p_np = {k: v.numpy().copy() for k, v in params.items()}
     ora = O.OracleNet(net, 'NCHW', False, params=params, gate='sigmoid' if smooth else 'hard_sigmoid')
     if not smooth:
         ora.gate = lambda x: O.hard_sigmoid(x)       # late-bound so TieWatch sees the calls
     sess = emu_session(net, data_format='NCHW', pad_image=False, batch=B, max_t=T, height=H, width=W,
                        precision='bf16x3', train=True, gate='sigmoid' if smooth else 'hard_sigmoid',
-                       lrelu_alpha=1.0 if smooth else 0.3)
+                       lrelu_alpha=1.0 if smooth else 0.3, in_channels=C)
     sess.set_params(p_np)
     names = ora.trainable_names()
     m = {n: torch.zeros_like(ora.params[n]) for n in names}
@@ -73,7 +73,7 @@ def run_case(net, B, T, H, W, seed, steps=2, smooth=False):
     lr = 1e-3
     n_compared = 0
     for step in range(1, steps + 1):          # second step: non-zero initial h/c (truncated BPTT) and updated weights
-        x = rng.standard_normal((B, T, 1, H, W)).astype(np.float32)
+        x = rng.standard_normal((B, T, C, H, W)).astype(np.float32)
         lab = rng.integers(-1, 3, size=(B, T, 1, H, W)).astype(np.float32)
         with TieWatch() as tw:
             ref_loss, ref_logits, _, ref_grads = O.train_step(ora, torch.from_numpy(x), torch.from_numpy(lab), CW, m, v, step, lr)
@@ -127,6 +127,13 @@ def test_train_step_smooth_variant_needs_no_tie_watch(monkeypatch):
     near-tie in the reference configuration (next test)."""
     monkeypatch.setattr(O, 'LRELU_ALPHA', 1.0)
     worst, n = run_case(NET_B, 2, 2, 8, 8, 21, smooth=True)
+    assert n == 2 and worst[1] < 1e-3
+
+
+def test_train_step_multi_channel_image(monkeypatch):
+    """in_channels = 3: weight gradients of the layers that read the image (no data gradient flows into it)."""
+    monkeypatch.setattr(O, 'LRELU_ALPHA', 1.0)
+    worst, n = run_case(NET_C, 1, 2, 16, 16, 5, smooth=True, C=3)
     assert n == 2 and worst[1] < 1e-3
 
 

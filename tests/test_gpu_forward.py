@@ -266,3 +266,22 @@ def test_variable_assign_and_per_block_state_reset():
     ref = ora(torch.from_numpy(x), False)[0].numpy()
     got = model(x, False)[0].numpy()
     assert rel_err(got, ref) < 1e-3 and rel_err(got, before) > 1e-2
+
+
+def test_multi_channel_image_reference_unit_test_case():
+    """The reference's own unit_test input (Networks.py:266-270): 3 image channels, channels-last, 35x35, pad_image,
+    successive stateful calls -- against the oracle (the soft-max axis quirk of channels-last included)."""
+    from lstm_unet_b200.Networks import ULSTMnet2D
+    params = O.init_params(NET_ODD, seed=21, randomize_bn=True, in_channels=3)
+    ora = O.OracleNet(NET_ODD, 'NHWC', True, params=params, in_channels=3)
+    model = ULSTMnet2D(NET_ODD, 'NHWC', True, precision='bf16x3')
+    model.set_weights_dict({k: v.numpy().copy() for k, v in params.items()})
+    rng = np.random.default_rng(2)
+    for call in range(3):
+        x = rng.standard_normal((2, 2, 35, 35, 3)).astype(np.float32)
+        ref_l, ref_s = ora(torch.from_numpy(x), False)
+        logits, softmax = model(x, False)
+        assert tuple(logits.shape) == (2, 2, 35, 35, 3)
+        assert rel_err(logits.numpy(), ref_l.numpy()) < 1e-3 and rel_err(softmax.numpy(), ref_s.numpy()) < 1e-3
+    with pytest.raises(ValueError):
+        model(np.zeros((2, 2, 35, 35, 1), np.float32), False)      # the channel count is frozen by the first call
