@@ -103,8 +103,8 @@ struct ConvPlan {
   int dz_buf = -1;                      // lstm: gradient wrt the gate pre-activations (frames,H,W,4*fpad)
   std::vector<int> dgrads[2];
   std::vector<uint16_t> kb_stage, kb_tap;
-  int wg_cached_T[2] = {-1, -1}, wg_n_tasks[2] = {0, 0};   // weight-gradient task lists resident on the device
-  size_t off_kb_stage = 0, off_kb_tap = 0, off_bwd_sums = 0, off_c_init = 0, off_dc = 0, off_wg_tasks = 0, off_bwd_means = 0;
+  int wg_cached_T[2] = {-1, -1}, wg_n_tasks[2] = {0, 0}, wg_n_ptasks[2] = {0, 0};   // weight-gradient task lists resident on the device
+  size_t off_kb_stage = 0, off_kb_tap = 0, off_bwd_sums = 0, off_c_init = 0, off_dc = 0, off_wg_tasks = 0, off_wg_ptasks = 0, off_bwd_means = 0;
 #ifndef LU_HOST_EMU
   CUtensorMap tmA[LU_MAX_SRC];
   CUtensorMap tmB, tmBh;
@@ -786,7 +786,7 @@ static int launch_conv(lu_handle_s* h, ConvPlan& cv, int frames, const int* mul,
   if (wide_env < 0) { const char* ce = getenv("LU_CLUSTER_WIDE"); wide_env = ce ? atoi(ce) : 1; }
   // thresholds of "large weight stream" (experiment switches LU_WIDE_MIN_K / LU_WIDE_MIN_BN)
   static int wide_min_k = -1, wide_min_bn = -1;
-  if (wide_min_k < 0) { const char* ce = getenv("LU_WIDE_MIN_K"); wide_min_k = ce ? atoi(ce) : 2048; }
+  if (wide_min_k < 0) { const char* ce = getenv("LU_WIDE_MIN_K"); wide_min_k = ce ? atoi(ce) : 1024; }      // round 2: 2048 -> 1024, +1 % on the C2 step
   if (wide_min_bn < 0) { const char* ce = getenv("LU_WIDE_MIN_BN"); wide_min_bn = ce ? atoi(ce) : 128; }
   const bool wide = wide_env == 1 && epi.kind != LU_EPI_LSTM && cv.ktot >= wide_min_k && cv.BN >= wide_min_bn && m_tiles >= 2 * h->num_sms;
   const bool cl2 = cluster_env == 2 && (epi.kind == LU_EPI_LSTM || wide) && cv.ptab_ok && (h->num_sms % 2 == 0);

@@ -705,7 +705,7 @@ __global__ void __launch_bounds__(lutc::kThreads, 1) lu_conv_tc_kernel(const __g
 }
 #endif  // !LU_HOST_EMU
 
-// one task of the tcgen05 weight-gradient kernel below (plain data: the task lists are built on the host, and the host
+// one task of the tcgen05 weight-gradient kernels below (plain data: the task lists are built on the host, and the host
 // test build replays them with scalar loops)
 struct LuWgTask {
   int16_t stage0, stage1;        // forward A stages giving rows [0,64) / [64,128); stage1 < 0: rows 64.. unused
@@ -716,21 +716,31 @@ struct LuWgTask {
   int32_t kb0[4], kb1[4];        // K block (64 rows of dWp) written by each tap for stage0 / stage1
   int32_t ychan[2];              // channel coordinate in dY of each 64-column chunk
 };
+// one task of the CTA-PAIR weight-gradient kernel: 256 output channels x (128 * nb) input channels x ntaps taps
+struct LuWgPairTask {
+  int16_t stage[4];              // forward A stages (64-channel chunks of ONE source with the same window geometry), in
+                                 // order of the accumulator columns; CTA r of the pair stages [r*nb, (r+1)*nb)
+  int16_t nb, ntaps;             // chunks per CTA (1 or 2); taps (<= 4 for nb == 1, <= 2 for nb == 2: 512 TMEM columns)
+  int32_t n0;                    // first packed column of the 256-column slab: CTA r owns columns [n0 + 128 r, + 128)
+  int32_t tile0, tile1;          // pixel-tile range [tile0, tile1)
+  int32_t off[4];                // tap offsets (rows) inside the window
+  int32_t kb[4][4];              // K block (64 rows of dWp) written by tap t for stage s
+  int32_t ychan[4];              // channel coordinate in dY of the slab's four 64-column chunks
+};
 
 #ifndef LU_HOST_EMU
 // =============================================================================================================
 // Weight gradient on tcgen05: dWp[n][k] += sum over pixels  A_k[pixel] * dY[pixel][n]      (packed space)
 //
 // Both operands are NHWC, i.e. MN-major for a reduction over pixels: the MMA "K" rows are pixels (128-byte rows of
-// 64 channels), exactly what the forward's halo windows already are.  One task = (up to 2 activation stages = 128
-// rows of channels, up to 4 taps, one 64/128-column slab of output channels, a range of pixel tiles); the 4 taps'
-// accumulators (128 x N fp32 each) stay in TMEM for the whole pixel range and are flushed with fp32 atomics.
+// 64 channels), exactly what the forward's halo windows already are.
 // =============================================================================================================
 struct LuWgParams {
   CUtensorMap tmA[LU_MAX_SRC];
   CUtensorMap tmY;
   LuConvParams cp;               // forward views / stage table
   const LuWgTask* tasks;
+  const LuWgPairTask* ptasks;
   float* dWp;
   int32_t tiles_x, tiles_y, T, skip_t0_src;
   int32_t dy_frame_mul, dy_frame_add, dy_planes, dy_cpad;
@@ -744,22 +754,17 @@ __device__ __forceinline__ uint32_t desc_lo_mn(uint32_t addr, uint32_t lbo_bytes
 }
 }  // namespace lutc
 
-// CL == 2: the two CTAs of a cluster run two tasks that differ only in their taps (same channel rows, column slab and
-// pixel range).  Every operand box of a stage is fetched from L2 by ONE of them and multicast into both CTAs' shared
-// memory (half the L2->SM traffic per MMA); a stage is released by both MMA issuers (multicast tcgen05.commit).  A task
-// with ntaps == 0 is a partner that only takes part in the staging.
-// CL == 3: the pair runs ONE M = 256 MMA per K step (tcgen05.mma.cta_group::2 issued by the even CTA).  Both tasks have
-// the same channel rows, pixel range and 128-column slab; the peer's taps are the leader's displaced by a constant
-// (off[i] of the odd task = off[i] of the even task + d, d >= 0), which the peer realises by displacing its window by d,
-// so that the leader's descriptors read the right pixels in both shared memories.  Each
-// CTA stages its own windows and ONE 64-column half of the dY tile (N = 128 split over the pair): per SM and K step the
-// operand read drops from 8 KB to 6 KB.  bf16 mode with two-chunk slabs only; the host falls back to CL == 1 otherwise.
-// (Compiled, not yet run on hardware: LU_WGRAD_CLUSTER=3 selects it.)
-template <int CL>
+// ---- independent CTAs -----------------------------------------------------------------------------------------------
+// One task = (up to 2 activation stages = 128 rows of input channels, up to 4 taps, one 64/128-column slab of output
+// channels, a range of pixel tiles); the 4 taps' accumulators (128 x N fp32 each) stay in TMEM for the whole pixel range
+// and are flushed with fp32 atomics.  With M = N = 128 an MMA reads 8 KB of operands per 64 clocks = the whole shared
+// memory bandwidth of the SM, on top of the TMA writes of the next stage: 70 % tensor-pipe activity (round-1 profile).
+// Used for the layers / slabs the pair kernel below cannot take (single-chunk sources, < 256 output columns, bf16x3).
+// (Round 2 measured and removed two cluster variants of THIS decomposition: operand boxes multicast to a CTA pair, and
+// one M = 256 MMA per pair whose CTAs take different taps -- both 0 % on the step: the first leaves the shared-memory
+// reads unchanged, the second re-stages every window once per CTA and moved 18 % more data from L2.)
 __global__ void __launch_bounds__(256, 1) lu_wgrad_tc_kernel(const __grid_constant__ LuWgParams P) {
   using namespace lutc;
-  constexpr bool PAIR = CL == 3;
-  const int crank = (CL >= 2) ? (int)cluster_ctarank() : 0;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t pad = ((raw_addr + 1023u) & ~1023u) - raw_addr;
@@ -779,30 +784,19 @@ __global__ void __launch_bounds__(256, 1) lu_wgrad_tc_kernel(const __grid_consta
   const int nyp = (P.dy_planes == 2 && !tk.a_is_lo) ? 2 : 1;
   const uint32_t b_off = 2u * (uint32_t)P.a_win_bytes;            // B region inside a stage
   const int tiles_per_frame = P.tiles_x * P.tiles_y;
-  int shift_y = 0, shift_x = 0;                                    // pair mode, odd CTA: displacement of its windows in pixels
-  if (PAIR && crank == 1 && tk.ntaps > 0) {
-    const int d = tk.off[0] - P.tasks[blockIdx.x ^ 1].off[0];      // rows of the window (pitch pixels per image row)
-    shift_y = (d + (v.pitch >> 1)) / v.pitch;
-    shift_x = d - shift_y * v.pitch;
-  }
 
   if (warp == 0 && lane == 0) { prefetch_tmap(&P.tmA[st0.src]); prefetch_tmap(&P.tmY); }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < nS; ++i) { mbar_init(full + 8u * i, 1); mbar_init(empty + 8u * i, CL == 2 ? 2 : 1); }
+    for (int i = 0; i < nS; ++i) { mbar_init(full + 8u * i, 1); mbar_init(empty + 8u * i, 1); }
     mbar_init(done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    if (PAIR) {
-      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
-      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-    } else {
-      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
-      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
-  if (CL == 1) __syncthreads(); else cluster_sync_all();
+  __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -815,41 +809,17 @@ __global__ void __launch_bounds__(256, 1) lu_wgrad_tc_kernel(const __grid_consta
       if (st0.src == P.skip_t0_src && (frame % P.T) == 0) continue;
       const int y0 = (rem / P.tiles_x) * LU_TILE_H, x0 = (rem % P.tiles_x) * LU_TILE_W;
       mbar_wait(empty + 8u * s, ph ^ 1u);
-      if (PAIR) {
-        // own windows (displaced by the task's shift) + own 64-column half of the dY tile; every byte of the pair is
-        // counted on the leader's barrier
-        if (elect_one()) {
-          const uint32_t base = s0 + (uint32_t)s * P.stage_bytes;
-          const uint32_t lfull = map_to_rank(full + 8u * s, 0u);
-          if (crank == 0) mbar_expect_tx(full + 8u * s, 2u * ((uint32_t)(v.rows * v.pitch) * 128u * (tk.stage1 >= 0 ? 2u : 1u) + 16384u));
-          const int fa = frame * v.frame_mul + v.frame_add;
-          const int xs = x0 + shift_x, ys = y0 + shift_y;
-          tma_load_5d_pair(base, &P.tmA[st0.src], lfull, st0.c, xs + st0.dx, st0.plane, ys + st0.dy, fa);
-          if (tk.stage1 >= 0)
-            tma_load_5d_pair(base + (uint32_t)P.a_win_bytes, &P.tmA[st1.src], lfull, st1.c, xs + st1.dx, st1.plane, ys + st1.dy, fa);
-          tma_load_5d_pair(base + b_off, &P.tmY, lfull, tk.ychan[crank], x0, 0, y0, frame * P.dy_frame_mul + P.dy_frame_add);
-        }
-      } else if (elect_one()) {
+      if (elect_one()) {
         const uint32_t base = s0 + (uint32_t)s * P.stage_bytes;
         mbar_expect_tx(full + 8u * s, bytes);
         const int fa = frame * v.frame_mul + v.frame_add;
-        int box = 0;                                   // boxes alternate between the two CTAs of a cluster
-        if (CL == 1) tma_load_5d(base, &P.tmA[st0.src], full + 8u * s, st0.c, x0 + st0.dx, st0.plane, y0 + st0.dy, fa);
-        else if ((box & 1) == crank) tma_load_5d_mc(base, &P.tmA[st0.src], full + 8u * s, st0.c, x0 + st0.dx, st0.plane, y0 + st0.dy, fa, (uint16_t)3);
-        ++box;
-        if (tk.stage1 >= 0) {
-          if (CL == 1) tma_load_5d(base + (uint32_t)P.a_win_bytes, &P.tmA[st1.src], full + 8u * s, st1.c, x0 + st1.dx, st1.plane, y0 + st1.dy, fa);
-          else if ((box & 1) == crank) tma_load_5d_mc(base + (uint32_t)P.a_win_bytes, &P.tmA[st1.src], full + 8u * s, st1.c, x0 + st1.dx, st1.plane, y0 + st1.dy, fa, (uint16_t)3);
-          ++box;
-        }
+        tma_load_5d(base, &P.tmA[st0.src], full + 8u * s, st0.c, x0 + st0.dx, st0.plane, y0 + st0.dy, fa);
+        if (tk.stage1 >= 0)
+          tma_load_5d(base + (uint32_t)P.a_win_bytes, &P.tmA[st1.src], full + 8u * s, st1.c, x0 + st1.dx, st1.plane, y0 + st1.dy, fa);
         const int fy = frame * P.dy_frame_mul + P.dy_frame_add;
         for (int dp = 0; dp < nyp; ++dp)
-          for (int c = 0; c < tk.nch; ++c) {
-            const uint32_t dst = base + b_off + (uint32_t)(dp * tk.nch + c) * 16384u;
-            if (CL == 1) tma_load_5d(dst, &P.tmY, full + 8u * s, tk.ychan[c] + dp * P.dy_cpad, x0, 0, y0, fy);
-            else if ((box & 1) == crank) tma_load_5d_mc(dst, &P.tmY, full + 8u * s, tk.ychan[c] + dp * P.dy_cpad, x0, 0, y0, fy, (uint16_t)3);
-            ++box;
-          }
+          for (int c = 0; c < tk.nch; ++c)
+            tma_load_5d(base + b_off + (uint32_t)(dp * tk.nch + c) * 16384u, &P.tmY, full + 8u * s, tk.ychan[c] + dp * P.dy_cpad, x0, 0, y0, fy);
       }
       __syncwarp();
       if (++s == nS) { s = 0; ph ^= 1u; }
@@ -858,7 +828,7 @@ __global__ void __launch_bounds__(256, 1) lu_wgrad_tc_kernel(const __grid_consta
     // ---------------------------------------------------------------- MMA issuer (MN-major A and B)
     int s = 0; uint32_t ph = 0;
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) |
-                           ((uint32_t)((PAIR ? 256 : 128) >> 4) << 24);
+                           ((uint32_t)(128 >> 4) << 24);
     const uint32_t a_hi = desc_hi_mn((uint32_t)v.pitch * 128u), b_hi = desc_hi_mn(1024u);
     const uint32_t a_lbo = tk.stage1 >= 0 ? (uint32_t)P.a_win_bytes : 0u;
     const uint32_t row2 = (uint32_t)v.pitch * 128u * 2u;           // two image rows = 16 pixels = one MMA K step
@@ -866,7 +836,6 @@ __global__ void __launch_bounds__(256, 1) lu_wgrad_tc_kernel(const __grid_consta
     for (int tile = tk.tile0; tile < tk.tile1; ++tile) {
       const int frame = tile / tiles_per_frame;
       if (st0.src == P.skip_t0_src && (frame % P.T) == 0) continue;
-      if (PAIR && crank != 0) continue;                          // the even CTA issues for the pair
       mbar_wait(full + 8u * s, ph);
       tc_fence_after();
       const uint32_t base = s0 + (uint32_t)s * P.stage_bytes;
@@ -877,24 +846,18 @@ __global__ void __launch_bounds__(256, 1) lu_wgrad_tc_kernel(const __grid_consta
           for (int dp = 0; dp < nyp; ++dp) {
             const uint32_t b0 = base + b_off + (uint32_t)(dp * tk.nch) * 16384u;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              if (PAIR) mma_bf16_pair(d_tmem, desc_lo_mn(a0 + (uint32_t)j * row2, a_lbo), a_hi, desc_lo_mn(b0 + (uint32_t)j * 2048u, 16384u), b_hi,
-                                      idesc, (first && dp == 0 && j == 0) ? 0u : 1u);
-              else mma_bf16(d_tmem, desc_lo_mn(a0 + (uint32_t)j * row2, a_lbo), a_hi, desc_lo_mn(b0 + (uint32_t)j * 2048u, 16384u), b_hi,
-                            idesc, (first && dp == 0 && j == 0) ? 0u : 1u);
-            }
+            for (int j = 0; j < 8; ++j)
+              mma_bf16(d_tmem, desc_lo_mn(a0 + (uint32_t)j * row2, a_lbo), a_hi, desc_lo_mn(b0 + (uint32_t)j * 2048u, 16384u), b_hi,
+                       idesc, (first && dp == 0 && j == 0) ? 0u : 1u);
           }
         }
-        if (PAIR) tc_commit_pair(empty + 8u * s, (uint16_t)3);     // both CTAs' halves of the stage
-        else if (CL == 2) tc_commit_mc(empty + 8u * s, (uint16_t)3);      // the stage is shared by the cluster
-        else tc_commit(empty + 8u * s);
+        tc_commit(empty + 8u * s);
       }
       __syncwarp();
       first = 0;
       if (++s == nS) { s = 0; ph ^= 1u; }
     }
-    if (PAIR) { if (crank == 0 && elect_one()) tc_commit_pair(done, (uint16_t)3); }   // both epilogues
-    else if (elect_one()) tc_commit(done);
+    if (elect_one()) tc_commit(done);
     __syncwarp();
   } else if (warp >= 4) {
     // ---------------------------------------------------------------- epilogue: TMEM -> fp32 atomics into dWp
@@ -925,11 +888,146 @@ __global__ void __launch_bounds__(256, 1) lu_wgrad_tc_kernel(const __grid_consta
     }
   }
   tc_fence_before();
-  if (CL == 1) __syncthreads(); else cluster_sync_all();       // no CTA may exit while its peer can still multicast into it
+  __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
-    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// ---- CTA pairs: the TRANSPOSED product, one M = 256 MMA per pair (tcgen05.mma.cta_group::2) -------------------------
+// D^T[output channel][input channel] per tap.  M = 256 output channels over the pair: CTA r stages ITS two 64-column
+// chunks of the dY tile (the MMA's A operand, 128 rows per CTA).  N = 128 * nb input channels: CTA r stages ITS nb
+// activation windows = its half of the MMA's B operand, and a tap is still a row offset into them.  Per CTA and K step
+// the operand read drops from 8 KB / 64 clk to 6 KB / 64 clk (nb = 1) or 8 KB / 128 clk (nb = 2), and a stage moves
+// 32 KB of dY + nb windows instead of 32 KB + 2 windows for the same MMA work (nb = 1).  Barriers as in the conv kernel's
+// pair mode: all "full" barriers live in the leader (both producers' bytes complete there), "empty" / "done" are
+// released in both CTAs by the leader's multicast commit.
+__global__ void __launch_bounds__(256, 1) lu_wgrad_pair_kernel(const __grid_constant__ LuWgParams P) {
+  using namespace lutc;
+  const uint32_t crank = cluster_ctarank();
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t pad = ((raw_addr + 1023u) & ~1023u) - raw_addr;
+  uint8_t* smem = smem_raw + pad;
+  const int nS = P.n_stages;
+  const uint32_t s0 = smem_u32(smem);
+  const uint32_t bars = s0 + (uint32_t)nS * P.stage_bytes;
+  const uint32_t full = bars, empty = full + 8u * nS, done = empty + 8u * nS, tmem_slot = done + 8u;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem + (size_t)nS * P.stage_bytes + 16u * nS + 8u);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const LuWgPairTask tk = P.ptasks[blockIdx.x >> 1];
+  const LuConvParams& cp = P.cp;
+  const int nb = tk.nb;
+  const LuAStage stw0 = cp.astages[tk.stage[crank * nb]];
+  const LuAStage stw1 = cp.astages[tk.stage[crank * nb + nb - 1]];
+  const LuSrcView& v = cp.src[stw0.src];
+  const int N = 128 * nb;                                          // accumulator columns per tap (both CTAs' halves)
+  const uint32_t w_off = 32768u;                                   // stage = [dY chunk a | dY chunk b | window(s)]
+  const int tiles_per_frame = P.tiles_x * P.tiles_y;
+
+  if (warp == 0 && lane == 0) { prefetch_tmap(&P.tmA[stw0.src]); prefetch_tmap(&P.tmY); }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < nS; ++i) { mbar_init(full + 8u * i, 1); mbar_init(empty + 8u * i, 1); }
+    mbar_init(done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- producer (both CTAs): own dY chunks + own windows
+    int s = 0; uint32_t ph = 0;
+    const uint32_t bytes_cta = (uint32_t)(v.rows * v.pitch) * 128u * (uint32_t)nb + 32768u;
+    for (int tile = tk.tile0; tile < tk.tile1; ++tile) {
+      const int frame = tile / tiles_per_frame, rem = tile % tiles_per_frame;
+      if (stw0.src == P.skip_t0_src && (frame % P.T) == 0) continue;
+      const int y0 = (rem / P.tiles_x) * LU_TILE_H, x0 = (rem % P.tiles_x) * LU_TILE_W;
+      mbar_wait(empty + 8u * s, ph ^ 1u);
+      if (elect_one()) {
+        const uint32_t base = s0 + (uint32_t)s * P.stage_bytes;
+        const uint32_t lfull = map_to_rank(full + 8u * s, 0u);
+        if (crank == 0) mbar_expect_tx(full + 8u * s, 2u * bytes_cta);            // the pair's bytes, counted on the leader
+        const int fy = frame * P.dy_frame_mul + P.dy_frame_add;
+        tma_load_5d_pair(base, &P.tmY, lfull, tk.ychan[2 * crank], x0, 0, y0, fy);
+        tma_load_5d_pair(base + 16384u, &P.tmY, lfull, tk.ychan[2 * crank + 1], x0, 0, y0, fy);
+        const int fa = frame * v.frame_mul + v.frame_add;
+        tma_load_5d_pair(base + w_off, &P.tmA[stw0.src], lfull, stw0.c, x0 + stw0.dx, stw0.plane, y0 + stw0.dy, fa);
+        if (nb == 2)
+          tma_load_5d_pair(base + w_off + (uint32_t)P.a_win_bytes, &P.tmA[stw1.src], lfull, stw1.c, x0 + stw1.dx, stw1.plane, y0 + stw1.dy, fa);
+      }
+      __syncwarp();
+      if (++s == nS) { s = 0; ph ^= 1u; }
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer: the even CTA issues for the pair
+    if (crank == 0) {
+      int s = 0; uint32_t ph = 0;
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) |
+                             ((uint32_t)(256 >> 4) << 24);
+      const uint32_t a_hi = desc_hi_mn(1024u), b_hi = desc_hi_mn((uint32_t)v.pitch * 128u);
+      const uint32_t b_lbo = nb == 2 ? (uint32_t)P.a_win_bytes : 0u;
+      const uint32_t row2 = (uint32_t)v.pitch * 128u * 2u;         // two image rows = 16 pixels = one MMA K step
+      uint32_t first = 1;
+      for (int tile = tk.tile0; tile < tk.tile1; ++tile) {
+        const int frame = tile / tiles_per_frame;
+        if (stw0.src == P.skip_t0_src && (frame % P.T) == 0) continue;
+        mbar_wait(full + 8u * s, ph);
+        tc_fence_after();
+        const uint32_t base = s0 + (uint32_t)s * P.stage_bytes;
+        if (elect_one()) {
+          for (int ti = 0; ti < tk.ntaps; ++ti) {
+            const uint32_t d_tmem = tmem_base + (uint32_t)(ti * N);
+            const uint32_t b0 = base + w_off + (uint32_t)tk.off[ti] * 128u;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              mma_bf16_pair(d_tmem, desc_lo_mn(base + (uint32_t)j * 2048u, 16384u), a_hi, desc_lo_mn(b0 + (uint32_t)j * row2, b_lbo), b_hi,
+                            idesc, (first && j == 0) ? 0u : 1u);
+          }
+          tc_commit_pair(empty + 8u * s, (uint16_t)3);             // frees the stage in both CTAs
+        }
+        __syncwarp();
+        first = 0;
+        if (++s == nS) { s = 0; ph ^= 1u; }
+      }
+      if (elect_one()) tc_commit_pair(done, (uint16_t)3);          // both epilogues
+      __syncwarp();
+    }
+  } else if (warp >= 4) {
+    // ---------------------------------------------------------------- epilogue (both CTAs): own 128 output channels
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    bool any = false;
+    for (int tile = tk.tile0; tile < tk.tile1 && !any; ++tile)
+      any = !(stw0.src == P.skip_t0_src && ((tile / tiles_per_frame) % P.T) == 0);
+    mbar_wait(done, 0);
+    tc_fence_after();
+    if (any) {
+      float* drow = P.dWp + (int64_t)(tk.n0 + (int)crank * 128 + row) * cp.ktot;
+      for (int ti = 0; ti < tk.ntaps; ++ti) {
+        const uint32_t taddr = tmem_base + (uint32_t)(ti * N) + ((uint32_t)(q * 32) << 16);
+        for (int col = 0; col < N; col += 16) {
+          float vv[16];
+          tmem_ld16(taddr + (uint32_t)col, vv);
+          tmem_wait16(vv);
+          float* dst = drow + (int64_t)tk.kb[ti][col >> 6] * LU_KBLK + (col & 63);      // 16 consecutive floats of this row
+#pragma unroll
+          for (int j = 0; j < 16; ++j) atomicAdd(dst + j, vv[j]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();                                               // no CTA may exit while its peer can still signal it
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
 }
 #endif  // !LU_HOST_EMU

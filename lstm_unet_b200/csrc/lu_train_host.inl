@@ -134,7 +134,8 @@ static void train_layout(lu_handle_s* h, size_t& off) {
     cv.off_kb_tap = take(cv.kb_tap.size() * 2);
     cv.off_bwd_sums = take((size_t)cv.npad * 2 * 8);
     cv.off_bwd_means = take((size_t)cv.npad * 2 * 4);
-    cv.off_wg_tasks = take((size_t)2 * LU_WG_MAX_TASKS * 96);
+    cv.off_wg_tasks = take((size_t)2 * LU_WG_MAX_TASKS * sizeof(LuWgTask));
+    cv.off_wg_ptasks = take((size_t)2 * LU_WG_MAX_TASKS * sizeof(LuWgPairTask));
     const size_t b = (size_t)cv.npad * cv.ktot * 4;
     if (b > dwp) dwp = b;
     if (cv.kind == LU_EPI_LSTM) {
@@ -190,16 +191,17 @@ static void run_colsum(lu_handle_s* h, int gbuf, int frames_used, float* dst, in
   rows(h, (int64_t)frames_used * g.H * g.W, g.cpad / 8, stream, cs);
 }
 
-// ---- tcgen05 weight gradient: task list for one forward conv (see lu_wgrad_tc_kernel) --------------------------------
-static void build_wg_tasks(lu_handle_s* h, const ConvPlan& f, int frames, int only_src, int pair, std::vector<LuWgTask>& out) {
+// ---- tcgen05 weight gradient: task lists for one forward conv (see lu_wgrad_tc_kernel / lu_wgrad_pair_kernel) ----------
+// nb_want: 0 = independent CTAs only; 1 / 2 = CTA-pair tasks (one or, where a source has >= 4 chunks, two 64-channel
+// chunks per CTA) for every group of chunks and every full 256-column slab, independent tasks for what is left.
+static void build_wg_tasks(lu_handle_s* h, const ConvPlan& f, int frames, int only_src, int nb_want,
+                           std::vector<LuWgTask>& out, std::vector<LuWgPairTask>& pout) {
   const bool x3 = h->planes == 2;
+  if (x3) nb_want = 0;
   const int tiles = frames * ((f.Hout + LU_TILE_H - 1) / LU_TILE_H) * ((f.Wout + LU_TILE_W - 1) / LU_TILE_W);
   // K block index of the first tap of every stage
   std::vector<int> kb_begin(f.astages.size());
   { int kb = 0; for (size_t s = 0; s < f.astages.size(); ++s) { kb_begin[s] = kb; kb += f.astages[s].ntaps; } }
-  struct Base { int s0, s1; std::vector<int> taps; int a_is_lo; };
-  std::vector<Base> bases;
-  std::vector<char> used(f.astages.size(), 0);
   auto valid_taps = [&](int s) {
     std::vector<int> t;
     for (int i = 0; i < f.astages[s].ntaps; ++i) if (f.packs[kb_begin[s] + i].wpart == 0) t.push_back(i);
@@ -213,178 +215,208 @@ static void build_wg_tasks(lu_handle_s* h, const ConvPlan& f, int frames, int on
     const int ctot = ab.cpad * ab.planes;
     return ((st.c % ctot) >= ab.cpad) ? 1 : 0;
   };
+  // groups of stages = the 64-channel chunks of one source that share window geometry and tap list
+  struct Group { std::vector<int> stages; std::vector<int> taps; int a_is_lo; };
+  std::vector<Group> groups;
+  std::vector<char> used(f.astages.size(), 0);
   for (size_t s = 0; s < f.astages.size(); ++s) {
     if (used[s]) continue;
     const LuAStage& a = f.astages[s];
     if (only_src >= 0 && a.src != only_src) continue;
-    Base b; b.s0 = (int)s; b.s1 = -1; b.taps = valid_taps((int)s); b.a_is_lo = a_is_lo((int)s);
+    Group g; g.stages.push_back((int)s); g.taps = valid_taps((int)s); g.a_is_lo = a_is_lo((int)s);
     used[s] = 1;
-    for (size_t s2 = s + 1; s2 < f.astages.size() && b.s1 < 0; ++s2) {
+    for (size_t s2 = s + 1; s2 < f.astages.size(); ++s2) {
       if (used[s2]) continue;
       const LuAStage& c = f.astages[s2];
-      if (c.src != a.src || c.plane != a.plane || c.dy != a.dy || c.dx != a.dx || a_is_lo((int)s2) != b.a_is_lo) continue;
+      if (c.src != a.src || c.plane != a.plane || c.dy != a.dy || c.dx != a.dx || a_is_lo((int)s2) != g.a_is_lo) continue;
       std::vector<int> t2 = valid_taps((int)s2);
-      if (t2.size() != b.taps.size()) continue;
+      if (t2.size() != g.taps.size()) continue;
       bool same = true;
       for (size_t i = 0; i < t2.size() && same; ++i)
-        same = f.taps[c.tap_begin + t2[i]] == f.taps[a.tap_begin + b.taps[i]];
+        same = f.taps[c.tap_begin + t2[i]] == f.taps[a.tap_begin + g.taps[i]];
       if (!same) continue;
-      b.s1 = (int)s2; used[s2] = 1;
+      g.stages.push_back((int)s2); used[s2] = 1;
     }
-    if (!b.taps.empty()) bases.push_back(b);
+    if (!g.taps.empty()) groups.push_back(g);
   }
-  // output-column slabs: 64-column chunks that exist in dY
-  const int nch_max = x3 ? 1 : 2;
-  std::vector<std::pair<int, int>> slabs;      // (first chunk, number of chunks)
   const int n_chunks = f.kind == LU_EPI_LSTM ? f.npad / 64 : ceil_to(f.cout, 64) / 64;
-  for (int c = 0; c < n_chunks; c += nch_max) slabs.push_back({c, (n_chunks - c) < nch_max ? (n_chunks - c) : nch_max});
-  // taps of a base are spread evenly over its tasks (at most 4 accumulators each); pair: an even number of tasks,
-  // consecutive ones forming the 2-CTA clusters that share every operand box
-  auto n_tasks_of = [&](size_t ntaps) {
-    int n = (int)((ntaps + 3) / 4);
-    if (pair && (n & 1)) ++n;
-    return n;
-  };
-  // pair == 3 (one M = 256 MMA per CTA pair): a task pair = (leader taps L, peer taps L + d) with ONE displacement d per
-  // pair, realised by the peer displacing its window (the kernel derives d from the two tasks' first offsets).  Taps are matched greedily with their right
-  // neighbour (d = one column), the rest with the tap below (d = one row); what is left runs with an idle partner.
-  struct PairTpl { std::vector<int> lead, peer; int sy, sx; };      // positions in Base::taps
-  auto pair_templates = [&](const Base& b) {
-    const int pitch = f.views[f.astages[b.s0].src].pitch;
-    const uint32_t tb = f.astages[b.s0].tap_begin;
-    const int n = (int)b.taps.size();
-    std::vector<int> rr(n), ss(n);
-    for (int i = 0; i < n; ++i) { const int off = f.taps[tb + b.taps[i]]; rr[i] = off / pitch; ss[i] = off % pitch; }
-    std::vector<char> done(n, 0);
-    auto find = [&](int r, int c) { for (int i = 0; i < n; ++i) if (!done[i] && rr[i] == r && ss[i] == c) return i; return -1; };
-    std::vector<PairTpl> tpl;
-    for (int pass = 0; pass < 3; ++pass) {
-      const int sy = pass == 1 ? 1 : 0, sx = pass == 0 ? 1 : 0;
-      std::vector<std::pair<int, int>> m;
-      for (int i = 0; i < n; ++i) {
-        if (done[i]) continue;
-        if (pass == 2) { done[i] = 1; m.push_back({i, -1}); continue; }
-        done[i] = 1;
-        const int j = find(rr[i] + sy, ss[i] + sx);
-        if (j < 0) { done[i] = 0; continue; }
-        done[j] = 1; m.push_back({i, j});
-      }
-      const int nt = ((int)m.size() + 3) / 4;
-      size_t at = 0;
-      for (int k = 0; k < nt; ++k) {
-        const int cnt = (int)m.size() / nt + (k < (int)m.size() % nt ? 1 : 0);
-        PairTpl t; t.sy = pass == 2 ? 0 : sy; t.sx = pass == 2 ? 0 : sx;
-        for (int q = 0; q < cnt; ++q, ++at) { t.lead.push_back(m[at].first); if (m[at].second >= 0) t.peer.push_back(m[at].second); }
-        tpl.push_back(t);
+  auto ychan_of = [&](int ci) { return f.kind == LU_EPI_LSTM ? (ci % 4) * f.fpad + (ci / 4) * 64 : ci * 64; };
+  const int full_slabs = nb_want > 0 ? n_chunks / 4 : 0;            // 256-column slabs the pair kernel takes
+  // units: what one task (family) covers in the channel-row direction
+  struct Unit { int st[4]; int n, nb; const Group* g; };             // pair: n = 2 * nb stages; single: n = 1 or 2, nb = 0
+  std::vector<Unit> punits, sunits_all, sunits_rest;                  // pair units; single units over ALL columns / over the remainder columns
+  for (auto& g : groups) {
+    size_t i = 0;
+    const size_t ns = g.stages.size();
+    if (full_slabs > 0) {
+      while (ns - i >= 2) {
+        const int nb = (nb_want >= 2 && ns - i >= 4) ? 2 : 1;
+        Unit u; u.n = 2 * nb; u.nb = nb; u.g = &g;
+        for (int k = 0; k < 4; ++k) u.st[k] = k < u.n ? g.stages[i + k] : -1;
+        punits.push_back(u);
+        for (int k = 0; k < u.n; k += 2) {                            // the same stages for the remainder columns
+          Unit r; r.n = 2; r.nb = 0; r.g = &g; r.st[0] = g.stages[i + k]; r.st[1] = g.stages[i + k + 1]; r.st[2] = r.st[3] = -1;
+          sunits_rest.push_back(r);
+        }
+        i += u.n;
       }
     }
-    return tpl;
-  };
-  int base_tasks = 0;
-  for (auto& b : bases) base_tasks += (pair == 3 ? 2 * (int)pair_templates(b).size() : n_tasks_of(b.taps.size())) * (int)slabs.size();
+    for (; i < ns; i += 2) {
+      Unit r; r.nb = 0; r.g = &g; r.st[0] = g.stages[i]; r.st[1] = i + 1 < ns ? g.stages[i + 1] : -1; r.n = r.st[1] >= 0 ? 2 : 1;
+      r.st[2] = r.st[3] = -1;
+      sunits_all.push_back(r);
+    }
+  }
+  // column slabs of the independent tasks: 64-column chunks that exist in dY
+  const int nch_max = x3 ? 1 : 2;
+  std::vector<std::pair<int, int>> slabs_all, slabs_rest;             // (first chunk, number of chunks)
+  for (int c = 0; c < n_chunks; c += nch_max) slabs_all.push_back({c, (n_chunks - c) < nch_max ? (n_chunks - c) : nch_max});
+  for (int c = full_slabs * 4; c < n_chunks; c += nch_max) slabs_rest.push_back({c, (n_chunks - c) < nch_max ? (n_chunks - c) : nch_max});
+  auto n_tap_tasks = [&](size_t ntaps, int per) { return (int)((ntaps + per - 1) / per); };
+  int base_ctas = 0;
+  for (auto& u : punits) base_ctas += 2 * n_tap_tasks(u.g->taps.size(), u.nb == 2 ? 2 : 4) * full_slabs;
+  for (auto& u : sunits_all) base_ctas += n_tap_tasks(u.g->taps.size(), 4) * (int)slabs_all.size();
+  for (auto& u : sunits_rest) base_ctas += n_tap_tasks(u.g->taps.size(), 4) * (int)slabs_rest.size();
   // enough tasks to fill the machine, and pixel ranges small enough (~256 tiles = 32k pixels) that the range's
   // activations + gradients stay L2-resident while the wave of tasks sharing it runs
-  int split = (4 * h->num_sms + base_tasks - 1) / (base_tasks > 0 ? base_tasks : 1);
+  int split = (4 * h->num_sms + base_ctas - 1) / (base_ctas > 0 ? base_ctas : 1);
   if (split < (tiles + 255) / 256) split = (tiles + 255) / 256;
-  if (base_tasks > 0 && (int64_t)split * base_tasks > LU_WG_MAX_TASKS) split = LU_WG_MAX_TASKS / base_tasks;
+  if (base_ctas > 0 && (int64_t)split * base_ctas > LU_WG_MAX_TASKS) split = LU_WG_MAX_TASKS / base_ctas;
   if (split < 1) split = 1;
   if (split > tiles) split = tiles;
-  // Pixel split OUTERMOST: the ~148 tasks resident at any time then stream the SAME pixel range (different channel
-  // rows / taps / column slabs), so activations and upstream gradients are fetched from DRAM once per range instead of
-  // once per task (measured before the reorder: 84 GB of DRAM reads for a 6 GB working set).
-  for (int sp = 0; sp < split; ++sp)
-    for (auto& b : bases) {
-      if (pair == 3) {
-        const std::vector<PairTpl> tpl = pair_templates(b);
-        const uint32_t tb = f.astages[b.s0].tap_begin;
-        for (auto& sl : slabs)
-          for (auto& t : tpl)
-            for (int who = 0; who < 2; ++who) {
-              LuWgTask tk; memset(&tk, 0, sizeof tk);
-              tk.stage0 = (int16_t)b.s0; tk.stage1 = (int16_t)b.s1; tk.a_is_lo = (int16_t)b.a_is_lo;
-              const std::vector<int>& mine = who == 0 ? t.lead : t.peer;
-              tk.ntaps = (int16_t)mine.size();
-              for (size_t i = 0; i < mine.size(); ++i) {
-                const int ti = b.taps[mine[i]];
-                tk.off[i] = f.taps[tb + ti];                    // own taps: the odd task's are the even task's + one constant
-                tk.kb0[i] = kb_begin[b.s0] + ti;
-                tk.kb1[i] = b.s1 >= 0 ? kb_begin[b.s1] + ti : -1;
-              }
-              tk.n0 = sl.first * 64; tk.nch = sl.second;
-              for (int c = 0; c < sl.second; ++c) {
-                const int ci = sl.first + c;
-                tk.ychan[c] = f.kind == LU_EPI_LSTM ? (ci % 4) * f.fpad + (ci / 4) * 64 : ci * 64;
-              }
-              tk.tile0 = (int)((int64_t)tiles * sp / split); tk.tile1 = (int)((int64_t)tiles * (sp + 1) / split);
-              if (tk.tile1 > tk.tile0) out.push_back(tk);
-            }
-        continue;
-      }
-      const int nt = n_tasks_of(b.taps.size());
-      const int per = (int)b.taps.size() / nt, extra = (int)b.taps.size() % nt;
-      for (auto& sl : slabs) {
-        size_t t0 = 0;
-        for (int ti_ = 0; ti_ < nt; ++ti_) {
-          LuWgTask tk; memset(&tk, 0, sizeof tk);
-          tk.stage0 = (int16_t)b.s0; tk.stage1 = (int16_t)b.s1; tk.a_is_lo = (int16_t)b.a_is_lo;
-          tk.ntaps = (int16_t)(per + (ti_ < extra ? 1 : 0));
-          for (int i = 0; i < tk.ntaps; ++i) {
-            const int ti = b.taps[t0 + i];
-            tk.off[i] = f.taps[f.astages[b.s0].tap_begin + ti];
-            tk.kb0[i] = kb_begin[b.s0] + ti;
-            tk.kb1[i] = b.s1 >= 0 ? kb_begin[b.s1] + ti : -1;
-          }
-          tk.n0 = sl.first * 64; tk.nch = sl.second;
-          for (int c = 0; c < sl.second; ++c) {
-            const int ci = sl.first + c;
-            tk.ychan[c] = f.kind == LU_EPI_LSTM ? (ci % 4) * f.fpad + (ci / 4) * 64 : ci * 64;
-          }
-          tk.tile0 = (int)((int64_t)tiles * sp / split); tk.tile1 = (int)((int64_t)tiles * (sp + 1) / split);
-          t0 += tk.ntaps;
-          if (tk.tile1 > tk.tile0) out.push_back(tk);
+  auto tap_range = [&](size_t ntaps, int nt, int ti_, int& t0, int& cnt) {   // taps of a unit spread evenly over its nt tasks
+    const int per = (int)ntaps / nt, extra = (int)ntaps % nt;
+    t0 = ti_ * per + (ti_ < extra ? ti_ : extra); cnt = per + (ti_ < extra ? 1 : 0);
+  };
+  auto emit_single = [&](const Unit& u, const std::vector<std::pair<int, int>>& slabs, int sp) {
+    const Group& g = *u.g;
+    const int nt = n_tap_tasks(g.taps.size(), 4);
+    for (auto& sl : slabs)
+      for (int ti_ = 0; ti_ < nt; ++ti_) {
+        int t0, cnt; tap_range(g.taps.size(), nt, ti_, t0, cnt);
+        LuWgTask tk; memset(&tk, 0, sizeof tk);
+        tk.stage0 = (int16_t)u.st[0]; tk.stage1 = (int16_t)u.st[1]; tk.a_is_lo = (int16_t)g.a_is_lo;
+        tk.ntaps = (int16_t)cnt;
+        for (int i = 0; i < cnt; ++i) {
+          const int ti = g.taps[t0 + i];
+          tk.off[i] = f.taps[f.astages[u.st[0]].tap_begin + ti];
+          tk.kb0[i] = kb_begin[u.st[0]] + ti;
+          tk.kb1[i] = u.st[1] >= 0 ? kb_begin[u.st[1]] + ti : -1;
         }
+        tk.n0 = sl.first * 64; tk.nch = sl.second;
+        for (int c = 0; c < sl.second; ++c) tk.ychan[c] = ychan_of(sl.first + c);
+        tk.tile0 = (int)((int64_t)tiles * sp / split); tk.tile1 = (int)((int64_t)tiles * (sp + 1) / split);
+        if (tk.tile1 > tk.tile0) out.push_back(tk);
       }
+  };
+  // Pixel split OUTERMOST: the tasks resident at any time then stream the SAME pixel range (different channel rows / taps /
+  // column slabs), so activations and upstream gradients are fetched from DRAM once per range instead of once per task
+  // (measured before the reorder: 84 GB of DRAM reads for a 6 GB working set).
+  for (int sp = 0; sp < split; ++sp) {
+    for (auto& u : punits) {
+      const Group& g = *u.g;
+      const int nt = n_tap_tasks(g.taps.size(), u.nb == 2 ? 2 : 4);
+      for (int sl = 0; sl < full_slabs; ++sl)
+        for (int ti_ = 0; ti_ < nt; ++ti_) {
+          int t0, cnt; tap_range(g.taps.size(), nt, ti_, t0, cnt);
+          LuWgPairTask tk; memset(&tk, 0, sizeof tk);
+          for (int k = 0; k < 4; ++k) tk.stage[k] = (int16_t)u.st[k];
+          tk.nb = (int16_t)u.nb; tk.ntaps = (int16_t)cnt;
+          for (int i = 0; i < cnt; ++i) {
+            const int ti = g.taps[t0 + i];
+            tk.off[i] = f.taps[f.astages[u.st[0]].tap_begin + ti];
+            for (int k = 0; k < u.n; ++k) tk.kb[i][k] = kb_begin[u.st[k]] + ti;
+          }
+          tk.n0 = sl * 256;
+          for (int c = 0; c < 4; ++c) tk.ychan[c] = ychan_of(sl * 4 + c);
+          tk.tile0 = (int)((int64_t)tiles * sp / split); tk.tile1 = (int)((int64_t)tiles * (sp + 1) / split);
+          if (tk.tile1 > tk.tile0) pout.push_back(tk);
+        }
     }
+    for (auto& u : sunits_rest) emit_single(u, slabs_rest, sp);
+    for (auto& u : sunits_all) emit_single(u, slabs_all, sp);
+  }
 }
 
 #ifdef LU_HOST_EMU
-// TEST-ONLY (host build): replays a task list with scalar loops, statement by statement what lu_wgrad_tc_kernel does
-// with it -- windows staged as flat [rows * pitch] arrays with the tensor map's zero fill, taps as row offsets into
-// them, 128-pixel tiles, dY boxes per column chunk / plane, accumulators per tap, flush into the packed gradient --
-// including the CTA-pair semantics of cluster mode 3 (the odd task's window displaced, the even task's offsets read in
-// both).  Lets the CPU suite check the task builder against the scalar mirror (tests/test_emu_wgrad_tasks.py).
-static void emulate_wg_tasks(const LuWgradMirror& w, const std::vector<LuWgTask>& tasks, int mode, int tiles_x, int tiles_y) {
+// TEST-ONLY (host build): replays the task lists with scalar loops, statement by statement what the two tcgen05 kernels do
+// with them -- windows staged as flat [rows * pitch] arrays with the tensor map's zero fill, taps as row offsets into
+// them, 128-pixel tiles, dY boxes per column chunk / plane, accumulators per tap, flush into the packed gradient; for a
+// pair task the transposed product (rows = the CTA's 128 output channels, columns = the stages of both CTAs).  Lets the CPU
+// suite check the task builder against the scalar mirror (tests/test_emu_wgrad_tasks.py).
+static void emu_stage_window(const LuAStage& st, const LuSrcView& v, int frame, int y0, int x0, std::vector<float>& dst) {
+  dst.assign((size_t)v.rows * v.pitch * 64, 0.f);
+  const int64_t n = (int64_t)frame * v.frame_mul + v.frame_add;
+  if (n < 0 || n >= v.dimN) return;
+  for (int wy = 0; wy < v.rows; ++wy)
+    for (int wx = 0; wx < v.pitch; ++wx) {
+      const int yy = y0 + wy, xx = x0 + wx;
+      if (yy < 0 || yy >= v.dimH || xx < 0 || xx >= v.dimW) continue;
+      const uint16_t* a = v.ptr + n * v.sn + (int64_t)yy * v.sh + (int64_t)st.plane * v.sp + (int64_t)xx * v.sw + st.c;
+      for (int kk = 0; kk < 64 && st.c + kk < v.dimC; ++kk) dst[((size_t)wy * v.pitch + wx) * 64 + kk] = lu_bf2f(a[kk]);
+    }
+}
+
+static void emulate_wg_tasks(const LuWgradMirror& w, const std::vector<LuWgTask>& tasks, int tiles_x, int tiles_y) {
   const LuConvParams& cp = w.p;
   const int tiles_per_frame = tiles_x * tiles_y;
   std::vector<float> win[2], D;
-  auto stage_window = [&](const LuAStage& st, const LuSrcView& v, int frame, int y0, int x0, std::vector<float>& dst) {
-    dst.assign((size_t)v.rows * v.pitch * 64, 0.f);
-    const int64_t n = (int64_t)frame * v.frame_mul + v.frame_add;
-    if (n < 0 || n >= v.dimN) return;
-    for (int wy = 0; wy < v.rows; ++wy)
-      for (int wx = 0; wx < v.pitch; ++wx) {
-        const int yy = y0 + wy, xx = x0 + wx;
-        if (yy < 0 || yy >= v.dimH || xx < 0 || xx >= v.dimW) continue;
-        const uint16_t* a = v.ptr + n * v.sn + (int64_t)yy * v.sh + (int64_t)st.plane * v.sp + (int64_t)xx * v.sw + st.c;
-        for (int kk = 0; kk < 64 && st.c + kk < v.dimC; ++kk) dst[((size_t)wy * v.pitch + wx) * 64 + kk] = lu_bf2f(a[kk]);
+  for (const LuWgTask& tk : tasks) {
+    const LuAStage st0 = cp.astages[tk.stage0];
+    const LuAStage st1 = cp.astages[tk.stage1 >= 0 ? tk.stage1 : tk.stage0];
+    const LuSrcView& v = cp.src[st0.src];
+    const int N = tk.nch * 64;
+    const int nyp = (w.dy_planes == 2 && !tk.a_is_lo) ? 2 : 1;
+    D.assign((size_t)tk.ntaps * 128 * N, 0.f);
+    bool any = false;
+    for (int tile = tk.tile0; tile < tk.tile1; ++tile) {
+      const int frame = tile / tiles_per_frame, rem = tile % tiles_per_frame;
+      if (st0.src == w.skip_t0_src && (frame % w.T) == 0) continue;
+      any = true;
+      const int y0 = (rem / tiles_x) * LU_TILE_H, x0 = (rem % tiles_x) * LU_TILE_W;
+      emu_stage_window(st0, v, frame, y0 + st0.dy, x0 + st0.dx, win[0]);
+      if (tk.stage1 >= 0) emu_stage_window(st1, cp.src[st1.src], frame, y0 + st1.dy, x0 + st1.dx, win[1]);
+      const int64_t fy = (int64_t)frame * w.dy_frame_mul + w.dy_frame_add;
+      for (int ti = 0; ti < tk.ntaps; ++ti)
+        for (int m = 0; m < 128; ++m) {
+          const int ty = m / LU_TILE_W, tx = m % LU_TILE_W;
+          const int y = y0 + ty, x = x0 + tx;
+          if (y >= w.H || x >= w.W) continue;                      // dY box: zero fill outside the frame
+          const size_t wi = (size_t)tk.off[ti] + (size_t)ty * v.pitch + tx;
+          const uint16_t* gy = w.dY + ((fy * w.H + y) * w.W + x) * (int64_t)(w.dy_cpad * w.dy_planes);
+          for (int row = 0; row < 128; ++row) {
+            if (row >= 64 && tk.stage1 < 0) break;
+            const float a = win[row >> 6][wi * 64 + (row & 63)];
+            if (a == 0.f) continue;
+            float* d = &D[((size_t)ti * 128 + row) * N];
+            for (int dp = 0; dp < nyp; ++dp)
+              for (int c = 0; c < tk.nch; ++c) {
+                const uint16_t* g = gy + tk.ychan[c] + dp * w.dy_cpad;
+                for (int j = 0; j < 64; ++j) d[c * 64 + j] += a * lu_bf2f(g[j]);
+              }
+          }
+        }
+    }
+    if (!any) continue;
+    for (int ti = 0; ti < tk.ntaps; ++ti)
+      for (int row = 0; row < 128; ++row) {
+        const int kb = row >= 64 ? (tk.stage1 >= 0 ? tk.kb1[ti] : -1) : tk.kb0[ti];
+        if (kb < 0) continue;
+        for (int col = 0; col < N; ++col)
+          w.dWp[(int64_t)(tk.n0 + col) * cp.ktot + (int64_t)kb * LU_KBLK + (row & 63)] += D[((size_t)ti * 128 + row) * N + col];
       }
-  };
-  const size_t step = mode == 3 ? 2 : 1;
-  for (size_t i = 0; i + step <= tasks.size(); i += step) {
-    const LuWgTask& lead = tasks[i];
-    for (size_t who = 0; who < step; ++who) {
-      const LuWgTask& tk = tasks[i + who];
-      if (tk.ntaps == 0) continue;                                   // idle partner
-      const LuAStage st0 = cp.astages[tk.stage0];
-      const LuAStage st1 = cp.astages[tk.stage1 >= 0 ? tk.stage1 : tk.stage0];
-      const LuSrcView& v = cp.src[st0.src];
-      int shift_y = 0, shift_x = 0;
-      if (mode == 3 && who == 1) {
-        const int d = tk.off[0] - lead.off[0];
-        shift_y = (d + (v.pitch >> 1)) / v.pitch; shift_x = d - shift_y * v.pitch;
-      }
-      const int N = tk.nch * 64;
-      const int nyp = (w.dy_planes == 2 && !tk.a_is_lo) ? 2 : 1;
+  }
+}
+
+static void emulate_wg_pair_tasks(const LuWgradMirror& w, const std::vector<LuWgPairTask>& tasks, int tiles_x, int tiles_y) {
+  const LuConvParams& cp = w.p;
+  const int tiles_per_frame = tiles_x * tiles_y;
+  std::vector<float> win[4], D;
+  for (const LuWgPairTask& tk : tasks) {
+    const int ns = 2 * tk.nb, N = 64 * ns;
+    const LuAStage st0 = cp.astages[tk.stage[0]];
+    const LuSrcView& v = cp.src[st0.src];
+    for (int crank = 0; crank < 2; ++crank) {                        // the two CTAs: 128 output channels each
       D.assign((size_t)tk.ntaps * 128 * N, 0.f);
       bool any = false;
       for (int tile = tk.tile0; tile < tk.tile1; ++tile) {
@@ -392,39 +424,32 @@ static void emulate_wg_tasks(const LuWgradMirror& w, const std::vector<LuWgTask>
         if (st0.src == w.skip_t0_src && (frame % w.T) == 0) continue;
         any = true;
         const int y0 = (rem / tiles_x) * LU_TILE_H, x0 = (rem % tiles_x) * LU_TILE_W;
-        stage_window(st0, v, frame, y0 + st0.dy + shift_y, x0 + st0.dx + shift_x, win[0]);
-        if (tk.stage1 >= 0) stage_window(st1, cp.src[st1.src], frame, y0 + st1.dy + shift_y, x0 + st1.dx + shift_x, win[1]);
+        for (int k = 0; k < ns; ++k) {                               // B operand: the windows of BOTH CTAs, in column order
+          const LuAStage st = cp.astages[tk.stage[k]];
+          emu_stage_window(st, cp.src[st.src], frame, y0 + st.dy, x0 + st.dx, win[k]);
+        }
         const int64_t fy = (int64_t)frame * w.dy_frame_mul + w.dy_frame_add;
-        for (int ti = 0; ti < tk.ntaps; ++ti) {
-          const int off = (mode == 3 ? lead : tk).off[ti];           // the issuing CTA's descriptors address both windows
+        for (int ti = 0; ti < tk.ntaps; ++ti)
           for (int m = 0; m < 128; ++m) {
             const int ty = m / LU_TILE_W, tx = m % LU_TILE_W;
             const int y = y0 + ty, x = x0 + tx;
-            if (y >= w.H || x >= w.W) continue;                      // dY box: zero fill outside the frame
-            const size_t wi = (size_t)off + (size_t)ty * v.pitch + tx;
+            if (y >= w.H || x >= w.W) continue;
+            const size_t wi = (size_t)tk.off[ti] + (size_t)ty * v.pitch + tx;
             const uint16_t* gy = w.dY + ((fy * w.H + y) * w.W + x) * (int64_t)(w.dy_cpad * w.dy_planes);
-            for (int row = 0; row < 128; ++row) {
-              if (row >= 64 && tk.stage1 < 0) break;
-              const float a = win[row >> 6][wi * 64 + (row & 63)];
-              if (a == 0.f) continue;
+            for (int row = 0; row < 128; ++row) {                    // A operand: this CTA's two dY chunks
+              const float g = lu_bf2f(gy[tk.ychan[2 * crank + (row >> 6)] + (row & 63)]);
+              if (g == 0.f) continue;
               float* d = &D[((size_t)ti * 128 + row) * N];
-              for (int dp = 0; dp < nyp; ++dp)
-                for (int c = 0; c < tk.nch; ++c) {
-                  const uint16_t* g = gy + tk.ychan[c] + dp * w.dy_cpad;
-                  for (int j = 0; j < 64; ++j) d[c * 64 + j] += a * lu_bf2f(g[j]);
-                }
+              for (int col = 0; col < N; ++col) d[col] += g * win[col >> 6][wi * 64 + (col & 63)];
             }
           }
-        }
       }
       if (!any) continue;
       for (int ti = 0; ti < tk.ntaps; ++ti)
-        for (int row = 0; row < 128; ++row) {
-          const int kb = row >= 64 ? (tk.stage1 >= 0 ? tk.kb1[ti] : -1) : tk.kb0[ti];
-          if (kb < 0) continue;
+        for (int row = 0; row < 128; ++row)
           for (int col = 0; col < N; ++col)
-            w.dWp[(int64_t)(tk.n0 + col) * cp.ktot + (int64_t)kb * LU_KBLK + (row & 63)] += D[((size_t)ti * 128 + row) * N + col];
-        }
+            w.dWp[(int64_t)(tk.n0 + crank * 128 + row) * cp.ktot + (int64_t)tk.kb[ti][col >> 6] * LU_KBLK + (col & 63)] +=
+                D[((size_t)ti * 128 + row) * N + col];
     }
   }
 }
@@ -442,17 +467,11 @@ static int run_wgrad(lu_handle_s* h, ConvPlan& f, int gbuf, int T, float* grads,
   const char* wg_env = getenv("LU_WGRAD_ENGINE");
   const bool use_tc = h->cfg.engine == LU_ENGINE_TCGEN05 && h->cfg.a_mode == LU_AMODE_HALO &&
                       !(wg_env && strcmp(wg_env, "simt") == 0);
-  // LU_WGRAD_CLUSTER=2: 2-CTA clusters sharing the operand staging by multicast.  Measured on B200 (round 1): no gain
-  // (level-1 ConvLSTM launch 26.9 vs 27.3 ms, whole step 280.5 vs 276.7 ms) -- the kernel is bound by shared-memory
-  // bandwidth at the MMA operand fetch (M = N = 128: 8 KB per 64-clock MMA = 128 B/clk/SM), not by L2->SM traffic;
-  // the default stays independent CTAs.  The way past that bound is cta_group::2 (each SM then supplies half of B).
-  static int wg_cluster_env = -1;
-  if (wg_cluster_env < 0) { const char* ce = getenv("LU_WGRAD_CLUSTER"); wg_cluster_env = ce ? atoi(ce) : 1; }
-  // LU_WGRAD_CLUSTER=3: that variant -- one M = 256 MMA per CTA pair, the partners' taps differing by a constant
-  // displacement (lu_wgrad_tc_kernel<3>; bf16 mode and an even number of 64-column chunks, else independent CTAs).
-  // Compiled and inspected, not yet run on hardware.
-  const bool mma_pair_ok = h->planes == 1 && ((f.kind == LU_EPI_LSTM ? f.npad / 64 : ceil_to(f.cout, 64) / 64) % 2) == 0;
-  const int wg_pair = wg_cluster_env == 2 ? 1 : (wg_cluster_env == 3 && mma_pair_ok ? 3 : 0);
+  // LU_WGRAD_PAIR = chunks per CTA of the CTA-pair kernel (lu_wgrad_pair_kernel: transposed product, one M = 256 MMA per
+  // pair): 2 (default: two chunks where a source has >= 4, else one), 1 (always one), 0 (independent CTAs only).
+  static int wg_pair_env = -1;
+  if (wg_pair_env < 0) { const char* ce = getenv("LU_WGRAD_PAIR"); wg_pair_env = ce ? atoi(ce) : 2; }
+  const int nb_want = h->planes == 1 ? wg_pair_env : 0;
   for (int pass = 0; pass < n_launch; ++pass) {
     LuWgradMirror w; memset(&w, 0, sizeof w);
     for (int i = 0; i < f.n_views; ++i) {
@@ -479,82 +498,96 @@ static int run_wgrad(lu_handle_s* h, ConvPlan& f, int gbuf, int T, float* grads,
     }
 #ifndef LU_HOST_EMU
     if (use_tc) {
-      // the task list depends only on (conv, T, pass): built and uploaded once, then reused every step
+      // the task lists depend only on (conv, T, pass): built and uploaded once, then reused every step
       LuWgTask* dtasks = reinterpret_cast<LuWgTask*>(h->ws + f.off_wg_tasks) + (size_t)pass * LU_WG_MAX_TASKS;
+      LuWgPairTask* dptasks = reinterpret_cast<LuWgPairTask*>(h->ws + f.off_wg_ptasks) + (size_t)pass * LU_WG_MAX_TASKS;
       if (f.wg_cached_T[pass] != T) {
         std::vector<LuWgTask> tasks;
-        build_wg_tasks(h, f, w.frames, w.only_src, wg_pair, tasks);
-        LU_REQUIRE(tasks.size() <= (size_t)LU_WG_MAX_TASKS, "too many weight-gradient tasks (%zu)", tasks.size());
-        if (!tasks.empty()) {
-          cudaError_t e = cudaMemcpyAsync(dtasks, tasks.data(), tasks.size() * sizeof(LuWgTask), cudaMemcpyHostToDevice, (cudaStream_t)stream);
-          LU_REQUIRE(e == cudaSuccess, "task upload: %s", cudaGetErrorString(e));
-          e = cudaStreamSynchronize((cudaStream_t)stream);          // the host vector dies at scope exit
-          LU_REQUIRE(e == cudaSuccess, "task upload sync: %s", cudaGetErrorString(e));
-        }
-        f.wg_cached_T[pass] = T; f.wg_n_tasks[pass] = (int)tasks.size();
+        std::vector<LuWgPairTask> ptasks;
+        build_wg_tasks(h, f, w.frames, w.only_src, nb_want, tasks, ptasks);
+        LU_REQUIRE(tasks.size() <= (size_t)LU_WG_MAX_TASKS && ptasks.size() <= (size_t)LU_WG_MAX_TASKS,
+                   "too many weight-gradient tasks (%zu + %zu)", tasks.size(), ptasks.size());
+        cudaError_t e = cudaSuccess;
+        if (!tasks.empty())
+          e = cudaMemcpyAsync(dtasks, tasks.data(), tasks.size() * sizeof(LuWgTask), cudaMemcpyHostToDevice, (cudaStream_t)stream);
+        if (e == cudaSuccess && !ptasks.empty())
+          e = cudaMemcpyAsync(dptasks, ptasks.data(), ptasks.size() * sizeof(LuWgPairTask), cudaMemcpyHostToDevice, (cudaStream_t)stream);
+        LU_REQUIRE(e == cudaSuccess, "task upload: %s", cudaGetErrorString(e));
+        e = cudaStreamSynchronize((cudaStream_t)stream);            // the host vectors die at scope exit
+        LU_REQUIRE(e == cudaSuccess, "task upload sync: %s", cudaGetErrorString(e));
+        f.wg_cached_T[pass] = T; f.wg_n_tasks[pass] = (int)tasks.size(); f.wg_n_ptasks[pass] = (int)ptasks.size();
       }
-      const int n_tasks = f.wg_n_tasks[pass];
-      if (n_tasks == 0) continue;
+      const int n_tasks = f.wg_n_tasks[pass], n_ptasks = f.wg_n_ptasks[pass];
+      if (n_tasks == 0 && n_ptasks == 0) continue;
       cudaError_t e;
       LuWgParams wp; memset(&wp, 0, sizeof wp);
       for (int i = 0; i < f.n_views; ++i) wp.tmA[i] = f.tmA[i];
       if (pass == 1) wp.tmA[1] = f.tmHstate[h->hcur ^ 1];
       wp.tmY = h->acts_tm[gbuf];
       wp.cp = w.p;
-      wp.tasks = dtasks; wp.dWp = dwp;
+      wp.tasks = dtasks; wp.ptasks = dptasks; wp.dWp = dwp;
       wp.tiles_x = (f.Wout + LU_TILE_W - 1) / LU_TILE_W; wp.tiles_y = (f.Hout + LU_TILE_H - 1) / LU_TILE_H;
       wp.T = T; wp.skip_t0_src = w.skip_t0_src;
       wp.dy_frame_mul = (int)w.dy_frame_mul; wp.dy_frame_add = (int)w.dy_frame_add; wp.dy_planes = g.planes; wp.dy_cpad = g.cpad;
-      // stage = two activation windows + two 16 KB dY boxes (bf16: 2 column chunks; bf16x3: hi and lo plane of one chunk)
-      wp.a_win_bytes = f.a_bytes; wp.stage_bytes = 2 * f.a_bytes + 2 * 16384;
-      if (wg_pair == 3) wp.stage_bytes = 2 * f.a_bytes + 16384;    // pair mode stages ONE 64-column half of dY per CTA: deeper ring
+      wp.a_win_bytes = f.a_bytes;
       const int budget = 232448 - 1024 - 256;
-      wp.n_stages = budget / wp.stage_bytes;
-      if (wp.n_stages > 4) wp.n_stages = 4;
-      LU_REQUIRE(wp.n_stages >= 1, "weight-gradient stage does not fit shared memory");
       bool& attr = h->wg_attr_set;
       if (!attr) {
-        e = cudaFuncSetAttribute(lu_wgrad_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+        e = cudaFuncSetAttribute(lu_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
         LU_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        e = cudaFuncSetAttribute(lu_wgrad_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
-        LU_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        e = cudaFuncSetAttribute(lu_wgrad_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+        e = cudaFuncSetAttribute(lu_wgrad_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
         LU_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         attr = true;
       }
-      h->launches++;
-      time_begin(h, LU_KC_WGRAD, stream);
-      const size_t wg_smem = (size_t)wp.n_stages * wp.stage_bytes + 1024 + 256;
-      if (wg_pair) {
-        LU_REQUIRE((n_tasks & 1) == 0, "paired weight-gradient task list has odd length %d", n_tasks);
+      if (n_ptasks > 0) {
+        // pair kernel: a stage = this CTA's two 16 KB dY chunks + up to two activation windows
+        wp.stage_bytes = 32768 + 2 * f.a_bytes;
+        wp.n_stages = budget / wp.stage_bytes;
+        if (wp.n_stages > 4) wp.n_stages = 4;
+        LU_REQUIRE(wp.n_stages >= 1, "weight-gradient stage does not fit shared memory");
+        h->launches++;
+        time_begin(h, LU_KC_WGRAD, stream);
         cudaLaunchConfig_t lc;
         memset(&lc, 0, sizeof lc);
-        lc.gridDim = dim3((unsigned)n_tasks); lc.blockDim = dim3(256); lc.dynamicSmemBytes = wg_smem;
+        lc.gridDim = dim3((unsigned)(2 * n_ptasks)); lc.blockDim = dim3(256);
+        lc.dynamicSmemBytes = (size_t)wp.n_stages * wp.stage_bytes + 1024 + 256;
         lc.stream = (cudaStream_t)stream;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         lc.attrs = at; lc.numAttrs = 1;
-        e = wg_pair == 3 ? cudaLaunchKernelEx(&lc, lu_wgrad_tc_kernel<3>, wp) : cudaLaunchKernelEx(&lc, lu_wgrad_tc_kernel<2>, wp);
-        LU_REQUIRE(e == cudaSuccess, "wgrad cluster launch (%s) failed: %s", f.name.c_str(), cudaGetErrorString(e));
-      } else {
-        lu_wgrad_tc_kernel<1><<<(unsigned)n_tasks, 256, wg_smem, (cudaStream_t)stream>>>(wp);
+        e = cudaLaunchKernelEx(&lc, lu_wgrad_pair_kernel, wp);
+        time_end(h, stream);
+        LU_REQUIRE(e == cudaSuccess, "wgrad pair launch (%s) failed: %s", f.name.c_str(), cudaGetErrorString(e));
       }
-      time_end(h, stream);
+      if (n_tasks > 0) {
+        // stage = two activation windows + two 16 KB dY boxes (bf16: 2 column chunks; bf16x3: hi and lo plane of one chunk)
+        wp.stage_bytes = 2 * f.a_bytes + 2 * 16384;
+        wp.n_stages = budget / wp.stage_bytes;
+        if (wp.n_stages > 4) wp.n_stages = 4;
+        LU_REQUIRE(wp.n_stages >= 1, "weight-gradient stage does not fit shared memory");
+        h->launches++;
+        time_begin(h, LU_KC_WGRAD, stream);
+        lu_wgrad_tc_kernel<<<(unsigned)n_tasks, 256, (size_t)wp.n_stages * wp.stage_bytes + 1024 + 256, (cudaStream_t)stream>>>(wp);
+        time_end(h, stream);
+      }
       e = cudaGetLastError();
       LU_REQUIRE(e == cudaSuccess, "wgrad launch (%s) failed: %s", f.name.c_str(), cudaGetErrorString(e));
       continue;
     }
 #endif
 #ifdef LU_HOST_EMU
-    // TEST-ONLY: LU_WGRAD_EMU_TASKS=1|2|3 replays the task list the tcgen05 kernel would get in that cluster mode
+    // TEST-ONLY: LU_WGRAD_EMU_TASKS=0|1|2 replays the task lists the tcgen05 kernels would get with that LU_WGRAD_PAIR
     if (const char* te = getenv("LU_WGRAD_EMU_TASKS")) {
-      int mode = atoi(te);
-      if (mode == 3 && !mma_pair_ok) mode = 1;
-      if (mode >= 1 && mode <= 3 && h->cfg.a_mode == LU_AMODE_HALO) {
+      const int mode = atoi(te);
+      if (mode >= 0 && mode <= 2 && h->cfg.a_mode == LU_AMODE_HALO) {
         std::vector<LuWgTask> tasks;
-        build_wg_tasks(h, f, w.frames, w.only_src, mode == 1 ? 0 : (mode == 2 ? 1 : 3), tasks);
-        emulate_wg_tasks(w, tasks, mode, (f.Wout + LU_TILE_W - 1) / LU_TILE_W, (f.Hout + LU_TILE_H - 1) / LU_TILE_H);
+        std::vector<LuWgPairTask> ptasks;
+        build_wg_tasks(h, f, w.frames, w.only_src, h->planes == 1 ? mode : 0, tasks, ptasks);
+        const int tx = (f.Wout + LU_TILE_W - 1) / LU_TILE_W, ty = (f.Hout + LU_TILE_H - 1) / LU_TILE_H;
+        emulate_wg_pair_tasks(w, ptasks, tx, ty);
+        emulate_wg_tasks(w, tasks, tx, ty);
+        if (getenv("LU_WGRAD_EMU_VERBOSE")) fprintf(stderr, "wgrad tasks %s pass %d: %zu pair, %zu single\n", f.name.c_str(), pass, ptasks.size(), tasks.size());
         continue;
       }
     }
