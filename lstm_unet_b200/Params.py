@@ -65,7 +65,7 @@ class ParamsBase(object):
     # debugging (the reference defaults dry_run to False; nothing is written here unless asked)
     dry_run=True, profile=False,
     # B200 backend (not in the reference)
-    precision='bf16')
+    precision='bf16', seed=None)
 class CTCParams(ParamsBase):
     def __init__(self, params_dict=None):
         self._override_params_(params_dict or {})
@@ -77,18 +77,47 @@ class CTCParams(ParamsBase):
         self.val_data_base_folders = [(os.path.join(ROOT_DATA_DIR, ds[0]), ds[1]) for ds in self.val_sequence_list]
         self._train_provider = self._val_provider = None
         now_string = datetime.now().strftime('%Y-%m-%d_%H%M%S')
-        self.experiment_log_dir = os.path.join(self.save_log_dir, self.tb_sub_folder, self.experiment_name, now_string)
-        self.experiment_save_dir = os.path.join(self.save_checkpoint_dir, self.tb_sub_folder, self.experiment_name,
-                                                now_string)
+        if self.load_checkpoint and self.continue_run:        # Params.py:132-142: keep writing into the run being continued
+            path = self.load_checkpoint_path
+            if os.path.isdir(path):
+                if path.endswith('tf-ckpt') or path.endswith('tf-ckpt/'):
+                    self.experiment_log_dir = self.experiment_save_dir = os.path.dirname(path)
+                else:
+                    self.experiment_log_dir = self.experiment_save_dir = path
+            else:
+                self.experiment_log_dir = self.experiment_save_dir = os.path.dirname(os.path.dirname(path))
+                self.load_checkpoint_path = os.path.join(path, 'tf-ckpt')
+        else:
+            self.experiment_log_dir = os.path.join(self.save_log_dir, self.tb_sub_folder, self.experiment_name, now_string)
+            self.experiment_save_dir = os.path.join(self.save_checkpoint_dir, self.tb_sub_folder, self.experiment_name,
+                                                    now_string)
         if not self.dry_run:
             os.makedirs(os.path.expanduser(self.experiment_save_dir), exist_ok=True)
         self.channel_axis = 1 if self.data_format == 'NCHW' else 3
 
     def _provider(self, folders, q_capacity, threads, seed):
-        return self.data_provider_class(sequence_folder_list=folders, image_crop_size=self.crop_size,
-                                        unroll_len=self.unroll_len, deal_with_end=0, batch_size=self.batch_size,
-                                        queue_capacity=q_capacity, data_format=self.data_format, randomize=True,
-                                        return_dist=False, num_threads=threads, seed=seed)
+        kw = dict(sequence_folder_list=folders, image_crop_size=self.crop_size, unroll_len=self.unroll_len, deal_with_end=0,
+                  batch_size=self.batch_size, queue_capacity=q_capacity, data_format=self.data_format, randomize=True,
+                  return_dist=False, num_threads=threads)
+        # the reference seeds from OS entropy (no seed argument, Params.py:108-129).  `seed` (a params_dict entry, default
+        # None) makes a run repeatable; in data-parallel training every rank gets its own stream (seed + rank), otherwise the
+        # ranks would draw identical crops and average identical gradients.  Passed only to providers that accept it.
+        import inspect
+        base = getattr(self, 'seed', None)
+        try:
+            accepts = 'seed' in inspect.signature(self.data_provider_class).parameters
+        except (TypeError, ValueError):
+            accepts = False
+        if accepts and base is not None:
+            rank = 0
+            try:
+                import torch.distributed as dist
+                if dist.is_available() and dist.is_initialized():
+                    rank = dist.get_rank()
+            except Exception:
+                pass
+            kw['seed'] = int(base) + 2 * rank + seed
+        return self.data_provider_class(**kw)
 
     @property
     def train_data_provider(self):

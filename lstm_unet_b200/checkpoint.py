@@ -63,6 +63,11 @@ class Checkpoint:
                     v[sl] = tensors[_var_path(e['name']) + _SLOT % 'v'].reshape(-1)
                     have = True
             self.optimizer.set_slots(int(np.asarray(tensors['optimizer/iter' + tfc.VAR_SUFFIX]).reshape(-1)[0]), m if have else None, v if have else None)
+            # tf.train.Checkpoint restores the optimizer's hyper-parameters with it
+            for attr, key in (('lr', 'learning_rate'), ('beta_1', 'beta_1'), ('beta_2', 'beta_2')):
+                k = 'optimizer/' + key + tfc.VAR_SUFFIX
+                if k in tensors:
+                    setattr(self.optimizer, attr, float(np.asarray(tensors[k]).reshape(-1)[0]))
         return self
 
 

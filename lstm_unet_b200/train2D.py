@@ -18,6 +18,14 @@ def log_print(*args):
     print(*args)
 
 
+def _is_writer_rank():
+    try:
+        import torch.distributed as dist
+        return not (dist.is_available() and dist.is_initialized()) or dist.get_rank() == 0
+    except Exception:
+        return True
+
+
 def train(num_iterations=None, allreduce=None, log=log_print):
     """Returns the list of per-step training losses (floats)."""
     train_data_provider = params.train_data_provider
@@ -62,35 +70,46 @@ def train(num_iterations=None, allreduce=None, log=log_print):
     losses_seen = []
     val_states = model.get_states()
     n_iter = params.num_iterations if num_iterations is None else num_iterations
-    for _ in range(step, n_iter):
-        image_sequence, seg_sequence, _, is_last_batch = train_data_provider.get_batch()
-        _, _, train_loss_value = train_step(image_sequence, seg_sequence)
-        step += 1
-        model.reset_states_per_batch(is_last_batch)          # reset states for sequences that ended (train2D.py:161)
-        losses_seen.append(float(train_loss_value))
-        if not step % params.print_to_console_interval:
-            log('Training: Step {}, Loss: {}'.format(step, losses_seen[-1]))
-        if not getattr(params, 'dry_run', True) and not step % getattr(params, 'save_checkpoint_iteration', 5000):
-            ckpt.step = step                                 # train2D.py:222-226
-            log('Saved checkpoint for step {}: {}'.format(step, manager.save(step)))
-        if not step % params.validation_interval:
-            train_states = model.get_states()
-            model.set_states(val_states)
-            val_image_sequence, val_seg_sequence, _, val_is_last_batch = val_data_provider.get_batch()
-            _, _, val_loss_value = val_step(val_image_sequence, val_seg_sequence)
-            model.reset_states_per_batch(val_is_last_batch)
-            log('Validation: Step {}, Loss: {}'.format(step, float(val_loss_value)))
-            val_states = model.get_states()
-            model.set_states(train_states)
+    writer = _is_writer_rank()                    # data-parallel runs: one rank writes checkpoints / the inference model
+    dry = getattr(params, 'dry_run', True)
     train.model = model
     train.metrics = metrics
-    if not getattr(params, 'dry_run', True):                 # train2D.py:232-240
-        save_dir = os.path.expanduser(params.experiment_save_dir)
-        os.makedirs(save_dir, exist_ok=True)
-        model_fname = os.path.join(save_dir, 'model.ckpt')
-        model.save_weights(model_fname, save_format='tf')
-        with open(os.path.join(save_dir, 'model_params.pickle'), 'wb') as fobj:
-            pickle.dump({'name': model.__class__.__name__, 'params': (params.net_kernel_params,)}, fobj,
-                        protocol=pickle.HIGHEST_PROTOCOL)
-        log('Saved Model to file: {}'.format(model_fname))
+    try:
+        for _ in range(step, n_iter):
+            image_sequence, seg_sequence, _, is_last_batch = train_data_provider.get_batch()
+            _, _, train_loss_value = train_step(image_sequence, seg_sequence)
+            step += 1
+            ckpt.step = step
+            model.reset_states_per_batch(is_last_batch)      # reset states for sequences that ended (train2D.py:161)
+            losses_seen.append(float(train_loss_value))
+            if not step % params.print_to_console_interval:
+                log('Training: Step {}, Loss: {}'.format(step, losses_seen[-1]))
+            # train2D.py:222-226: every save_checkpoint_iteration steps AND at the last step
+            if not dry and writer and (not step % getattr(params, 'save_checkpoint_iteration', 5000) or step == n_iter):
+                log('Saved checkpoint for step {}: {}'.format(step, manager.save(step)))
+            if not step % params.validation_interval:
+                train_states = model.get_states()
+                model.set_states(val_states)
+                val_image_sequence, val_seg_sequence, _, val_is_last_batch = val_data_provider.get_batch()
+                _, _, val_loss_value = val_step(val_image_sequence, val_seg_sequence)
+                model.reset_states_per_batch(val_is_last_batch)
+                log('Validation: Step {}, Loss: {}'.format(step, float(val_loss_value)))
+                val_states = model.get_states()
+                model.set_states(train_states)
+    except (KeyboardInterrupt, ValueError) as err:           # train2D.py:225-230: checkpoint, then leave the loop quietly
+        if not dry and writer:
+            log('Saving Model Before closing due to error: {}'.format(str(err)))
+            log('Saved checkpoint for step {}: {}'.format(step, manager.save(step)))
+    finally:                                                 # train2D.py:232-240: the inference model, whatever happened
+        if not dry and writer and model._sess is not None:
+            save_dir = os.path.expanduser(params.experiment_save_dir)
+            os.makedirs(save_dir, exist_ok=True)
+            model_fname = os.path.join(save_dir, 'model.ckpt')
+            model.save_weights(model_fname, save_format='tf')
+            with open(os.path.join(save_dir, 'model_params.pickle'), 'wb') as fobj:
+                pickle.dump({'name': model.__class__.__name__, 'params': (params.net_kernel_params,)}, fobj,
+                            protocol=pickle.HIGHEST_PROTOCOL)
+            log('Saved Model to file: {}'.format(model_fname))
+        elif dry:
+            log('WARNING: dry_run flag is ON! Not Saving Model')
     return losses_seen

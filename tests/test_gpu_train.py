@@ -1,6 +1,7 @@
-"""Training-step parity on the GPU (tcgen05 forward + data gradients, scalar weight gradients) vs autograd through
-the oracle, and the train2D / Inference2D call mirrors.  Tolerance: 5e-3 relative per gradient tensor in the bf16x3
-parity mode (measured ~5e-5)."""
+"""Training-step parity on the GPU (tcgen05 forward, data gradients and weight gradients -- lu_wgrad_tc_kernel /
+lu_wgrad_pair_kernel) vs autograd through the oracle, the tcgen05 weight gradients vs the scalar engine on identical
+activations, and the train2D / Inference2D call mirrors.  Tolerance: 5e-3 relative per gradient tensor in the bf16x3
+parity mode (measured ~5e-5); the CTC-size network is in tests/test_gpu_ctc_parity.py."""
 import numpy as np
 import pytest
 import torch
@@ -125,3 +126,45 @@ def test_wgrad_tcgen05_matches_scalar_wgrad_wide(precision, tol):
             if scale < 1e-6 or (e['name'].endswith('bias') and scale < 1e-4):
                 continue          # conv biases in front of a BatchNorm: analytically zero, atomics-order noise
             assert np.abs(a - b).max() / scale < tol, (call, e['name'], np.abs(a - b).max() / scale)
+
+
+def test_train2d_mirror_saves_like_the_reference(tmp_path):
+    """train2D.py:222-240: a checkpoint at the last step, a checkpoint when the loop dies of ValueError / KeyboardInterrupt,
+    and the inference model (model.ckpt + model_params.pickle) in a `finally`, whatever happened."""
+    import os
+    from lstm_unet_b200 import Params, train2D, checkpoint as ck
+    net = {'down_conv_kernels': [[(3, 16)], [(3, 32)]], 'lstm_kernels': [[(3, 16)], [(3, 32)]],
+           'up_conv_kernels': [[(3, 16)], [(3, 16), (1, 3)]]}
+    base = {'net_kernel_params': net, 'crop_size': (32, 32), 'batch_size': 2, 'unroll_len': 2, 'learning_rate': 1e-3,
+            'validation_interval': 100, 'print_to_console_interval': 100, 'save_checkpoint_iteration': 4, 'dry_run': False,
+            'save_checkpoint_dir': str(tmp_path), 'save_log_dir': str(tmp_path), 'seed': 3}
+    p = Params.CTCParams(dict(base, experiment_name='full'))
+    train2D.params = p
+    train2D.train(num_iterations=6, log=lambda *a: None)
+    d = p.experiment_save_dir
+    assert os.path.exists(os.path.join(d, 'model.ckpt.index')) and os.path.exists(os.path.join(d, 'model_params.pickle'))
+    assert ck.latest_checkpoint(os.path.join(d, 'tf_ckpts')).endswith('ckpt-6')          # step 4, and the final step 6
+
+    p = Params.CTCParams(dict(base, experiment_name='interrupted'))
+    train2D.params = p
+    prov = p.train_data_provider
+    real, calls = prov.get_batch, []
+
+    def flaky():
+        calls.append(1)
+        if len(calls) == 4:
+            raise ValueError('queue closed')
+        return real()
+    prov.get_batch = flaky
+    losses = train2D.train(num_iterations=10, log=lambda *a: None)
+    assert len(losses) == 3
+    d = p.experiment_save_dir
+    assert ck.latest_checkpoint(os.path.join(d, 'tf_ckpts')).endswith('ckpt-3')
+    assert os.path.exists(os.path.join(d, 'model.ckpt.index'))
+    # continue_run: the next run writes into the directory of the run it continues (Params.py:132-142)
+    p2 = Params.CTCParams(dict(base, experiment_name='interrupted', load_checkpoint=True, continue_run=True,
+                               load_checkpoint_path=os.path.join(d, 'tf_ckpts')))
+    assert p2.experiment_save_dir in (d, os.path.join(d, 'tf_ckpts'))
+    train2D.params = p2
+    more = train2D.train(num_iterations=5, log=lambda *a: None)
+    assert len(more) == 2                                                                  # resumed at step 3

@@ -181,7 +181,7 @@ for name, allowed in (('CTCParams', {'dry_run'}), ('CTCInferenceParams', {'dry_r
     r, m = attrs(getattr(RP, name)), attrs(getattr(MP, name))
     bad += ['%%s.%%s missing' %% (name, k) for k in set(r) - set(m)]
     bad += ['%%s.%%s = %%r, reference %%r' %% (name, k, m[k], r[k]) for k in set(r) & set(m) if r[k] != m[k] and k not in allowed]
-    assert set(m) - set(r) <= {'precision', 'train_data_provider', 'val_data_provider'}, set(m) - set(r)
+    assert set(m) - set(r) <= {'precision', 'seed', 'train_data_provider', 'val_data_provider'}, set(m) - set(r)
 print('BAD:' + ';'.join(bad))
 ''' % ROOT
     r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=300)
