@@ -1058,6 +1058,8 @@ static int run_conv_layer(lu_handle_s* h, ConvPlan& cv, int T, int training, voi
     e.out_raw = raw;                                            // logits: raw fp32 only
   } else if (bn_batch) {
     e.out_raw = raw;                                            // batch statistics need the whole output first
+    // ... and are accumulated by the conv epilogue itself (per-channel sum / sum of squares of output - bias)
+    if (cv.npad <= 512) e.bn_sums = reinterpret_cast<double*>(h->ws + cv.off_sums);
   } else {
     const ActBuf& ob = h->acts[cv.out_buf];
     e.out_act = reinterpret_cast<uint16_t*>(h->ws + ob.off); e.out_cpad = ob.cpad; e.out_planes = ob.planes;
@@ -1069,11 +1071,12 @@ static int run_conv_layer(lu_handle_s* h, ConvPlan& cv, int T, int training, voi
     const ActBuf& ob = h->acts[cv.out_buf];
     const int64_t npix = (int64_t)N * cv.Hout * cv.Wout;
     LuBnStats st;
-    st.raw = raw; st.sums = reinterpret_cast<double*>(h->ws + cv.off_sums); st.shift_src = raw;
+    st.raw = raw; st.sums = reinterpret_cast<double*>(h->ws + cv.off_sums);
+    st.shift_src = e.bn_sums ? e.bias : raw;                   // the shift the sums are taken about: the bias, or (separate pass) the first pixel
     st.cpad = cv.raw_cpad; st.c_real = cv.cout;
-    rows(h, npix, cv.raw_cpad / 8, stream, st);
+    if (!e.bn_sums) rows(h, npix, cv.raw_cpad / 8, stream, st);        // layers wider than the epilogue's 512-column accumulators
     LuBnFinalize fin;
-    fin.sums = st.sums; fin.shift_src = raw;
+    fin.sums = st.sums; fin.shift_src = st.shift_src;
     fin.gamma = h->dparams + h->params[cv.gamma].offset; fin.beta = h->dparams + h->params[cv.beta].offset;
     fin.mov_mean = h->dparams + h->params[cv.mov_mean].offset; fin.mov_var = h->dparams + h->params[cv.mov_var].offset;
     fin.scale = reinterpret_cast<float*>(h->ws + cv.off_bscale); fin.shift = reinterpret_cast<float*>(h->ws + cv.off_bshift);
@@ -1084,7 +1087,7 @@ static int run_conv_layer(lu_handle_s* h, ConvPlan& cv, int T, int training, voi
       // statistics over the GLOBAL batch (the reference's single-device semantics): local moments ->
       // in-place sum over the ranks by the caller (one small fp64 vector per BN layer) -> combined mean / variance
       LuBnMoments mo;
-      mo.sums = st.sums; mo.shift_src = raw; mo.mom = reinterpret_cast<double*>(h->ws + cv.off_mom);
+      mo.sums = st.sums; mo.shift_src = st.shift_src; mo.mom = reinterpret_cast<double*>(h->ws + cv.off_mom);
       mo.npix = npix; mo.cpad = cv.raw_cpad; mo.c_real = cv.cout;
       pf(h, cv.raw_cpad, stream, mo);
       h->bn_sync_fn(mo.mom, (int64_t)3 * cv.raw_cpad, h->bn_sync_user);

@@ -214,6 +214,11 @@ LU_HDI void lu_conv_mirror_item(const LuConvParams& p, int64_t item) {
     float v[16];
     lu_mirror_acc16(p, frame, y0, x0, m, n0 + chunk * 16, v);
     const int n = n0 + chunk * 16;
+    if (e.bn_sums != nullptr && n < e.raw_cpad)
+      for (int j = 0; j < 16; ++j) {
+        lu_atomic_add(&e.bn_sums[n + j], (double)v[j]);
+        lu_atomic_add(&e.bn_sums[e.raw_cpad + n + j], (double)v[j] * (double)v[j]);
+      }
     lu_epi_conv_chunk(e, pix_out, n, v, e.bias + n, e.scale ? e.scale + n : nullptr, e.shift ? e.shift + n : nullptr);
   } else if (e.kind == LU_EPI_GRAD) {
     float v[16];
@@ -635,6 +640,14 @@ __global__ void __launch_bounds__(lutc::kThreads, 1) lu_conv_tc_kernel(const __g
     const int m = q * 32 + lane;
     const int ep_tid = threadIdx.x - 128;
     const LuEpi& e = cp.epi;
+    // training-mode BatchNorm: per-channel sum / sum of squares of the accumulators (= output - bias) of this CTA's tiles,
+    // kept in the scale / shift slots of the constant staging area (unused in this mode): stage 0's for the sums, stage 1's
+    // for the squares, indexed by the packed column (npad <= 512)
+    const bool bn_stats = (EPI == LU_EPI_CONV) && e.bn_sums != nullptr;
+    float* s_sum = s_const + 256;
+    float* s_sq = s_const + kConstFloats + 256;
+    if (bn_stats)
+      for (int i = ep_tid; i < 512; i += kEpiThreads) { s_sum[i] = 0.f; s_sq[i] = 0.f; }
     int acc = 0; uint32_t phacc = 0;
     for (int tile = item0; tile < P.total_tiles; tile += item_step) {
       int nt, mt; bool dummy;
@@ -649,7 +662,7 @@ __global__ void __launch_bounds__(lutc::kThreads, 1) lu_conv_tc_kernel(const __g
       // per-column constants of this tile -> shared memory (double-buffered with the accumulator stage)
       float* cst = s_const + acc * kConstFloats;
       if (EPI != LU_EPI_GRAD) {
-        for (int i = ep_tid; i < 3 * BN; i += kEpiThreads) {
+        for (int i = ep_tid; i < (bn_stats ? 1 : 3) * BN; i += kEpiThreads) {
           const int which = i / BN, j = i - which * BN;
           const float* src = which == 0 ? e.bias : (which == 1 ? e.scale : e.shift);
           cst[which * 256 + j] = (src != nullptr) ? src[n0 + j] : 0.f;
@@ -664,6 +677,23 @@ __global__ void __launch_bounds__(lutc::kThreads, 1) lu_conv_tc_kernel(const __g
           float v[16];
           tmem_ld16(taddr + (uint32_t)col, v);
           tmem_wait16(v);
+          if (bn_stats) {
+            // column sums over the warp's 32 pixel rows by recursive halving: 31 shuffles for 16 sums + 16 squares, lane L
+            // ends up with the total of value L (L < 16: sum of column col + L; else: squares of column col + L - 16)
+            float a[32];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { const float w = valid ? v[j] : 0.f; a[j] = w; a[16 + j] = w * w; }
+#pragma unroll
+            for (int off = 16, n = 16; off >= 1; off >>= 1, n >>= 1) {
+              const bool up = (lane & off) != 0;
+#pragma unroll
+              for (int i = 0; i < n; ++i) {
+                const float send = up ? a[i] : a[i + n], keep = up ? a[i + n] : a[i];
+                a[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+              }
+            }
+            atomicAdd((lane < 16 ? s_sum : s_sq) + n0 + col + (lane & 15), a[0]);
+          }
           if (valid) lu_epi_conv_chunk(e, pix_out, n0 + col, v, cst + col, cst + 256 + col, cst + 512 + col);
         }
       } else if (EPI == LU_EPI_GRAD) {
@@ -692,6 +722,13 @@ __global__ void __launch_bounds__(lutc::kThreads, 1) lu_conv_tc_kernel(const __g
       if (PAIR && crank != 0) mbar_arrive_cluster(leader(tmem_empty + 8u * acc));   // the issuer waits for both epilogues
       else mbar_arrive(tmem_empty + 8u * acc);
       if (++acc == 2) { acc = 0; phacc ^= 1u; }
+    }
+    if (bn_stats) {                                  // this CTA's partial sums -> the layer's fp64 accumulators
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+      for (int n = ep_tid; n < e.raw_cpad && n < 512; n += kEpiThreads) {
+        const float su = s_sum[n], sq = s_sq[n];
+        if (su != 0.f || sq != 0.f) { atomicAdd(&e.bn_sums[n], (double)su); atomicAdd(&e.bn_sums[e.raw_cpad + n], (double)sq); }
+      }
     }
   }
 

@@ -145,6 +145,8 @@ struct LuEpi {
   int32_t out_cpad, out_planes;
   float* out_raw;             // NHWC fp32 (acc + bias), NULL if unused
   int32_t raw_cpad;
+  double* bn_sums;            // training-mode BatchNorm: per-channel [sum | sum of squares] of (output - bias) over the
+                              // valid pixels, accumulated by the epilogue itself (no separate pass over out_raw); NULL: off
   float alpha;                // LeakyReLU slope
   // lstm
   float* c_state;             // (B,H,W,f_pad) fp32, updated in place
@@ -182,6 +184,21 @@ LU_HDI int lu_col_of(const LuColMap& m, int n) {
   int tile = n / bn, r = n % bn, g = r / m.ch_tile, j = r % m.ch_tile;
   int ch = tile * m.ch_tile + j;
   return ch < m.F ? g * m.F + ch : -1;
+}
+
+LU_HDI void lu_atomic_add(double* p, double v) {
+#ifdef __CUDA_ARCH__
+  atomicAdd(p, v);
+#else
+  *p += v;
+#endif
+}
+LU_HDI void lu_atomic_add(float* p, float v) {
+#ifdef __CUDA_ARCH__
+  atomicAdd(p, v);
+#else
+  *p += v;
+#endif
 }
 
 LU_HDI float lu_hard_sigmoid(float x) { return fminf(fmaxf(0.2f * x + 0.5f, 0.0f), 1.0f); }

@@ -23,21 +23,6 @@ static void lu_parallel_for_impl(int64_t n, void* stream, F f) {
   lu_pf_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(n, f);
 }
 #endif
-LU_HDI void lu_atomic_add(double* p, double v) {
-#ifdef __CUDA_ARCH__
-  atomicAdd(p, v);
-#else
-  *p += v;
-#endif
-}
-LU_HDI void lu_atomic_add(float* p, float v) {
-#ifdef __CUDA_ARCH__
-  atomicAdd(p, v);
-#else
-  *p += v;
-#endif
-}
-
 // 8 x bf16 (16 bytes) loads / stores
 LU_HDI void lu_load8_bf16(const uint16_t* src, float* v) {
 #ifdef __CUDA_ARCH__
