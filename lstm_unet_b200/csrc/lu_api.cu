@@ -1058,8 +1058,13 @@ static int run_conv_layer(lu_handle_s* h, ConvPlan& cv, int T, int training, voi
     e.out_raw = raw;                                            // logits: raw fp32 only
   } else if (bn_batch) {
     e.out_raw = raw;                                            // batch statistics need the whole output first
-    // ... and are accumulated by the conv epilogue itself (per-channel sum / sum of squares of output - bias)
-    if (cv.npad <= 512) e.bn_sums = reinterpret_cast<double*>(h->ws + cv.off_sums);
+    // ... and are accumulated by the conv epilogue itself (per-channel sum / sum of squares of output - bias).  The epilogue
+    // combines its warps' partial sums with fp32 shared-memory atomics, so the statistics -- and with them the training
+    // forward -- are reproducible to the last bits only, not bitwise (like cuDNN's atomics-based reductions);
+    // LU_BN_STATS=separate selects the fixed-order separate pass (1.5 ms per C3 step) for bitwise-repeatable runs.
+    static int bn_separate = -1;
+    if (bn_separate < 0) { const char* ce = getenv("LU_BN_STATS"); bn_separate = (ce && strcmp(ce, "separate") == 0) ? 1 : 0; }
+    if (cv.npad <= 512 && !bn_separate) e.bn_sums = reinterpret_cast<double*>(h->ws + cv.off_sums);
   } else {
     const ActBuf& ob = h->acts[cv.out_buf];
     e.out_act = reinterpret_cast<uint16_t*>(h->ws + ob.off); e.out_cpad = ob.cpad; e.out_planes = ob.planes;
