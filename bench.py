@@ -125,11 +125,12 @@ class ClockSampler:
 def workload_config(args, world, training=False):
     """`config` of the JSON line: names the workload only, identical for `--impl ours` and `--impl reference`."""
     B, T, S = args.batch, args.unroll, args.size
+    c5 = (S, T, B) == (1024, 16, 1)                  # BASELINE.json configs[4]: long-sequence stress, one sequence per GPU
     if args.mode == 'train' or training:
-        wl = ('C3/C4: ConvLSTM-UNet (CTCParams net, 74.6M params) full train step (fwd + WeightedCELoss + bwd + gradient '
+        wl = (('C5' if c5 else 'C3/C4') + ': ConvLSTM-UNet (CTCParams net, 74.6M params) full train step (fwd + WeightedCELoss + bwd + gradient '
               'all-reduce + Adam), %dx%d, T=%d, batch %d per GPU, pad_image=False, stateful' % (S, S, T, B))
     else:
-        wl = ('C2: ConvLSTM-UNet (CTCParams net, 74.6M params) inference forward, %dx%d, T=%d, batch %d per GPU, '
+        wl = (('C5 (inference)' if c5 else 'C2') + ': ConvLSTM-UNet (CTCParams net, 74.6M params) inference forward, %dx%d, T=%d, batch %d per GPU, '
               'pad_image=True, stateful' % (S, S, T, B))
     return {'workload': wl, 'global_batch': B * world,
             'l2_policy': 'inputs+activations per step (>6 GB) exceed the 126 MB L2; no flush needed'}

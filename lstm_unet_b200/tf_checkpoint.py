@@ -15,6 +15,11 @@ TensorFlow itself; say so when reporting parity):
 * Keras object-graph variable keys: ``<attr path>/.ATTRIBUTES/VARIABLE_VALUE`` -- e.g.
   ``DownLayers/0/ConvLSTM/0/cell/kernel/.ATTRIBUTES/VARIABLE_VALUE`` -- optionally prefixed with ``net/`` when written
   through ``tf.train.Checkpoint(net=model)``.
+* ``_CHECKPOINTABLE_OBJECT_GRAPH``: a scalar DT_STRING tensor holding a serialized ``TrackableObjectGraph`` proto
+  (nodes with ``children`` edges {node_id, local_name}, ``attributes`` {name, full_name, checkpoint_key} and the
+  optimizer's ``slot_variables``) -- what Keras' object-based ``load_weights`` / ``tf.train.Checkpoint.restore`` match
+  against the live objects.  Written as the trie of the variable keys' attribute paths; string tensors are stored as
+  [varint64 lengths][masked CRC-32C of the lengths as uint32][bytes] (tensor_bundle.cc, WriteStringTensor).
 """
 import os
 import struct
@@ -22,7 +27,8 @@ import struct
 import numpy as np
 
 TABLE_MAGIC = 0xdb4775248b80fb57
-DT_FLOAT, DT_DOUBLE, DT_INT32, DT_INT64 = 1, 2, 3, 9
+DT_FLOAT, DT_DOUBLE, DT_INT32, DT_STRING, DT_INT64 = 1, 2, 3, 7, 9
+OBJECT_GRAPH_KEY = '_CHECKPOINTABLE_OBJECT_GRAPH'
 _NP_OF_DT = {DT_FLOAT: np.float32, DT_DOUBLE: np.float64, DT_INT32: np.int32, DT_INT64: np.int64}
 VAR_SUFFIX = '/.ATTRIBUTES/VARIABLE_VALUE'
 
@@ -255,8 +261,42 @@ def write_table(path, items, block_size=4096):
 
 
 # ---------------------------------------------------------------------------------------------------- tensor bundle
-def read_bundle(prefix, verify=True):
-    """-> {tensor key: numpy array} for the numeric tensors of a TF2 checkpoint (string tensors are skipped)."""
+def _string_tensor_bytes(strings):
+    """On-disk form of a DT_STRING tensor and its (unmasked) running CRC: [varint64 len]*, masked CRC-32C of the lengths
+    (each taken as a little-endian uint32, uint64 above 2^32), then the bytes (tensor_bundle.cc: WriteStringTensor)."""
+    lengths, crc = b'', 0
+    for st in strings:
+        lengths += _put_varint(len(st))
+        crc = crc32c(struct.pack('<Q' if len(st) > 0xFFFFFFFF else '<I', len(st)), crc)
+    cks = struct.pack('<I', mask_crc(crc))
+    crc = crc32c(cks, crc)
+    for st in strings:
+        crc = crc32c(st, crc)
+    return lengths + cks + b''.join(strings), crc
+
+
+def _decode_string_tensor(raw, entry, verify, key):
+    n = 1
+    for d in entry['shape']:
+        n *= d
+    pos, lens = 0, []
+    for _ in range(n):
+        ln, pos = _get_varint(raw, pos)
+        lens.append(ln)
+    pos += 4
+    out = []
+    for ln in lens:
+        out.append(bytes(raw[pos:pos + ln])); pos += ln
+    if verify and entry['crc32c'] is not None:
+        _, crc = _string_tensor_bytes(out)
+        if mask_crc(crc) != entry['crc32c']:
+            raise ValueError('string tensor %s: checksum mismatch' % key)
+    return out[0] if not entry['shape'] else out
+
+
+def read_bundle(prefix, verify=True, strings=False):
+    """-> {tensor key: numpy array} for the numeric tensors of a TF2 checkpoint; with ``strings`` also the DT_STRING
+    tensors (bytes for a scalar, e.g. the serialized object graph under OBJECT_GRAPH_KEY)."""
     entries = read_table(prefix + '.index', verify)
     header = entries.pop(b'', None)
     num_shards = 1
@@ -270,26 +310,90 @@ def read_bundle(prefix, verify=True):
     out = {}
     for key, val in entries.items():
         e = _parse_entry(val)
-        if e['dtype'] not in _NP_OF_DT:
+        if e['dtype'] not in _NP_OF_DT and not (strings and e['dtype'] == DT_STRING):
             continue
         sid = e['shard_id']
         if sid not in shards:
             shards[sid] = open('%s.data-%05d-of-%05d' % (prefix, sid, num_shards), 'rb').read()
         raw = shards[sid][e['offset']:e['offset'] + e['size']]
+        if e['dtype'] == DT_STRING:
+            out[key.decode()] = _decode_string_tensor(raw, e, verify, key.decode())
+            continue
         if verify and e['crc32c'] is not None and mask_crc(crc32c(raw)) != e['crc32c']:
             raise ValueError('tensor %s: checksum mismatch' % key.decode())
         out[key.decode()] = np.frombuffer(raw, dtype=_NP_OF_DT[e['dtype']]).reshape(e['shape']).copy()
     return out
 
 
-def write_bundle(prefix, tensors):
-    """tensors: {key: array} (float32, or int64 for integer arrays).  One shard.  Name-based readers (tf.train.load_checkpoint(prefix).get_tensor(key))
-    can read the result; Keras' object-based ``load_weights`` additionally needs the serialized object graph, which is
-    not written."""
+def _pb_field(num, payload):
+    return _put_varint((num << 3) | 2) + _put_varint(len(payload)) + payload
+
+
+def encode_object_graph(var_keys):
+    """Serialized ``TrackableObjectGraph`` for a set of variable checkpoint keys: node 0 is the root, every component of a
+    key's attribute path is a ``children`` edge, the leaf carries the ``VARIABLE_VALUE`` attribute with its checkpoint key;
+    ``<var>/.OPTIMIZER_SLOT/<optimizer path>/<slot>`` keys become slot-variable nodes referenced from the optimizer node
+    (trackable_object_graph.proto: nodes = 1; children = 1 {node_id = 1, local_name = 2}; attributes = 2 {name = 1,
+    full_name = 2, checkpoint_key = 3}; slot_variables = 3 {original_variable_node_id = 1, slot_name = 2,
+    slot_variable_node_id = 3})."""
+    nodes = [{'children': {}, 'attrs': [], 'slots': []}]
+
+    def walk(path):
+        cur = 0
+        for part in path:
+            nxt = nodes[cur]['children'].get(part)
+            if nxt is None:
+                nodes.append({'children': {}, 'attrs': [], 'slots': []})
+                nxt = len(nodes) - 1
+                nodes[cur]['children'][part] = nxt
+            cur = nxt
+        return cur
+    slot_keys = []
+    for key in sorted(var_keys):
+        obj = key[:-len(VAR_SUFFIX)]
+        if '/.OPTIMIZER_SLOT/' in obj:
+            slot_keys.append(key)
+            continue
+        nid = walk(obj.split('/'))
+        nodes[nid]['attrs'].append(('VARIABLE_VALUE', obj, key))
+    for key in slot_keys:
+        obj = key[:-len(VAR_SUFFIX)]
+        var_path, rest = obj.split('/.OPTIMIZER_SLOT/')
+        opt_path, slot_name = rest.rsplit('/', 1)
+        var_id, opt_id = walk(var_path.split('/')), walk(opt_path.split('/'))
+        nodes.append({'children': {}, 'attrs': [('VARIABLE_VALUE', var_path + '/' + slot_name, key)], 'slots': []})
+        nodes[opt_id]['slots'].append((var_id, slot_name, len(nodes) - 1))
+    out = b''
+    for n in nodes:
+        body = b''
+        for name, nid in n['children'].items():
+            body += _pb_field(1, b'\x08' + _put_varint(nid) + _pb_field(2, name.encode()))
+        for name, full, ckey in n['attrs']:
+            body += _pb_field(2, _pb_field(1, name.encode()) + _pb_field(2, full.encode()) + _pb_field(3, ckey.encode()))
+        for var_id, slot_name, slot_id in n['slots']:
+            body += _pb_field(3, b'\x08' + _put_varint(var_id) + _pb_field(2, slot_name.encode()) + b'\x18' + _put_varint(slot_id))
+        out += _pb_field(1, body)
+    return out
+
+
+def write_bundle(prefix, tensors, object_graph=True):
+    """tensors: {key: array} (float32, or int64 for integer arrays; bytes = a scalar string tensor).  One shard.  With
+    ``object_graph`` the serialized ``TrackableObjectGraph`` of the variable keys is stored under OBJECT_GRAPH_KEY, which is
+    what Keras' object-based ``load_weights`` / ``tf.train.Checkpoint.restore`` need besides the tensors; name-based readers
+    (``tf.train.load_checkpoint(prefix).get_tensor(key)``) use the keys alone."""
     data, items, offset = bytearray(), [], 0
     header = b'\x08\x01' + b'\x1a\x02\x08\x01'        # num_shards = 1, version { producer: 1 }
     items.append((b'', header))
+    tensors = dict(tensors)
+    if object_graph and OBJECT_GRAPH_KEY not in tensors:
+        tensors[OBJECT_GRAPH_KEY] = encode_object_graph([k for k in tensors if k.endswith(VAR_SUFFIX)])
     for key in sorted(tensors):
+        if isinstance(tensors[key], (bytes, bytearray)):              # scalar DT_STRING (the object graph)
+            raw, crc = _string_tensor_bytes([bytes(tensors[key])])
+            items.append((key.encode(), _encode_entry(DT_STRING, (), 0, offset, len(raw), mask_crc(crc))))
+            data += raw
+            offset += len(raw)
+            continue
         a = np.asarray(tensors[key])
         dt = DT_INT64 if a.dtype.kind in 'iu' else DT_FLOAT          # step counters are int64 in TF checkpoints
         a = np.ascontiguousarray(a, dtype=_NP_OF_DT[dt])

@@ -169,3 +169,60 @@ def test_crc32c_and_masking_against_tensorboards_implementation():
         assert T.mask_crc(T.crc32c(buf)) == pw.masked_crc32c(buf), n
     a, b = os.urandom(100), os.urandom(77)
     assert T.crc32c(b, T.crc32c(a)) == pw.crc32c(a + b)          # incremental form used for the multi-part tensors
+
+
+def test_object_graph_is_written_and_parses_with_the_tensorflow_schema(tmp_path):
+    """``save_weights(save_format='tf')`` and the training checkpoints carry ``_CHECKPOINTABLE_OBJECT_GRAPH``: a scalar string
+    tensor (lengths + length checksum + bytes) holding a TrackableObjectGraph.  Parsed here with the TensorFlow proto schema
+    that TensorBoard bundles: every variable is reachable from the root along its Keras attribute path
+    (DownLayers -> 0 -> ConvLSTM -> 0 -> cell -> kernel), carries its checkpoint key, and the Adam moments hang off the
+    optimizer node as slot variables of the right original variable."""
+    pb = pytest.importorskip('tensorboard.compat.proto.trackable_object_graph_pb2')
+    from lstm_unet_b200 import checkpoint as ck
+    from lstm_unet_b200.Networks import ULSTMnet2D, Adam
+    from oracle import lstm_unet_oracle as O
+    net = {'down_conv_kernels': [[(3, 6)]], 'lstm_kernels': [[(3, 5)]], 'up_conv_kernels': [[(3, 5), (1, 3)]]}
+    params = {k: v.numpy() for k, v in O.init_params(net, seed=4, randomize_bn=True).items()}
+    m = ULSTMnet2D(net, 'NCHW', True, train=True)
+    m.set_weights_dict(params)
+    prefix = str(tmp_path / 'model.ckpt')
+    m.save_weights(prefix, save_format='tf')
+    raw = T.read_bundle(prefix, strings=True)
+    g = pb.TrackableObjectGraph()
+    g.ParseFromString(raw[T.OBJECT_GRAPH_KEY])
+
+    def follow(graph, path):
+        nid = 0
+        for part in path.split('/'):
+            nxt = [c.node_id for c in graph.nodes[nid].children if c.local_name == part]
+            assert len(nxt) == 1, (path, part)
+            nid = nxt[0]
+        return nid
+    for name in params:
+        key = T.keras_key(name)
+        node = g.nodes[follow(g, key[:-len(T.VAR_SUFFIX)])]
+        assert [(a.name, a.checkpoint_key) for a in node.attributes] == [('VARIABLE_VALUE', key)]
+        assert key in raw
+    # training checkpoint: net/ prefix, step, optimizer slots
+    n_train = sum(e['count'] for e in m._variable_layout() if e['trainable'])
+    opt = Adam(lr=1e-4)
+    opt.set_slots(3, np.ones(n_train, np.float32), np.ones(n_train, np.float32))
+    c = ck.Checkpoint(m, opt, step=3)
+    p2 = c.write(str(tmp_path / 'ckpt-3'))
+    raw2 = T.read_bundle(p2, strings=True)
+    g2 = pb.TrackableObjectGraph()
+    g2.ParseFromString(raw2[T.OBJECT_GRAPH_KEY])
+    opt_node = g2.nodes[follow(g2, 'optimizer')]
+    kid = follow(g2, 'net/DownLayers/0/ConvLSTM/0/cell/kernel')
+    slots = {(s.original_variable_node_id, s.slot_name): s.slot_variable_node_id for s in opt_node.slot_variables}
+    assert (kid, 'm') in slots and (kid, 'v') in slots
+    assert g2.nodes[slots[(kid, 'm')]].attributes[0].checkpoint_key == \
+        'net/DownLayers/0/ConvLSTM/0/cell/kernel/.OPTIMIZER_SLOT/optimizer/m' + T.VAR_SUFFIX
+    assert follow(g2, 'step') > 0 and follow(g2, 'optimizer/iter') > 0
+    # a flipped byte inside the string tensor is caught by its checksum
+    data = bytearray(open(p2 + '.data-00000-of-00001', 'rb').read())
+    e = T._parse_entry(T.read_table(p2 + '.index')[T.OBJECT_GRAPH_KEY.encode()])
+    data[e['offset'] + e['size'] - 3] ^= 0x40
+    open(p2 + '.data-00000-of-00001', 'wb').write(bytes(data))
+    with pytest.raises(ValueError):
+        T.read_bundle(p2, strings=True)
