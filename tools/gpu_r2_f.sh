@@ -3,7 +3,7 @@
 # launch lists and ncu --set full captures of the dominant kernels (copied into profiles/ by tools/r2_collect.py).
 mkdir -p gpurun_out
 timeout -k 10 1800 python -m pytest tests -m gpu -q 2>&1 | grep -v "^$" | tail -30 > gpurun_out/f_pytest.log; echo "pytest rc=${PIPESTATUS[0]}"; tail -4 gpurun_out/f_pytest.log
-run() { tag=$1; shift; /usr/bin/time -f "%e s wall" timeout -k 10 1500 "$@" > gpurun_out/f_$tag.json 2> gpurun_out/f_$tag.err; echo "$tag rc=$? $(tail -1 gpurun_out/f_$tag.err)"; }
+run() { tag=$1; shift; timeout -k 10 1500 "$@" > gpurun_out/f_$tag.json 2> gpurun_out/f_$tag.err; echo "$tag rc=$? $(tail -1 gpurun_out/f_$tag.err)"; }
 run bench python bench.py --steps 20 --warmup 5
 run reference python bench.py --impl reference --steps 20 --warmup 5
 run stream python bench.py --mode stream --no-parity --no-variants --steps 200 --warmup 20 --no-cpu
