@@ -34,9 +34,9 @@ CTC_NET = {   # Params.py:49-69
 }
 
 
-def lstm_traffic_bytes():
-    """DRAM bytes of one level-1 ConvLSTM launch from the committed `ncu --set full` summary (profiles/), or None."""
-    p = os.path.join(ROOT, 'profiles', 'r1_ncu_prof_lstm_l1.txt')
+def profile_traffic_bytes(name='r2_ncu_prof_lstm_l1_pair.txt'):
+    """DRAM bytes (read + written) of the launch captured in a committed `ncu --set full` summary (profiles/), or None."""
+    p = os.path.join(ROOT, 'profiles', name)
     try:
         tot = 0.0
         for line in open(p):
@@ -522,8 +522,9 @@ def run_ours(args):
         frames = B * T * world
         tf = roofline_of('lstm_fwd', 'lu_conv_tc_kernel<LSTM> forward launches, all 4 ConvLSTM levels', inf['kt'],
                          inf['lstm_flops_step'], args.steps, ms,
-                         {'traffic': lstm_traffic_bytes(),
-                          'traffic_note': 'DRAM bytes of one level-1 ConvLSTM launch (ncu --set full, profiles/r1_ncu_prof_lstm_l1.txt)',
+                         {'traffic': profile_traffic_bytes(),
+                          'traffic_note': 'DRAM bytes of one level-1 ConvLSTM launch (ncu --set full, profiles/r2_ncu_prof_lstm_l1_pair.txt; '
+                                          'algorithmic: x 0.14 + h_in 0.14 + h_out 0.14 + c read/write 0.57 + weights 0.02 = 1.0 GB)',
                           'whole_step_tflops': inf['flops_step'] * args.steps / (ms * 1e-3) / 1e12})
         cfg = workload_config(args, world)
         cfg.update({'parallelism': 'batch-sharded replicas x%d (no data-path collective)' % world, 'a_mode': args.a_mode,
@@ -556,6 +557,10 @@ def run_ours(args):
         var_ms = {k: next(it) for k in sorted(trn['variants'])}
         frames = B * T * world
         cf = trn['class_flops']
+        wg_traffic = {'traffic': profile_traffic_bytes('r2_ncu_prof_wgrad_pair.txt'),
+                      'traffic_note': 'DRAM bytes of the level-0 ConvLSTM weight-gradient launch (frames t >= 1 of the recurrent term: '
+                                      '28 of 32 frames; profiles/r2_ncu_prof_wgrad_pair.txt; algorithmic: h 1.9 + dz 7.5 GB read once, '
+                                      '6.6 MB of fp32 gradient atomics)'}
         blk = {
             'workload': workload_config(args, world, training=True)['workload'],
             'value': frames * args.steps / (ms * 1e-3), 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps,
@@ -572,10 +577,14 @@ def run_ours(args):
                     'h2d_bytes_per_step': int(x_host.nbytes) * 2, 'd2h_bytes_per_step': 4, 'steps': trn['e2e_steps'],
                     'ms_per_step': e2e_ms / trn['e2e_steps'],
                     'api': 'ULSTMnet2D.train_step(host frames, host labels, ...) + float(loss) (train2D.py:87-103)'},
-            'roofline': roofline_of('wgrad', 'lu_wgrad_tc_kernel (dominant kernel of the train step)', trn['kt'], cf['wgrad'], args.steps, ms),
+            'roofline': roofline_of('wgrad', 'lu_wgrad_pair_kernel + lu_wgrad_tc_kernel (weight gradient: dominant kernel class of the train step)',
+                                    trn['kt'], cf['wgrad'], args.steps, ms, wg_traffic),
             'rooflines': {
-                'wgrad': roofline_of('wgrad', 'lu_wgrad_tc_kernel', trn['kt'], cf['wgrad'], args.steps, ms),
-                'dgrad': roofline_of('dgrad', 'lu_conv_tc_kernel<GRAD>', trn['kt'], cf['dgrad'], args.steps, ms),
+                'wgrad': roofline_of('wgrad', 'lu_wgrad_pair_kernel + lu_wgrad_tc_kernel', trn['kt'], cf['wgrad'], args.steps, ms, wg_traffic),
+                'dgrad': roofline_of('dgrad', 'lu_conv_tc_kernel<GRAD>', trn['kt'], cf['dgrad'], args.steps, ms,
+                                     {'traffic': profile_traffic_bytes('r2_ncu_prof_dgrad_pair.txt'),
+                                      'traffic_note': 'DRAM bytes of one level-1 recurrent data-gradient launch (one time step; '
+                                                      'profiles/r2_ncu_prof_dgrad_pair.txt; algorithmic: dz 0.54 + dh 0.13 r/w + weights 0.01 GB)'}),
                 'lstm_fwd': roofline_of('lstm_fwd', 'lu_conv_tc_kernel<LSTM>', trn['kt'], cf['lstm_fwd'], args.steps, ms),
                 'conv_fwd': roofline_of('conv_fwd', 'lu_conv_tc_kernel<CONV>', trn['kt'], cf['conv_fwd'], args.steps, ms),
             },

@@ -34,6 +34,9 @@ enum { LU_PREC_BF16 = 0, LU_PREC_BF16X3 = 1, LU_PREC_FP16 = 2 };
 enum { LU_ENGINE_TCGEN05 = 0, LU_ENGINE_SIMT = 1 };   /* SIMT = on-GPU scalar mirror used to debug the TC path */
 enum { LU_GATE_HARD_SIGMOID = 0, LU_GATE_SIGMOID = 1 };
 enum { LU_AMODE_HALO = 0, LU_AMODE_DIRECT = 1 };      /* how activation tiles are staged in shared memory */
+/* what the handle runs: the whole ULSTMnet2D, or one of its blocks on its own the way the reference's
+ * DownBlock2D.unit_test / UpBlock2D.unit_test construct and call them (Networks.py:100-119,155-175) */
+enum { LU_BLOCK_NET = 0, LU_BLOCK_DOWN = 1, LU_BLOCK_UP = 2 };
 
 /* Architecture-as-data: mirrors the `net_kernel_params` dict (Params.py:49-69, Networks.py:12-32) plus the
  * constructor arguments of ULSTMnet2D (Networks.py:179) and the first-call shapes that freeze the stateful
@@ -60,6 +63,15 @@ typedef struct lu_config {
   int32_t train;           /* 1: allocate what forward(training=True)+backward need */
   float lrelu_alpha;       /* slope of the LeakyReLU after every BatchNorm; 0.3 = Keras-2 LeakyReLU() as the reference
                               constructs it (Networks.py:58,139) -- the caller must set it */
+  /* stand-alone blocks (0 / LU_BLOCK_NET everywhere for the network).  LU_BLOCK_DOWN = DownBlock2D(conv_kernels,
+   * lstm_kernels, stride, data_format) (Networks.py:37-75): n_levels = 1, level 0 of the lstm / down lists, in_channels,
+   * height x width of the input, no padding.  LU_BLOCK_UP = UpBlock2D(kernels, up_factor, data_format, return_logits)
+   * (Networks.py:124-153): n_levels = 1, entry 0 of the up list, in_channels / height / width of the LOW-resolution
+   * input, skip_channels of the skip input (block_stride x larger), batch = frames, max_t = 1. */
+  int32_t block_kind;      /* LU_BLOCK_* */
+  int32_t block_stride;    /* DownBlock2D: stride of its first convolution (1 or 2); UpBlock2D: up_factor (1 or 2) */
+  int32_t skip_channels;   /* UpBlock2D: channels of the skip input */
+  int32_t return_logits;   /* UpBlock2D(return_logits=True): the last convolution's output, before BN (Networks.py:148-149) */
 } lu_config;
 
 typedef struct lu_handle_s* lu_handle;
@@ -95,6 +107,17 @@ int lu_params_changed(lu_handle h, void* stream);
  * statistics (and keeps what backward needs when cfg.train). */
 int lu_forward(lu_handle h, const float* dev_x, int32_t T, int32_t training, float* dev_logits,
                float* dev_softmax, void* stream);
+
+/* DownBlock2D.call (Networks.py:60-75) / UpBlock2D.call (Networks.py:141-153) of a handle created with block_kind =
+ * LU_BLOCK_DOWN / LU_BLOCK_UP.  DOWN: x is (B,T,C,H,W) / (B,T,H,W,C), dev_skip NULL; dev_out receives `activ`, the 4-D
+ * (B*T, F, H/stride, W/stride) / (B*T, H/stride, W/stride, F) tensor the block returns second (its first return value is
+ * the same data reshaped to 5-D); mutates the block's recurrent states.  UP: x is (N,C,h,w) / (N,h,w,C), skip
+ * (N,Cs,f*h,f*w) / (N,f*h,f*w,Cs), T = 1; dev_out is (N,F,f*h,f*w) / (N,f*h,f*w,F).  lu_block_out_shape gives
+ * {frames per time step (B or N), F, H_out, W_out}.  training selects BatchNorm batch statistics (forward only: block
+ * handles have no backward). */
+int lu_block_forward(lu_handle h, const float* dev_x, const float* dev_skip, int32_t T, int32_t training,
+                     float* dev_out, void* stream);
+int lu_block_out_shape(lu_handle h, int64_t* shape4);
 
 /* Launch-bound shapes (Inference2D's per-frame call, B=1, T=1: Inference2D.py:59): replay the inference forward as an
  * instantiated CUDA graph (one per T and recurrent-state ping-pong parity; inputs / outputs pass through fixed staging

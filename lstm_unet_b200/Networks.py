@@ -15,7 +15,9 @@ Same names, constructor arguments, call signature and error behaviour as the ref
           set_states          (:77-98,279-291)    [block][layer][h, c] numpy lists, None before the first call)
     trainable_variables, save_weights,           named views into one flat fp32 device buffer; npz with Keras variable
           load_weights (keras.Model)              names and layouts
-    DownBlock2D / UpBlock2D   (:35-175)           structural descriptors of the blocks (state fan-out goes through them)
+    DownBlock2D / UpBlock2D   (:35-175)           inside a network: descriptors of the blocks (state fan-out goes through
+                                                  them); constructed on their own (the reference's unit_test usage): the same
+                                                  kernels on a handle of their own (lu_config.block_kind)
 
 There is no CPU fallback: constructing a model without the CUDA library or calling it without a CUDA device raises.
 """
@@ -120,35 +122,219 @@ class Variable:
             self._session.params_changed()
 
 
-class DownBlock2D:
-    """Structure of one encoder block (Networks.py:35-98): ConvLSTM2D x n then [Conv2D, BN, LeakyReLU] x m."""
+def _to_dev(x, dev):
+    """numpy / torch (host or cuda) -> flat contiguous fp32 cuda tensor."""
+    import torch
+    if not isinstance(x, torch.Tensor):
+        x = torch.from_numpy(np.ascontiguousarray(np.asarray(x, dtype=np.float32)))
+    return x.to(device=dev, dtype=torch.float32).contiguous().reshape(-1)
 
-    def __init__(self, conv_kernels, lstm_kernels, stride=2, data_format='NCHW', _owner=None, _level=0):
+
+class _StandAloneBlock:
+    """What a block needs to run outside a ULSTMnet2D: its own library handle (lu_config.block_kind), created by the
+    first call like every Keras variable and state shape, default-initialised with the Keras initialisers."""
+    _precision, _engine, _a_mode, _seed = 'bf16', 'tcgen05', 'halo', 0
+
+    def _open(self, cfg):
+        be = TorchCudaBackend(None)
+        sess = LuSession(_lib.load_library(), be, cfg)
+        sess.set_params(self._pending_weights or keras_default_init(sess.layout, self._seed))
+        self._pending_weights = None
+        self._be, self._sess = be, sess
+        return sess
+
+    def close(self):
+        if getattr(self, '_sess', None) is not None:
+            self._sess.close()
+            self._sess = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_weights_dict(self, named):
+        """{variable name: array}; names as inside a network, block index 0 (`DownLayers/0/Conv/1/kernel`, ...)."""
+        if getattr(self, '_sess', None) is None:
+            self._pending_weights = dict(named)
+        else:
+            self._sess.set_params(named)
+
+    def get_weights_dict(self):
+        return self._sess.get_params()
+
+
+class DownBlock2D(_StandAloneBlock):
+    """One encoder block (Networks.py:35-98): ConvLSTM2D x n then [Conv2D, BN, LeakyReLU] x m.  Inside a ULSTMnet2D it
+    is the structural descriptor the state fan-out goes through (the network's handle runs it); constructed on its own
+    -- the reference's `DownBlock2D.unit_test` (Networks.py:100-119) -- it owns a handle of the same kernels and
+    `block(inputs, training)` returns `(activ_down, activ)` like Networks.py:60-75."""
+
+    def __init__(self, conv_kernels, lstm_kernels, stride=2, data_format='NCHW', _owner=None, _level=0, *,
+                 precision='bf16', engine='tcgen05', a_mode='halo', seed=0):
         self.conv_kernels, self.lstm_kernels, self.stride = list(conv_kernels), list(lstm_kernels), stride
         self.data_format = data_format
-        self.total_stride = stride
+        self.channel_axis = 1 if data_format[1] == 'C' else -1
+        self.total_stride = stride                # Networks.py:52-54: only the first convolution is strided
         self._owner, self._level = _owner, _level
+        self._precision, self._engine, self._a_mode, self._seed = precision, engine, a_mode, seed
+        self._sess = self._pending_weights = self._shape = None
 
-    def _need_owner(self):
-        if self._owner is None:
-            raise NotImplementedError('DownBlock2D runs as part of ULSTMnet2D on this backend')
-        return self._owner
+    # ---- on its own -------------------------------------------------------------------------------------
+    def __call__(self, inputs, training=None, mask=None):
+        import torch
+        if self._owner is not None:
+            raise NotImplementedError('this block belongs to a ULSTMnet2D: call the network')
+        shape = tuple(inputs.shape)
+        if len(shape) != 5:
+            raise ValueError('expected a 5-D input, got shape %s' % (shape,))
+        B, T = shape[:2]
+        C, H, W = shape[2:] if self.channel_axis == 1 else (shape[4], shape[2], shape[3])
+        if self._sess is not None and ((B, C, H, W) != self._shape or T > self._max_t):
+            if (B, C, H, W) != self._shape:
+                raise ValueError('stateful ConvLSTM states were built for (B,C,H,W)=%s, got %s' % (self._shape, (B, C, H, W)))
+            states, weights = self.get_states(), self._sess.get_params()      # longer unroll: carry both over
+            self.close()
+            self._pending_weights = weights
+            self._open_for(B, T, C, H, W)
+            self.set_states(states)
+        elif self._sess is None:
+            self._open_for(B, T, C, H, W)
+        sess, dev = self._sess, self._be.device
+        n, F, Ho, Wo = sess.block_out_shape()
+        out_shape = (B * T, F, Ho, Wo) if self.channel_axis == 1 else (B * T, Ho, Wo, F)
+        out = torch.empty(out_shape, dtype=torch.float32, device=dev)
+        xd = _to_dev(inputs, dev)
+        sess.block_forward(xd.data_ptr(), None, T, bool(training), out.data_ptr())
+        return _wrap(out.reshape((B, T) + out_shape[1:])), _wrap(out)       # Networks.py:73-75
 
+    call = __call__
+
+    def _open_for(self, B, T, C, H, W):
+        try:
+            self._open(_lib.make_down_block_config(self.conv_kernels, self.lstm_kernels, self.stride, self.data_format,
+                                                   batch=B, max_t=T, height=H, width=W, in_channels=C,
+                                                   precision=self._precision, engine=self._engine, a_mode=self._a_mode))
+        except LuError as e:
+            raise ValueError(str(e))
+        self._shape, self._max_t = (B, C, H, W), T
+
+    # ---- state API (Networks.py:77-98): through the network when the block is part of one -----------------
     def reset_states_per_batch(self, is_last_batch):
-        self._need_owner()._reset_level(self._level, is_last_batch)
+        import torch
+        if self._owner is not None:
+            return self._owner._reset_level(self._level, is_last_batch)
+        if self._sess is None:
+            return
+        m = torch.as_tensor(np.asarray(is_last_batch, dtype=np.float32)).reshape(-1)
+        if m.numel() != self._shape[0]:
+            raise ValueError('mask has %d entries for batch size %d' % (m.numel(), self._shape[0]))
+        md = m.to(self._be.device)
+        self._sess.reset_level_states(0, md.data_ptr())
+        torch.cuda.current_stream(self._be.device).synchronize()          # md must outlive the kernel
 
     def get_states(self):
-        return self._need_owner()._get_level_states(self._level)
+        import torch
+        if self._owner is not None:
+            return self._owner._get_level_states(self._level)
+        out = []
+        for j in range(len(self.lstm_kernels)):
+            if self._sess is None:
+                out.append([None, None])
+                continue
+            shp = self._sess.state_shape(0, j)
+            pair = []
+            for which in (0, 1):
+                t = torch.empty(shp, dtype=torch.float32, device=self._be.device)
+                self._sess.get_state(0, j, which, t.data_ptr())
+                pair.append(t.cpu().numpy())
+            out.append(pair)
+        return out
 
     def set_states(self, states):
-        self._need_owner()._set_level_states(self._level, states)
+        if self._owner is not None:
+            return self._owner._set_level_states(self._level, states)
+        if self._sess is None:
+            raise ValueError('the states of a block exist after its first call')
+        keep = []
+        for j, st in enumerate(states):
+            for which in (0, 1):
+                if st is None or st[0] is None:                           # Networks.py:96-98: reset_states(None)
+                    self._sess.set_state(0, j, which, None)
+                else:
+                    keep.append(_to_dev(st[which], self._be.device))
+                    self._sess.set_state(0, j, which, keep[-1].data_ptr())
+        self._be.synchronize()
+
+    @classmethod
+    def unit_test(cls):
+        """The reference's shape check (Networks.py:100-119): 50 x 50 x 3 channels-last input, stride 2."""
+        conv_kernels = [(3, 16), (3, 32), (3, 64)]
+        lstm_kernels = [(3, 16), (3, 32), (3, 64)]
+        model = cls(conv_kernels, lstm_kernels, 2, 'NHWC')
+        for i in range(4):
+            input_sequence = np.random.randn(2, 3, 50, 50, 3).astype(np.float32)
+            model_out = model(input_sequence, True)
+            print(i, tuple(model_out[0].shape), tuple(model_out[1].shape))
+        return model_out
 
 
-class UpBlock2D:
-    """Structure of one decoder block (Networks.py:122-153): bilinear resize, concat([up, skip]), conv stack."""
+class UpBlock2D(_StandAloneBlock):
+    """One decoder block (Networks.py:122-153): bilinear resize, concat([up, skip]), conv stack.  A descriptor inside a
+    ULSTMnet2D; constructed on its own (`UpBlock2D.unit_test`, Networks.py:155-175) `block((inputs, skip), training)`
+    runs it on a handle of its own."""
 
-    def __init__(self, kernels, up_factor=2, data_format='NCHW', return_logits=False):
+    def __init__(self, kernels, up_factor=2, data_format='NCHW', return_logits=False, *, precision='bf16',
+                 engine='tcgen05', a_mode='halo', seed=0):
         self.kernels, self.up_factor, self.data_format, self.return_logits = list(kernels), up_factor, data_format, return_logits
+        self.channel_axis = 1 if data_format[1] == 'C' else -1
+        self._precision, self._engine, self._a_mode, self._seed = precision, engine, a_mode, seed
+        self._sess = self._pending_weights = self._shape = None
+
+    def __call__(self, inputs, training=None, mask=None):
+        import torch
+        x, skip = inputs
+        xs, ss = tuple(x.shape), tuple(skip.shape)
+        if len(xs) != 4 or len(ss) != 4:
+            raise ValueError('expected 4-D (input, skip), got shapes %s and %s' % (xs, ss))
+        N = xs[0]
+        C, h, w = xs[1:] if self.channel_axis == 1 else (xs[3], xs[1], xs[2])
+        Cs, H, W = ss[1:] if self.channel_axis == 1 else (ss[3], ss[1], ss[2])
+        if ss[0] != N or (H, W) != (h * self.up_factor, w * self.up_factor):
+            raise ValueError('skip of shape %s does not match the x%d up-sampled input of shape %s' % (ss, self.up_factor, xs))
+        key = (N, C, h, w, Cs)
+        if self._sess is not None and key != self._shape:
+            weights = self._sess.get_params()                              # convolutions are shape-agnostic: new handle
+            self.close()
+            self._pending_weights = weights
+        if self._sess is None:
+            try:
+                self._open(_lib.make_up_block_config(self.kernels, self.up_factor, self.data_format, self.return_logits,
+                                                     frames=N, height=h, width=w, in_channels=C, skip_channels=Cs,
+                                                     precision=self._precision, engine=self._engine, a_mode=self._a_mode))
+            except LuError as e:
+                raise ValueError(str(e))
+            self._shape = key
+        sess, dev = self._sess, self._be.device
+        n, F, Ho, Wo = sess.block_out_shape()
+        out = torch.empty((N, F, Ho, Wo) if self.channel_axis == 1 else (N, Ho, Wo, F), dtype=torch.float32, device=dev)
+        xd, sd = _to_dev(x, dev), _to_dev(skip, dev)
+        sess.block_forward(xd.data_ptr(), sd.data_ptr(), 1, bool(training), out.data_ptr())
+        return _wrap(out)
+
+    call = __call__
+
+    @classmethod
+    def unit_test(cls):
+        """The reference's shape check (Networks.py:155-175)."""
+        model = cls([(3, 16), (3, 32), (3, 64)], 2, 'NHWC')
+        for i in range(4):
+            input_sequence = np.random.randn(6, 50, 50, 3).astype(np.float32)
+            skip = np.random.randn(6, 100, 100, 3).astype(np.float32)
+            model_out = model((input_sequence, skip), True)
+            print(i, tuple(model_out.shape))
+        return model_out
 
 
 def _glorot_uniform(shape, rng):

@@ -12,6 +12,7 @@ ENGINES = {'tcgen05': 0, 'simt': 1}
 GATES = {'hard_sigmoid': 0, 'sigmoid': 1}
 KERNEL_CLASSES = ('lstm_fwd', 'conv_fwd', 'dgrad', 'wgrad')     # LU_KC_* of include/lstm_unet_b200.h
 A_MODES = {'halo': 0, 'direct': 1}
+BLOCK_NET, BLOCK_DOWN, BLOCK_UP = 0, 1, 2                      # LU_BLOCK_*
 
 _I32 = ctypes.c_int32
 _A1 = _I32 * LU_MAX_LEVELS
@@ -28,6 +29,7 @@ class lu_config(ctypes.Structure):
         ('batch', _I32), ('max_t', _I32), ('height', _I32), ('width', _I32),
         ('precision', _I32), ('engine', _I32), ('gate', _I32), ('a_mode', _I32), ('train', _I32),
         ('lrelu_alpha', ctypes.c_float),
+        ('block_kind', _I32), ('block_stride', _I32), ('skip_channels', _I32), ('return_logits', _I32),
     ]
 
 
@@ -68,6 +70,8 @@ def bind(lib):
         'lu_bind_params': [vp, vp],
         'lu_params_changed': [vp, vp],
         'lu_forward': [vp, vp, i32, i32, vp, vp, vp],
+        'lu_block_forward': [vp, vp, vp, i32, i32, vp, vp],
+        'lu_block_out_shape': [vp, P(i64)],
         'lu_set_graph_mode': [vp, i32, P(i32)],
         'lu_reset_states': [vp, vp, vp],
         'lu_reset_level_states': [vp, i32, vp, vp],
@@ -103,7 +107,7 @@ def bind(lib):
 
 EXPORTED_SYMBOLS = ['lu_last_error', 'lu_version', 'lu_is_cuda_build', 'lu_create', 'lu_destroy', 'lu_workspace_bytes',
                     'lu_bind_workspace', 'lu_param_count', 'lu_param_info', 'lu_bind_params', 'lu_params_changed',
-                    'lu_forward', 'lu_set_graph_mode', 'lu_reset_states', 'lu_reset_level_states', 'lu_state_shape', 'lu_get_state', 'lu_set_state',
+                    'lu_forward', 'lu_block_forward', 'lu_block_out_shape', 'lu_set_graph_mode', 'lu_reset_states', 'lu_reset_level_states', 'lu_state_shape', 'lu_get_state', 'lu_set_state',
                     'lu_loss_backward', 'lu_set_grad_bucket_callback', 'lu_set_bn_sync_callback', 'lu_adam_step', 'lu_debug_buffer', 'lu_launch_count', 'lu_forward_flops', 'lu_lstm_flops',
                     'lu_lstm_kernel_time', 'lu_kernel_times', 'lu_class_flops', 'lu_post_workspace_bytes', 'lu_postprocess', 'lu_post_launch_count',
                     'lu_seg_workspace_bytes', 'lu_seg_measure', 'lu_aug_workspace_bytes', 'lu_augment_sequence',
@@ -165,3 +169,49 @@ def make_config(net_params, data_format='NCHW', pad_image=True, batch=1, max_t=1
     c.train = 1 if train else 0
     c.lrelu_alpha = float(lrelu_alpha)      # Keras-2 LeakyReLU() default (Networks.py:58,139)
     return c
+
+
+def _common(c, data_format, batch, max_t, height, width, precision, engine, gate, a_mode, in_channels, lrelu_alpha):
+    c.in_channels = int(in_channels)
+    c.channels_first = 1 if data_format[1] == 'C' else 0
+    c.pad_image = 0
+    c.batch, c.max_t, c.height, c.width = int(batch), int(max_t), int(height), int(width)
+    c.precision, c.engine, c.gate, c.a_mode = PRECISIONS[precision], ENGINES[engine], GATES[gate], A_MODES[a_mode]
+    c.train = 0
+    c.lrelu_alpha = float(lrelu_alpha)
+    return c
+
+
+def _fill(c, prefix, layer):
+    if len(layer) > LU_MAX_PER_LEVEL:
+        raise ValueError('at most %d layers per block are supported' % LU_MAX_PER_LEVEL)
+    getattr(c, 'n_' + prefix)[0] = len(layer)
+    for j, (k, f) in enumerate(layer):
+        getattr(c, prefix + '_k')[0][j] = int(k)
+        getattr(c, prefix + '_f')[0][j] = int(f)
+
+
+def make_down_block_config(conv_kernels, lstm_kernels, stride=2, data_format='NCHW', batch=1, max_t=1, height=0, width=0,
+                           in_channels=1, precision='bf16', engine='tcgen05', gate='hard_sigmoid', a_mode='halo',
+                           lrelu_alpha=0.3):
+    """DownBlock2D(conv_kernels, lstm_kernels, stride, data_format) on its own (Networks.py:37-75)."""
+    c = lu_config()
+    c.n_levels = 1
+    _fill(c, 'lstm', lstm_kernels)
+    _fill(c, 'down', conv_kernels)
+    c.block_kind, c.block_stride = BLOCK_DOWN, int(stride)
+    return _common(c, data_format, batch, max_t, height, width, precision, engine, gate, a_mode, in_channels, lrelu_alpha)
+
+
+def make_up_block_config(kernels, up_factor=2, data_format='NCHW', return_logits=False, frames=1, height=0, width=0,
+                         in_channels=1, skip_channels=1, precision='bf16', engine='tcgen05', a_mode='halo',
+                         lrelu_alpha=0.3):
+    """UpBlock2D(kernels, up_factor, data_format, return_logits) on its own (Networks.py:124-153); height / width /
+    in_channels describe the low-resolution input."""
+    c = lu_config()
+    c.n_levels = 1
+    _fill(c, 'up', kernels)
+    c.block_kind, c.block_stride = BLOCK_UP, int(up_factor)
+    c.skip_channels, c.return_logits = int(skip_channels), 1 if return_logits else 0
+    return _common(c, data_format, frames, 1, height, width, precision, engine, 'hard_sigmoid', a_mode, in_channels,
+                   lrelu_alpha)

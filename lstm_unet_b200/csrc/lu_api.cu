@@ -131,6 +131,8 @@ struct lu_handle_s {
   std::vector<UpStage> ups;       // per up block (src_buf = -1: no resize)
   int logits_conv = -1;
   int img_buf = -1;               // in_channels > 1: the reflect-padded image as an ordinary NHWC activation buffer
+  int skip_in_buf = -1;           // LU_BLOCK_UP: the skip input
+  int block_out_conv = -1;        // stand-alone blocks: the convolution whose output the block returns
   size_t off_patches = 0, off_raw_scratch = 0, raw_scratch_bytes = 0, off_logits_raw = 0;
   size_t ws_bytes = 0;
   uint8_t* ws = nullptr;
@@ -229,7 +231,9 @@ static void build_params(lu_handle_s* h) {
   char nm[128];
   int cin = c.in_channels;
   std::vector<int> skip_ch;
-  for (int l = 0; l < h->L; ++l) {
+  const bool only_up = c.block_kind == LU_BLOCK_UP, only_down = c.block_kind == LU_BLOCK_DOWN;
+  if (only_up) skip_ch.push_back(c.skip_channels);
+  for (int l = 0; l < h->L && !only_up; ++l) {
     skip_ch.push_back(cin);
     for (int j = 0; j < c.n_lstm[l]; ++j) {
       const int k = c.lstm_k[l][j], f = c.lstm_f[l][j];
@@ -252,14 +256,15 @@ static void build_params(lu_handle_s* h) {
       cin = f;
     }
   }
-  for (int u = 0; u < h->L; ++u) {
+  for (int u = 0; u < h->L && !only_down; ++u) {
     cin += skip_ch[h->L - 1 - u];
     for (int j = 0; j < c.n_up[u]; ++j) {
       const int k = c.up_k[u][j], f = c.up_f[u][j];
       snprintf(nm, sizeof nm, "UpLayers/%d/Conv/%d/", u, j);
       add_param(all, std::string(nm) + "kernel", {k, k, cin, f}, true);
       add_param(all, std::string(nm) + "bias", {f}, true);
-      const bool is_logits = (u == h->L - 1) && (j == c.n_up[u] - 1);
+      // the BN / LeakyReLU objects of the logits convolution are never called and own no variables (Networks.py:148-149)
+      const bool is_logits = (u == h->L - 1) && (j == c.n_up[u] - 1) && (!only_up || c.return_logits);
       if (!is_logits) {
         snprintf(nm, sizeof nm, "UpLayers/%d/BN/%d/", u, j);
         add_param(all, std::string(nm) + "gamma", {f}, true);
@@ -479,16 +484,26 @@ static int new_act(lu_handle_s* h, int frames, int H, int W, int creal) {
 static int build_plan(lu_handle_s* h) {
   const lu_config& c = h->cfg;
   const int L = h->L, B = c.batch, N = c.batch * c.max_t;
+  const bool net = c.block_kind == LU_BLOCK_NET, only_down = c.block_kind == LU_BLOCK_DOWN, only_up = c.block_kind == LU_BLOCK_UP;
   const int ts = 1 << (L - 1);                                  // total_stride (Networks.py:197-199)
-  const int minpad = c.pad_image ? ts : 0;                      // Networks.py:210
+  const int minpad = (net && c.pad_image) ? ts : 0;             // Networks.py:210; a block on its own never pads
   h->pad_y0 = minpad; h->pad_x0 = minpad;
-  const int pad_y1 = minpad + (ts - c.height % ts) % ts, pad_x1 = minpad + (ts - c.width % ts) % ts;
+  const int pad_y1 = net ? minpad + (ts - c.height % ts) % ts : 0, pad_x1 = net ? minpad + (ts - c.width % ts) % ts : 0;
   LU_REQUIRE(pad_y1 < c.height && pad_x1 < c.width && minpad < c.height && minpad < c.width,
              "REFLECT padding needs pad < image size (H=%d W=%d pad=%d/%d)", c.height, c.width, pad_y1, pad_x1);
   h->Hp = c.height + minpad + pad_y1; h->Wp = c.width + minpad + pad_x1;
-  for (int l = 0; l <= L; ++l) { h->lvlH[l] = h->Hp >> (l < L ? l : L - 1); h->lvlW[l] = h->Wp >> (l < L ? l : L - 1); }
+  // stride of the first convolution of each encoder block: 2 except in the last one (Networks.py:195-196), or what the
+  // caller of a stand-alone DownBlock2D passed
+  int lvl_stride[LU_MAX_LEVELS];
+  for (int l = 0; l < L; ++l) lvl_stride[l] = only_down ? c.block_stride : (l < L - 1 ? 2 : 1);
+  h->lvlH[0] = h->Hp; h->lvlW[0] = h->Wp;
+  for (int l = 0; l < L; ++l) {
+    LU_REQUIRE(h->lvlH[l] % lvl_stride[l] == 0 && h->lvlW[l] % lvl_stride[l] == 0,
+               "a stride-%d block needs even input sizes, got %d x %d", lvl_stride[l], h->lvlH[l], h->lvlW[l]);
+    h->lvlH[l + 1] = h->lvlH[l] / lvl_stride[l]; h->lvlW[l + 1] = h->lvlW[l] / lvl_stride[l];
+  }
   LU_REQUIRE(c.in_channels >= 1 && c.in_channels <= 4096, "bad in_channels=%d", c.in_channels);
-  if (c.in_channels == 1) {
+  if (c.in_channels == 1 && net) {
     // the CTC path: the 1-channel image is expanded into pw x pw patches (64 "channels", one 1x1 tap);
     // patch window = the largest kernel that reads the image directly
     h->pw = c.lstm_k[0][0];
@@ -500,12 +515,18 @@ static int build_plan(lu_handle_s* h) {
   h->ups.assign(L, UpStage());
   char nm[128];
   int cur_buf = -1, cur_c = c.in_channels;      // -1 = image patches
-  if (c.in_channels > 1) {                      // multi-channel images (the reference unit_test feeds 3, Networks.py:266):
+  if (c.in_channels > 1 || !net) {              // multi-channel images (the reference unit_test feeds 3, Networks.py:266):
     h->img_buf = new_act(h, N, h->Hp, h->Wp, c.in_channels);      // generic path, the image is just another NHWC source
     cur_buf = h->img_buf;
   }
   std::vector<int> skip_buf, skip_c;
-  for (int l = 0; l < L; ++l) {
+  if (only_up) {                                // UpBlock2D alone: the skip tensor is the second input (Networks.py:142)
+    LU_REQUIRE(c.skip_channels >= 1 && c.skip_channels <= 4096, "bad skip_channels=%d", c.skip_channels);
+    h->lvlH[0] = h->Hp * c.block_stride; h->lvlW[0] = h->Wp * c.block_stride;
+    h->skip_in_buf = new_act(h, N, h->lvlH[0], h->lvlW[0], c.skip_channels);
+    skip_buf.push_back(h->skip_in_buf); skip_c.push_back(c.skip_channels);
+  }
+  for (int l = 0; l < L && !only_up; ++l) {
     const int H = h->lvlH[l], W = h->lvlW[l];
     skip_buf.push_back(cur_buf); skip_c.push_back(cur_c);
     for (int j = 0; j < c.n_lstm[l]; ++j) {
@@ -534,10 +555,9 @@ static int build_plan(lu_handle_s* h) {
     for (int j = 0; j < c.n_down[l]; ++j) {
       ConvPlan cv;
       snprintf(nm, sizeof nm, "DownLayers/%d/Conv/%d", l, j);
-      cv.name = nm; cv.k = c.down_k[l][j]; cv.stride = (j == 0 && l < L - 1) ? 2 : 1;
+      cv.name = nm; cv.k = c.down_k[l][j]; cv.stride = (j == 0) ? lvl_stride[l] : 1;
       const int Hi = (j == 0) ? H : h->lvlH[l + 1], Wi = (j == 0) ? W : h->lvlW[l + 1];
       cv.Hin = Hi; cv.Win = Wi; cv.Hout = h->lvlH[l + 1]; cv.Wout = h->lvlW[l + 1];
-      if (l == L - 1) { cv.Hout = H; cv.Wout = W; cv.Hin = H; cv.Win = W; }
       cv.cout = c.down_f[l][j]; cv.BN = pick_bn(cv.cout); cv.npad = ceil_to(cv.cout, cv.BN); cv.n_tiles_n = cv.npad / cv.BN;
       cv.cm.kind = LU_COL_IDENTITY; cv.cm.n_real = cv.cout;
       cv.out_buf = new_act(h, N, cv.Hout, cv.Wout, cv.cout);
@@ -552,15 +572,16 @@ static int build_plan(lu_handle_s* h) {
       if (build_tables(h, cv)) return 1;
       cv.macs_per_frame *= (double)cv.Hout * cv.Wout;
       h->conv_of_level[l].push_back((int)h->convs.size());
+      if (only_down) h->block_out_conv = (int)h->convs.size();
       h->convs.push_back(cv);
       cur_buf = cv.out_buf; cur_c = cv.cout;
     }
   }
-  for (int u = 0; u < L; ++u) {
+  for (int u = 0; u < L && !only_down; ++u) {
     const int sl = L - 1 - u;                        // skip index (skip list reversed, Networks.py:242)
     const int H = h->lvlH[sl], W = h->lvlW[sl];
     int up_buf = cur_buf;
-    if (u > 0) {                                     // up_factor 2 except for the first block (Networks.py:202)
+    if (only_up ? c.block_stride == 2 : u > 0) {     // up_factor 2 except for the first block (Networks.py:202)
       up_buf = new_act(h, N, H, W, cur_c);
       h->ups[u].src_buf = cur_buf; h->ups[u].dst_buf = up_buf;
     }
@@ -571,7 +592,7 @@ static int build_plan(lu_handle_s* h) {
       cv.name = nm; cv.k = c.up_k[u][j]; cv.stride = 1;
       cv.Hin = cv.Hout = H; cv.Win = cv.Wout = W;
       cv.cout = c.up_f[u][j];
-      const bool is_logits = (u == L - 1) && (j == c.n_up[u] - 1);
+      const bool is_logits = (u == L - 1) && (j == c.n_up[u] - 1) && (!only_up || c.return_logits);
       cv.BN = pick_bn(cv.cout); cv.npad = ceil_to(cv.cout, cv.BN); cv.n_tiles_n = cv.npad / cv.BN;
       cv.cm.kind = LU_COL_IDENTITY; cv.cm.n_real = cv.cout;
       const int wparam = find_param(h, std::string(nm) + "/kernel");
@@ -596,11 +617,13 @@ static int build_plan(lu_handle_s* h) {
       if (build_tables(h, cv)) return 1;
       cv.macs_per_frame *= (double)H * W;
       h->conv_of_up[u].push_back((int)h->convs.size());
+      if (only_up) h->block_out_conv = (int)h->convs.size();
       h->convs.push_back(cv);
       cur_buf = cv.out_buf; cur_c = cv.cout;
     }
   }
-  LU_REQUIRE(h->logits_conv >= 0, "network has no output convolution");
+  LU_REQUIRE(!net || h->logits_conv >= 0, "network has no output convolution");
+  LU_REQUIRE(net || h->block_out_conv >= 0, "the block has no convolution");
   (void)B;
   if (c.train && build_train_plan(h)) return 1;
   return 0;
@@ -614,7 +637,7 @@ static void layout_workspace(lu_handle_s* h) {
   const int B = c.batch, N = c.batch * c.max_t;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return o; };
-  h->off_patches = take(c.in_channels == 1 ? (size_t)N * h->Hp * h->Wp * 64 * 2 : 1024);
+  h->off_patches = take(h->img_buf < 0 ? (size_t)N * h->Hp * h->Wp * 64 * 2 : 1024);
   for (auto& a : h->acts) a.off = take(a.bytes());
   h->raw_scratch_bytes = 0;
   for (auto& cv : h->convs) {
@@ -656,7 +679,7 @@ static void layout_workspace(lu_handle_s* h) {
   for (auto& cv : h->convs)
     if (cv.off_raw == (size_t)-1) cv.off_raw = h->off_raw_scratch;
   train_layout(h, off);
-  h->graph_ok = !c.train && N <= 8;
+  h->graph_ok = !c.train && N <= 8 && c.block_kind == LU_BLOCK_NET;
   if (h->graph_ok) {
     h->g_x_bytes = (size_t)N * c.in_channels * c.height * c.width * 4;
     h->g_out_bytes = (size_t)N * h->convs[h->logits_conv].cout * c.height * c.width * 4;
@@ -878,10 +901,21 @@ int lu_create(const lu_config* cfg, lu_handle* out) {
   LU_REQUIRE(cfg->n_levels >= 1 && cfg->n_levels <= LU_MAX_LEVELS, "n_levels must be in [1,%d]", LU_MAX_LEVELS);
   LU_REQUIRE(cfg->batch >= 1 && cfg->max_t >= 1 && cfg->height >= 1 && cfg->width >= 1, "bad shape");
   LU_REQUIRE(cfg->lrelu_alpha >= 0.f && cfg->lrelu_alpha <= 1.f, "lrelu_alpha must be in [0, 1] (Keras LeakyReLU default: 0.3), got %g", (double)cfg->lrelu_alpha);
+  LU_REQUIRE(cfg->block_kind == LU_BLOCK_NET || cfg->block_kind == LU_BLOCK_DOWN || cfg->block_kind == LU_BLOCK_UP,
+             "unknown block_kind %d", cfg->block_kind);
+  if (cfg->block_kind != LU_BLOCK_NET) {
+    LU_REQUIRE(cfg->n_levels == 1, "a stand-alone block is described by level 0 of the lists (n_levels = 1)");
+    LU_REQUIRE(cfg->block_stride == 1 || cfg->block_stride == 2, "stride / up_factor must be 1 or 2, got %d", cfg->block_stride);
+    LU_REQUIRE(!cfg->train, "stand-alone blocks are forward-only handles");
+    LU_REQUIRE(cfg->block_kind == LU_BLOCK_DOWN || cfg->max_t == 1, "UpBlock2D takes 4-D inputs: max_t must be 1");
+  }
   for (int l = 0; l < cfg->n_levels; ++l) {
-    LU_REQUIRE(cfg->n_lstm[l] >= (l == 0 ? 1 : 0) && cfg->n_lstm[l] <= LU_MAX_PER_LEVEL, "bad ConvLSTM count at level %d", l);
-    LU_REQUIRE(cfg->n_down[l] >= 1 && cfg->n_down[l] <= LU_MAX_PER_LEVEL, "bad conv count at level %d", l);
-    LU_REQUIRE(cfg->n_up[l] >= 1 && cfg->n_up[l] <= LU_MAX_PER_LEVEL, "bad up-conv count at level %d", l);
+    if (cfg->block_kind != LU_BLOCK_UP) {
+      LU_REQUIRE(cfg->n_lstm[l] >= (l == 0 ? 1 : 0) && cfg->n_lstm[l] <= LU_MAX_PER_LEVEL, "bad ConvLSTM count at level %d", l);
+      LU_REQUIRE(cfg->n_down[l] >= 1 && cfg->n_down[l] <= LU_MAX_PER_LEVEL, "bad conv count at level %d", l);
+    }
+    if (cfg->block_kind != LU_BLOCK_DOWN)
+      LU_REQUIRE(cfg->n_up[l] >= 1 && cfg->n_up[l] <= LU_MAX_PER_LEVEL, "bad up-conv count at level %d", l);
   }
 #ifdef LU_HOST_EMU
   LU_REQUIRE(cfg->engine == LU_ENGINE_SIMT, "host test build only has the scalar mirror engine");
@@ -1141,7 +1175,7 @@ static int run_lstm_layer(lu_handle_s* h, ConvPlan& cv, int T, int training, voi
 }
 
 static int forward_body(lu_handle h, const float* dev_x, int32_t T, int32_t training, float* dev_logits,
-                        float* dev_softmax, void* stream);
+                        float* dev_softmax, void* stream, const float* dev_skip = nullptr);
 
 int lu_set_graph_mode(lu_handle h, int32_t enable, int32_t* effective) {
   LU_REQUIRE(h, "null handle");
@@ -1156,6 +1190,7 @@ int lu_set_graph_mode(lu_handle h, int32_t enable, int32_t* effective) {
 int lu_forward(lu_handle h, const float* dev_x, int32_t T, int32_t training, float* dev_logits, float* dev_softmax,
                void* stream) {
   LU_REQUIRE(h && h->bound && h->dparams, "bind workspace and parameters first");
+  LU_REQUIRE(h->cfg.block_kind == LU_BLOCK_NET, "this handle is a stand-alone block: call lu_block_forward");
   LU_REQUIRE(dev_x && dev_logits && dev_softmax, "null tensor");
   LU_REQUIRE(T >= 1 && T <= h->cfg.max_t, "T=%d outside [1,%d]", T, h->cfg.max_t);
   if (!h->packed && lu_params_changed(h, stream)) return 1;
@@ -1209,9 +1244,17 @@ int lu_forward(lu_handle h, const float* dev_x, int32_t T, int32_t training, flo
 }
 
 static int forward_body(lu_handle h, const float* dev_x, int32_t T, int32_t training, float* dev_logits,
-                        float* dev_softmax, void* stream) {
+                        float* dev_softmax, void* stream, const float* dev_skip) {
   const lu_config& c = h->cfg;
   const int N = c.batch * T;
+  if (h->skip_in_buf >= 0) {                      // UpBlock2D alone: its second input
+    const ActBuf& sb = h->acts[h->skip_in_buf];
+    LuPrepImage pi;
+    pi.x = dev_skip; pi.out = reinterpret_cast<uint16_t*>(h->ws + sb.off);
+    pi.C = c.skip_channels; pi.H = sb.H; pi.W = sb.W; pi.Hp = sb.H; pi.Wp = sb.W; pi.pad_y0 = 0; pi.pad_x0 = 0;
+    pi.cpad = sb.cpad; pi.planes = sb.planes; pi.fmt = h->fmt; pi.channels_first = c.channels_first;
+    pf(h, (int64_t)N * sb.H * sb.W * (sb.cpad / 8), stream, pi);
+  }
   if (h->img_buf >= 0) {
     const ActBuf& ib = h->acts[h->img_buf];
     LuPrepImage pi;
@@ -1244,7 +1287,21 @@ static int forward_body(lu_handle h, const float* dev_x, int32_t T, int32_t trai
     for (int ci : h->conv_of_up[u])
       if (run_conv_layer(h, h->convs[ci], T, training, stream)) return 1;
   }
-  {
+  if (c.block_kind != LU_BLOCK_NET) {
+    // what the block returns (Networks.py:75,153): the last activation, or the last convolution's raw output
+    // (return_logits), as fp32 in the caller's layout
+    ConvPlan& oc = h->convs[h->block_out_conv];
+    LuBlockOut bo;
+    memset(&bo, 0, sizeof bo);
+    bo.out = dev_logits; bo.C = oc.cout; bo.H = oc.Hout; bo.W = oc.Wout; bo.channels_first = c.channels_first; bo.fmt = h->fmt;
+    if (oc.out_buf >= 0) {
+      const ActBuf& ob = h->acts[oc.out_buf];
+      bo.act = reinterpret_cast<const uint16_t*>(h->ws + ob.off); bo.cpad = ob.cpad; bo.planes = ob.planes;
+    } else {
+      bo.raw = reinterpret_cast<const float*>(h->ws + oc.off_raw); bo.cpad = oc.raw_cpad;
+    }
+    pf(h, (int64_t)N * oc.Hout * oc.Wout * oc.cout, stream, bo);
+  } else {
     ConvPlan& lc = h->convs[h->logits_conv];
     LuSoftmaxCrop sm;
     sm.raw = reinterpret_cast<const float*>(h->ws + lc.off_raw); sm.logits = dev_logits; sm.softmax = dev_softmax;
@@ -1259,6 +1316,25 @@ static int forward_body(lu_handle h, const float* dev_x, int32_t T, int32_t trai
   cudaError_t e = cudaGetLastError();
   LU_REQUIRE(e == cudaSuccess, "forward: %s", cudaGetErrorString(e));
 #endif
+  return 0;
+}
+
+int lu_block_forward(lu_handle h, const float* dev_x, const float* dev_skip, int32_t T, int32_t training, float* dev_out,
+                     void* stream) {
+  LU_REQUIRE(h && h->bound && h->dparams, "bind workspace and parameters first");
+  LU_REQUIRE(h->cfg.block_kind != LU_BLOCK_NET, "this handle is the whole network: call lu_forward");
+  LU_REQUIRE(dev_x && dev_out, "null tensor");
+  LU_REQUIRE((h->cfg.block_kind == LU_BLOCK_UP) == (dev_skip != nullptr), "the skip input belongs to UpBlock2D (and only to it)");
+  LU_REQUIRE(T >= 1 && T <= h->cfg.max_t, "T=%d outside [1,%d]", T, h->cfg.max_t);
+  if (!h->packed && lu_params_changed(h, stream)) return 1;
+  return forward_body(h, dev_x, T, training, dev_out, nullptr, stream, dev_skip);
+}
+
+int lu_block_out_shape(lu_handle h, int64_t* shape4) {
+  LU_REQUIRE(h && shape4, "null argument");
+  LU_REQUIRE(h->cfg.block_kind != LU_BLOCK_NET, "not a stand-alone block");
+  const ConvPlan& oc = h->convs[h->block_out_conv];
+  shape4[0] = h->cfg.batch; shape4[1] = oc.cout; shape4[2] = oc.Hout; shape4[3] = oc.Wout;
   return 0;
 }
 

@@ -534,6 +534,26 @@ struct LuDebugRead {     // bf16 planes NHWC (padded channels) -> fp32 NHWC (rea
   }
 };
 
+// stand-alone blocks: the returned tensor as fp32 in the caller's layout, from the 16-bit activation planes (NHWC, padded
+// channels) or from a convolution's fp32 raw output; item = one output element
+struct LuBlockOut {
+  const uint16_t* act; const float* raw; float* out;
+  int C, H, W, cpad, planes, fmt, channels_first;
+  LU_HD void operator()(int64_t i) const {
+    int c, y, x; int64_t n;
+    if (channels_first) { x = (int)(i % W); int64_t q = i / W; y = (int)(q % H); q /= H; c = (int)(q % C); n = q / C; }
+    else { c = (int)(i % C); int64_t q = i / C; x = (int)(q % W); q /= W; y = (int)(q % H); n = q / H; }
+    const int64_t p = (n * H + y) * (int64_t)W + x;
+    float v;
+    if (raw) v = raw[p * cpad + c];
+    else {
+      v = lu_h162f(act[p * (int64_t)(cpad * planes) + c], fmt);
+      if (planes == 2) v += lu_bf2f(act[p * (int64_t)(cpad * planes) + cpad + c]);
+    }
+    out[i] = v;
+  }
+};
+
 // generic conv-mirror launcher functor
 struct LuMirrorItem {
   LuConvParams p;

@@ -113,6 +113,17 @@ class LuSession:
         self._check(self.lib.lu_forward(self.h, x_ptr, int(T), 1 if training else 0, logits_ptr, softmax_ptr,
                                         self.be.stream()))
 
+    def block_forward(self, x_ptr, skip_ptr, T, training, out_ptr):
+        """A stand-alone DownBlock2D / UpBlock2D handle (lu_block_forward); skip_ptr is None for a DownBlock2D."""
+        self._check(self.lib.lu_block_forward(self.h, x_ptr, skip_ptr, int(T), 1 if training else 0, out_ptr,
+                                              self.be.stream()))
+
+    def block_out_shape(self):
+        """(frames per time step, channels, H_out, W_out) of what a stand-alone block returns."""
+        s = (ctypes.c_int64 * 4)()
+        self._check(self.lib.lu_block_out_shape(self.h, s))
+        return tuple(int(v) for v in s)
+
     def set_graph_mode(self, enable):
         eff = ctypes.c_int32()
         self._check(self.lib.lu_set_graph_mode(self.h, 1 if enable else 0, ctypes.byref(eff)))

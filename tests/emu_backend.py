@@ -80,3 +80,26 @@ def emu_forward(sess, x, training=False):
     softmax = np.zeros(shape, dtype=np.float32)
     sess.forward(x.ctypes.data, T, training, logits.ctypes.data, softmax.ctypes.data)
     return logits, softmax
+
+
+def emu_block_session(cfg):
+    """A stand-alone DownBlock2D / UpBlock2D handle (cfg from _lib.make_down_block_config / make_up_block_config)."""
+    from lstm_unet_b200 import _lib
+    from lstm_unet_b200.session import LuSession
+    lib = _lib.load_library(build_emu())
+    return LuSession(lib, NumpyBackend(), cfg)
+
+
+def emu_block_forward(sess, x, skip=None, training=False):
+    """-> the 4-D tensor the block returns (`activ` of DownBlock2D.call, the output of UpBlock2D.call), API layout."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    T = x.shape[1] if skip is None else 1
+    n, C, H, W = sess.block_out_shape()
+    shape = (n * T, C, H, W) if sess.cfg.channels_first else (n * T, H, W, C)
+    out = np.zeros(shape, dtype=np.float32)
+    sp = None
+    if skip is not None:
+        skip = np.ascontiguousarray(skip, dtype=np.float32)
+        sp = skip.ctypes.data
+    sess.block_forward(x.ctypes.data, sp, T, training, out.ctypes.data)
+    return out

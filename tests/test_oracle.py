@@ -181,3 +181,29 @@ def test_bilinear_x2_agrees_with_opencv():
         mine = O.resize_bilinear(torch.from_numpy(x), 2)[0, 0].numpy()
         ref = cv2.resize(x[0, 0], (2 * w, 2 * h), interpolation=cv2.INTER_LINEAR)
         assert np.abs(mine - ref).max() < 1e-6
+
+
+def test_blocks_on_their_own_chain_to_the_network():
+    """oracle/blocks_oracle.py (the reference's blocks called alone, Networks.py:100-119,155-175) chained the way
+    ULSTMnet2D.call chains them (Networks.py:233-245) reproduces OracleNet: one arithmetic on both sides."""
+    from oracle import blocks_oracle as BO
+    net = {'down_conv_kernels': [[(3, 8), (3, 8)], [(3, 12)]], 'lstm_kernels': [[(3, 6)], [(5, 10), (3, 10)]],
+           'up_conv_kernels': [[(3, 8)], [(3, 6), (1, 3)]]}
+    params = O.init_params(net, seed=4, randomize_bn=True, in_channels=2)
+    ora = O.OracleNet(net, 'NCHW', False, params=params, in_channels=2)
+    x = torch.randn(2, 3, 2, 16, 24, generator=torch.Generator().manual_seed(0))
+
+    def sub(prefix):
+        return {k.replace(prefix, prefix[:-2] + '0/'): v.clone() for k, v in params.items() if k.startswith(prefix)}
+    d0 = BO.OracleDownBlock(net['down_conv_kernels'][0], net['lstm_kernels'][0], 2, 'NCHW', params=sub('DownLayers/0/'))
+    d1 = BO.OracleDownBlock(net['down_conv_kernels'][1], net['lstm_kernels'][1], 1, 'NCHW', params=sub('DownLayers/1/'))
+    u0 = BO.OracleUpBlock(net['up_conv_kernels'][0], 1, 'NCHW', False, params=sub('UpLayers/0/'))
+    u1 = BO.OracleUpBlock(net['up_conv_kernels'][1], 2, 'NCHW', True, params=sub('UpLayers/1/'))
+    for call in range(2):                                        # second call: stateful carry in both
+        ref_logits, _ = ora(x + call, training=False)
+        xi = x + call
+        down0, skip0 = d0(xi, False)
+        down1, skip1 = d1(down0, False)
+        up = u0((skip1, skip0), False)
+        logits = u1((up, xi.reshape(6, 2, 16, 24)), False)
+        assert torch.allclose(logits.reshape(2, 3, 3, 16, 24), ref_logits, atol=1e-5), call
