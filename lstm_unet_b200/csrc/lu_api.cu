@@ -141,6 +141,7 @@ struct lu_handle_s {
   int last_T = 0, last_training = 0;
   int64_t launches = 0;
   bool bound = false, packed = false;
+  bool bn_fold_stale = false;     // a training forward moved the moving statistics: re-fold them before the next inference forward
   int num_sms = 148;
   TrainState tr;
 #ifndef LU_HOST_EMU
@@ -1051,6 +1052,20 @@ int lu_bind_params(lu_handle h, float* dev_params) {
   return 0;
 }
 
+// inference BatchNorm: moving statistics folded into the per-channel scale / shift of the conv epilogue
+static void fold_bn(lu_handle_s* h, void* stream) {
+  for (auto& cv : h->convs) {
+    if (cv.kind == LU_EPI_GRAD || !cv.has_bn) continue;
+    LuBnFold f;
+    f.gamma = h->dparams + h->params[cv.gamma].offset; f.beta = h->dparams + h->params[cv.beta].offset;
+    f.mov_mean = h->dparams + h->params[cv.mov_mean].offset; f.mov_var = h->dparams + h->params[cv.mov_var].offset;
+    f.scale = reinterpret_cast<float*>(h->ws + cv.off_scale); f.shift = reinterpret_cast<float*>(h->ws + cv.off_shift);
+    f.c_real = cv.cout; f.eps = 1e-3f;
+    pf(h, cv.npad, stream, f);
+  }
+  h->bn_fold_stale = false;
+}
+
 int lu_params_changed(lu_handle h, void* stream) {
   LU_REQUIRE(h && h->bound && h->dparams, "bind workspace and parameters first");
   for (auto& cv : h->convs) {
@@ -1062,15 +1077,8 @@ int lu_params_changed(lu_handle h, void* stream) {
     LuPackVec pb;
     pb.src = h->dparams + h->params[cv.bias_param].offset; pb.out = reinterpret_cast<float*>(h->ws + cv.off_bias); pb.cm = cv.cm;
     pf(h, cv.npad, stream, pb);
-    if (cv.has_bn) {
-      LuBnFold f;
-      f.gamma = h->dparams + h->params[cv.gamma].offset; f.beta = h->dparams + h->params[cv.beta].offset;
-      f.mov_mean = h->dparams + h->params[cv.mov_mean].offset; f.mov_var = h->dparams + h->params[cv.mov_var].offset;
-      f.scale = reinterpret_cast<float*>(h->ws + cv.off_scale); f.shift = reinterpret_cast<float*>(h->ws + cv.off_shift);
-      f.c_real = cv.cout; f.eps = 1e-3f;
-      pf(h, cv.npad, stream, f);
-    }
   }
+  fold_bn(h, stream);
   h->packed = true;
   return 0;
 }
@@ -1194,6 +1202,9 @@ int lu_forward(lu_handle h, const float* dev_x, int32_t T, int32_t training, flo
   LU_REQUIRE(dev_x && dev_logits && dev_softmax, "null tensor");
   LU_REQUIRE(T >= 1 && T <= h->cfg.max_t, "T=%d outside [1,%d]", T, h->cfg.max_t);
   if (!h->packed && lu_params_changed(h, stream)) return 1;
+  // model(x, training=True) updates the BatchNorm moving statistics (Keras does so without any optimizer step, as in the
+  // reference's unit_test loops): the next inference forward must normalise with the new ones
+  if (!training && h->bn_fold_stale) fold_bn(h, stream);
 #ifndef LU_HOST_EMU
   if (h->graph_mode && !training && !h->time_on) {
     // replay path: stage the input, launch the instantiated graph of this (T, state parity), copy the outputs out
@@ -1312,6 +1323,7 @@ static int forward_body(lu_handle h, const float* dev_x, int32_t T, int32_t trai
   }
   h->hcur ^= 1;                  // the last step of every ConvLSTM wrote h_T into the other buffer
   h->last_T = T; h->last_training = training;
+  if (training) h->bn_fold_stale = true;
 #ifndef LU_HOST_EMU
   cudaError_t e = cudaGetLastError();
   LU_REQUIRE(e == cudaSuccess, "forward: %s", cudaGetErrorString(e));
@@ -1327,6 +1339,7 @@ int lu_block_forward(lu_handle h, const float* dev_x, const float* dev_skip, int
   LU_REQUIRE((h->cfg.block_kind == LU_BLOCK_UP) == (dev_skip != nullptr), "the skip input belongs to UpBlock2D (and only to it)");
   LU_REQUIRE(T >= 1 && T <= h->cfg.max_t, "T=%d outside [1,%d]", T, h->cfg.max_t);
   if (!h->packed && lu_params_changed(h, stream)) return 1;
+  if (!training && h->bn_fold_stale) fold_bn(h, stream);
   return forward_body(h, dev_x, T, training, dev_out, nullptr, stream, dev_skip);
 }
 

@@ -35,7 +35,7 @@ def test_down_block_alone_matches_oracle(data_format, stride):
     sess.set_params(_np(ora.params))
     rng = np.random.default_rng(0)
     shape = (B, T, C, H, W) if data_format == 'NCHW' else (B, T, H, W, C)
-    for call, training in enumerate((False, False, True)):        # stateful carry, then BatchNorm batch statistics
+    for call, training in enumerate((False, False, True, False)):  # stateful carry, BatchNorm batch statistics, new moving statistics
         x = rng.standard_normal(shape).astype(np.float32)
         down, activ = ora(torch.from_numpy(x), training)
         got = emu_block_forward(sess, x, training=training)
@@ -62,7 +62,7 @@ def test_up_block_alone_matches_oracle(data_format, up_factor, return_logits):
     sess.set_params(_np(ora.params))
     rng = np.random.default_rng(1)
     H, W = h * up_factor, w * up_factor
-    for training in (False, True):
+    for training in (False, True, False):
         x = rng.standard_normal((N, C, h, w) if data_format == 'NCHW' else (N, h, w, C)).astype(np.float32)
         skip = rng.standard_normal((N, Cs, H, W) if data_format == 'NCHW' else (N, H, W, Cs)).astype(np.float32)
         ref = ora((torch.from_numpy(x), torch.from_numpy(skip)), training).numpy()

@@ -71,6 +71,23 @@ def test_forward_training_bn_and_moving_stats():
     sess.close()
 
 
+def test_inference_after_training_forward_uses_the_new_moving_statistics():
+    """model(x, True) moves the BatchNorm moving statistics without any optimizer step (the reference's unit_test loops,
+    Networks.py:256-277); the next model(x, False) must normalise with them, not with the constants folded earlier."""
+    net, B, T, H, W = NET_B, 2, 2, 10, 12
+    p_t, p_np = oracle_params_np(net, 7)
+    ora = O.OracleNet(net, 'NCHW', False, params=p_t)
+    sess = emu_session(net, data_format='NCHW', pad_image=False, batch=B, max_t=T, height=H, width=W, precision='bf16x3')
+    sess.set_params(p_np)
+    rng = np.random.default_rng(2)
+    for call, training in enumerate((False, True, True, False, False)):
+        x = (3.0 * rng.standard_normal((B, T, 1, H, W)) + 1.0).astype(np.float32)     # far from the moving statistics
+        ref_l, _ = ora(torch.from_numpy(x), training)
+        got_l, _ = emu_forward(sess, x, training)
+        assert rel_err(got_l, ref_l.numpy()) < 1e-3, (call, training, rel_err(got_l, ref_l.numpy()))
+    sess.close()
+
+
 def test_forward_bf16_mode_is_close():
     net, B, T, H, W = NET_A, 1, 2, 16, 16
     p_t, p_np = oracle_params_np(net, 7)

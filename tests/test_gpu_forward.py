@@ -67,6 +67,20 @@ def test_tcgen05_bf16x3_parity(net, B, T, H, W, pad, a_mode):
     assert model.launch_count() > 0
 
 
+def test_inference_after_training_forwards_reference_unit_test_loop():
+    """The reference's ULSTMnet2D.unit_test calls model(x, training=True) four times in a row (Networks.py:256-277): no
+    optimizer step in between, the BatchNorm moving statistics move with every call, and an inference call afterwards
+    normalises with the moved statistics."""
+    B, T, H, W = 2, 2, 35, 35
+    ora, model = make_pair(NET_ODD, 'NCHW', True, 9, precision='bf16x3')
+    rng = np.random.default_rng(4)
+    for call, training in enumerate((False, True, True, False, True, False)):
+        x = (2.0 * rng.standard_normal((B, T, 1, H, W)) + 0.5).astype(np.float32)
+        ref_l, _ = ora(torch.from_numpy(x), training)
+        logits, _ = model(x, training=training)
+        assert rel_err(logits.numpy(), ref_l.numpy()) < 1e-3, (call, training, rel_err(logits.numpy(), ref_l.numpy()))
+
+
 def test_tcgen05_bf16_mode_close():
     ora, model = make_pair(NET_WIDE, 'NCHW', True, 5, precision='bf16')
     x = np.random.default_rng(1).standard_normal((2, 2, 1, 40, 56)).astype(np.float32)
