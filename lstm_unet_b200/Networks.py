@@ -157,7 +157,7 @@ class _StandAloneBlock:
     def set_weights_dict(self, named):
         """{variable name: array}; names as inside a network, block index 0 (`DownLayers/0/Conv/1/kernel`, ...)."""
         if getattr(self, '_sess', None) is None:
-            self._pending_weights = dict(named)
+            self._pending_weights = {k: np.array(v, dtype=np.float32, copy=True) for k, v in named.items()}
         else:
             self._sess.set_params(named)
 

@@ -62,7 +62,7 @@ def test_up_block_unit_test_shapes_and_values(data_format, up_factor, return_log
     blk.set_weights_dict({k: v.numpy() for k, v in ora.params.items()})
     rng = np.random.default_rng(2)
     H, W = h * up_factor, w * up_factor
-    for training in (True, False):
+    for training in (True, False, True, False):     # first call in training mode (the reference's unit_test loop)
         x = rng.standard_normal((N, h, w, C) if data_format == 'NHWC' else (N, C, h, w)).astype(np.float32)
         skip = rng.standard_normal((N, H, W, C) if data_format == 'NHWC' else (N, C, H, W)).astype(np.float32)
         ref = ora((torch.from_numpy(x), torch.from_numpy(skip)), training).numpy()
