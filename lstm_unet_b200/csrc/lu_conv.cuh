@@ -757,11 +757,14 @@ struct LuWgTask {
 struct LuWgPairTask {
   int16_t stage[4];              // forward A stages (64-channel chunks of ONE source with the same window geometry), in
                                  // order of the accumulator columns; CTA r of the pair stages [r*nb, (r+1)*nb)
-  int16_t nb, ntaps;             // chunks per CTA (1 or 2); taps (<= 4 for nb == 1, <= 2 for nb == 2: 512 TMEM columns)
+  int16_t nb, ntaps;             // chunks per CTA (1 or 2); accumulator entries (their widths add up to <= 512 TMEM columns)
   int32_t n0;                    // first packed column of the 256-column slab: CTA r owns columns [n0 + 128 r, + 128)
   int32_t tile0, tile1;          // pixel-tile range [tile0, tile1)
   int32_t off[4];                // tap offsets (rows) inside the window
-  int32_t kb[4][4];              // K block (64 rows of dWp) written by tap t for stage s
+  int32_t disp[4];               // nb == 1 only: != 0 makes the entry a TAP PAIR -- a second tap `disp` window rows further is the
+                                 // second 64-channel group of each CTA's B half (N = 256 instead of 128, the dY operand is read
+                                 // once for both taps); 0 = a single tap
+  int32_t kb[4][4];              // K block (64 rows of dWp) written by the entry's accumulator column group (col >> 6)
   int32_t ychan[4];              // channel coordinate in dY of the slab's four 64-column chunks
 };
 
@@ -782,6 +785,7 @@ struct LuWgParams {
   int32_t tiles_x, tiles_y, T, skip_t0_src;
   int32_t dy_frame_mul, dy_frame_add, dy_planes, dy_cpad;
   int32_t a_win_bytes, stage_bytes, n_stages;
+  int32_t flush_scalar;          // pair kernel: 4-byte instead of 16-byte reductions in the flush (experiment switch)
 };
 
 namespace lutc {
@@ -1006,8 +1010,7 @@ __global__ void __launch_bounds__(256, 1) lu_wgrad_pair_kernel(const __grid_cons
     // ---------------------------------------------------------------- MMA issuer: the even CTA issues for the pair
     if (crank == 0) {
       int s = 0; uint32_t ph = 0;
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) |
-                             ((uint32_t)(256 >> 4) << 24);
+      const uint32_t idesc0 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(256 >> 4) << 24);
       const uint32_t a_hi = desc_hi_mn(1024u), b_hi = desc_hi_mn((uint32_t)v.pitch * 128u);
       const uint32_t b_lbo = nb == 2 ? (uint32_t)P.a_win_bytes : 0u;
       const uint32_t row2 = (uint32_t)v.pitch * 128u * 2u;         // two image rows = 16 pixels = one MMA K step
@@ -1019,12 +1022,18 @@ __global__ void __launch_bounds__(256, 1) lu_wgrad_pair_kernel(const __grid_cons
         tc_fence_after();
         const uint32_t base = s0 + (uint32_t)s * P.stage_bytes;
         if (elect_one()) {
+          uint32_t col0 = 0;
           for (int ti = 0; ti < tk.ntaps; ++ti) {
-            const uint32_t d_tmem = tmem_base + (uint32_t)(ti * N);
+            const bool tap_pair = tk.disp[ti] != 0;
+            const uint32_t Ni = tap_pair ? 256u : (uint32_t)N;
+            const uint32_t lbo = tap_pair ? (uint32_t)tk.disp[ti] * 128u : b_lbo;
+            const uint32_t idesc = idesc0 | ((Ni >> 3) << 17);
+            const uint32_t d_tmem = tmem_base + col0;
             const uint32_t b0 = base + w_off + (uint32_t)tk.off[ti] * 128u;
+            col0 += Ni;
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-              mma_bf16_pair(d_tmem, desc_lo_mn(base + (uint32_t)j * 2048u, 16384u), a_hi, desc_lo_mn(b0 + (uint32_t)j * row2, b_lbo), b_hi,
+              mma_bf16_pair(d_tmem, desc_lo_mn(base + (uint32_t)j * 2048u, 16384u), a_hi, desc_lo_mn(b0 + (uint32_t)j * row2, lbo), b_hi,
                             idesc, (first && j == 0) ? 0u : 1u);
           }
           tc_commit_pair(empty + 8u * s, (uint16_t)3);             // frees the stage in both CTAs
@@ -1047,15 +1056,28 @@ __global__ void __launch_bounds__(256, 1) lu_wgrad_pair_kernel(const __grid_cons
     tc_fence_after();
     if (any) {
       float* drow = P.dWp + (int64_t)(tk.n0 + (int)crank * 128 + row) * cp.ktot;
+      uint32_t col0 = 0;
       for (int ti = 0; ti < tk.ntaps; ++ti) {
-        const uint32_t taddr = tmem_base + (uint32_t)(ti * N) + ((uint32_t)(q * 32) << 16);
-        for (int col = 0; col < N; col += 16) {
+        const int Ni = tk.disp[ti] != 0 ? 256 : N;
+        const uint32_t taddr = tmem_base + col0 + ((uint32_t)(q * 32) << 16);
+        col0 += (uint32_t)Ni;
+        for (int col = 0; col < Ni; col += 16) {
           float vv[16];
           tmem_ld16(taddr + (uint32_t)col, vv);
           tmem_wait16(vv);
           float* dst = drow + (int64_t)tk.kb[ti][col >> 6] * LU_KBLK + (col & 63);      // 16 consecutive floats of this row
+          // a warp's 32 lanes are 32 rows of dWp = 32 different sectors per instruction whatever its width: four 16-byte
+          // reductions per 16 floats instead of sixteen 4-byte ones (r2_ncu_prof_wgrad_pair.txt: 367 M atomic sectors per
+          // launch = ~64 k clocks of flush per task at one sector per clock, on top of ~460 k clocks of MMAs)
+          if (P.flush_scalar) {                                      // LU_WGRAD_RED4=0: the round-2 form, for A/B runs
 #pragma unroll
-          for (int j = 0; j < 16; ++j) atomicAdd(dst + j, vv[j]);
+            for (int j = 0; j < 16; ++j) atomicAdd(dst + j, vv[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(vv[j]), "f"(vv[j + 1]), "f"(vv[j + 2]),
+                           "f"(vv[j + 3]) : "memory");
+          }
         }
       }
     }

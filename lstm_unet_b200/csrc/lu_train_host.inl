@@ -193,7 +193,9 @@ static void run_colsum(lu_handle_s* h, int gbuf, int frames_used, float* dst, in
 
 // ---- tcgen05 weight gradient: task lists for one forward conv (see lu_wgrad_tc_kernel / lu_wgrad_pair_kernel) ----------
 // nb_want: 0 = independent CTAs only; 1 / 2 = CTA-pair tasks (one or, where a source has >= 4 chunks, two 64-channel
-// chunks per CTA) for every group of chunks and every full 256-column slab, independent tasks for what is left.
+// chunks per CTA) for every group of chunks and every full 256-column slab, independent tasks for what is left;
+// 3 = CTA-pair tasks with one chunk per CTA whose accumulator entries are TAP PAIRS (N = 256: each CTA's B half is its
+// window at two tap offsets, so the dY operand is read once per two taps).
 static void build_wg_tasks(lu_handle_s* h, const ConvPlan& f, int frames, int only_src, int nb_want,
                            std::vector<LuWgTask>& out, std::vector<LuWgPairTask>& pout) {
   const bool x3 = h->planes == 2;
@@ -250,7 +252,7 @@ static void build_wg_tasks(lu_handle_s* h, const ConvPlan& f, int frames, int on
     const size_t ns = g.stages.size();
     if (full_slabs > 0) {
       while (ns - i >= 2) {
-        const int nb = (nb_want >= 2 && ns - i >= 4) ? 2 : 1;
+        const int nb = (nb_want == 2 && ns - i >= 4) ? 2 : 1;
         Unit u; u.n = 2 * nb; u.nb = nb; u.g = &g;
         for (int k = 0; k < 4; ++k) u.st[k] = k < u.n ? g.stages[i + k] : -1;
         punits.push_back(u);
@@ -279,8 +281,10 @@ static void build_wg_tasks(lu_handle_s* h, const ConvPlan& f, int frames, int on
   for (auto& u : sunits_rest) base_ctas += n_tap_tasks(u.g->taps.size(), 4) * (int)slabs_rest.size();
   // enough tasks to fill the machine, and pixel ranges small enough (~256 tiles = 32k pixels) that the range's
   // activations + gradients stay L2-resident while the wave of tasks sharing it runs
+  static int range_env = -1;                                         // LU_WGRAD_RANGE: pixel tiles per task (experiment switch)
+  if (range_env < 0) { const char* ce = getenv("LU_WGRAD_RANGE"); range_env = ce && atoi(ce) > 0 ? atoi(ce) : 256; }
   int split = (4 * h->num_sms + base_ctas - 1) / (base_ctas > 0 ? base_ctas : 1);
-  if (split < (tiles + 255) / 256) split = (tiles + 255) / 256;
+  if (split < (tiles + range_env - 1) / range_env) split = (tiles + range_env - 1) / range_env;
   if (base_ctas > 0 && (int64_t)split * base_ctas > LU_WG_MAX_TASKS) split = LU_WG_MAX_TASKS / base_ctas;
   if (split < 1) split = 1;
   if (split > tiles) split = tiles;
@@ -316,6 +320,37 @@ static void build_wg_tasks(lu_handle_s* h, const ConvPlan& f, int frames, int on
     for (auto& u : punits) {
       const Group& g = *u.g;
       const int nt = n_tap_tasks(g.taps.size(), u.nb == 2 ? 2 : 4);
+      if (nb_want == 3) {
+        // tap pairs: consecutive taps of the list (window offsets increase along it), a last single one if their number is odd;
+        // two entries (2 x 256 accumulator columns) per task
+        std::vector<std::pair<int, int>> ent;
+        for (size_t i = 0; i < g.taps.size(); i += 2) ent.push_back({g.taps[i], i + 1 < g.taps.size() ? g.taps[i + 1] : -1});
+        const int nte = n_tap_tasks(ent.size(), 2);                  // == nt
+        const uint32_t tb = f.astages[u.st[0]].tap_begin;
+        for (int sl = 0; sl < full_slabs; ++sl)
+          for (int ti_ = 0; ti_ < nte; ++ti_) {
+            int t0, cnt; tap_range(ent.size(), nte, ti_, t0, cnt);
+            LuWgPairTask tk; memset(&tk, 0, sizeof tk);
+            for (int k = 0; k < 4; ++k) tk.stage[k] = (int16_t)u.st[k];
+            tk.nb = 1; tk.ntaps = (int16_t)cnt;
+            for (int i = 0; i < cnt; ++i) {
+              const int ta = ent[t0 + i].first, tb2 = ent[t0 + i].second;
+              tk.off[i] = f.taps[tb + ta];
+              if (tb2 >= 0) {
+                tk.disp[i] = (int)f.taps[tb + tb2] - (int)f.taps[tb + ta];
+                tk.kb[i][0] = kb_begin[u.st[0]] + ta; tk.kb[i][1] = kb_begin[u.st[0]] + tb2;
+                tk.kb[i][2] = kb_begin[u.st[1]] + ta; tk.kb[i][3] = kb_begin[u.st[1]] + tb2;
+              } else {
+                tk.kb[i][0] = kb_begin[u.st[0]] + ta; tk.kb[i][1] = kb_begin[u.st[1]] + ta;
+              }
+            }
+            tk.n0 = sl * 256;
+            for (int c = 0; c < 4; ++c) tk.ychan[c] = ychan_of(sl * 4 + c);
+            tk.tile0 = (int)((int64_t)tiles * sp / split); tk.tile1 = (int)((int64_t)tiles * (sp + 1) / split);
+            if (tk.tile1 > tk.tile0) pout.push_back(tk);
+          }
+        continue;
+      }
       for (int sl = 0; sl < full_slabs; ++sl)
         for (int ti_ = 0; ti_ < nt; ++ti_) {
           int t0, cnt; tap_range(g.taps.size(), nt, ti_, t0, cnt);
@@ -416,8 +451,13 @@ static void emulate_wg_pair_tasks(const LuWgradMirror& w, const std::vector<LuWg
     const int ns = 2 * tk.nb, N = 64 * ns;
     const LuAStage st0 = cp.astages[tk.stage[0]];
     const LuSrcView& v = cp.src[st0.src];
+    // accumulator column group (64 columns) k of entry ti: which staged window it reads and at which extra row offset
+    // (two-window form: window k; tap-pair form: CTA k >> 1's window, second tap for odd k)
+    auto width = [&](int ti) { return tk.disp[ti] != 0 ? 256 : N; };
+    auto win_of = [&](int ti, int k) { return tk.disp[ti] != 0 ? (k >> 1) : k; };
+    auto extra_of = [&](int ti, int k) { return tk.disp[ti] != 0 ? (size_t)(k & 1) * (size_t)tk.disp[ti] : (size_t)0; };
     for (int crank = 0; crank < 2; ++crank) {                        // the two CTAs: 128 output channels each
-      D.assign((size_t)tk.ntaps * 128 * N, 0.f);
+      D.assign((size_t)tk.ntaps * 128 * 256, 0.f);
       bool any = false;
       for (int tile = tk.tile0; tile < tk.tile1; ++tile) {
         const int frame = tile / tiles_per_frame, rem = tile % tiles_per_frame;
@@ -439,17 +479,18 @@ static void emulate_wg_pair_tasks(const LuWgradMirror& w, const std::vector<LuWg
             for (int row = 0; row < 128; ++row) {                    // A operand: this CTA's two dY chunks
               const float g = lu_bf2f(gy[tk.ychan[2 * crank + (row >> 6)] + (row & 63)]);
               if (g == 0.f) continue;
-              float* d = &D[((size_t)ti * 128 + row) * N];
-              for (int col = 0; col < N; ++col) d[col] += g * win[col >> 6][wi * 64 + (col & 63)];
+              float* d = &D[((size_t)ti * 128 + row) * 256];
+              for (int col = 0; col < width(ti); ++col)
+                d[col] += g * win[win_of(ti, col >> 6)][(wi + extra_of(ti, col >> 6)) * 64 + (col & 63)];
             }
           }
       }
       if (!any) continue;
       for (int ti = 0; ti < tk.ntaps; ++ti)
         for (int row = 0; row < 128; ++row)
-          for (int col = 0; col < N; ++col)
+          for (int col = 0; col < width(ti); ++col)
             w.dWp[(int64_t)(tk.n0 + crank * 128 + row) * cp.ktot + (int64_t)tk.kb[ti][col >> 6] * LU_KBLK + (col & 63)] +=
-                D[((size_t)ti * 128 + row) * N + col];
+                D[((size_t)ti * 128 + row) * 256 + col];
     }
   }
 }
@@ -470,7 +511,8 @@ static int run_wgrad(lu_handle_s* h, ConvPlan& f, int gbuf, int T, float* grads,
   // LU_WGRAD_PAIR = chunks per CTA of the CTA-pair kernel (lu_wgrad_pair_kernel: transposed product, one M = 256 MMA per
   // pair): 1 (default), 2 (two chunks where a source has >= 4: fewer shared-memory reads per MMA but as much L2 -> SM
   // traffic as the independent form), 0 (independent CTAs only).  Measured on B200 (round 2, C3 train step, weight-gradient
-  // launches per step): 0 -> 88.5 ms, 1 -> 83.2 ms, 2 -> 84.0 ms.
+  // launches per step): 0 -> 88.5 ms, 1 -> 83.2 ms, 2 -> 84.0 ms.  3 = one chunk per CTA with TAP-PAIR accumulator entries (N = 256:
+  // the dY operand is read from shared memory once per two taps -- 64 instead of 96 B/clk of operand reads per SM).
   static int wg_pair_env = -1;
   if (wg_pair_env < 0) { const char* ce = getenv("LU_WGRAD_PAIR"); wg_pair_env = ce ? atoi(ce) : 1; }
   const int nb_want = h->planes == 1 ? wg_pair_env : 0;
@@ -532,6 +574,9 @@ static int run_wgrad(lu_handle_s* h, ConvPlan& f, int gbuf, int T, float* grads,
       wp.T = T; wp.skip_t0_src = w.skip_t0_src;
       wp.dy_frame_mul = (int)w.dy_frame_mul; wp.dy_frame_add = (int)w.dy_frame_add; wp.dy_planes = g.planes; wp.dy_cpad = g.cpad;
       wp.a_win_bytes = f.a_bytes;
+      static int red4_env = -1;
+      if (red4_env < 0) { const char* ce = getenv("LU_WGRAD_RED4"); red4_env = ce ? atoi(ce) : 1; }
+      wp.flush_scalar = red4_env == 0 ? 1 : 0;
       const int budget = 232448 - 1024 - 256;
       bool& attr = h->wg_attr_set;
       if (!attr) {
@@ -582,7 +627,7 @@ static int run_wgrad(lu_handle_s* h, ConvPlan& f, int gbuf, int T, float* grads,
     // TEST-ONLY: LU_WGRAD_EMU_TASKS=0|1|2 replays the task lists the tcgen05 kernels would get with that LU_WGRAD_PAIR
     if (const char* te = getenv("LU_WGRAD_EMU_TASKS")) {
       const int mode = atoi(te);
-      if (mode >= 0 && mode <= 2 && h->cfg.a_mode == LU_AMODE_HALO) {
+      if (mode >= 0 && mode <= 3 && h->cfg.a_mode == LU_AMODE_HALO) {
         std::vector<LuWgTask> tasks;
         std::vector<LuWgPairTask> ptasks;
         build_wg_tasks(h, f, w.frames, w.only_src, h->planes == 1 ? mode : 0, tasks, ptasks);

@@ -6,7 +6,7 @@ lu_wgrad_tc_kernel / lu_wgrad_pair_kernel do with a task: halo windows with the 
 into them, 128-pixel tiles, one accumulator per tap, the flush into the packed gradient; for a pair task the transposed
 product (each CTA: its 128 output channels x the input-channel chunks of both CTAs).  LU_WGRAD_EMU_TASKS = the
 LU_WGRAD_PAIR setting replayed: 0 = independent CTAs only, 1 = CTA pairs with one input chunk per CTA, 2 = two chunks per
-CTA where a source has four.  What this pins on the CPU is the task builder: every (stage, tap, column chunk, pixel range)
+CTA where a source has four, 3 = one chunk per CTA with tap-pair accumulator entries (N = 256).  What this pins on the CPU is the task builder: every (stage, tap, column chunk, pixel range)
 exactly once across the two lists, K block indices, which columns / chunks fall back to independent tasks.  The
 instruction-level protocol of the kernels is covered by the -m gpu tests."""
 import os
@@ -79,7 +79,7 @@ def compare(ref, got, layout, tol):
             assert err < tol, (step, e['name'], err)
 
 
-@pytest.mark.parametrize('mode', [0, 1, 2])
+@pytest.mark.parametrize('mode', [0, 1, 2, 3])
 def test_task_replay_equals_scalar_mirror_bf16(mode):
     """bf16 mode, wide net (few layers can pair: most sources have one chunk)"""
     ref, layout = grads_of(NET_W, 'bf16', None)
@@ -88,7 +88,7 @@ def test_task_replay_equals_scalar_mirror_bf16(mode):
     compare(ref, got, layout, 2e-5)
 
 
-@pytest.mark.parametrize('mode', [1, 2])
+@pytest.mark.parametrize('mode', [1, 2, 3])
 def test_pair_task_replay_equals_scalar_mirror(mode, capfd):
     """a net whose layers DO pair: 2- and 4-chunk sources, 4 and 8 output chunks"""
     os.environ['LU_WGRAD_EMU_VERBOSE'] = '1'
