@@ -885,6 +885,16 @@ static int launch_conv(lu_handle_s* h, ConvPlan& cv, int frames, const int* mul,
 // ------------------------------------------------------------------------------------------------------------------
 // C-ABI
 // ------------------------------------------------------------------------------------------------------------------
+template <int PW>
+static void prep_patches(lu_handle_s* h, const float* dev_x, int N, void* stream) {
+  const lu_config& c = h->cfg;
+  LuPrepPatchesT<PW> pp;
+  pp.x = dev_x; pp.out = reinterpret_cast<uint16_t*>(h->ws + h->off_patches);
+  pp.H = c.height; pp.W = c.width; pp.Hp = h->Hp; pp.Wp = h->Wp; pp.pad_y0 = h->pad_y0; pp.pad_x0 = h->pad_x0;
+  pp.pw = h->pw; pp.x3 = h->planes == 2; pp.fmt = h->fmt;
+  pf(h, (int64_t)N * h->Hp * h->Wp, stream, pp);
+}
+
 extern "C" {
 
 const char* lu_last_error(void) { return g_err.c_str(); }
@@ -1274,11 +1284,9 @@ static int forward_body(lu_handle h, const float* dev_x, int32_t T, int32_t trai
     pi.cpad = ib.cpad; pi.planes = ib.planes; pi.fmt = h->fmt; pi.channels_first = c.channels_first;
     pf(h, (int64_t)N * h->Hp * h->Wp * (ib.cpad / 8), stream, pi);
   } else {
-    LuPrepPatches pp;
-    pp.x = dev_x; pp.out = reinterpret_cast<uint16_t*>(h->ws + h->off_patches);
-    pp.H = c.height; pp.W = c.width; pp.Hp = h->Hp; pp.Wp = h->Wp; pp.pad_y0 = h->pad_y0; pp.pad_x0 = h->pad_x0;
-    pp.pw = h->pw; pp.x3 = h->planes == 2; pp.fmt = h->fmt;
-    pf(h, (int64_t)N * h->Hp * h->Wp, stream, pp);
+    if (h->pw == 5) prep_patches<5>(h, dev_x, N, stream);
+    else if (h->pw == 3) prep_patches<3>(h, dev_x, N, stream);
+    else prep_patches<0>(h, dev_x, N, stream);
   }
   for (int l = 0; l < h->L; ++l) {
     for (int ci : h->lstm_of_level[l])

@@ -159,26 +159,33 @@ LU_HDI int lu_reflect(int i, int n) {     // tf.pad REFLECT index (no edge repea
 // out (N,Hp,Wp,64) bf16.  Channel t < pw*pw holds the padded image at (y + t/pw - (pw-1)/2, x + t%pw - (pw-1)/2),
 // zero outside the padded image (that is the SAME zero padding of the consuming convolutions).  In bf16x3 mode
 // channels [32, 32+pw*pw) hold the lo parts.
-struct LuPrepPatches {
+// PW > 0: compile-time window size -- the loops unroll, every r[] index is a constant and the 64 channel values stay in
+// registers (with a run-time window the array lives in local memory: 128 bytes of stack per thread, ptxas -v);
+// PW == 0: any window size (run-time loops).  The host picks the instantiation (5 and 3 are the reference's kernels).
+template <int PW>
+struct LuPrepPatchesT {
   const float* x; uint16_t* out;
   int H, W, Hp, Wp, pad_y0, pad_x0, pw, x3, fmt;
   LU_HD void operator()(int64_t p) const {        // item = one pixel of the padded frame: 64 channels = 128 bytes
+    const int w_ = PW > 0 ? PW : pw;
     const int xx = (int)(p % Wp); int64_t q = p / Wp;
     const int yy = (int)(q % Hp); const int64_t n = q / Hp;
     uint16_t r[64];
 #pragma unroll
     for (int j = 0; j < 64; ++j) r[j] = 0;
-    const int c = (pw - 1) / 2;
+    const int c = (w_ - 1) / 2;
     const float* img = x + n * (int64_t)H * W;
-    for (int dy = 0; dy < pw; ++dy) {
+#pragma unroll
+    for (int dy = 0; dy < w_; ++dy) {
       const int py = yy + dy - c;
       if (py < 0 || py >= Hp) continue;
       const float* row = img + (int64_t)lu_reflect(py - pad_y0, H) * W;
-      for (int dx = 0; dx < pw; ++dx) {
+#pragma unroll
+      for (int dx = 0; dx < w_; ++dx) {
         const int px = xx + dx - c;
         if (px < 0 || px >= Wp) continue;
         const float v = row[lu_reflect(px - pad_x0, W)];
-        const int t = dy * pw + dx;
+        const int t = dy * w_ + dx;
         if (x3) { uint16_t h, l; lu_split(v, h, l); r[t] = h; r[32 + t] = l; }
         else r[t] = lu_f2h16(v, fmt);
       }

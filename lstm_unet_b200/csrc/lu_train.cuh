@@ -203,30 +203,31 @@ struct LuBnBwdParams {   // dgamma = sum g*xhat, dbeta = sum g, per-channel mean
 };
 
 // ---- bilinear x2 backward (transpose of LuUpsample2x): dsrc (=|+=) sum of the up-sampled gradient ---------------
-struct LuUpsample2xBwd {   // item = (n, iy, ix, c)
+struct LuUpsample2xBwd {   // item = (n, iy, ix, group of 8 channels)
   const uint16_t* gup; uint16_t* gsrc; int h, w, cpad, planes, accumulate;
-  LU_HD static int taps1d(int j, int n, int* idx, float* wt) {
-    int k = 0;
-    if (j >= 1) { idx[k] = 2 * j - 1; wt[k++] = 0.25f; }
-    idx[k] = 2 * j; wt[k++] = 0.75f;
-    idx[k] = 2 * j + 1; wt[k++] = 0.75f;
-    if (j <= n - 2) { idx[k] = 2 * j + 2; wt[k++] = 0.25f; }
-    if (j == 0) { idx[k] = 0; wt[k++] = 0.25f; }                 // clamped i-1 at the first output
-    if (j == n - 1) { idx[k] = 2 * n - 1; wt[k++] = 0.25f; }     // clamped i+1 at the last output
-    return k;
+  // Input pixel j receives from the up-sampled positions 2j-1, 2j, 2j+1, 2j+2 with weights .25, .75, .75, .25; the edge
+  // clamp of the forward (in[-1] := in[0], in[n] := in[n-1]) adds .25 to position 0 at j == 0 and to position 2n-1 at
+  // j == n-1, and the outer positions do not exist there.  Four fixed taps: absent ones get weight 0 at a clamped index.
+  LU_HD static void taps1d(int j, int n, int* idx, float* wt) {
+    idx[0] = j >= 1 ? 2 * j - 1 : 0;              wt[0] = j >= 1 ? 0.25f : 0.f;
+    idx[1] = 2 * j;                               wt[1] = j == 0 ? 1.0f : 0.75f;
+    idx[2] = 2 * j + 1;                           wt[2] = j == n - 1 ? 1.0f : 0.75f;
+    idx[3] = j <= n - 2 ? 2 * j + 2 : 2 * n - 1;  wt[3] = j <= n - 2 ? 0.25f : 0.f;
   }
-  LU_HD void operator()(int64_t i) const {          // item = (n, iy, ix, group of 8 channels)
+  LU_HD void operator()(int64_t i) const {
     const int cg = cpad / 8;
     const int c = (int)(i % cg) * 8; int64_t p = i / cg;
     const int ix = (int)(p % w); p /= w; const int iy = (int)(p % h); const int64_t n = p / h;
-    int yi[6], xi[6]; float yw[6], xw[6];
-    const int ny = taps1d(iy, h, yi, yw), nx = taps1d(ix, w, xi, xw);
+    int yi[4], xi[4]; float yw[4], xw[4];
+    taps1d(iy, h, yi, yw); taps1d(ix, w, xi, xw);
     const int ct = cpad * planes;
     float s[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) s[j] = 0.f;
-    for (int a = 0; a < ny; ++a)
-      for (int b = 0; b < nx; ++b) {
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
         float t[8];
         lu_ld8planes(gup + (((n * 2 * h + yi[a]) * 2 * w) + xi[b]) * (int64_t)ct + c, cpad, planes, t);
         const float wgt = yw[a] * xw[b];
