@@ -81,3 +81,25 @@ def test_reference_unit_tests_run():
     assert tuple(down.shape) == (2, 3, 25, 25, 64) and tuple(activ.shape) == (6, 25, 25, 64)
     assert tuple(UpBlock2D.unit_test().shape) == (6, 100, 100, 64)
     assert np.isfinite(activ.numpy()).all()
+
+
+def test_down_block_unroll_growth_keeps_weights_and_states():
+    """A longer unroll than the first call's re-opens the block's handle; weights and recurrent states carry over (the
+    stateful ConvLSTM state is per block, Networks.py:48-50), and a different B / H / W is refused like Keras does."""
+    from lstm_unet_b200.Networks import DownBlock2D
+    from oracle import blocks_oracle as BO
+    conv_kernels, lstm_kernels = [(3, 24)], [(5, 20)]
+    ora = BO.OracleDownBlock(conv_kernels, lstm_kernels, 1, 'NCHW', in_channels=1, seed=17)
+    blk = DownBlock2D(conv_kernels, lstm_kernels, 1, 'NCHW', precision='bf16x3')
+    blk.set_weights_dict({k: v.numpy() for k, v in ora.params.items()})
+    rng = np.random.default_rng(5)
+    for T in (2, 1, 4, 3):
+        x = rng.standard_normal((2, T, 1, 21, 19)).astype(np.float32)          # odd sizes are fine at stride 1
+        ref = ora(torch.from_numpy(x), False)[1].numpy()
+        got = blk(x, False)[1].numpy()
+        assert _rel(got, ref) < 1e-3, (T, _rel(got, ref))
+    with pytest.raises(ValueError):
+        blk(np.zeros((3, 1, 1, 21, 19), np.float32), False)
+    with pytest.raises(ValueError):
+        DownBlock2D(conv_kernels, lstm_kernels, 2, 'NCHW')(np.zeros((1, 1, 1, 21, 19), np.float32), False)   # stride 2, odd size
+    blk.close()
