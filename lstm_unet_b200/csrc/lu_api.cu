@@ -837,6 +837,16 @@ static int launch_conv(lu_handle_s* h, ConvPlan& cv, int frames, const int* mul,
   static int resident_env = -1;
   if (resident_env < 0) { const char* ce = getenv("LU_B_RESIDENT"); resident_env = ce ? atoi(ce) : 1; }
   tp.b_resident = (cv.b_resident && !cl2 && resident_env == 1) ? 1 : 0;
+  static int cst_env = -1;
+  if (cst_env < 0) { const char* ce = getenv("LU_CST_PER_TILE"); cst_env = ce ? atoi(ce) : 0; }
+  tp.cst_per_tile = cst_env;
+  // experiment switch LU_ACC_SPLIT (default off; measured no effect, see LuTcParams::acc_split): R partial accumulators for
+  // narrow N tiles
+  static int split_env = -1;
+  if (split_env < 0) { const char* ce = getenv("LU_ACC_SPLIT"); split_env = ce ? atoi(ce) : 1; }
+  tp.acc_split = 1;
+  if (epi.kind != LU_EPI_LSTM && !cl2 && (split_env == 2 || split_env == 4) && cv.BN * split_env * 2 <= 512 && cv.BN <= 64)
+    tp.acc_split = split_env;
   tp.tables_in_params = cv.ptab_ok ? 1 : 0;
   if (cv.ptab_ok) {
     memcpy(tp.st_tab, cv.pstages.data(), cv.pstages.size() * sizeof(LuAStage));

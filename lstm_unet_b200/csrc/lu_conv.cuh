@@ -251,6 +251,12 @@ struct LuTcParams {
   int32_t n_a_stages, n_b_stages, a_stage_bytes, b_stage_bytes;
   int32_t b_group;               // K blocks per weight stage (one mbarrier wait / commit per group)
   int32_t b_resident;            // 1: n_b_stages holds the whole weight panel; loaded for the CTA's first tile only
+  int32_t cst_per_tile;          // experiment switch (LU_CST_PER_TILE=1): re-stage the per-column constants for every tile
+  int32_t acc_split;             // experiment switch (LU_ACC_SPLIT = 2 / 4, default 1): R partial accumulators per tile for narrow N
+                                 // tiles -- the K = 16 MMAs of a K block go round-robin to R TMEM accumulators of BN columns each, summed
+                                 // by the epilogue, so that consecutive MMAs do not wait on the same accumulator.  Parity-green; measured
+                                 // no effect on B200 (the non-ConvLSTM part of the C2 step 12.4 -> 12.5 ms): dependent-MMA latency is not
+                                 // what bounds the 32 / 64-channel convs
   uint32_t idesc;
   int32_t total_tiles;           // work items: tiles (cluster 1) or pairs of M tiles sharing an N tile (cluster 2)
   int32_t num_mt;                // number of M tiles (frames * tiles per frame)
@@ -579,7 +585,8 @@ __global__ void __launch_bounds__(lutc::kThreads, 1) lu_conv_tc_kernel(const __g
       for (int tile = item0; tile < P.total_tiles; tile += item_step) {
         mbar_wait(tmem_empty + 8u * acc, phacc ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        const int R = (EPI == LU_EPI_LSTM) ? 1 : P.acc_split;
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN * R);
         uint32_t accum = 0;
         int gi = 0;                                             // position inside the current weight group
         uint32_t b_lo = 0;
@@ -603,8 +610,11 @@ __global__ void __launch_bounds__(lutc::kThreads, 1) lu_conv_tc_kernel(const __g
             }
 #pragma unroll
             for (int k = 0; k < LU_KBLK / 16; ++k) {
-              if (PAIR) mma_bf16_pair(d_tmem, a_lo + off8 + 2u * k, a_hi, b_lo + 2u * k, b_hi, idesc, accum | (uint32_t)k);
-              else mma_bf16(d_tmem, a_lo + off8 + 2u * k, a_hi, b_lo + 2u * k, b_hi, idesc, accum | (uint32_t)k);
+              // partial accumulator k mod R; the first R MMAs of a tile overwrite, everything after accumulates
+              const uint32_t d_k = d_tmem + (uint32_t)((k & (R - 1)) * BN);
+              const uint32_t acc_k = accum | (uint32_t)(k >= R);
+              if (PAIR) mma_bf16_pair(d_k, a_lo + off8 + 2u * k, a_hi, b_lo + 2u * k, b_hi, idesc, acc_k);
+              else mma_bf16(d_k, a_lo + off8 + 2u * k, a_hi, b_lo + 2u * k, b_hi, idesc, acc_k);
             }
             accum = 1;
             b_lo += bn_bytes16;
@@ -648,6 +658,22 @@ __global__ void __launch_bounds__(lutc::kThreads, 1) lu_conv_tc_kernel(const __g
     float* s_sq = s_const + kConstFloats + 256;
     if (bn_stats)
       for (int i = ep_tid; i < 512; i += kEpiThreads) { s_sum[i] = 0.f; s_sq[i] = 0.f; }
+    // Per-column constants (bias / folded-BN scale / shift) go through shared memory.  A convolution with ONE N tile has the
+    // same constants for every tile: staged once for both accumulator stages instead of a global-load round trip and a
+    // 256-thread barrier per 128-pixel tile (those showed as barrier + long-scoreboard stalls in the ncu capture of the
+    // 32-channel decoder convs).  Measured same-box A/B (LU_CST_PER_TILE): forward convs 10.0 -> 9.7 ms per train step, the
+    // inference step unchanged within noise -- it was not what bounds those launches.
+    const bool cst_per_tile = (EPI != LU_EPI_GRAD) && (cp.n_tiles_n > 1 || bn_stats || P.cst_per_tile);
+    if (EPI != LU_EPI_GRAD && !cst_per_tile) {
+      for (int i = ep_tid; i < 3 * BN; i += kEpiThreads) {
+        const int which = i / BN, j = i - which * BN;
+        const float* src = which == 0 ? e.bias : (which == 1 ? e.scale : e.shift);
+        const float val = (src != nullptr) ? src[j] : 0.f;
+        s_const[which * 256 + j] = val;
+        s_const[kConstFloats + which * 256 + j] = val;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+    }
     int acc = 0; uint32_t phacc = 0;
     for (int tile = item0; tile < P.total_tiles; tile += item_step) {
       int nt, mt; bool dummy;
@@ -661,22 +687,30 @@ __global__ void __launch_bounds__(lutc::kThreads, 1) lu_conv_tc_kernel(const __g
       const int64_t pix_out = (fout * e.OH + yo) * e.OW + xo;
       // per-column constants of this tile -> shared memory (double-buffered with the accumulator stage)
       float* cst = s_const + acc * kConstFloats;
-      if (EPI != LU_EPI_GRAD) {
+      if (cst_per_tile) {
         for (int i = ep_tid; i < (bn_stats ? 1 : 3) * BN; i += kEpiThreads) {
           const int which = i / BN, j = i - which * BN;
           const float* src = which == 0 ? e.bias : (which == 1 ? e.scale : e.shift);
           cst[which * 256 + j] = (src != nullptr) ? src[n0 + j] : 0.f;
         }
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
       }
-      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
       mbar_wait(tmem_full + 8u * acc, phacc);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(q * 32) << 16);
+      const int R = (EPI == LU_EPI_LSTM) ? 1 : P.acc_split;
+      const uint32_t taddr = tmem_base + (uint32_t)(acc * BN * R) + ((uint32_t)(q * 32) << 16);
       if (EPI == LU_EPI_CONV) {
         for (int col = half * 16; col < BN; col += 32) {
           float v[16];
           tmem_ld16(taddr + (uint32_t)col, v);
           tmem_wait16(v);
+          for (int r = 1; r < R; ++r) {                         // partial accumulators of a split tile
+            float w[16];
+            tmem_ld16(taddr + (uint32_t)(r * BN + col), w);
+            tmem_wait16(w);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] += w[j];
+          }
           if (bn_stats) {
             // column sums over the warp's 32 pixel rows by recursive halving: 31 shuffles for 16 sums + 16 squares, lane L
             // ends up with the total of value L (L < 16: sum of column col + L; else: squares of column col + L - 16)
@@ -701,6 +735,13 @@ __global__ void __launch_bounds__(lutc::kThreads, 1) lu_conv_tc_kernel(const __g
           float v[16];
           tmem_ld16(taddr + (uint32_t)col, v);
           tmem_wait16(v);
+          for (int r = 1; r < R; ++r) {
+            float w[16];
+            tmem_ld16(taddr + (uint32_t)(r * BN + col), w);
+            tmem_wait16(w);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] += w[j];
+          }
           if (valid) lu_epi_grad_chunk(e, pix_out, n0 + col, v);
         }
       } else {
