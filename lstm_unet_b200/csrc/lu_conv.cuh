@@ -251,6 +251,7 @@ struct LuTcParams {
   int32_t n_a_stages, n_b_stages, a_stage_bytes, b_stage_bytes;
   int32_t b_group;               // K blocks per weight stage (one mbarrier wait / commit per group)
   int32_t b_resident;            // 1: n_b_stages holds the whole weight panel; loaded for the CTA's first tile only
+  int32_t two_issuers;           // resident-weight convolutions: a second issuing thread (warp 2) takes the odd tiles / accumulator 1
   int32_t cst_per_tile;          // experiment switch (LU_CST_PER_TILE=1): re-stage the per-column constants for every tile
   int32_t acc_split;             // experiment switch (LU_ACC_SPLIT = 2 / 4, default 1): R partial accumulators per tile for narrow N
                                  // tiles -- the K = 16 MMAs of a K block go round-robin to R TMEM accumulators of BN columns each, summed
@@ -568,13 +569,21 @@ __global__ void __launch_bounds__(lutc::kThreads, 1) lu_conv_tc_kernel(const __g
         if (++sb == nB) { sb = 0; ph ^= 1u; }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 || (warp == 2 && !PAIR && P.two_issuers != 0)) {
     // ------------------------------------------------------------------ MMA issuer
     // One lane is elected ONCE and runs the whole loop nest (waits included); inside, everything it touches is
     // warp-uniform by construction, so ptxas keeps descriptors in uniform registers and the per-tap cost is a
     // handful of instructions.
+    // Narrow N tiles (resident weights, N <= 64) are bound by THIS loop -- ~40 dependent scalar instructions around four
+    // 16-clock MMAs per tap (source-level ncu sampling) -- so a second issuing thread (warp 2, idle after the TMEM
+    // allocation) takes the CTA's odd tiles: issuer w owns accumulator stage w and every second group of n_astages
+    // activation stages; the barriers are per stage, a commit covers the issuing thread's own MMAs.
+    const int nw = (!PAIR && P.two_issuers != 0) ? 2 : 1;
+    const int w = (warp == 2) ? 1 : 0;
     if ((!PAIR || crank == 0) && elect_one()) {                 // pair mode: the even CTA issues for both
-      int sa = 0, sb = 0, acc = 0; uint32_t pha = 0, phb = 0, phacc = 0;
+      int sa = 0, sb = 0, acc = w; uint32_t pha = 0, phb = 0, phacc = 0;
+      auto skip_a = [&](int n) { for (int i = 0; i < n; ++i) if (++sa == nA) { sa = 0; pha ^= 1u; } };
+      skip_a(w * cp.n_astages);                                 // the stages of tile 0 belong to issuer 0
       const int G = P.b_group;
       const uint32_t b_hi = desc_hi(1024u);
       const uint32_t bn_bytes16 = (uint32_t)(PAIR ? (BN >> 1) : BN) * 8u;   // one K block of weights in this CTA, in 16-byte units
@@ -582,7 +591,7 @@ __global__ void __launch_bounds__(lutc::kThreads, 1) lu_conv_tc_kernel(const __g
       const uint32_t idesc = PAIR ? ((P.idesc & ~(0x1Fu << 24)) | ((uint32_t)(256 >> 4) << 24)) : P.idesc;
       const bool resident = P.b_resident != 0;
       bool first_tile = true;
-      for (int tile = item0; tile < P.total_tiles; tile += item_step) {
+      for (int tile = item0 + w * item_step; tile < P.total_tiles; tile += nw * item_step) {
         mbar_wait(tmem_empty + 8u * acc, phacc ^ 1u);
         tc_fence_after();
         const int R = (EPI == LU_EPI_LSTM) ? 1 : P.acc_split;
@@ -639,7 +648,8 @@ __global__ void __launch_bounds__(lutc::kThreads, 1) lu_conv_tc_kernel(const __g
         first_tile = false;
         if (PAIR) tc_commit_pair(tmem_full + 8u * acc, (uint16_t)3);   // both halves of the M = 256 accumulator
         else tc_commit(tmem_full + 8u * acc);                   // accumulator complete -> epilogue
-        if (++acc == 2) { acc = 0; phacc ^= 1u; }
+        if (nw == 2) { phacc ^= 1u; skip_a(cp.n_astages); }     // own accumulator stage again; the other issuer's windows skipped
+        else if (++acc == 2) { acc = 0; phacc ^= 1u; }
       }
     }
     __syncwarp();
