@@ -850,17 +850,14 @@ static int launch_conv(lu_handle_s* h, ConvPlan& cv, int frames, const int* mul,
   static int two_env = -1;
   if (two_env < 0) { const char* ce = getenv("LU_TWO_ISSUERS"); two_env = ce ? atoi(ce) : 0; }
   // EXPERIMENTAL (LU_TWO_ISSUERS=1, default off): a second issuing thread for the resident-weight (narrow) convolutions.
-  // Measured on the C2 bench (n_astages 1-4, 8 activation stages): the non-ConvLSTM part of the step 12.5 -> 11.8 ms.  The two
-  // issuers walk ONE in-order ring of activation stages, each skipping the other's tiles; that is only sound when every ring
-  // slot always belongs to the same issuer, i.e. the ring depth is a multiple of 2 * n_astages -- otherwise an issuer reaches a
-  // slot two laps after it last looked at it and the parity wait aliases (the first version hung on a bf16x3 network with three
-  // stages per tile).  The ring is cut to such a depth here, or the mode is refused; not yet re-run on hardware with this guard.
-  tp.two_issuers = 0;
-  if (tp.b_resident && !cl2 && epi.kind != LU_EPI_LSTM && two_env == 1) {
-    const int per2 = 2 * (int)cv.astages.size();
-    const int depth = per2 > 0 ? (tp.n_a_stages / per2) * per2 : 0;
-    if (depth >= per2) { tp.two_issuers = 1; tp.n_a_stages = depth; }
-  }
+  // Measured on the C2 bench (1-4 activation stages per tile, 8 ring slots): the non-ConvLSTM part of the step 12.5 -> 11.8 ms.
+  // The two issuers walk ONE in-order ring of activation stages, each skipping the other's tiles without looking at their
+  // barriers.  That is sound only while the ring is DEEPER than one tile's stages: with n_a_stages <= n_astages an issuer can
+  // reach a slot two laps after the producer last filled it, and the parity wait aliases (it passes before the data of that
+  // lap has landed) -- the first version hung on hardware in the per-tap `direct` staging mode (27 stages per tile, 8 slots).
+  // tests/test_ring_protocol.py models the protocol and pins the rule; not yet re-run on hardware with this guard.
+  tp.two_issuers = (tp.b_resident && !cl2 && epi.kind != LU_EPI_LSTM && two_env == 1 &&
+                    tp.n_a_stages > (int)cv.astages.size()) ? 1 : 0;
   tp.tables_in_params = cv.ptab_ok ? 1 : 0;
   if (cv.ptab_ok) {
     memcpy(tp.st_tab, cv.pstages.data(), cv.pstages.size() * sizeof(LuAStage));
