@@ -529,8 +529,7 @@ def run_ours(args):
         cfg = workload_config(args, world)
         cfg.update({'parallelism': 'batch-sharded replicas x%d (no data-path collective)' % world, 'a_mode': args.a_mode,
                     'step_tflop': inf['flops_step'] / 1e12, 'cuda_graph': inf['graph'],
-                    'switches': {k: os.environ[k] for k in ('LU_PAIR', 'LU_WGRAD_CLUSTER', 'LU_CLUSTER', 'LU_CLUSTER_WIDE',
-                                                            'LU_B_RESIDENT', 'LU_WGRAD_ENGINE') if k in os.environ}})
+                    'switches': {k: v for k, v in sorted(os.environ.items()) if k.startswith('LU_')}})
         dt = {'bf16': 'bf16', 'fp16': 'fp16', 'bf16x3': 'bf16x3(split-bf16, fp32-equivalent)'}
         line = {
             'metric': METRIC, 'value': frames * args.steps / (ms * 1e-3), 'unit': 'frames/s', 'n_gpus': world,
@@ -596,8 +595,7 @@ def run_ours(args):
         else:
             cfg = workload_config(args, world, training=True)
             cfg.update({'parallelism': blk['parallelism'], 'a_mode': args.a_mode, 'step_tflop': blk['step_tflop'],
-                        'switches': {k: os.environ[k] for k in ('LU_PAIR', 'LU_WGRAD_CLUSTER', 'LU_CLUSTER', 'LU_CLUSTER_WIDE',
-                                                                'LU_B_RESIDENT', 'LU_WGRAD_ENGINE') if k in os.environ}})
+                        'switches': {k: v for k, v in sorted(os.environ.items()) if k.startswith('LU_')}})
             line = {'metric': METRIC, 'value': blk['value'], 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps,
                     'warmup': args.warmup, 'ms_per_step': blk['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak',
                     'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic', 'config': cfg, 'e2e': blk['e2e'],
